@@ -1,0 +1,156 @@
+"""Generate tests/golden/*.npz from the reference's OWN modules.
+
+Run in the build container (where /root/reference is mounted):
+
+    python tests/golden/make_golden.py
+
+It executes the reference's files verbatim (oracle/ref_loader.py loads them by
+path; nothing is copied) on seeded inputs and stores inputs' seeds + outputs.
+Weights are NOT stored: they are regenerated from the seed by
+``led-net_b200/synth.py`` (numpy PCG64, platform-stable), keeping fixtures small.
+
+Fixtures
+* r0_head_k2.npz  : DDRNet(channels=32,ppm=128) trunk with stem taps + LEDHead(K=2)
+                    eval on 1x3x64x128 -> c5/x1/x2 features, 3 head logits, the
+                    patched predict_by_feat fusion, argmax.
+* fuse_odd.npz    : predict_by_feat on odd sizes (ceil paths), K=2.
+* iou.npz         : IoUMetric.intersect_and_union + total_area_to_metrics + compute.
+* ohem.npz        : OhemCrossEntropy (with and without class_weight) + accuracy,
+                    forward values and d(loss)/d(score).
+* train_k2.npz    : train-mode LEDHead.loss_by_feat losses on a 2x3x64x64 batch.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+OUT = os.path.dirname(os.path.abspath(__file__))
+
+from oracle import ref_loader  # noqa: E402
+import lednet_b200  # noqa: E402,F401  (import shim for the hyphenated package dir)
+from lednet_b200 import synth  # noqa: E402
+
+
+class _PixelData:
+    def __init__(self, data):
+        self.data = data
+        self.shape = data.shape[-2:]
+
+
+class _Sample:
+    def __init__(self, label):
+        self.gt_sem_seg = _PixelData(label)
+
+
+def ref_backbone_with_taps(ddr, x):
+    """R0 = verbatim DDRNet forward plus the two stem taps (stem[0], stem[1])."""
+    taps = {}
+    h0 = ddr.stem[0].register_forward_hook(lambda m, i, o: taps.__setitem__('x1', o.clone()))
+    h1 = ddr.stem[1].register_forward_hook(lambda m, i, o: taps.__setitem__('x2', o.clone()))
+    out = ddr(x)
+    h0.remove(), h1.remove()
+    return out, taps['x1'], taps['x2']
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(4)
+    ref = ref_loader.load()
+
+    # ---------------- r0_head_k2 -------------------------------------------------
+    ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,
+                     norm_cfg=dict(type='BN', requires_grad=True), align_corners=False)
+    head = ref.LEDHead(in_channels=128, channels=64, num_classes=2, dropout_ratio=0.,
+                       norm_cfg=dict(type='BN', requires_grad=True), align_corners=False,
+                       loss_decode=[dict(type='OhemCrossEntropy', thres=0.9, min_kept=131072,
+                                         loss_weight=1.0),
+                                    dict(type='OhemCrossEntropy', thres=0.9, min_kept=131072,
+                                         loss_weight=0.4)])
+    ddr.load_state_dict(synth.make_state_dict(ddr.state_dict(), seed=2))
+    head.load_state_dict(synth.make_state_dict(head.state_dict(), seed=3))
+    ddr.eval(), head.eval()
+    from oracle import preprocess
+    img = synth.make_images_u8(1, 64, 128, seed=0)
+    x = preprocess(img)
+    with torch.no_grad():
+        c5, x1, x2 = ref_backbone_with_taps(ddr, x)
+        xc, h1, h2 = head.forward((c5, x1, x2))
+        fused = head.predict_by_feat((xc, h1, h2), [dict(img_shape=(64, 128))])
+        pred = fused.argmax(dim=1)
+    np.savez_compressed(os.path.join(OUT, 'r0_head_k2.npz'), c5=c5.numpy(), x1=x1.numpy(),
+                        x2=x2.numpy(), xc=xc.numpy(), h1=h1.numpy(), h2=h2.numpy(),
+                        fused=fused.numpy(), pred=pred.numpy().astype(np.uint8),
+                        n_params_backbone=sum(p.numel() for p in ddr.parameters()),
+                        n_params_head=sum(p.numel() for p in head.parameters()))
+
+    # ---------------- fuse_odd ---------------------------------------------------
+    g = np.random.default_rng(11)
+    xc_o = torch.from_numpy(g.normal(size=(2, 2, 13, 7)).astype(np.float32))
+    h2_o = torch.from_numpy(np.maximum(g.normal(size=(2, 2, 25, 13)), 0).astype(np.float32))
+    h1_o = torch.from_numpy(np.maximum(g.normal(size=(2, 2, 50, 26)), 0).astype(np.float32))
+    with torch.no_grad():
+        fo = head.predict_by_feat((xc_o, h1_o, h2_o), [dict(img_shape=(100, 52))])
+    np.savez_compressed(os.path.join(OUT, 'fuse_odd.npz'), xc=xc_o.numpy(), h1=h1_o.numpy(),
+                        h2=h2_o.numpy(), fused=fo.numpy())
+
+    # ---------------- iou --------------------------------------------------------
+    K = 19
+    pred_i = torch.from_numpy(g.integers(0, K, (3, 96, 160)))
+    lab_i = synth.make_labels(3, 96, 160, K, seed=5)
+    lab_i[0, :4, :4] = 40              # out-of-range, not ignore: histc drops it from area_label
+    res = [ref.IoUMetric.intersect_and_union(pred_i[i], lab_i[i], K, 255) for i in range(3)]
+    cols = tuple(zip(*res))
+    tot = [sum(c) for c in cols]
+    met = ref.IoUMetric.total_area_to_metrics(*tot, ['mIoU', 'mDice', 'mFscore'], None, 1)
+    m = ref.IoUMetric(ignore_index=255, iou_metrics=['mIoU'])
+    m.dataset_meta = dict(classes=[str(i) for i in range(K)])
+    summary = m.compute_metrics(list(res))
+    np.savez_compressed(
+        os.path.join(OUT, 'iou.npz'), pred=pred_i.numpy().astype(np.uint8),
+        label=lab_i.numpy().astype(np.uint8),
+        areas=np.stack([torch.stack(list(c)).numpy() for c in cols]),   # [4,3,K]
+        **{'met_' + k: v for k, v in met.items()},
+        **{'sum_' + k: np.float64(v) for k, v in summary.items()})
+
+    # ---------------- ohem -------------------------------------------------------
+    Kc = 5
+    score = torch.from_numpy(g.normal(scale=2.0, size=(2, Kc, 24, 40)).astype(np.float32))
+    target = synth.make_labels(2, 24, 40, Kc, seed=7, block=8)
+    cw = [0.8, 1.2, 1.0, 0.5, 1.5]
+    out = dict(score=score.numpy(), target=target.numpy().astype(np.uint8), class_weight=np.array(cw))
+    for tag, kw in [('a', dict(thres=0.9, min_kept=500, loss_weight=1.0)),
+                    ('b', dict(thres=0.3, min_kept=1200, loss_weight=0.4)),
+                    ('c', dict(thres=0.7, min_kept=100000, loss_weight=1.0, class_weight=cw))]:
+        s = score.clone().requires_grad_(True)
+        loss = ref.OhemCrossEntropy(**kw)(s, target)
+        loss.backward()
+        out['loss_' + tag] = loss.detach().numpy()
+        out['grad_' + tag] = s.grad.numpy()
+    out['acc'] = ref.accuracy(score, target, ignore_index=255).numpy()
+    np.savez_compressed(os.path.join(OUT, 'ohem.npz'), **out)
+
+    # ---------------- train_k2 ---------------------------------------------------
+    ddr.train(), head.train()
+    img_t = synth.make_images_u8(2, 64, 64, seed=9)
+    lab_t = synth.make_labels(2, 64, 64, 2, seed=10, block=8)
+    xt = preprocess(img_t)
+    (c3, c5t), x1t, x2t = ref_backbone_with_taps(ddr, xt)
+    logits = head.forward((c3, c5t, x1t, x2t))
+    samples = [_Sample(lab_t[i:i + 1]) for i in range(2)]
+    # small min_kept so the k-th statistic (not only `thres`) is exercised
+    for l in head.loss_decode:
+        l.min_kept = 1000
+    losses = head.loss_by_feat(logits, samples)
+    np.savez_compressed(os.path.join(OUT, 'train_k2.npz'),
+                        **{k: v.detach().numpy() for k, v in losses.items()},
+                        c3=c3.detach().numpy())
+    for f in sorted(os.listdir(OUT)):
+        if f.endswith('.npz'):
+            print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == '__main__':
+    main()
