@@ -1,0 +1,300 @@
+#!/usr/bin/env python
+"""LED-Net hot-path benchmark (BASELINE.json: img/s @1024x2048 bf16, % of roofline).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the hot path over one batch of synthetic input on every rank:
+normalised fp32 NCHW images (what `model(inputs, mode='predict')` receives in the reference's
+tools/analysis_tools/benchmark.py:88-101 - preprocessing excluded, fusion/argmax included) ->
+backbone -> head -> fused 3-level logit fusion + argmax -> confusion matrix vs synthetic labels
+(+ one int64 all-reduce of the (K+1)xK matrix when N > 1).  Workload = BASELINE config 2:
+batch 16 per GPU, 1024x2048, K=19, bf16 activations.  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOAD = dict(workload='LED-Net(R0 trunk)+LEDHead whole inference, fused argmax + confusion matrix',
+                batch_per_gpu=16, height=1024, width=2048, num_classes=19)
+METRIC, UNIT = 'LED-Net img/s @1024x2048 bf16', 'img/s'
+
+
+def peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.isfile(p):
+        d = json.load(open(p))
+        return dict(hbm=d['hbm_gbs'], tc_burst=d['bf16_tflops'], tc_sustained=d['bf16_tflops_sustained'],
+                    source='measured (MEASURED_PEAKS.json)')
+    return dict(hbm=6650.0, tc_burst=1590.0, tc_sustained=1400.0, source='fallback (B200_PROFILING.md)')
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ('index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,'
+         'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+         'clocks_event_reasons.sw_power_cap')
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', f'--query-gpu={self.Q}', '--format=csv,noheader,nounits',
+                                          '-lms', '100', '-i', str(self.index)], stdout=subprocess.PIPE, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(',')])
+
+    def stop(self):
+        if not self.proc:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=['nvidia-smi unavailable'])
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = sorted(float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit())
+        reasons = set()
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        for r in self.rows:
+            if len(r) >= 8:
+                for n, v in zip(names, r[4:8]):
+                    if v.lower().startswith('active'):
+                        reasons.add(n)
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        return dict(sm_mhz=sm[len(sm) // 2] if sm else None, sm_max_mhz=max(mx) if mx else None,
+                    reasons=sorted(reasons), samples=len(sm))
+
+
+def cpu_reference_run(steps, warmup, threads=None):
+    """The reference's own CPU implementation of the path (oracle restatement of the mmseg modules,
+    same ATen CPU kernels): fp32 NCHW, eval, no_grad, batch 1 at 1024x2048, K=19."""
+    import torch
+    import oracle
+    import lednet_b200  # noqa: F401
+    from lednet_b200 import synth
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    K, H, W = WORKLOAD['num_classes'], WORKLOAD['height'], WORKLOAD['width']
+    o = oracle.OracleSegmentor(num_classes=K).eval()
+    o.load_state_dict(synth.make_state_dict(o.state_dict(), seed=2))
+    x = oracle.preprocess(synth.make_images_u8(1, H, W, seed=0))
+    lab = synth.make_labels(1, H, W, K, seed=1)
+    for _ in range(warmup):
+        o.predict_and_score(x, lab)
+    ts = []
+    for _ in range(steps):
+        t0 = time.perf_counter()
+        o.predict_and_score(x, lab)
+        ts.append(time.perf_counter() - t0)
+    total = sum(ts)
+    return dict(value=steps / total, ms_per_step=1e3 * total / steps, cores=cores,
+                sample=f'{steps} x 1 image 1024x2048 K=19 fp32 (oracle = reference modules restated), '
+                       f'{warmup} warm-up, {torch.get_num_threads()} threads')
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=10)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--batch', type=int, default=WORKLOAD['batch_per_gpu'])
+    ap.add_argument('--height', type=int, default=WORKLOAD['height'])
+    ap.add_argument('--width', type=int, default=WORKLOAD['width'])
+    ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--profile-ops', action='store_true', help='print the per-op table to stderr')
+    ap.add_argument('--conv-backend', type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return
+        r = cpu_reference_run(max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+        line = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
+                    vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
+                    config=dict(WORKLOAD, batch_per_gpu=1, note='CPU host cores; bounded sample of the same workload'),
+                    cpu_baseline=dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample']),
+                    e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import warnings
+    import torch
+    import lednet_b200 as L
+    from lednet_b200 import synth, ops
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=dev)
+
+    K, N, H, W = WORKLOAD['num_classes'], args.batch, args.height, args.width
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
+                                                       dropout_ratio=0.),
+                             data_preprocessor=dict(type='SegDataPreProcessor', bgr_to_rgb=True),
+                             compute_dtype=args.dtype).eval()
+    m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
+    if args.conv_backend:
+        sd = {'backbone.' + k: v for k, v in m.backbone.state_dict().items()}
+        sd.update({'decode_head.' + k: v for k, v in m.decode_head.state_dict().items()})
+        m._engine = L.Engine(sd, K, dtype=args.dtype, conv_backend=args.conv_backend)
+    eng = m.engine()
+
+    # synthetic inputs, resident in HBM (seeded per rank: every rank owns its own shard of images)
+    img_u8_host = synth.make_images_u8(N, H, W, seed=100 + rank).pin_memory()
+    lab_host = synth.make_labels(N, H, W, K, seed=200 + rank).to(torch.uint8).pin_memory()
+    img_u8 = img_u8_host.to(dev, non_blocking=True)
+    mean = torch.tensor(L.engine.MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(L.engine.STD, device=dev).view(1, 3, 1, 1)
+    x = ((img_u8[:, [2, 1, 0]].float() - mean) / std).contiguous()     # 403 MB > 126 MB L2
+    lab = lab_host.to(dev, non_blocking=True)
+    pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((K + 1, K), dtype=torch.int64, device=dev)
+
+    def step():
+        eng.forward_infer(x, pred=pred)
+        ops.confusion_accumulate(pred, lab, K, 255, cm)
+        if dist is not None:
+            # the eval collective of the path: one int64 (K+1)xK all-reduce (2.9 KB)
+            g = cm.clone()
+            dist.all_reduce(g)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.15)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = t.item() / args.steps
+    clocks = sampler.stop() if rank == 0 else None
+    launches_per_step = eng.plan_launches() + 1
+
+    # ---- end-to-end through the public API with HOST buffers: pinned uint8 images + labels in,
+    #      (fused-preprocess) forward, confusion matrix, matrix read back to the host
+    cm_host = torch.empty((K + 1, K), dtype=torch.int64).pin_memory()
+    img_dev = torch.empty_like(img_u8)
+    lab_dev = torch.empty_like(lab)
+
+    def e2e_step():
+        img_dev.copy_(img_u8_host, non_blocking=True)
+        lab_dev.copy_(lab_host, non_blocking=True)
+        p = m.predict_labels(img_dev, pred=pred)
+        c = ops.confusion_accumulate(p, lab_dev, K, 255)
+        if dist is not None:
+            dist.all_reduce(c)
+        cm_host.copy_(c, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e2e_steps = max(3, args.steps // 2)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+    e2e_ms = t2.item() / e2e_steps
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- per-op roofline (events on the launching stream; algorithmic FLOPs/bytes from the engine)
+    pk = peaks()
+    eng.forward_infer(x, pred=pred)
+    prof = eng.profile_ops(iters=3)
+    info = eng.op_info()
+    fam = {}
+    roof_ms = 0.0
+    for (name, t_ms), (_, kind, fl, by) in zip(prof, info):
+        f = fam.setdefault(kind, dict(ms=0.0, flops=0.0, bytes=0.0, n=0))
+        f['ms'] += t_ms; f['flops'] += fl; f['bytes'] += by; f['n'] += 1
+        roof_ms += max(fl / (pk['tc_sustained'] * 1e12), by / (pk['hbm'] * 1e9)) * 1e3
+    if args.profile_ops:
+        for (name, t_ms), (_, kind, fl, by) in zip(prof, info):
+            r = max(fl / (pk['tc_sustained'] * 1e12), by / (pk['hbm'] * 1e9)) * 1e3
+            print(f'{name:55s} {kind:13s} {t_ms:8.3f} ms  roof {r:7.3f} ms  {100 * r / max(t_ms, 1e-9):5.1f}%  '
+                  f'{fl / 1e9:8.2f} GF {by / 1e6:8.1f} MB', file=sys.stderr)
+    dom_kind, dom = max(fam.items(), key=lambda kv: kv[1]['ms'])
+    tensor_bound = dom['flops'] / (pk['tc_sustained'] * 1e12) > dom['bytes'] / (pk['hbm'] * 1e9)
+    if tensor_bound:
+        ach = dom['flops'] / (dom['ms'] * 1e-3) / 1e12
+        roof = dict(bound='tensor', achieved=ach, peak=pk['tc_sustained'], unit='TFLOP/s', frac=ach / pk['tc_sustained'])
+    else:
+        ach = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
+        roof = dict(bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'])
+    roof.update(traffic=None, kernel=dom_kind, launches_per_step=dom['n'], kernel_ms_per_step=dom['ms'],
+                kernel_share_of_step=dom['ms'] / sum(f['ms'] for f in fam.values()),
+                peak_source=pk['source'], step_roofline_ms=roof_ms,
+                step_frac_of_per_layer_roofline=roof_ms / ms_step)
+
+    cpu = None
+    if not args.no_cpu_baseline:
+        r = cpu_reference_run(3, 1)
+        cpu = dict(value=r['value'], unit=UNIT, cores=r['cores'], kind='port', sample=r['sample'])
+
+    line = dict(
+        metric=METRIC, value=world * N / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
+        warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
+        dtype=args.dtype, data='synthetic',
+        config=dict(WORKLOAD, batch_per_gpu=N, height=H, width=W, global_batch=world * N,
+                    parallelism=f'dp{world} (batch-sharded, one int64 confusion-matrix all-reduce per step)',
+                    l2='inputs larger than L2 (403 MB fp32 images per step vs 126 MB L2)',
+                    input='normalised fp32 NCHW resident in HBM; raw uint8 from pinned host memory for e2e'),
+        clocks=clocks, gpu_launches=launches_per_step * args.steps,
+        e2e=dict(value=world * N / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
+                 h2d_bytes_per_step=img_u8_host.numel() + lab_host.numel(), d2h_bytes_per_step=cm_host.numel() * 8),
+        roofline=roof, cpu_baseline=cpu)
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

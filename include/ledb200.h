@@ -1,0 +1,194 @@
+/*
+ * ledb200.h - C ABI of libledb200.so: hand-written sm_100a CUDA kernels for the
+ * LED-Net data-parallel hot path (backbone forward -> bilateral fusion -> seg head
+ * -> 3-level logit fusion -> argmax -> IoU confusion matrix; OHEM cross-entropy).
+ *
+ * The reference (ly27253/LED-Net, an mmsegmentation-1.2.2 fork) is pure Python on
+ * stock PyTorch; it has no FFI of its own.  The boundary the reference exposes for
+ * this path is the mmseg registry (mmseg/registry/registry.py:56 MODELS, :90 METRICS)
+ * and the module methods built from it.  Each entry point below names the reference
+ * method(s) whose device work it replaces; the Python modules registered under the
+ * reference names (led-net_b200/{backbone,head,losses,metrics,segmentor}.py) bind
+ * these through ctypes (INTEGRATION.md shows the stub).
+ *
+ * Conventions
+ *   - return 0 on success, a negative LEDB200_E* code otherwise; nothing throws or
+ *     aborts across the ABI; ledb200_last_error() returns a thread-local message.
+ *   - the caller owns every input/output buffer (device pointers unless the name
+ *     says host); the library owns only a handle's folded weights and its
+ *     activation workspace (allocated at first use of a shape, grown on demand -
+ *     no cudaMalloc in steady state).
+ *   - all work is enqueued on the cudaStream_t passed in (as void*); no implicit
+ *     synchronisation.  One handle per (process, GPU); a handle is not re-entrant.
+ *   - activations inside the library are NHWC; dtype mode 0 = fp32 storage with
+ *     fp32 CUDA-core math (parity mode, 1e-4), 1 = bf16 storage, fp32 accumulate,
+ *     tcgen05/TMEM implicit-GEMM convolutions.
+ */
+#ifndef LEDB200_H_
+#define LEDB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LEDB200_VERSION 100 /* 0.1.0 */
+
+enum {
+  LEDB200_OK = 0,
+  LEDB200_EINVAL = -1,   /* bad argument / unsupported shape            */
+  LEDB200_ECUDA = -2,    /* CUDA runtime / driver error                 */
+  LEDB200_ESTATE = -3,   /* call order (e.g. forward before finalize)   */
+  LEDB200_ENOMEM = -4,
+  LEDB200_ENOTFOUND = -5 /* unknown parameter / buffer name             */
+};
+
+enum { LEDB200_F32 = 0, LEDB200_BF16 = 1, LEDB200_U8 = 2, LEDB200_I64 = 3, LEDB200_I32 = 4 };
+
+/* image layouts accepted by the forward entry points */
+enum {
+  LEDB200_IMG_NCHW_F32 = 0, /* normalised float, what LEDNet.forward(x) receives        */
+  LEDB200_IMG_NCHW_U8 = 1,  /* raw BGR uint8 CHW: SegDataPreProcessor fused into stem   */
+  LEDB200_IMG_NHWC_U8 = 2   /* raw BGR uint8 HWC (decoder output order)                 */
+};
+
+typedef struct ledb200_handle ledb200_handle;
+
+/* Constructor arguments of the two registered modules
+ * (configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:24-52). */
+typedef struct ledb200_cfg {
+  int32_t in_channels;   /* LEDNet(in_channels=3)                         */
+  int32_t channels;      /* LEDNet(channels=32)                           */
+  int32_t ppm_channels;  /* LEDNet(ppm_channels=128)                      */
+  int32_t head_channels; /* LEDHead(channels=64)                          */
+  int32_t num_classes;   /* LEDHead(num_classes=K)                        */
+  int32_t align_corners; /* must be 0 (config); 1 is rejected             */
+  int32_t dtype;         /* LEDB200_F32 or LEDB200_BF16 (activation mode) */
+  int32_t device;        /* CUDA device ordinal                           */
+  int32_t variant;       /* 0 = R0 trunk (DDRNet-23-slim body + stem taps) */
+  int32_t conv_backend;  /* 0 = auto (tcgen05 where eligible in bf16 mode), 1 = force CUDA-core */
+  float mean[3];         /* SegDataPreProcessor mean (RGB order)          */
+  float std[3];          /* SegDataPreProcessor std                       */
+  int32_t bgr_to_rgb;    /* SegDataPreProcessor bgr_to_rgb                */
+  int32_t reserved[7];
+} ledb200_cfg;
+
+int ledb200_version(void);
+const char* ledb200_last_error(void);
+
+/* ---- handle life cycle --------------------------------------------------------------
+ * Replaces MODELS.build(dict(type='LEDNet', ...)) / MODELS.build(dict(type='LEDHead', ...))
+ * (mmseg/models/segmentors/encoder_decoder.py:89,102) for the device side. */
+int ledb200_create(const ledb200_cfg* cfg, ledb200_handle** out);
+int ledb200_destroy(ledb200_handle* h);
+
+/* Feed one state-dict entry under its reference name, e.g.
+ * "backbone.stem.0.conv.weight", "decode_head.head.0.bn.running_var",
+ * "decode_head.conv_seg.bias" (module paths of ddrnet.py / led_head.py / decode_head.py:158).
+ * `data` is HOST memory, fp32 (dtype LEDB200_F32) or int64 (ignored: num_batches_tracked).
+ * Replaces load_state_dict / load_checkpoint (mmseg/apis/inference.py:60). */
+int ledb200_set_param(ledb200_handle* h, const char* name, const void* data,
+                      const int64_t* shape, int32_t ndim, int32_t dtype);
+/* Number of parameters the engine expects, and the i-th expected name (for diagnostics). */
+int ledb200_num_params(ledb200_handle* h);
+const char* ledb200_param_name(ledb200_handle* h, int32_t i);
+
+/* Fold eval-mode BatchNorm into the convolutions (W*g/sqrt(v+eps), b-m*g/sqrt(v+eps)),
+ * repack OIHW fp32 -> [Cout][kh][kw][Cin] bf16 (tensor-core path) and
+ * [kh][kw][Cin][Cout] fp32 (CUDA-core path), upload.  Fails with LEDB200_ESTATE and a
+ * message listing what is missing if any expected parameter was not set. */
+int ledb200_finalize(ledb200_handle* h);
+
+/* ---- inference ----------------------------------------------------------------------
+ * Whole path in one call: EncoderDecoder.predict (encoder_decoder.py:187-222) =
+ * extract_feat (:117-122) -> LEDHead.forward eval (led_head.py:76-81) ->
+ * predict_by_feat fusion (decode_head.py:362-379) -> postprocess_result argmax
+ * (segmentors/base.py:187-188).
+ *   img        device, layout per img_layout, N x 3 x H x W
+ *   pred       device, [N, Ho, Wo] with Ho = 2*ceil(H/2), Wo = 2*ceil(W/2)
+ *              (the reference's output size is 2*head_x1.shape, decode_head.py:363);
+ *              pred_dtype LEDB200_U8 or LEDB200_I64 (argmax(dim=0) returns int64)
+ *   logits_opt device or NULL: full-resolution fused logits [N, K, Ho, Wo] fp32 NCHW
+ *              (what predict_by_feat returns); NULL keeps them out of HBM entirely. */
+int ledb200_forward_infer(ledb200_handle* h, const void* img, int32_t img_layout, int32_t N,
+                          int32_t H, int32_t W, void* pred, int32_t pred_dtype,
+                          float* logits_opt, void* stream);
+
+/* LEDNet.forward in eval mode (contract: led_head.py:76-81 consumes (c5, x1, x2)).
+ * Outputs are fp32 NCHW device tensors owned by the caller:
+ *   c5 [N,4C,ceil(H/8),ceil(W/8)], x1 [N,C,H/2,W/2], x2 [N,C,H/4,W/4]. */
+int ledb200_backbone_forward(ledb200_handle* h, const void* img, int32_t img_layout, int32_t N,
+                             int32_t H, int32_t W, float* c5, float* x1, float* x2, void* stream);
+
+/* LEDHead.forward in eval mode (led_head.py:76-81) on caller-supplied fp32 NCHW features:
+ * returns x_c [N,K,h8,w8], head_x1 [N,K,h2,w2], head_x2 [N,K,h4,w4] (fp32 NCHW). */
+int ledb200_head_forward(ledb200_handle* h, const float* c5, const float* x1, const float* x2,
+                         int32_t N, int32_t h8, int32_t w8, int32_t h2, int32_t w2, int32_t h4,
+                         int32_t w4, float* xc, float* hx1, float* hx2, void* stream);
+
+/* Copy a named internal activation of the last forward to HOST as fp32 NCHW (tests /
+ * layer-wise parity).  `capacity` in floats; writes the shape to shape4 = {N,C,H,W}.
+ * Synchronises the stream. */
+int ledb200_debug_fetch(ledb200_handle* h, const char* buffer_name, float* host_out,
+                        int64_t capacity, int32_t* shape4, void* stream);
+/* Per-op timing of the last plan (runs each op `iters` times between CUDA events);
+ * writes up to `cap` entries; names via ledb200_op_name.  Returns the op count. */
+int ledb200_profile_ops(ledb200_handle* h, int32_t iters, float* ms_out, int32_t cap, void* stream);
+const char* ledb200_op_name(ledb200_handle* h, int32_t i);
+/* Algorithmic work of op i of the last plan: out3 = {FLOPs, bytes, kind} with kind
+ * 0 conv (CUDA cores), 1 conv (tcgen05), 2 upsample+add, 3 avg-pool, 4 affine+ReLU, 5 fused tail,
+ * 6 layout conversion.  bench.py builds the per-layer roofline from these. */
+int ledb200_op_info(ledb200_handle* h, int32_t i, double* out3);
+/* Number of kernel launches one forward of the current plan issues. */
+int ledb200_plan_launches(ledb200_handle* h);
+
+/* ---- stand-alone fused kernels --------------------------------------------------------
+ * BaseDecodeHead.predict_by_feat (decode_head.py:362-379) + postprocess argmax
+ * (base.py:187-188) in one kernel: r = hx2 + up(xc); r = hx1 + up(r); out = up(r -> 2*hx1.HW);
+ * pred = first-max argmax over K.  Inputs NHWC, dtype F32 or BF16:
+ * xc [N,hc,wc,K], hx2 [N,h4,w4,K], hx1 [N,h2,w2,K]; output [N,2*h2,2*w2].
+ * logits_opt: optional fp32 NCHW [N,K,2*h2,2*w2]. */
+int ledb200_head_fuse_argmax(const void* xc, const void* hx2, const void* hx1, int32_t dtype,
+                             int32_t N, int32_t K, int32_t hc, int32_t wc, int32_t h4, int32_t w4,
+                             int32_t h2, int32_t w2, void* pred, int32_t pred_dtype,
+                             float* logits_opt, void* stream);
+
+/* IoUMetric.intersect_and_union (evaluation/metrics/iou_metric.py:163-200) and
+ * calculate_confusion_matrix (tools/analysis_tools/confusion_matrix.py:66-74):
+ * cm[(K+1) x K] int64 += bincount(K*gt + pred) over pixels with gt != ignore_index;
+ * rows = GT, cols = prediction; row K collects GT values outside [0,K) that are not
+ * ignore_index (histc drops those from area_label but keeps them in area_pred_label).
+ * pred_dtype / gt_dtype: LEDB200_U8 or LEDB200_I64.  Accumulates (does not zero). */
+int ledb200_confusion_accumulate(const void* pred, const void* gt, int32_t pred_dtype,
+                                 int32_t gt_dtype, int64_t n, int32_t K, int32_t ignore_index,
+                                 int64_t* cm_inout, void* stream);
+
+/* OhemCrossEntropy.forward (+ autograd backward) (losses/ohem_cross_entropy_loss.py:52-90)
+ * and accuracy (losses/accuracy.py:41-60) in one pass family:
+ *   logits  fp32 NCHW [N,K,H,W]; target int64 [N,H,W]
+ *   class_weight_opt device fp32 [K] or NULL
+ *   out3    device fp32[3]: {loss (already * loss_weight), kept count, top-1 accuracy in %}
+ *   dlogits_opt device fp32 NCHW or NULL: d(loss)/d(logits)
+ *   workspace device, >= ledb200_ohem_workspace_bytes(N*H*W) bytes */
+int64_t ledb200_ohem_workspace_bytes(int64_t npix);
+int ledb200_ohem_ce(const float* logits, const int64_t* target, int32_t N, int32_t K, int32_t H,
+                    int32_t W, int32_t ignore_label, float thres, int64_t min_kept,
+                    float loss_weight, const float* class_weight_opt, float* out3,
+                    float* dlogits_opt, void* workspace, void* stream);
+
+/* One convolution through the same launchers the engine uses (unit tests, SESP etc.).
+ * NHWC in/out of `dtype`; weight host fp32 OIHW [Cout,Cin,kh,kw] folded by the caller;
+ * bias host fp32 [Cout] or NULL; pre_scale/pre_shift host fp32 [Cin] or NULL
+ * (pre-activation BN+ReLU applied before zero padding, mmcv ConvModule order
+ * ('norm','act','conv'): led_head.py:94, ppm.py:42-43); residual NHWC or NULL.
+ * backend 0 auto, 1 CUDA-core, 2 tcgen05 (fails if the shape is not eligible). */
+int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtype, int32_t N,
+                   int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride,
+                   int32_t relu, const float* weight_oihw, const float* bias,
+                   const float* pre_scale, const float* pre_shift, int32_t backend, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LEDB200_H_ */

@@ -1,0 +1,252 @@
+// HBM-bound elementwise / resampling kernels (north_star kernel 3 and DAPPM glue).
+//
+//  * upsample_add : `x_s += resize(comp_c, size=out_size, mode='bilinear', align_corners=False)`
+//                   (mmseg/models/backbones/ddrnet.py:195-199, 208-212, 218-224) and the DAPPM
+//                   `F.interpolate(scale_i(x)) + feats[i-1]` (mmseg/models/utils/ppm.py:124-127),
+//                   with the consumer's ReLU / pre-activation BN+ReLU fused so each branch is
+//                   read once and the sum is written once.
+//  * avgpool_bnrelu : nn.AvgPool2d(5,2,2)/(9,4,4)/(17,8,8) and AdaptiveAvgPool2d(1) of DAPPM
+//                   (ppm.py:66-90) + the following ConvModule's BN+ReLU prologue.
+//  * affine_relu  : per-channel BN+ReLU prologue feeding two pre-activation 1x1 convs
+//                   (DAPPM scales[0] and shortcut, ppm.py:57-63, 110-117).
+//  * nchw<->nhwc  : the boundary to the reference's NCHW fp32 tensors.
+// All NHWC, 8 channels (16 B bf16 / 32 B fp32) per thread, grid sized to 148 SMs x 8 CTAs.
+#include "kernels.h"
+
+namespace ledb {
+namespace {
+
+constexpr int kThreads = 256;
+inline int grid_for(int64_t work) {
+  int64_t b = ceil_div64(work, kThreads);
+  const int64_t cap = 148 * 16;
+  return (int)(b < cap ? (b < 1 ? 1 : b) : cap);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) upsample_add_kernel(UpAddArgs a, float sh, float sw) {
+  const int cg = a.C / 8;
+  const int64_t total = (int64_t)a.N * a.H * a.W * cg;
+  const T* base = reinterpret_cast<const T*>(a.base);
+  const T* src = reinterpret_cast<const T*>(a.src);
+  T* out = reinterpret_cast<T*>(a.out);
+  T* out2 = reinterpret_cast<T*>(a.out2);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int g = (int)(i % cg);
+    int64_t p = i / cg;
+    const int x = (int)(p % a.W);
+    const int y = (int)((p / a.W) % a.H);
+    const int n = (int)(p / ((int64_t)a.W * a.H));
+    int y0, y1, x0, x1;
+    float ly0, ly1, lx0, lx1;
+    bilinear_coord(y, sh, a.h, y0, y1, ly0, ly1);
+    bilinear_coord(x, sw, a.w, x0, x1, lx0, lx1);
+    const T* s = src + ((int64_t)n * a.h * a.w) * a.C + g * 8;
+    float v00[8], v01[8], v10[8], v11[8], v[8];
+    load8(s + ((int64_t)y0 * a.w + x0) * a.C, v00);
+    load8(s + ((int64_t)y0 * a.w + x1) * a.C, v01);
+    load8(s + ((int64_t)y1 * a.w + x0) * a.C, v10);
+    load8(s + ((int64_t)y1 * a.w + x1) * a.C, v11);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const float r0 = fmaf(v01[c], lx1, v00[c] * lx0);
+      const float r1 = fmaf(v11[c], lx1, v10[c] * lx0);
+      v[c] = fmaf(r1, ly1, r0 * ly0);
+    }
+    if (base) {
+      float b[8];
+      load8(base + p * a.C + g * 8, b);
+#pragma unroll
+      for (int c = 0; c < 8; ++c) v[c] += b[c];
+    }
+    if (out) {
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = a.relu ? fmaxf(v[c], 0.f) : v[c];
+      store8(out + p * a.out_ld + g * 8, o);
+    }
+    if (out2) {
+      float o[8];
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const int ch = g * 8 + c;
+        const float t = a.o2_scale ? fmaf(v[c], a.o2_scale[ch], a.o2_shift[ch]) : v[c];
+        o[c] = fmaxf(t, 0.f);
+      }
+      store8(out2 + p * a.out2_ld + g * 8, o);
+    }
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) avgpool_kernel(PoolArgs a) {
+  const int cg = a.C / 8;
+  const int64_t total = (int64_t)a.N * a.Ho * a.Wo * cg;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* out = reinterpret_cast<T*>(a.out);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int g = (int)(i % cg);
+    int64_t p = i / cg;
+    const int ox = (int)(p % a.Wo);
+    const int oy = (int)((p / a.Wo) % a.Ho);
+    const int n = (int)(p / ((int64_t)a.Wo * a.Ho));
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int y0, y1, x0, x1;
+    float inv;
+    if (a.k == 0) {   // global
+      y0 = 0; y1 = a.H; x0 = 0; x1 = a.W;
+      inv = 1.f / (float)(a.H * a.W);
+    } else {          // count_include_pad=True: divisor is always k*k
+      y0 = oy * a.s - a.p; y1 = y0 + a.k; x0 = ox * a.s - a.p; x1 = x0 + a.k;
+      // PyTorch clips the window to the padded extent before counting (pool_size uses
+      // min(hend, H+pad)); with k <= 2*pad+1 windows here never leave it.
+      const int hend = min(y1, a.H + a.p), wend = min(x1, a.W + a.p);
+      inv = 1.f / (float)((hend - y0) * (wend - x0));
+      y0 = max(y0, 0); x0 = max(x0, 0); y1 = min(y1, a.H); x1 = min(x1, a.W);
+    }
+    for (int y = y0; y < y1; ++y)
+      for (int x = x0; x < x1; ++x) {
+        float v[8];
+        load8(in + (((int64_t)n * a.H + y) * a.W + x) * a.C + g * 8, v);
+#pragma unroll
+        for (int c = 0; c < 8; ++c) acc[c] += v[c];
+      }
+    float o[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) {
+      const int ch = g * 8 + c;
+      float v = acc[c] * inv;
+      if (a.scale) v = fmaxf(fmaf(v, a.scale[ch], a.shift[ch]), 0.f);
+      o[c] = v;
+    }
+    store8(out + p * a.C + g * 8, o);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kThreads) affine_relu_kernel(AffineArgs a) {
+  const int cg = a.C / 8;
+  const int64_t total = a.npix * cg;
+  const T* in = reinterpret_cast<const T*>(a.in);
+  T* oa = reinterpret_cast<T*>(a.out_a);
+  T* ob = reinterpret_cast<T*>(a.out_b);
+  for (int64_t i = blockIdx.x * (int64_t)kThreads + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * kThreads) {
+    const int g = (int)(i % cg);
+    float v[8], o[8];
+    load8(in + i * 8, v);
+    if (oa) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = fmaxf(fmaf(v[c], a.sa[g * 8 + c], a.ba[g * 8 + c]), 0.f);
+      store8(oa + i * 8, o);
+    }
+    if (ob) {
+#pragma unroll
+      for (int c = 0; c < 8; ++c) o[c] = fmaxf(fmaf(v[c], a.sb[g * 8 + c], a.bb[g * 8 + c]), 0.f);
+      store8(ob + i * 8, o);
+    }
+  }
+}
+
+// NCHW fp32 -> NHWC T through a 32x32 smem transpose per (n, 32 pixels, 32 channels)
+template <typename T>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ in, T* __restrict__ out, int C, int64_t HW) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;   // 32 x 8
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t p = p0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? in[((int64_t)n * C + c) * HW + p] : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t p = p0 + j;
+    const int c = c0 + tx;
+    if (c < C && p < HW) out[((int64_t)n * HW + p) * C + c] = from_f32<T>(tile[tx][j]);
+  }
+}
+
+template <typename T>
+__global__ void nhwc_to_nchw_kernel(const T* __restrict__ in, float* __restrict__ out, int C, int64_t HW, int ld) {
+  __shared__ float tile[32][33];
+  const int n = blockIdx.z;
+  const int64_t p0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x, ty = threadIdx.y;
+  for (int j = ty; j < 32; j += 8) {
+    const int64_t p = p0 + j;
+    const int c = c0 + tx;
+    tile[j][tx] = (c < C && p < HW) ? to_f32(in[((int64_t)n * HW + p) * ld + c]) : 0.f;
+  }
+  __syncthreads();
+  for (int j = ty; j < 32; j += 8) {
+    const int c = c0 + j;
+    const int64_t p = p0 + tx;
+    if (c < C && p < HW) out[((int64_t)n * C + c) * HW + p] = tile[tx][j];
+  }
+}
+
+}  // namespace
+
+int launch_upsample_add(const UpAddArgs& a, cudaStream_t st) {
+  if (a.C % 8) return fail(LEDB200_EINVAL, "upsample_add: C must be a multiple of 8");
+  const float sh = (float)a.h / (float)a.H, sw = (float)a.w / (float)a.W;
+  const int64_t total = (int64_t)a.N * a.H * a.W * (a.C / 8);
+  if (a.dtype == LEDB200_BF16)
+    upsample_add_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, st>>>(a, sh, sw);
+  else
+    upsample_add_kernel<float><<<grid_for(total), kThreads, 0, st>>>(a, sh, sw);
+  LEDB_LAUNCH_OK("upsample_add_kernel");
+  return LEDB200_OK;
+}
+
+int launch_avgpool_bnrelu(const PoolArgs& a, cudaStream_t st) {
+  if (a.C % 8) return fail(LEDB200_EINVAL, "avgpool: C must be a multiple of 8");
+  const int64_t total = (int64_t)a.N * a.Ho * a.Wo * (a.C / 8);
+  if (a.dtype == LEDB200_BF16)
+    avgpool_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, st>>>(a);
+  else
+    avgpool_kernel<float><<<grid_for(total), kThreads, 0, st>>>(a);
+  LEDB_LAUNCH_OK("avgpool_kernel");
+  return LEDB200_OK;
+}
+
+int launch_affine_relu(const AffineArgs& a, cudaStream_t st) {
+  if (a.C % 8) return fail(LEDB200_EINVAL, "affine_relu: C must be a multiple of 8");
+  const int64_t total = a.npix * (a.C / 8);
+  if (a.dtype == LEDB200_BF16)
+    affine_relu_kernel<__nv_bfloat16><<<grid_for(total), kThreads, 0, st>>>(a);
+  else
+    affine_relu_kernel<float><<<grid_for(total), kThreads, 0, st>>>(a);
+  LEDB_LAUNCH_OK("affine_relu_kernel");
+  return LEDB200_OK;
+}
+
+int launch_nchw_to_nhwc(const float* in, void* out, int out_dtype, int N, int C, int H, int W, cudaStream_t st) {
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)ceil_div64(HW, 32), ceil_div(C, 32), N), block(32, 8);
+  if (out_dtype == LEDB200_BF16)
+    nchw_to_nhwc_kernel<__nv_bfloat16><<<grid, block, 0, st>>>(in, (__nv_bfloat16*)out, C, HW);
+  else
+    nchw_to_nhwc_kernel<float><<<grid, block, 0, st>>>(in, (float*)out, C, HW);
+  LEDB_LAUNCH_OK("nchw_to_nhwc_kernel");
+  return LEDB200_OK;
+}
+
+int launch_nhwc_to_nchw(const void* in, int in_dtype, float* out, int N, int C, int H, int W, int in_ld, cudaStream_t st) {
+  const int64_t HW = (int64_t)H * W;
+  dim3 grid((unsigned)ceil_div64(HW, 32), ceil_div(C, 32), N), block(32, 8);
+  if (in_dtype == LEDB200_BF16)
+    nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, out, C, HW, in_ld);
+  else
+    nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)in, out, C, HW, in_ld);
+  LEDB_LAUNCH_OK("nhwc_to_nchw_kernel");
+  return LEDB200_OK;
+}
+
+}  // namespace ledb

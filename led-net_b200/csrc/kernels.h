@@ -1,0 +1,104 @@
+// Launcher declarations shared by the engine (engine.cu) and the raw C-ABI ops (api.cu).
+#pragma once
+#include "common.cuh"
+
+namespace ledb {
+
+// One convolution layer (BN folded by the host side).  NHWC unless strides say otherwise.
+struct ConvArgs {
+  const void* in = nullptr;
+  int in_dtype = LEDB200_F32;
+  int64_t in_sn = 0, in_sh = 0, in_sw = 0, in_sc = 1;   // element strides of the input
+  void* out = nullptr;          // may be null when only out2 is wanted
+  int out_dtype = LEDB200_F32;
+  int out_ld = 0;               // pixel stride (elements) of out
+  void* out2 = nullptr;         // optional: relu(o2_scale*v + o2_shift), v = pre-ReLU value
+  int out2_ld = 0;
+  const float* o2_scale = nullptr;  // null => identity affine
+  const float* o2_shift = nullptr;
+  const void* res = nullptr;    // optional residual, same dtype as out
+  int res_ld = 0;
+  const float* bias = nullptr;  // [Cout] (device)
+  const float* pre_scale = nullptr;  // [Cin] prologue affine (device), CUDA-core path only
+  const float* pre_shift = nullptr;
+  int pre_relu = 1;
+  const float* w_direct = nullptr;         // [k*k][Cin][cout_pad16] fp32 (device)
+  const __nv_bfloat16* w_tc = nullptr;     // [cout_padN][k*k*Cin] bf16 (device), K-major
+  int cout_pad16 = 0;
+  int cout_pad_tc = 0;
+  int N = 0, H = 0, W = 0, Cin = 0, Ho = 0, Wo = 0, Cout = 0;
+  int ksize = 3, stride = 1, pad = 1, dil = 1;
+  int relu = 0;
+};
+
+int launch_conv_direct(const ConvArgs& a, cudaStream_t st);
+// tcgen05/TMEM implicit GEMM (conv_tc.cu).  conv_tc_eligible() says whether the shape fits.
+bool conv_tc_eligible(const ConvArgs& a);
+int launch_conv_tc(const ConvArgs& a, cudaStream_t st);
+
+// out = [relu](base + bilinear(src -> base HW)), out2 = relu(s2*v + b2) ; NHWC, same dtype.
+struct UpAddArgs {
+  const void* base = nullptr;   // [N,H,W,C]; may be null (pure upsample)
+  const void* src = nullptr;    // [N,h,w,C]
+  void* out = nullptr;          // optional
+  void* out2 = nullptr;         // optional
+  int out_ld = 0, out2_ld = 0;
+  const float* o2_scale = nullptr;
+  const float* o2_shift = nullptr;
+  int dtype = LEDB200_F32;
+  int N = 0, H = 0, W = 0, C = 0, h = 0, w = 0;
+  int relu = 0;
+};
+int launch_upsample_add(const UpAddArgs& a, cudaStream_t st);
+
+// AvgPool2d(k,s,p, count_include_pad=True) or global average (k == 0), followed by the
+// consumer's pre-activation BN+ReLU: out = relu(scale*avg + shift).  (ppm.py:68-90)
+struct PoolArgs {
+  const void* in = nullptr;
+  void* out = nullptr;
+  const float* scale = nullptr;
+  const float* shift = nullptr;
+  int dtype = LEDB200_F32;
+  int N = 0, H = 0, W = 0, C = 0, Ho = 0, Wo = 0, k = 0, s = 1, p = 0;
+};
+int launch_avgpool_bnrelu(const PoolArgs& a, cudaStream_t st);
+
+// out = relu(scale*x + shift) per channel; up to two outputs from one read.
+struct AffineArgs {
+  const void* in = nullptr;
+  void* out_a = nullptr;
+  void* out_b = nullptr;
+  const float *sa = nullptr, *ba = nullptr, *sb = nullptr, *bb = nullptr;
+  int dtype = LEDB200_F32;
+  int64_t npix = 0;
+  int C = 0;
+};
+int launch_affine_relu(const AffineArgs& a, cudaStream_t st);
+
+// layout conversion helpers (engine boundary): NCHW fp32 <-> NHWC T
+int launch_nchw_to_nhwc(const float* in, void* out, int out_dtype, int N, int C, int H, int W, cudaStream_t st);
+int launch_nhwc_to_nchw(const void* in, int in_dtype, float* out, int N, int C, int H, int W, int in_ld, cudaStream_t st);
+
+// fused head tail: 3-level bilinear ladder + argmax (tail.cu)
+struct TailArgs {
+  const void* xc = nullptr;   // [N,hc,wc,K]
+  const void* hx2 = nullptr;  // [N,h4,w4,K]
+  const void* hx1 = nullptr;  // [N,h2,w2,K]
+  int xc_ld = 0, hx2_ld = 0, hx1_ld = 0;   // pixel strides (elements)
+  int dtype = LEDB200_F32;
+  int N = 0, K = 0, hc = 0, wc = 0, h4 = 0, w4 = 0, h2 = 0, w2 = 0;
+  void* pred = nullptr;       // [N,2*h2,2*w2]
+  int pred_dtype = LEDB200_U8;
+  float* logits = nullptr;    // optional fp32 NCHW
+};
+int launch_tail(const TailArgs& a, cudaStream_t st);
+
+int launch_confusion(const void* pred, const void* gt, int pred_dtype, int gt_dtype, int64_t n, int K,
+                     int ignore_index, int64_t* cm, cudaStream_t st);
+
+int64_t ohem_workspace_bytes(int64_t npix);
+int launch_ohem(const float* logits, const int64_t* target, int N, int K, int H, int W, int ignore_label,
+                float thres, int64_t min_kept, float loss_weight, const float* class_weight, float* out3,
+                float* dlogits, void* workspace, cudaStream_t st);
+
+}  // namespace ledb

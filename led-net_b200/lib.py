@@ -1,0 +1,99 @@
+"""ctypes binding of libledb200.so (declared in include/ledb200.h).
+
+The product path has NO CPU fallback: if the shared library is missing or a call fails,
+`LedB200Error` is raised with the library's own message.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'libledb200.so')
+
+F32, BF16, U8, I64, I32 = 0, 1, 2, 3, 4
+IMG_NCHW_F32, IMG_NCHW_U8, IMG_NHWC_U8 = 0, 1, 2
+
+# every symbol include/ledb200.h declares (tests check the .so exports all of them)
+SYMBOLS = [
+    'ledb200_version', 'ledb200_last_error', 'ledb200_create', 'ledb200_destroy',
+    'ledb200_set_param', 'ledb200_num_params', 'ledb200_param_name', 'ledb200_finalize',
+    'ledb200_forward_infer', 'ledb200_backbone_forward', 'ledb200_head_forward',
+    'ledb200_debug_fetch', 'ledb200_profile_ops', 'ledb200_op_info', 'ledb200_op_name', 'ledb200_plan_launches',
+    'ledb200_head_fuse_argmax', 'ledb200_confusion_accumulate', 'ledb200_ohem_workspace_bytes',
+    'ledb200_ohem_ce', 'ledb200_conv2d',
+]
+
+
+class LedB200Error(RuntimeError):
+    pass
+
+
+class Cfg(C.Structure):
+    _fields_ = [('in_channels', C.c_int32), ('channels', C.c_int32), ('ppm_channels', C.c_int32),
+                ('head_channels', C.c_int32), ('num_classes', C.c_int32),
+                ('align_corners', C.c_int32), ('dtype', C.c_int32), ('device', C.c_int32),
+                ('variant', C.c_int32), ('conv_backend', C.c_int32), ('mean', C.c_float * 3),
+                ('std', C.c_float * 3), ('bgr_to_rgb', C.c_int32), ('reserved', C.c_int32 * 7)]
+
+
+_lib = None
+
+
+def get():
+    """Load the library once; fail loudly if it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.isfile(LIB_PATH):
+        raise LedB200Error(
+            f'{LIB_PATH} is missing: build it with `python led-net_b200/build.py` '
+            '(or __graft_entry__.build()).  There is no CPU fallback.')
+    lib = C.CDLL(LIB_PATH)
+    vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
+    lib.ledb200_version.restype = C.c_int
+    lib.ledb200_last_error.restype = C.c_char_p
+    lib.ledb200_create.argtypes = [C.POINTER(Cfg), C.POINTER(vp)]
+    lib.ledb200_destroy.argtypes = [vp]
+    lib.ledb200_set_param.argtypes = [vp, C.c_char_p, vp, C.POINTER(i64), i32, i32]
+    lib.ledb200_num_params.argtypes = [vp]
+    lib.ledb200_param_name.argtypes = [vp, i32]
+    lib.ledb200_param_name.restype = C.c_char_p
+    lib.ledb200_finalize.argtypes = [vp]
+    lib.ledb200_forward_infer.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
+    lib.ledb200_backbone_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
+    lib.ledb200_head_forward.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp, vp, vp]
+    lib.ledb200_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64, C.POINTER(i32), vp]
+    lib.ledb200_profile_ops.argtypes = [vp, i32, vp, i32, vp]
+    lib.ledb200_op_name.argtypes = [vp, i32]
+    lib.ledb200_op_info.argtypes = [vp, i32, C.POINTER(C.c_double)]
+    lib.ledb200_op_name.restype = C.c_char_p
+    lib.ledb200_plan_launches.argtypes = [vp]
+    lib.ledb200_head_fuse_argmax.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, i32, vp, vp]
+    lib.ledb200_confusion_accumulate.argtypes = [vp, vp, i32, i32, i64, i32, i32, vp, vp]
+    lib.ledb200_ohem_workspace_bytes.argtypes = [i64]
+    lib.ledb200_ohem_workspace_bytes.restype = i64
+    lib.ledb200_ohem_ce.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, i64, f32, vp, vp, vp, vp, vp]
+    lib.ledb200_conv2d.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, vp, vp, vp, i32, vp]
+    for name in SYMBOLS:
+        fn = getattr(lib, name)
+        if fn.restype is C.c_int and name not in ('ledb200_version',):
+            fn.restype = C.c_int
+    _lib = lib
+    return lib
+
+
+def check(rc, what=''):
+    if rc < 0:
+        msg = get().ledb200_last_error()
+        raise LedB200Error(f'{what} failed ({rc}): {msg.decode() if msg else "?"}')
+    return rc
+
+
+def stream_ptr(device=None):
+    import torch
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def torch_dtype_code(t):
+    import torch
+    return {torch.float32: F32, torch.bfloat16: BF16, torch.uint8: U8, torch.int64: I64,
+            torch.int32: I32}[t.dtype]

@@ -1,0 +1,128 @@
+"""`IoUMetric` (METRICS) - reference surface of ``mmseg/evaluation/metrics/iou_metric.py:18-295``.
+
+Device work is one confusion-matrix kernel launch per image (csrc/metrics.cu) instead of two
+boolean gathers, three float32 `histc` calls and three device->host syncs; nothing leaves the GPU
+until `compute_metrics`.  Across ranks the (K+1) x K int64 matrix is summed with ONE NCCL
+all-reduce (2.9 KB at K=19) instead of mmengine's pickled `collect_results` object gather.
+"""
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import ops
+from .registry import METRICS
+
+
+def _areas_from_cm(cm):
+    """[K+1,K] int64 -> (intersect, union, pred_label, label) int64 [K] (rows GT, cols pred)."""
+    k = cm.shape[1]
+    inter = torch.diagonal(cm[:k])
+    area_l = cm[:k].sum(1)
+    area_p = cm.sum(0)
+    return inter, area_p + area_l - inter, area_p, area_l
+
+
+@METRICS.register_module()
+class IoUMetric:
+
+    def __init__(self, ignore_index=255, iou_metrics=('mIoU',), nan_to_num=None, beta=1,
+                 collect_device='cpu', output_dir=None, format_only=False, prefix=None, **kwargs):
+        self.ignore_index = ignore_index
+        self.metrics = list(iou_metrics) if not isinstance(iou_metrics, str) else [iou_metrics]
+        self.nan_to_num, self.beta = nan_to_num, beta
+        self.collect_device, self.output_dir, self.format_only, self.prefix = \
+            collect_device, output_dir, format_only, prefix
+        if output_dir is not None or format_only:
+            raise NotImplementedError('PNG dumping (format_only / output_dir) is outside the hot path')
+        self.results = []
+        self.dataset_meta = None
+        self._cm = None
+
+    # -- reference API --------------------------------------------------------------------
+    def process(self, data_batch, data_samples):
+        """iou_metric.py:67-100: one entry per image in self.results (here: its int64 matrix)."""
+        num_classes = len(self.dataset_meta['classes'])
+        for s in data_samples:
+            pred = s['pred_sem_seg']['data'].squeeze()
+            label = s['gt_sem_seg']['data'].squeeze().to(pred.device)
+            self.results.append(ops.confusion_accumulate(pred, label, num_classes, self.ignore_index))
+
+    def process_batch(self, pred, label, num_classes=None):
+        """Batched fast path: accumulate a whole [N,H,W] prediction/label pair into the running matrix."""
+        k = num_classes or len(self.dataset_meta['classes'])
+        self._cm = ops.confusion_accumulate(pred, label, k, self.ignore_index, self._cm)
+        return self._cm
+
+    @staticmethod
+    def intersect_and_union(pred_label, label, num_classes, ignore_index):
+        """iou_metric.py:163-200: four float32 [K] CPU tensors (exact while counts <= 2**24)."""
+        cm = ops.confusion_accumulate(pred_label, label.to(pred_label.device), num_classes, ignore_index)
+        return tuple(a.to(torch.float32).cpu() for a in _areas_from_cm(cm))
+
+    def total_confusion(self, results=None, reduce_ranks=True):
+        """Sum of every per-image matrix + the running matrix; all-reduced over ranks (int64)."""
+        results = self.results if results is None else results
+        mats = [r for r in results if torch.is_tensor(r)]
+        if self._cm is not None:
+            mats.append(self._cm)
+        if not mats:
+            return None
+        total = torch.stack(mats).sum(0) if len(mats) > 1 else mats[0].clone()
+        if reduce_ranks and torch.distributed.is_available() and torch.distributed.is_initialized() \
+                and torch.distributed.get_world_size() > 1:
+            torch.distributed.all_reduce(total, op=torch.distributed.ReduceOp.SUM)
+        return total
+
+    def compute_metrics(self, results=None):
+        """iou_metric.py:102-161.  Accepts this class's matrices or reference-style 4-tuples."""
+        results = self.results if results is None else results
+        if len(results) and not torch.is_tensor(results[0]):
+            cols = tuple(zip(*results))
+            assert len(cols) == 4
+            tot = [sum(c) for c in cols]
+        else:
+            cm = self.total_confusion(results)
+            # the reference sums float32 histograms; int64 counts converted once are exact <= 2**24
+            tot = [a.to(torch.float32).cpu() for a in _areas_from_cm(cm)]
+        ret = self.total_area_to_metrics(*tot, self.metrics, self.nan_to_num, self.beta)
+        out = {}
+        for k, v in ret.items():
+            val = np.round(np.nanmean(v) * 100, 2)
+            out[k if k == 'aAcc' else 'm' + k] = val
+        self.per_class = OrderedDict((k, np.round(v * 100, 2)) for k, v in ret.items() if k != 'aAcc')
+        return out
+
+    def evaluate(self, size=None):
+        m = self.compute_metrics(self.results)
+        self.results.clear()
+        self._cm = None
+        return m
+
+    @staticmethod
+    def total_area_to_metrics(total_area_intersect, total_area_union, total_area_pred_label,
+                              total_area_label, metrics=('mIoU',), nan_to_num=None, beta=1):
+        """iou_metric.py:202-295 (host-side float math on [K] vectors; negligible cost)."""
+        def f_score(p, r):
+            return (1 + beta ** 2) * (p * r) / ((beta ** 2 * p) + r)
+        if isinstance(metrics, str):
+            metrics = [metrics]
+        if not set(metrics).issubset({'mIoU', 'mDice', 'mFscore'}):
+            raise KeyError(f'metrics {metrics} is not supported')
+        ti, tu, tp, tl = (torch.as_tensor(np.asarray(a)) if not torch.is_tensor(a) else a
+                          for a in (total_area_intersect, total_area_union, total_area_pred_label,
+                                    total_area_label))
+        ret = OrderedDict(aAcc=ti.sum() / tl.sum())
+        for m in metrics:
+            if m == 'mIoU':
+                ret['IoU'], ret['Acc'] = ti / tu, ti / tl
+            if m in ('mIoU', 'mFscore'):
+                p, r = ti / tp, ti / tl
+                ret['Fscore'] = torch.tensor([f_score(a, b) for a, b in zip(p, r)])
+                ret['Precision'], ret['Recall'] = p, r
+            if m == 'mDice':
+                ret['Dice'], ret['Acc'] = 2 * ti / (tp + tl), ti / tl
+        ret = OrderedDict((k, v.numpy()) for k, v in ret.items())
+        if nan_to_num is not None:
+            ret = OrderedDict((k, np.nan_to_num(v, nan=nan_to_num)) for k, v in ret.items())
+        return ret

@@ -1,0 +1,96 @@
+"""Functional wrappers over the stand-alone C-ABI kernels (include/ledb200.h).
+
+Layout changes between the reference's NCHW tensors and the library's NHWC are views/copies made
+with torch (plumbing); the arithmetic is in the CUDA kernels.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _need_cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise L.LedB200Error('LED-Net B200 ops need CUDA tensors (no CPU fallback)')
+
+
+def head_fuse_argmax(xc, hx2, hx1, pred_dtype=torch.uint8, want_logits=False, channels_last=False):
+    """predict_by_feat + argmax (decode_head.py:362-379, base.py:187-188).
+
+    xc/hx2/hx1: [N,K,h,w] (NCHW, default) or [N,h,w,K] (channels_last=True), fp32 or bf16.
+    Returns (pred [N,2*h2,2*w2], logits or None)."""
+    _need_cuda(xc, hx2, hx1)
+    if not channels_last:
+        xc, hx2, hx1 = (t.permute(0, 2, 3, 1).contiguous() for t in (xc, hx2, hx1))
+    else:
+        xc, hx2, hx1 = (t.contiguous() for t in (xc, hx2, hx1))
+    assert xc.dtype == hx2.dtype == hx1.dtype and xc.dtype in (torch.float32, torch.bfloat16)
+    N, hc, wc, K = xc.shape
+    _, h4, w4, _ = hx2.shape
+    _, h2, w2, _ = hx1.shape
+    pred = torch.empty((N, 2 * h2, 2 * w2), dtype=pred_dtype, device=xc.device)
+    logits = torch.empty((N, K, 2 * h2, 2 * w2), dtype=torch.float32, device=xc.device) if want_logits else None
+    L.check(L.get().ledb200_head_fuse_argmax(
+        _p(xc), _p(hx2), _p(hx1), L.torch_dtype_code(xc), N, K, hc, wc, h4, w4, h2, w2, _p(pred),
+        L.torch_dtype_code(pred), _p(logits), L.stream_ptr(xc.device)), 'ledb200_head_fuse_argmax')
+    return pred, logits
+
+
+def confusion_accumulate(pred, gt, num_classes, ignore_index=255, cm=None):
+    """cm[(K+1),K] int64 += bincount(K*gt+pred) over gt != ignore (rows GT; row K = out-of-range GT)."""
+    _need_cuda(pred, gt)
+    pred, gt = pred.contiguous(), gt.contiguous()
+    assert pred.numel() == gt.numel(), 'prediction and label must have the same number of pixels'
+    if cm is None:
+        cm = torch.zeros((num_classes + 1, num_classes), dtype=torch.int64, device=pred.device)
+    L.check(L.get().ledb200_confusion_accumulate(
+        _p(pred), _p(gt), L.torch_dtype_code(pred), L.torch_dtype_code(gt), pred.numel(), num_classes,
+        ignore_index, _p(cm), L.stream_ptr(pred.device)), 'ledb200_confusion_accumulate')
+    return cm
+
+
+def ohem_ce(score, target, ignore_label=255, thres=0.7, min_kept=100000, loss_weight=1.0,
+            class_weight=None, want_grad=False):
+    """Returns (out3 = [loss, kept, accuracy%] device tensor, dlogits or None)."""
+    _need_cuda(score, target)
+    score = score.contiguous().float()
+    target = target.contiguous().to(torch.int64)
+    N, K, H, W = score.shape
+    lib = L.get()
+    ws = torch.empty(lib.ledb200_ohem_workspace_bytes(N * H * W), dtype=torch.uint8, device=score.device)
+    out3 = torch.empty(3, dtype=torch.float32, device=score.device)
+    grad = torch.empty_like(score) if want_grad else None
+    cw = None
+    if class_weight is not None:
+        cw = torch.as_tensor(class_weight, dtype=torch.float32, device=score.device).contiguous()
+        assert cw.numel() == K
+    L.check(lib.ledb200_ohem_ce(_p(score), _p(target), N, K, H, W, ignore_label, float(thres),
+                                int(min_kept), float(loss_weight), _p(cw), _p(out3), _p(grad), _p(ws),
+                                L.stream_ptr(score.device)), 'ledb200_ohem_ce')
+    return out3, grad
+
+
+def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, residual=None, pre_scale=None,
+           pre_shift=None, backend=0):
+    """One convolution (3x3 pad 1 or 1x1) on an NHWC fp32/bf16 CUDA tensor; weights host fp32."""
+    _need_cuda(x_nhwc, residual)
+    x = x_nhwc.contiguous()
+    N, H, W, Cin = x.shape
+    w = weight_oihw.detach().to('cpu', torch.float32).contiguous()
+    Cout, _, k, _ = w.shape
+    pad = k // 2
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    host = [None if t is None else t.detach().to('cpu', torch.float32).contiguous()
+            for t in (bias, pre_scale, pre_shift)]
+    res = residual.contiguous() if residual is not None else None
+    L.check(L.get().ledb200_conv2d(_p(x), _p(out), _p(res), L.torch_dtype_code(x), N, H, W, Cin, Cout, k,
+                                   stride, int(relu), _p(w), _p(host[0]), _p(host[1]), _p(host[2]),
+                                   backend, L.stream_ptr(x.device)), 'ledb200_conv2d')
+    return out

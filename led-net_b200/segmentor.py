@@ -1,0 +1,160 @@
+"""`EncoderDecoder` and `SegDataPreProcessor` (MODELS) - the callers either side of the hot path.
+
+Reference surface: ``mmseg/models/segmentors/encoder_decoder.py:117-132, 187-345``,
+``mmseg/models/segmentors/base.py:127-200`` and ``mmseg/models/data_preprocessor.py:98-151``.
+`predict_labels` is the fused fast path (one C-ABI call: image batch -> label map, full-resolution
+logits never materialised); `predict` keeps the reference's return shape (seg_logits + pred_sem_seg
+per image) and therefore does materialise the logits.
+"""
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .engine import Engine, MEAN, STD
+from .registry import MODELS
+
+
+@MODELS.register_module()
+class SegDataPreProcessor(nn.Module):
+    """Holds mean/std/bgr_to_rgb.  On the fused path these are folded into the stem convolution's
+    prologue (raw uint8 in); `forward` is the stand-alone torch version for callers that want the
+    normalised float batch (plumbing, data_preprocessor.py:112-149, test-time branch)."""
+
+    def __init__(self, mean=MEAN, std=STD, size=None, size_divisor=None, pad_val=0, seg_pad_val=255,
+                 bgr_to_rgb=False, rgb_to_bgr=False, batch_augments=None, test_cfg=None):
+        super().__init__()
+        assert not (bgr_to_rgb and rgb_to_bgr)
+        self.channel_conversion = bgr_to_rgb or rgb_to_bgr
+        self.size, self.size_divisor, self.pad_val, self.seg_pad_val = size, size_divisor, pad_val, seg_pad_val
+        self.test_cfg = test_cfg
+        self.register_buffer('mean', torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), False)
+        self.register_buffer('std', torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), False)
+
+    def forward(self, data, training=False):
+        inputs = data['inputs']
+        if isinstance(inputs, (list, tuple)):
+            inputs = torch.stack(list(inputs), 0)
+        if self.channel_conversion and inputs.shape[1] == 3:
+            inputs = inputs[:, [2, 1, 0]]
+        inputs = (inputs.float() - self.mean) / self.std
+        if training and self.size is not None:
+            ph, pw = max(self.size[0] - inputs.shape[-2], 0), max(self.size[1] - inputs.shape[-1], 0)
+            inputs = F.pad(inputs, (0, pw, 0, ph), value=self.pad_val)
+        return dict(inputs=inputs, data_samples=data.get('data_samples'))
+
+
+@MODELS.register_module()
+class EncoderDecoder(nn.Module):
+
+    def __init__(self, backbone, decode_head, neck=None, auxiliary_head=None, train_cfg=None,
+                 test_cfg=None, data_preprocessor=None, pretrained=None, init_cfg=None,
+                 compute_dtype='bf16'):
+        super().__init__()
+        assert neck is None and auxiliary_head is None, 'the LED-Net config has neither'
+        self.backbone = MODELS.build(backbone) if isinstance(backbone, dict) else backbone
+        self.decode_head = MODELS.build(decode_head) if isinstance(decode_head, dict) else decode_head
+        self.data_preprocessor = (MODELS.build(data_preprocessor) if isinstance(data_preprocessor, dict)
+                                  else data_preprocessor)
+        self.align_corners = self.decode_head.align_corners       # encoder_decoder.py:103-105
+        self.num_classes = self.decode_head.num_classes
+        self.out_channels = self.decode_head.out_channels
+        self.train_cfg, self.test_cfg = train_cfg, dict(test_cfg or dict(mode='whole'))
+        self.compute_dtype = compute_dtype
+        self._engine = None
+        self.register_load_state_dict_post_hook(lambda m, keys: m.reset_engine())
+
+    # -- engine ---------------------------------------------------------------------------
+    def reset_engine(self):
+        self._engine = None
+
+    def set_compute_dtype(self, dtype):
+        if dtype != self.compute_dtype:
+            self.compute_dtype, self._engine = dtype, None
+        return self
+
+    def engine(self):
+        if self._engine is None:
+            state = {'backbone.' + k: v for k, v in self.backbone.state_dict().items()}
+            state.update({'decode_head.' + k: v for k, v in self.decode_head.state_dict().items()})
+            pp = self.data_preprocessor
+            kw = {}
+            if pp is not None:
+                kw = dict(mean=tuple(pp.mean.flatten().tolist()), std=tuple(pp.std.flatten().tolist()),
+                          bgr_to_rgb=pp.channel_conversion)
+            self._engine = Engine(state, self.num_classes, self.backbone.channels,
+                                  self.backbone.ppm_channels, self.decode_head.channels,
+                                  dtype=self.compute_dtype, **kw)
+        return self._engine
+
+    # -- reference API --------------------------------------------------------------------
+    def extract_feat(self, inputs):
+        return self.engine().backbone_forward(inputs)
+
+    def encode_decode(self, inputs, batch_img_metas=None):
+        """encoder_decoder.py:124-132: full-resolution logits [N,K,H,W] (fused, one call)."""
+        return self.engine().forward_infer(inputs, want_logits=True)[1]
+
+    def whole_inference(self, inputs, batch_img_metas=None):
+        return self.encode_decode(inputs, batch_img_metas)
+
+    def slide_inference(self, inputs, batch_img_metas=None):
+        """encoder_decoder.py:241-292; accumulation uses torch ops (a fused scatter is a 'next' row)."""
+        h_stride, w_stride = self.test_cfg['stride']
+        h_crop, w_crop = self.test_cfg['crop_size']
+        n, _, h_img, w_img = inputs.shape
+        h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
+        w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
+        preds = inputs.new_zeros((n, self.out_channels, h_img, w_img), dtype=torch.float32)
+        count = inputs.new_zeros((n, 1, h_img, w_img), dtype=torch.float32)
+        for hi in range(h_grids):
+            for wi in range(w_grids):
+                y1, x1 = hi * h_stride, wi * w_stride
+                y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
+                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
+                logit = self.encode_decode(inputs[:, :, y1:y2, x1:x2].contiguous())
+                preds += F.pad(logit, (x1, w_img - x2, y1, h_img - y2))
+                count[:, :, y1:y2, x1:x2] += 1
+        assert (count == 0).sum() == 0
+        return preds / count
+
+    def inference(self, inputs, batch_img_metas=None):
+        mode = self.test_cfg.get('mode', 'whole')
+        assert mode in ['slide', 'whole'], \
+            f'Only "slide" or "whole" test mode are supported, but got {mode}.'
+        return self.slide_inference(inputs, batch_img_metas) if mode == 'slide' \
+            else self.whole_inference(inputs, batch_img_metas)
+
+    def postprocess_result(self, seg_logits, data_samples=None):
+        """base.py:153-198 for C > 1 with identity un-pad / resize (all benchmark configs)."""
+        out = []
+        for i in range(seg_logits.shape[0]):
+            lg = seg_logits[i]
+            out.append({'seg_logits': {'data': lg},
+                        'pred_sem_seg': {'data': lg.argmax(dim=0, keepdim=True)}})
+        return out
+
+    def predict(self, inputs, data_samples=None):
+        """encoder_decoder.py:187-222: list of {'seg_logits','pred_sem_seg'} per image."""
+        if self.test_cfg.get('mode', 'whole') == 'whole':
+            pred, logits = self.engine().forward_infer(inputs, pred_dtype=torch.int64, want_logits=True)
+            res = [{'seg_logits': {'data': logits[i]}, 'pred_sem_seg': {'data': pred[i:i + 1]}}
+                   for i in range(pred.shape[0])]
+        else:
+            res = self.postprocess_result(self.inference(inputs), data_samples)
+        if data_samples is not None:
+            for r, s in zip(res, data_samples):
+                if isinstance(s, dict):
+                    r.update({k: v for k, v in s.items() if k not in r})
+        return res
+
+    @torch.no_grad()
+    def predict_labels(self, inputs, pred=None, pred_dtype=torch.uint8):
+        """Fused fast path: [N,3,H,W] float (normalised) or uint8 (raw BGR) -> labels [N,H,W]."""
+        return self.engine().forward_infer(inputs, pred=pred, pred_dtype=pred_dtype)
+
+    def forward(self, inputs, data_samples=None, mode='tensor'):
+        if mode == 'predict':
+            return self.predict(inputs, data_samples)
+        if mode == 'tensor':
+            return self.decode_head.forward(self.extract_feat(inputs))
+        raise NotImplementedError("mode='loss' needs the backward kernels (SURVEY section 8a row T4)")

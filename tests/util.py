@@ -1,0 +1,37 @@
+import warnings
+
+import torch
+
+import oracle
+import lednet_b200 as L
+from lednet_b200 import synth
+
+
+def build_pair(num_classes, seed=2, dtype='fp32', channels=32, ppm=128, head_ch=64):
+    """(oracle segmentor on CPU, product EncoderDecoder) sharing one synthetic state dict."""
+    torch.manual_seed(0)
+    o = oracle.OracleSegmentor(num_classes=num_classes, channels=channels, ppm_channels=ppm,
+                               head_channels=head_ch).eval()
+    sd = synth.make_state_dict(o.state_dict(), seed=seed)
+    o.load_state_dict(sd)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(
+            dict(type='LEDNet', channels=channels, ppm_channels=ppm),
+            dict(type='LEDHead', in_channels=4 * channels, channels=head_ch, num_classes=num_classes,
+                 dropout_ratio=0., tap_channels=channels),
+            data_preprocessor=dict(type='SegDataPreProcessor', bgr_to_rgb=True),
+            compute_dtype=dtype).eval()
+    m.load_state_dict(sd, strict=True)
+    return o, m
+
+
+def rel_err(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).abs().max() / b.abs().max().clamp_min(1e-30))
+
+
+def near_tie_mask(logits, tol):
+    """pixels whose top-2 logits differ by less than tol * max|logit| (argmax may legitimately flip)."""
+    top2 = logits.topk(2, dim=1).values
+    return (top2[:, 0] - top2[:, 1]) < tol * logits.abs().max()
