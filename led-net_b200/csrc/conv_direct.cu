@@ -130,7 +130,7 @@ conv_direct_kernel(ConvArgs a) {
       const float vr = a.relu ? fmaxf(v, 0.f) : v;
       if (a.out) o[co] = from_f32<Tout>(vr);
       if (o2) {
-        float v2 = a.o2_scale ? fmaf(v, a.o2_scale[co], a.o2_shift[co]) : v;
+        float v2 = a.o2_scale ? fmaf(vr, a.o2_scale[co], a.o2_shift[co]) : vr;
         o2[co] = from_f32<Tout>(fmaxf(v2, 0.f));
       }
     }

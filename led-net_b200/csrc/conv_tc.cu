@@ -1,6 +1,562 @@
-// tcgen05/TMEM implicit-GEMM convolution - placeholder until the kernel lands.
+// Implicit-GEMM convolution on the 5th-gen tensor cores (north_star kernel 1).
+//
+// Replaces mmcv ConvModule = Conv2d(3x3 pad 1 | 1x1, stride 1 | 2) + folded BatchNorm (+ReLU)
+// (+ residual add of BasicBlock/Bottleneck.forward) for every dense layer of the trunk and head:
+//   mmseg/models/utils/basic_block.py:43-75, 186-221, mmseg/models/backbones/ddrnet.py:68-105,
+//   mmseg/models/utils/ppm.py:57-117, mmseg/models/decode_heads/led_head.py:84-99,
+//   mmseg/models/decode_heads/decode_head.py:241-246 (cls_seg).
+//
+// GEMM view: D[M = 128 output pixels (TH x TW tile)][N = Cout] += A[M][K] * B[N][K]^T with
+// K = taps * Cin walked as (Cin chunk of KC channels) x (filter tap).
+//   A  NHWC bf16 activations.  TMA (cp.async.bulk.tensor, tiled mode, hardware zero fill for the
+//      conv padding) stages, per Cin chunk, one "slab" per filter column: (TH+2) x TW pixels x KC
+//      channels, 128B- (KC=64) or 64B-swizzled (KC=32).  The three filter rows of that column are
+//      three row-shifted windows of the same slab: the UMMA shared-memory descriptor just starts
+//      TW*kh pixels later, so the input is fetched 3x (not 9x) from L2 and never re-laid out.
+//      Stride 2 uses a 5-D view [N][H/2][2][W/2][2*C] of the same tensor (row/column parity
+//      split), which turns the strided taps back into dense boxes.
+//   B  folded weights bf16 [CoutPad][taps*Cin] (K-major), TMA 2-D boxes of NT x KC; kept resident in
+//      shared memory for the whole persistent CTA when they fit, else streamed through a ring.
+//   D  fp32 accumulators in TMEM (tcgen05.mma cta_group::1, M=128, N=NT<=256), double buffered so
+//      the epilogue of tile i overlaps the MMAs of tile i+1.
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM owner + single-thread MMA issuer,
+// warps 2-5 = epilogue (tcgen05.ld 32x32b -> +bias (+residual) -> ReLU -> bf16 -> 16 B stores; an
+// optional second output relu(s*v+b) feeds the next layer's pre-activation BN+ReLU).
+// Persistent grid of min(tiles, #SM) CTAs, static round-robin tile schedule.
+#include <cuda.h>
+
+#include <map>
+#include <mutex>
+#include <tuple>
+#include <vector>
+#include <cstdlib>
+
 #include "kernels.h"
+
 namespace ledb {
-bool conv_tc_eligible(const ConvArgs&) { return false; }
-int launch_conv_tc(const ConvArgs&, cudaStream_t) { return fail(LEDB200_EINVAL, "tcgen05 conv not built"); }
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int TH = 16, TW = 8;            // output tile: 16 rows x 8 cols = 128 pixels = UMMA M
+constexpr int MAX_SLABS = 6, MAX_TAPS = 9;
+constexpr uint32_t SMEM_BUDGET = 220 * 1024;
+
+struct Slab {
+  int c_mul;      // channel offset multiplier (stride 2: column parity -> + c_mul * ld)
+  int dw, dh;     // box origin offsets (in units of the tensor-map W / H dims)
+  int ph;         // stride 2: row parity coordinate
+  int ntaps;
+  int tap_pix[MAX_TAPS];   // first pixel of the tap's window inside the slab
+  int tap_id[MAX_TAPS];    // filter tap index kh*3+kw (weight column block)
+};
+
+struct TcParams {
+  Slab slabs[MAX_SLABS];
+  int nslabs;
+  int Cin, Cout, NT, ntiles_n;       // NT = N tile (<=256, multiple of 16)
+  int ntaps_total;                   // ksize * ksize
+  int KC, nchunks;                   // channels per k-block, Cin / KC
+  int N, Ho, Wo, tiles_h, tiles_w;
+  int64_t total_tiles;
+  int in_ld;                         // pixel stride of the input (elements)
+  int sbo_bytes;                     // stride between 8-row groups of the A window
+  int base_off_mode;                 // experimental (halo layout): 0 -> 0, 1 -> (addr>>7)&7
+  uint32_t a_stage_bytes, b_tile_bytes;   // padded to 1024 B (ring strides)
+  uint32_t a_box_bytes, b_box_bytes;      // bytes one TMA box actually writes (expect_tx)
+  int SA, SB, b_resident;
+  uint32_t tmem_cols;
+  // epilogue
+  __nv_bfloat16* out; int out_ld;
+  __nv_bfloat16* out2; int out2_ld;
+  const float* o2_scale; const float* o2_shift;
+  const __nv_bfloat16* res; int res_ld;
+  const float* bias;
+  int relu;
+};
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {
+      printf("conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// UMMA shared-memory descriptor, K-major operand, rows of KC*2 bytes (128B or 64B swizzle).
+// Layout per cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout type [61,64).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t base_off) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;                                // LBO (unused for swizzled K-major) = 1
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
+  d |= (uint64_t)(base_off & 7) << 49;
+  d |= (uint64_t)(layout_type & 7) << 61;
+  return d;
+}
+
+template <bool S2>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ TcParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve: [A ring][B ring or resident B][barriers]
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;
+  uint8_t* sB = sA + (size_t)P.SA * P.a_stage_bytes;
+  const int nb_tiles = P.b_resident ? P.nchunks * 9 : P.SB;   // resident: indexed [chunk][tap]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_tiles * P.b_tile_bytes);
+  uint64_t* a_full = bars;                 // [SA]
+  uint64_t* a_empty = a_full + P.SA;       // [SA]
+  uint64_t* b_full = a_empty + P.SA;       // [SB] (resident: [0] only)
+  uint64_t* b_empty = b_full + 8;          // [SB]
+  uint64_t* t_full = b_empty + 8;          // [2]
+  uint64_t* t_empty = t_full + 2;          // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const uint32_t row_bytes = P.KC * 2;
+  const uint32_t layout_type = (P.KC == 64) ? 2u : (P.KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
+  const int ksteps = P.KC / 16;
+
+  if (warp == 0) {
+    // =========================== TMA producer ===========================
+    if (lane == 0) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      if (P.b_resident) {
+        // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
+        mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
+        for (int ch = 0; ch < P.nchunks; ++ch)
+          for (int t = 0; t < P.ntaps_total; ++t)
+            tma_load_2d(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes, &tmB, &b_full[0], t * P.Cin + ch * P.KC, 0);
+      }
+      for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        const int nt = (int)(tile % P.ntiles_n);
+        int64_t r = tile / P.ntiles_n;
+        const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
+        const int th = (int)(r % P.tiles_h);
+        const int n = (int)(r / P.tiles_h);
+        const int h0 = th * TH, w0 = tw * TW;
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          for (int s = 0; s < P.nslabs; ++s) {
+            const Slab& sl = P.slabs[s];
+            mbar_wait(&a_empty[sa], pa ^ 1, 1);
+            mbar_expect_tx(&a_full[sa], P.a_box_bytes);
+            void* dst = sA + (size_t)sa * P.a_stage_bytes;
+            if (S2) tma_load_5d(dst, &tmA, &a_full[sa], sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
+            else    tma_load_4d(dst, &tmA, &a_full[sa], ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+            if (!P.b_resident) {
+              for (int t = 0; t < sl.ntaps; ++t) {
+                mbar_wait(&b_empty[sb], pb ^ 1, 2);
+                mbar_expect_tx(&b_full[sb], P.b_box_bytes);
+                tma_load_2d(sB + (size_t)sb * P.b_tile_bytes, &tmB, &b_full[sb], sl.tap_id[t] * P.Cin + ch * P.KC, nt * P.NT);
+                if (++sb == P.SB) { sb = 0; pb ^= 1; }
+              }
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =========================== MMA issuer (single thread) ===========================
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      int ts = 0, tp = 0;
+      bool b_ready = false;
+      for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+        mbar_wait(&t_empty[ts], tp ^ 1, 3);       // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
+        uint32_t acc = 0;
+        if (P.b_resident && !b_ready) { mbar_wait(&b_full[0], 0, 4); b_ready = true; tc_fence_after(); }
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          for (int s = 0; s < P.nslabs; ++s) {
+            const Slab& sl = P.slabs[s];
+            mbar_wait(&a_full[sa], pa, 5);
+            tc_fence_after();
+            const uint32_t a_base = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+            for (int t = 0; t < sl.ntaps; ++t) {
+              uint32_t b_base;
+              if (P.b_resident) {
+                b_base = smem_u32(sB + (size_t)(ch * 9 + sl.tap_id[t]) * P.b_tile_bytes);
+              } else {
+                mbar_wait(&b_full[sb], pb, 6);
+                tc_fence_after();
+                b_base = smem_u32(sB + (size_t)sb * P.b_tile_bytes);
+              }
+              const uint32_t a_tap = a_base + (uint32_t)sl.tap_pix[t] * row_bytes;
+              const uint32_t boff = P.base_off_mode ? ((a_tap >> 7) & 7u) : 0u;
+#pragma unroll 4
+              for (int k = 0; k < ksteps; ++k) {
+                const uint64_t ad = make_desc(a_tap + k * 32, (uint32_t)P.sbo_bytes, layout_type, boff);
+                const uint64_t bd = make_desc(b_base + k * 32, 8 * row_bytes, layout_type, 0);
+                tc_mma(d_tmem, ad, bd, idesc, acc);
+                acc = 1;
+              }
+              if (!P.b_resident) {
+                tc_commit(&b_empty[sb]);          // frees the B stage when these MMAs retire
+                if (++sb == P.SB) { sb = 0; pb ^= 1; }
+              }
+            }
+            tc_commit(&a_empty[sa]);              // frees the A slab
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(&t_full[ts]);                   // accumulator complete -> epilogue
+        if (++ts == 2) { ts = 0; tp ^= 1; }
+      }
+    }
+  } else {
+    // =========================== epilogue warps ===========================
+    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+    const int m = q * 32 + lane;                  // tile row = output pixel within the tile
+    const int ph = m / TW, pw = m % TW;
+    int ts = 0, tp = 0;
+    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % P.ntiles_n);
+      int64_t r = tile / P.ntiles_n;
+      const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
+      const int th = (int)(r % P.tiles_h);
+      const int n = (int)(r / P.tiles_h);
+      const int oh = th * TH + ph, ow = tw * TW + pw;
+      const bool pvalid = (oh < P.Ho) && (ow < P.Wo);
+      const int64_t pix = ((int64_t)n * P.Ho + oh) * P.Wo + ow;
+      mbar_wait(&t_full[ts], tp, 7);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * P.NT);
+      for (int c16 = 0; c16 < P.NT; c16 += 16) {
+        uint32_t v[16];
+        tc_ld16(taddr + c16, v);
+        tc_wait_ld();
+        const int c0 = nt * P.NT + c16;
+        if (pvalid && c0 < P.Cout) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          const bool full = (c0 + 16 <= P.Cout);
+          if (P.bias) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] += __ldg(P.bias + c0 + j);     // bias is padded to CoutPad
+          }
+          if (P.res) {
+            const __nv_bfloat16* rp = P.res + pix * P.res_ld + c0;
+            if (full) {
+              float a[8], b[8];
+              load8(rp, a); load8(rp + 8, b);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { f[j] += a[j]; f[8 + j] += b[j]; }
+            } else {
+              for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+            }
+          }
+          if (P.relu) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          if (P.out) {
+            __nv_bfloat16* op = P.out + pix * P.out_ld + c0;
+            const float* o = f;
+            if (full) { store8(op, o); store8(op + 8, o + 8); }
+            else { for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) op[j] = __float2bfloat16_rn(o[j]); }
+          }
+          if (P.out2) {
+            __nv_bfloat16* op = P.out2 + pix * P.out2_ld + c0;
+            float o[16];
+            if (P.o2_scale) {
+              for (int j = 0; j < 16; ++j) {
+                const int c = (c0 + j < P.Cout) ? c0 + j : P.Cout - 1;
+                o[j] = fmaxf(fmaf(f[j], __ldg(P.o2_scale + c), __ldg(P.o2_shift + c)), 0.f);
+              }
+            } else {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) o[j] = fmaxf(f[j], 0.f);
+            }
+            if (full) { store8(op, o); store8(op + 8, o + 8); }
+            else { for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) op[j] = __float2bfloat16_rn(o[j]); }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[ts]);
+      if (++ts == 2) { ts = 0; tp ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+
+int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+           const uint32_t* box, int kc) {
+  EncodeFn fn = get_encode();
+  if (!fn) return fail(LEDB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LEDB200_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return LEDB200_OK;
+}
+
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
+int num_sms() {
+  static int n = 0;
+  if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+  return n;
+}
+int layout_mode() {   // experimental: LEDB200_TC_LAYOUT=D0|D1 -> single halo slab
+  const char* e = getenv("LEDB200_TC_LAYOUT");
+  if (!e) return 0;
+  if (e[0] == 'D') return e[1] == '1' ? 2 : 1;
+  return 0;
+}
+
+}  // namespace
+
+bool conv_tc_eligible(const ConvArgs& a) {
+  if (a.in_dtype != LEDB200_BF16 || a.out_dtype != LEDB200_BF16) return false;
+  if (a.pre_scale) return false;
+  if (a.ksize != 1 && a.ksize != 3) return false;
+  if (a.stride != 1 && a.stride != 2) return false;
+  if (a.dil != 1 && a.ksize == 3) return false;
+  if (a.Cin < 16 || a.Cin % 16) return false;
+  if (a.in_sc != 1 || a.in_sw % 8) return false;                     // NHWC, 16 B aligned pixels
+  if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;       // parity-split view needs even H, W
+  if (a.out && a.out_ld % 8) return false;
+  if (a.out2 && a.out2_ld % 8) return false;
+  if (a.res && a.res_ld % 8) return false;
+  const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : (a.Cout + 15) / 16 * 16;
+  if (cp > 256 && cp % 256) return false;
+  return true;
+}
+
+int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
+  if (!conv_tc_eligible(a)) return fail(LEDB200_EINVAL, "conv_tc: shape not eligible");
+  TcParams P{};
+  const int lm = (a.ksize == 3 && a.stride == 1) ? layout_mode() : 0;
+  const bool s2 = a.stride == 2;
+  P.Cin = a.Cin; P.Cout = a.Cout;
+  const int cp = a.cout_pad_tc;
+  P.NT = cp > 256 ? 256 : cp;
+  P.ntiles_n = cp / P.NT;
+  P.KC = pick_kc(a.Cin);
+  P.nchunks = a.Cin / P.KC;
+  P.N = a.N; P.Ho = a.Ho; P.Wo = a.Wo;
+  P.tiles_h = ceil_div(a.Ho, TH); P.tiles_w = ceil_div(a.Wo, TW);
+  P.total_tiles = (int64_t)a.N * P.tiles_h * P.tiles_w * P.ntiles_n;
+  P.in_ld = (int)a.in_sw;
+  const int row_bytes = P.KC * 2;
+  int box_w = TW, box_rows = TH;
+  P.sbo_bytes = 8 * row_bytes;
+  // ---- slab tables
+  if (a.ksize == 3 && !s2) {
+    if (lm == 0) {
+      P.nslabs = 3; box_rows = TH + 2;
+      for (int kw = 0; kw < 3; ++kw) {
+        Slab& s = P.slabs[kw];
+        s.c_mul = 0; s.dw = kw - 1; s.dh = -1; s.ph = 0; s.ntaps = 3;
+        for (int kh = 0; kh < 3; ++kh) { s.tap_pix[kh] = kh * TW; s.tap_id[kh] = kh * 3 + kw; }
+      }
+    } else {   // experimental: ONE halo slab (TH+2) x (TW+2); every tap is a row- AND column-shifted
+               // window of it (start address not atom aligned, SBO = (TW+2) rows).  1.4x instead of
+               // 3.4x input fetch; enabled only after the hardware probe confirms the semantics.
+      P.nslabs = 1; box_rows = TH + 2; box_w = TW + 2;
+      P.sbo_bytes = box_w * row_bytes;
+      P.base_off_mode = lm == 2 ? 1 : 0;
+      Slab& s = P.slabs[0];
+      s.c_mul = 0; s.dw = -1; s.dh = -1; s.ph = 0; s.ntaps = 9;
+      for (int kh = 0; kh < 3; ++kh)
+        for (int kw = 0; kw < 3; ++kw) { s.tap_pix[kh * 3 + kw] = kh * box_w + kw; s.tap_id[kh * 3 + kw] = kh * 3 + kw; }
+    }
+  } else if (a.ksize == 1 && !s2) {
+    P.nslabs = 1;
+    Slab& s = P.slabs[0];
+    s.c_mul = 0; s.dw = 0; s.dh = 0; s.ph = 0; s.ntaps = 1; s.tap_pix[0] = 0; s.tap_id[0] = 0;
+  } else if (a.ksize == 3 && s2) {
+    // input row 2*oh-1+kh -> (parity, half-row): kh=0 -> (1, oh-1), kh=1 -> (0, oh), kh=2 -> (1, oh); same for columns
+    P.nslabs = 6; box_rows = TH + 1;
+    int i = 0;
+    for (int kw = 0; kw < 3; ++kw) {
+      const int pw = (kw == 1) ? 0 : 1, dw = (kw == 0) ? -1 : 0;
+      Slab& s1 = P.slabs[i++];
+      s1.c_mul = pw; s1.dw = dw; s1.ph = 1; s1.dh = -1; s1.ntaps = 2;
+      s1.tap_pix[0] = 0; s1.tap_id[0] = 0 * 3 + kw;          // kh = 0: half-row oh-1
+      s1.tap_pix[1] = TW; s1.tap_id[1] = 2 * 3 + kw;         // kh = 2: half-row oh
+      Slab& s0 = P.slabs[i++];
+      s0.c_mul = pw; s0.dw = dw; s0.ph = 0; s0.dh = 0; s0.ntaps = 1;
+      s0.tap_pix[0] = 0; s0.tap_id[0] = 1 * 3 + kw;          // kh = 1
+    }
+  } else {   // 1x1 stride 2: parity (0,0) only
+    P.nslabs = 1;
+    Slab& s = P.slabs[0];
+    s.c_mul = 0; s.dw = 0; s.dh = 0; s.ph = 0; s.ntaps = 1; s.tap_pix[0] = 0; s.tap_id[0] = 0;
+  }
+  P.a_stage_bytes = (uint32_t)((box_rows * box_w * row_bytes + 1023) / 1024 * 1024);
+  P.b_tile_bytes = (uint32_t)((P.NT * row_bytes + 1023) / 1024 * 1024);
+  P.a_box_bytes = (uint32_t)(box_rows * box_w * row_bytes);
+  P.b_box_bytes = (uint32_t)(P.NT * row_bytes);
+  const int taps = a.ksize * a.ksize;
+  P.ntaps_total = taps;
+  // ---- shared-memory plan
+  const uint32_t bar_bytes = 1024;
+  const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
+  P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= 100 * 1024) ? 1 : 0;
+  if (getenv("LEDB200_TC_NO_RESIDENT")) P.b_resident = 0;
+  uint32_t left = SMEM_BUDGET - bar_bytes - 1024;
+  if (P.b_resident) {
+    left -= b_res_bytes;
+    P.SB = 1;
+  } else {
+    P.SB = (int)std::min<uint32_t>(8, std::max<uint32_t>(2, (left * 6 / 10) / P.b_tile_bytes));
+    left -= P.SB * P.b_tile_bytes;
+  }
+  P.SA = (int)std::min<uint32_t>(6, left / P.a_stage_bytes);
+  if (P.SA < 2) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
+  const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
+                      (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * P.NT)) cols <<= 1;
+  P.tmem_cols = cols;
+  P.out = (__nv_bfloat16*)a.out; P.out_ld = a.out_ld;
+  P.out2 = (__nv_bfloat16*)a.out2; P.out2_ld = a.out2_ld; P.o2_scale = a.o2_scale; P.o2_shift = a.o2_shift;
+  P.res = (const __nv_bfloat16*)a.res; P.res_ld = a.res_ld; P.bias = a.bias; P.relu = a.relu;
+
+  // ---- tensor maps
+  CUtensorMap tmA, tmB;
+  const uint64_t ld = (uint64_t)a.in_sw;
+  int rc;
+  if (!s2) {
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t str[3] = {ld * 2, (uint64_t)a.W * ld * 2, (uint64_t)a.H * a.W * ld * 2};
+    const uint32_t box[4] = {(uint32_t)P.KC, (uint32_t)box_w, (uint32_t)box_rows, 1};
+    rc = encode(&tmA, a.in, 4, dims, str, box, P.KC);
+  } else {
+    const uint64_t dims[5] = {ld + (uint64_t)a.Cin, (uint64_t)a.W / 2, 2, (uint64_t)a.H / 2, (uint64_t)a.N};
+    const uint64_t str[4] = {2 * ld * 2, (uint64_t)a.W * ld * 2, 2 * (uint64_t)a.W * ld * 2, (uint64_t)a.H * a.W * ld * 2};
+    const uint32_t box[5] = {(uint32_t)P.KC, (uint32_t)box_w, 1, (uint32_t)box_rows, 1};
+    rc = encode(&tmA, a.in, 5, dims, str, box, P.KC);
+  }
+  if (rc) return rc;
+  {
+    const uint64_t dims[2] = {(uint64_t)taps * a.Cin, (uint64_t)cp};
+    const uint64_t str[1] = {(uint64_t)taps * a.Cin * 2};
+    const uint32_t box[2] = {(uint32_t)P.KC, (uint32_t)P.NT};
+    rc = encode(&tmB, a.w_tc, 2, dims, str, box, P.KC);
+  }
+  if (rc) return rc;
+
+  const int grid = (int)std::min<int64_t>(P.total_tiles, num_sms());
+  if (s2) {
+    LEDB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+  } else {
+    LEDB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    conv_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+  }
+  LEDB_LAUNCH_OK("conv_tc_kernel");
+  return LEDB200_OK;
+}
+
 }  // namespace ledb

@@ -60,12 +60,11 @@ __global__ void __launch_bounds__(kThreads) upsample_add_kernel(UpAddArgs a, flo
 #pragma unroll
       for (int c = 0; c < 8; ++c) v[c] += b[c];
     }
-    if (out) {
-      float o[8];
+    if (a.relu) {
 #pragma unroll
-      for (int c = 0; c < 8; ++c) o[c] = a.relu ? fmaxf(v[c], 0.f) : v[c];
-      store8(out + p * a.out_ld + g * 8, o);
+      for (int c = 0; c < 8; ++c) v[c] = fmaxf(v[c], 0.f);
     }
+    if (out) store8(out + p * a.out_ld + g * 8, v);
     if (out2) {
       float o[8];
 #pragma unroll

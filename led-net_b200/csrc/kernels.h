@@ -12,7 +12,7 @@ struct ConvArgs {
   void* out = nullptr;          // may be null when only out2 is wanted
   int out_dtype = LEDB200_F32;
   int out_ld = 0;               // pixel stride (elements) of out
-  void* out2 = nullptr;         // optional: relu(o2_scale*v + o2_shift), v = pre-ReLU value
+  void* out2 = nullptr;         // optional: relu(o2_scale*y + o2_shift), y = the primary output value (after `relu`)
   int out2_ld = 0;
   const float* o2_scale = nullptr;  // null => identity affine
   const float* o2_shift = nullptr;
