@@ -182,11 +182,15 @@ int ledb200_ohem_ce(const float* logits, const int64_t* target, int32_t N, int32
  * bias host fp32 [Cout] or NULL; pre_scale/pre_shift host fp32 [Cin] or NULL
  * (pre-activation BN+ReLU applied before zero padding, mmcv ConvModule order
  * ('norm','act','conv'): led_head.py:94, ppm.py:42-43); residual NHWC or NULL.
- * backend 0 auto, 1 CUDA-core, 2 tcgen05 (fails if the shape is not eligible). */
+ * backend 0 auto, 1 CUDA-core, 2 tcgen05 (fails if the shape is not eligible).
+ * in_ld / out_ld / res_ld: pixel strides in elements (0 = dense, i.e. Cin / Cout / Cout); the
+ * tcgen05 path needs them to be multiples of 8 (16-byte pixels), so a 19-class output is
+ * stored with out_ld = 24 exactly as the engine does. */
 int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtype, int32_t N,
                    int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride,
                    int32_t relu, const float* weight_oihw, const float* bias,
-                   const float* pre_scale, const float* pre_shift, int32_t backend, void* stream);
+                   const float* pre_scale, const float* pre_shift, int32_t backend,
+                   int32_t in_ld, int32_t out_ld, int32_t res_ld, void* stream);
 
 #ifdef __cplusplus
 }

@@ -39,11 +39,16 @@ int ledb200_ohem_ce(const float* logits, const int64_t* target, int32_t N, int32
 
 int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtype, int32_t N, int32_t H, int32_t W,
                    int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride, int32_t relu, const float* weight_oihw,
-                   const float* bias, const float* pre_scale, const float* pre_shift, int32_t backend, void* stream) {
+                   const float* bias, const float* pre_scale, const float* pre_shift, int32_t backend, int32_t in_ld,
+                   int32_t out_ld, int32_t res_ld, void* stream) {
   if (!in || !out || !weight_oihw) return fail(LEDB200_EINVAL, "conv2d: null buffer");
   if (ksize != 1 && ksize != 3) return fail(LEDB200_EINVAL, "conv2d: ksize must be 1 or 3");
   if (stride != 1 && stride != 2) return fail(LEDB200_EINVAL, "conv2d: stride must be 1 or 2");
   if (dtype != LEDB200_F32 && dtype != LEDB200_BF16) return fail(LEDB200_EINVAL, "conv2d: dtype must be F32 or BF16");
+  if (in_ld == 0) in_ld = Cin;
+  if (out_ld == 0) out_ld = Cout;
+  if (res_ld == 0) res_ld = Cout;
+  if (in_ld < Cin || out_ld < Cout || res_ld < Cout) return fail(LEDB200_EINVAL, "conv2d: pixel stride smaller than the channel count");
   cudaStream_t st = (cudaStream_t)stream;
   const int taps = ksize * ksize, cp16 = (Cout + 15) / 16 * 16;
   std::vector<float> wd((size_t)taps * Cin * cp16, 0.f), bz(cp16, 0.f);
@@ -72,8 +77,8 @@ int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtyp
   if (!rc) {
     ConvArgs a;
     const int pad = ksize / 2;
-    a.in = in; a.in_dtype = dtype; a.in_sc = 1; a.in_sw = Cin; a.in_sh = (int64_t)W * Cin; a.in_sn = (int64_t)H * W * Cin;
-    a.out = out; a.out_dtype = dtype; a.out_ld = Cout; a.res = residual; a.res_ld = Cout;
+    a.in = in; a.in_dtype = dtype; a.in_sc = 1; a.in_sw = in_ld; a.in_sh = (int64_t)W * in_ld; a.in_sn = (int64_t)H * W * in_ld;
+    a.out = out; a.out_dtype = dtype; a.out_ld = out_ld; a.res = residual; a.res_ld = res_ld;
     a.bias = d_b; a.pre_scale = d_ps; a.pre_shift = d_pb; a.pre_relu = 1;
     a.w_direct = d_wd; a.w_tc = d_wt; a.cout_pad16 = cp16; a.cout_pad_tc = cp16;
     a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride; a.pad = pad; a.dil = 1;

@@ -121,6 +121,30 @@ conv_direct_kernel(ConvArgs a) {
     Tout* o = reinterpret_cast<Tout*>(a.out) + pix * a.out_ld;
     Tout* o2 = a.out2 ? reinterpret_cast<Tout*>(a.out2) + pix * a.out2_ld : nullptr;
     const Tout* r = a.res ? reinterpret_cast<const Tout*>(a.res) + pix * a.res_ld : nullptr;
+    // fast path: a full, 16 B aligned group of 16 channels -> vector loads/stores
+    const bool vec_ok = (co0 + COT <= a.Cout) && (a.out_ld % 8 == 0) && (!o2 || a.out2_ld % 8 == 0) &&
+                        (!r || a.res_ld % 8 == 0);
+    if (vec_ok) {
+      float v[COT], rr[COT];
+      if (r) { load8(r + co0, rr); load8(r + co0 + 8, rr + 8); }
+#pragma unroll
+      for (int j = 0; j < COT; ++j) {
+        float t = acc[i][j] + (a.bias ? a.bias[co0 + j] : 0.f);
+        if (r) t += rr[j];
+        v[j] = a.relu ? fmaxf(t, 0.f) : t;
+      }
+      if (a.out) { store8(o + co0, v); store8(o + co0 + 8, v + 8); }
+      if (o2) {
+        float w[COT];
+#pragma unroll
+        for (int j = 0; j < COT; ++j) {
+          const float t = a.o2_scale ? fmaf(v[j], a.o2_scale[co0 + j], a.o2_shift[co0 + j]) : v[j];
+          w[j] = fmaxf(t, 0.f);
+        }
+        store8(o2 + co0, w); store8(o2 + co0 + 8, w + 8);
+      }
+      continue;
+    }
 #pragma unroll
     for (int j = 0; j < COT; ++j) {
       const int co = co0 + j;

@@ -60,10 +60,11 @@ struct TcParams {
   int64_t total_tiles;
   int in_ld;                         // pixel stride of the input (elements)
   int sbo_bytes;                     // stride between 8-row groups of the A window
-  int base_off_mode;                 // experimental (halo layout): 0 -> 0, 1 -> (addr>>7)&7
   uint32_t a_stage_bytes, b_tile_bytes;   // padded to 1024 B (ring strides)
   uint32_t a_box_bytes, b_box_bytes;      // bytes one TMA box actually writes (expect_tx)
   int SA, SB, b_resident;
+  int cp;                            // Cout padded to the N tiling (ntiles_n * NT)
+  uint32_t stage_bytes;              // epilogue staging: 16 KB (+16 KB with a second output)
   uint32_t tmem_cols;
   // epilogue
   __nv_bfloat16* out; int out_ld;
@@ -96,27 +97,32 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   return ok != 0;
 }
 // Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int tag) {
-  if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
-      printf("conv_tc: mbarrier timeout tag=%d block=%d thread=%d parity=%u\n", tag, blockIdx.x, threadIdx.x, parity);
-      __trap();
-    }
+    if (++spins > (1u << 28)) __trap();
   }
 }
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
 }
-__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3) {
+__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
   asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
 }
-__device__ __forceinline__ void tma_load_5d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2, int c3, int c4) {
+__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
   asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-               ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -130,7 +136,7 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t v[16]) {
+__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
@@ -141,16 +147,27 @@ __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sy
 
 // UMMA shared-memory descriptor, K-major operand, rows of KC*2 bytes (128B or 64B swizzle).
 // Layout per cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout type [61,64).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout_type, uint32_t base_off) {
-  uint64_t d = 0;
-  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
-  d |= (uint64_t)1 << 16;                                // LBO (unused for swizzled K-major) = 1
-  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
-  d |= (uint64_t)1 << 46;                                // descriptor version (Blackwell)
-  d |= (uint64_t)(base_off & 7) << 49;
-  d |= (uint64_t)(layout_type & 7) << 61;
-  return d;
+// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout type [61,64).  The high word is
+// constant per operand; the MMA loop only rebuilds the low word (start address).
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t saddr) {
+  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);   // LBO (unused for swizzled K-major) = 1
+  return ((uint64_t)hi << 32) | lo;
+}
+
+// 128B XOR swizzle of a linear byte offset (bank-conflict-free epilogue staging)
+__device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&h);
+}
+__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
 }
 
 template <bool S2>
@@ -158,16 +175,20 @@ __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve: [A ring][B ring or resident B][barriers]
+  // carve: [A ring][B ring or resident B][epilogue staging][bias / out2 affine][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = sA + (size_t)P.SA * P.a_stage_bytes;
   const int nb_tiles = P.b_resident ? P.nchunks * 9 : P.SB;   // resident: indexed [chunk][tap]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + (size_t)nb_tiles * P.b_tile_bytes);
-  uint64_t* a_full = bars;                 // [SA]
-  uint64_t* a_empty = a_full + P.SA;       // [SA]
-  uint64_t* b_full = a_empty + P.SA;       // [SB] (resident: [0] only)
-  uint64_t* b_empty = b_full + 8;          // [SB]
+  uint8_t* sStage = sB + (size_t)nb_tiles * P.b_tile_bytes;   // 4 warps x (1 or 2) x 4 KB
+  float* s_bias = reinterpret_cast<float*>(sStage + P.stage_bytes);   // [cp]
+  float* s_o2s = s_bias + P.cp;                                       // [cp]
+  float* s_o2b = s_o2s + P.cp;                                        // [cp]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_o2b + P.cp);
+  uint64_t* a_full = bars;                 // [8]
+  uint64_t* a_empty = a_full + 8;          // [8]
+  uint64_t* b_full = a_empty + 8;          // [8] (resident: [0] only)
+  uint64_t* b_empty = b_full + 8;          // [8]
   uint64_t* t_full = b_empty + 8;          // [2]
   uint64_t* t_empty = t_full + 2;          // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
@@ -175,14 +196,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < P.SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
-    for (int i = 0; i < 8; ++i) { mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1); }
+    for (int i = 0; i < 8; ++i) {
+      mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // per-channel epilogue constants, zero padded to cp so no channel guard is needed later
+  for (int c = threadIdx.x; c < P.cp; c += kThreads) {
+    const bool in = c < P.Cout;
+    s_bias[c] = (P.bias && in) ? P.bias[c] : 0.f;
+    s_o2s[c] = in ? (P.o2_scale ? P.o2_scale[c] : 1.f) : 0.f;
+    s_o2b[c] = (P.o2_shift && in) ? P.o2_shift[c] : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -194,99 +223,110 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int ksteps = P.KC / 16;
 
   if (warp == 0) {
-    // =========================== TMA producer ===========================
-    if (lane == 0) {
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      if (P.b_resident) {
-        // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
-        mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
-        for (int ch = 0; ch < P.nchunks; ++ch)
-          for (int t = 0; t < P.ntaps_total; ++t)
-            tma_load_2d(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes, &tmB, &b_full[0], t * P.Cin + ch * P.KC, 0);
-      }
-      for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        const int nt = (int)(tile % P.ntiles_n);
-        int64_t r = tile / P.ntiles_n;
-        const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
-        const int th = (int)(r % P.tiles_h);
-        const int n = (int)(r / P.tiles_h);
-        const int h0 = th * TH, w0 = tw * TW;
-        for (int ch = 0; ch < P.nchunks; ++ch) {
-          for (int s = 0; s < P.nslabs; ++s) {
-            const Slab& sl = P.slabs[s];
-            mbar_wait(&a_empty[sa], pa ^ 1, 1);
+    // =========================== TMA producer (whole warp loops, one elected lane issues) =========
+    const bool leader = elect_one();
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    if (P.b_resident && leader) {
+      // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
+      mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
+      for (int ch = 0; ch < P.nchunks; ++ch)
+        for (int t = 0; t < P.ntaps_total; ++t)
+          tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
+                      t * P.Cin + ch * P.KC, 0);
+    }
+    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      const int nt = (int)(tile % P.ntiles_n);
+      int64_t r = tile / P.ntiles_n;
+      const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
+      const int th = (int)(r % P.tiles_h);
+      const int n = (int)(r / P.tiles_h);
+      const int h0 = th * TH, w0 = tw * TW;
+      for (int ch = 0; ch < P.nchunks; ++ch) {
+        for (int s = 0; s < P.nslabs; ++s) {
+          const Slab& sl = P.slabs[s];
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          if (leader) {
             mbar_expect_tx(&a_full[sa], P.a_box_bytes);
-            void* dst = sA + (size_t)sa * P.a_stage_bytes;
-            if (S2) tma_load_5d(dst, &tmA, &a_full[sa], sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
-            else    tma_load_4d(dst, &tmA, &a_full[sa], ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
-            if (++sa == P.SA) { sa = 0; pa ^= 1; }
-            if (!P.b_resident) {
-              for (int t = 0; t < sl.ntaps; ++t) {
-                mbar_wait(&b_empty[sb], pb ^ 1, 2);
+            const uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+            if (S2) tma_load_5d(dst, &tmA, smem_u32(&a_full[sa]), sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
+            else    tma_load_4d(dst, &tmA, smem_u32(&a_full[sa]), ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
+          }
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          if (!P.b_resident) {
+            for (int t = 0; t < sl.ntaps; ++t) {
+              mbar_wait(&b_empty[sb], pb ^ 1);
+              if (leader) {
                 mbar_expect_tx(&b_full[sb], P.b_box_bytes);
-                tma_load_2d(sB + (size_t)sb * P.b_tile_bytes, &tmB, &b_full[sb], sl.tap_id[t] * P.Cin + ch * P.KC, nt * P.NT);
-                if (++sb == P.SB) { sb = 0; pb ^= 1; }
+                tma_load_2d(smem_u32(sB + (size_t)sb * P.b_tile_bytes), &tmB, smem_u32(&b_full[sb]),
+                            sl.tap_id[t] * P.Cin + ch * P.KC, nt * P.NT);
               }
+              if (++sb == P.SB) { sb = 0; pb ^= 1; }
             }
           }
         }
       }
     }
   } else if (warp == 1) {
-    // =========================== MMA issuer (single thread) ===========================
-    if (lane == 0) {
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-      int sa = 0, pa = 0, sb = 0, pb = 0;
-      int ts = 0, tp = 0;
-      bool b_ready = false;
-      for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-        mbar_wait(&t_empty[ts], tp ^ 1, 3);       // epilogue has drained this accumulator stage
-        tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
-        uint32_t acc = 0;
-        if (P.b_resident && !b_ready) { mbar_wait(&b_full[0], 0, 4); b_ready = true; tc_fence_after(); }
-        for (int ch = 0; ch < P.nchunks; ++ch) {
-          for (int s = 0; s < P.nslabs; ++s) {
-            const Slab& sl = P.slabs[s];
-            mbar_wait(&a_full[sa], pa, 5);
-            tc_fence_after();
-            const uint32_t a_base = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
-            for (int t = 0; t < sl.ntaps; ++t) {
-              uint32_t b_base;
-              if (P.b_resident) {
-                b_base = smem_u32(sB + (size_t)(ch * 9 + sl.tap_id[t]) * P.b_tile_bytes);
-              } else {
-                mbar_wait(&b_full[sb], pb, 6);
-                tc_fence_after();
-                b_base = smem_u32(sB + (size_t)sb * P.b_tile_bytes);
-              }
-              const uint32_t a_tap = a_base + (uint32_t)sl.tap_pix[t] * row_bytes;
-              const uint32_t boff = P.base_off_mode ? ((a_tap >> 7) & 7u) : 0u;
+    // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
+    const bool leader = elect_one();
+    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
+    const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
+    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    int sa = 0, pa = 0, sb = 0, pb = 0;
+    int ts = 0, tp = 0;
+    if (P.b_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+      mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
+      uint32_t acc = 0;
+      for (int ch = 0; ch < P.nchunks; ++ch) {
+        for (int s = 0; s < P.nslabs; ++s) {
+          const Slab& sl = P.slabs[s];
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_base = sA_u + (uint32_t)sa * P.a_stage_bytes;
+          for (int t = 0; t < sl.ntaps; ++t) {
+            uint32_t b_base;
+            if (P.b_resident) {
+              b_base = sB_u + (uint32_t)(ch * 9 + sl.tap_id[t]) * P.b_tile_bytes;
+            } else {
+              mbar_wait(&b_full[sb], pb);
+              tc_fence_after();
+              b_base = sB_u + (uint32_t)sb * P.b_tile_bytes;
+            }
+            const uint32_t a_tap = a_base + (uint32_t)sl.tap_pix[t] * row_bytes;
+            if (leader) {
 #pragma unroll 4
               for (int k = 0; k < ksteps; ++k) {
-                const uint64_t ad = make_desc(a_tap + k * 32, (uint32_t)P.sbo_bytes, layout_type, boff);
-                const uint64_t bd = make_desc(b_base + k * 32, 8 * row_bytes, layout_type, 0);
-                tc_mma(d_tmem, ad, bd, idesc, acc);
+                tc_mma(d_tmem, make_desc(a_hi, a_tap + k * 32), make_desc(b_hi, b_base + k * 32), idesc, acc);
                 acc = 1;
               }
-              if (!P.b_resident) {
-                tc_commit(&b_empty[sb]);          // frees the B stage when these MMAs retire
-                if (++sb == P.SB) { sb = 0; pb ^= 1; }
-              }
             }
-            tc_commit(&a_empty[sa]);              // frees the A slab
-            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+            if (!P.b_resident) {
+              if (leader) tc_commit(&b_empty[sb]);          // frees the B stage when these MMAs retire
+              if (++sb == P.SB) { sb = 0; pb ^= 1; }
+            }
           }
+          if (leader) tc_commit(&a_empty[sa]);              // frees the A slab
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
         }
-        tc_commit(&t_full[ts]);                   // accumulator complete -> epilogue
-        if (++ts == 2) { ts = 0; tp ^= 1; }
       }
+      if (leader) tc_commit(&t_full[ts]);                   // accumulator complete -> epilogue
+      __syncwarp();
+      if (++ts == 2) { ts = 0; tp ^= 1; }
     }
   } else {
     // =========================== epilogue warps ===========================
+    // TMEM -> registers (thread = output pixel) -> +bias (+residual) -> ReLU -> bf16 -> warp-private
+    // swizzled staging tile -> 16 B stores with consecutive lanes on consecutive addresses.
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;                  // tile row = output pixel within the tile
     const int ph = m / TW, pw = m % TW;
+    uint8_t* st1 = sStage + (size_t)q * 4096;
+    uint8_t* st2 = sStage + 16384 + (size_t)q * 4096;
+    const int cout8 = (P.Cout + 7) & ~7;          // stores cover whole 8-channel groups (buffers are padded)
     int ts = 0, tp = 0;
     for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       const int nt = (int)(tile % P.ntiles_n);
@@ -297,59 +337,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int oh = th * TH + ph, ow = tw * TW + pw;
       const bool pvalid = (oh < P.Ho) && (ow < P.Wo);
       const int64_t pix = ((int64_t)n * P.Ho + oh) * P.Wo + ow;
-      mbar_wait(&t_full[ts], tp, 7);
+      const int64_t pix_w0 = ((int64_t)n * P.Ho + th * TH + q * 4) * P.Wo + tw * TW;   // first pixel of this warp's 4 rows
+      mbar_wait(&t_full[ts], tp);
       tc_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * P.NT);
-      for (int c16 = 0; c16 < P.NT; c16 += 16) {
-        uint32_t v[16];
-        tc_ld16(taddr + c16, v);
+      for (int c0 = 0; c0 < P.NT; c0 += 32) {
+        const int ncol = min(32, P.NT - c0);       // 16 or 32
+        const int cg0 = nt * P.NT + c0;            // first global output channel of this block
+        uint32_t v[32];
+        tc_ld16(taddr + c0, v);
+        if (ncol == 32) tc_ld16(taddr + c0 + 16, v + 16);
+        uint4 rr[4];
+        bool rv[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rv[g] = P.res && pvalid && (8 * g < ncol) && (cg0 + 8 * g < cout8);
+          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(P.res + pix * P.res_ld + cg0 + 8 * g));
+        }
         tc_wait_ld();
-        const int c0 = nt * P.NT + c16;
-        if (pvalid && c0 < P.Cout) {
-          float f[16];
+        const int slice_c = c0 & 63;               // column of this block inside the 64-channel staging slice
+        const int slice_cols = min(64, P.NT - (c0 - slice_c));
+        const uint32_t row_off = (uint32_t)lane * (uint32_t)(slice_cols * 2);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-          const bool full = (c0 + 16 <= P.Cout);
-          if (P.bias) {
+        for (int g = 0; g < 4; ++g) {
+          if (8 * g < ncol) {
+            float f[8];
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cg0 + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cg0 + 8 * g + 4);
+            f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+            f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+            f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+            f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+            if (rv[g]) {
+              float t[8];
+              unpack8(rr[g], t);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] += __ldg(P.bias + c0 + j);     // bias is padded to CoutPad
-          }
-          if (P.res) {
-            const __nv_bfloat16* rp = P.res + pix * P.res_ld + c0;
-            if (full) {
-              float a[8], b[8];
-              load8(rp, a); load8(rp + 8, b);
+              for (int j = 0; j < 8; ++j) f[j] += t[j];
+            }
+            if (P.relu) {
 #pragma unroll
-              for (int j = 0; j < 8; ++j) { f[j] += a[j]; f[8 + j] += b[j]; }
-            } else {
-              for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) f[j] += __bfloat162float(rp[j]);
+              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
+            }
+            const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
+            if (P.out)
+              *reinterpret_cast<uint4*>(st1 + so) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
+                                                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            if (P.out2) {
+              const float4 s0 = *reinterpret_cast<const float4*>(s_o2s + cg0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(s_o2s + cg0 + 8 * g + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(s_o2b + cg0 + 8 * g);
+              const float4 h1 = *reinterpret_cast<const float4*>(s_o2b + cg0 + 8 * g + 4);
+              float o[8];
+              o[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f); o[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
+              o[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f); o[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
+              o[4] = fmaxf(fmaf(f[4], s1.x, h1.x), 0.f); o[5] = fmaxf(fmaf(f[5], s1.y, h1.y), 0.f);
+              o[6] = fmaxf(fmaf(f[6], s1.z, h1.z), 0.f); o[7] = fmaxf(fmaf(f[7], s1.w, h1.w), 0.f);
+              *reinterpret_cast<uint4*>(st2 + so) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
+                                                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
             }
           }
-          if (P.relu) {
-#pragma unroll
-            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-          }
-          if (P.out) {
-            __nv_bfloat16* op = P.out + pix * P.out_ld + c0;
-            const float* o = f;
-            if (full) { store8(op, o); store8(op + 8, o + 8); }
-            else { for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) op[j] = __float2bfloat16_rn(o[j]); }
-          }
-          if (P.out2) {
-            __nv_bfloat16* op = P.out2 + pix * P.out2_ld + c0;
-            float o[16];
-            if (P.o2_scale) {
-              for (int j = 0; j < 16; ++j) {
-                const int c = (c0 + j < P.Cout) ? c0 + j : P.Cout - 1;
-                o[j] = fmaxf(fmaf(f[j], __ldg(P.o2_scale + c), __ldg(P.o2_shift + c)), 0.f);
-              }
-            } else {
-#pragma unroll
-              for (int j = 0; j < 16; ++j) o[j] = fmaxf(f[j], 0.f);
+        }
+        // ---- flush a completed staging slice (up to 64 channels x 32 pixels) with coalesced stores
+        if (slice_c + ncol == slice_cols) {
+          __syncwarp();
+          const int sc0 = nt * P.NT + (c0 - slice_c);          // first global channel of the slice
+          const uint32_t sbytes = (uint32_t)slice_cols * 2;    // bytes per pixel in the slice
+          const uint32_t total = 32u * sbytes;
+          for (uint32_t L = (uint32_t)lane * 16; L < total; L += 512) {
+            const uint32_t p = L / sbytes, b = L - p * sbytes; // staged pixel (0..31), byte inside its slice
+            const int prow = (int)(p >> 3), pcol = (int)(p & 7);
+            const int c = sc0 + (int)(b >> 1);
+            const bool ok = (th * TH + q * 4 + prow < P.Ho) && (tw * TW + pcol < P.Wo) && (c < cout8);
+            if (ok) {
+              const int64_t gp = pix_w0 + (int64_t)prow * P.Wo + pcol;
+              const uint32_t so = swz(L);
+              if (P.out) *reinterpret_cast<uint4*>(P.out + gp * P.out_ld + c) = *reinterpret_cast<const uint4*>(st1 + so);
+              if (P.out2) *reinterpret_cast<uint4*>(P.out2 + gp * P.out2_ld + c) = *reinterpret_cast<const uint4*>(st2 + so);
             }
-            if (full) { store8(op, o); store8(op + 8, o + 8); }
-            else { for (int j = 0; j < 16 && c0 + j < P.Cout; ++j) op[j] = __float2bfloat16_rn(o[j]); }
           }
+          __syncwarp();
         }
       }
       tc_fence_before();
@@ -406,11 +472,13 @@ int num_sms() {
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
   return n;
 }
-int layout_mode() {   // experimental: LEDB200_TC_LAYOUT=D0|D1 -> single halo slab
-  const char* e = getenv("LEDB200_TC_LAYOUT");
-  if (!e) return 0;
-  if (e[0] == 'D') return e[1] == '1' ? 2 : 1;
-  return 0;
+int layout_mode() {   // 1 = single halo slab per Cin chunk (default); LEDB200_TC_LAYOUT=E -> three column slabs
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("LEDB200_TC_LAYOUT");
+    mode = (e && e[0] == 'E') ? 0 : 1;
+  }
+  return mode;
 }
 
 }  // namespace
@@ -424,9 +492,10 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.Cin < 16 || a.Cin % 16) return false;
   if (a.in_sc != 1 || a.in_sw % 8) return false;                     // NHWC, 16 B aligned pixels
   if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;       // parity-split view needs even H, W
-  if (a.out && a.out_ld % 8) return false;
-  if (a.out2 && a.out2_ld % 8) return false;
-  if (a.res && a.res_ld % 8) return false;
+  const int c8 = (a.Cout + 7) / 8 * 8;                               // stores cover whole 8-channel groups
+  if (a.out && (a.out_ld % 8 || a.out_ld < c8)) return false;
+  if (a.out2 && (a.out2_ld % 8 || a.out2_ld < c8)) return false;
+  if (a.res && (a.res_ld % 8 || a.res_ld < c8)) return false;
   const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : (a.Cout + 15) / 16 * 16;
   if (cp > 256 && cp % 256) return false;
   return true;
@@ -459,12 +528,13 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
         s.c_mul = 0; s.dw = kw - 1; s.dh = -1; s.ph = 0; s.ntaps = 3;
         for (int kh = 0; kh < 3; ++kh) { s.tap_pix[kh] = kh * TW; s.tap_id[kh] = kh * 3 + kw; }
       }
-    } else {   // experimental: ONE halo slab (TH+2) x (TW+2); every tap is a row- AND column-shifted
-               // window of it (start address not atom aligned, SBO = (TW+2) rows).  1.4x instead of
-               // 3.4x input fetch; enabled only after the hardware probe confirms the semantics.
+    } else {   // ONE halo slab (TH+2) x (TW+2) per Cin chunk; every tap is a row- AND column-shifted window
+               // of it: the descriptor start address is not swizzle-atom aligned and SBO = (TW+2) rows.
+               // The hardware applies the swizzle XOR on absolute shared-memory address bits (probed on
+               // B200: tests/probe_tc_layout.py, profiles/r1_notes.md), so this reads exactly what TMA
+               // wrote.  Input fetch 1.4x instead of 3.4x, one TMA per chunk instead of three.
       P.nslabs = 1; box_rows = TH + 2; box_w = TW + 2;
       P.sbo_bytes = box_w * row_bytes;
-      P.base_off_mode = lm == 2 ? 1 : 0;
       Slab& s = P.slabs[0];
       s.c_mul = 0; s.dw = -1; s.dh = -1; s.ph = 0; s.ntaps = 9;
       for (int kh = 0; kh < 3; ++kh)
@@ -500,10 +570,13 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   const int taps = a.ksize * a.ksize;
   P.ntaps_total = taps;
   // ---- shared-memory plan
-  const uint32_t bar_bytes = 1024;
+  P.cp = cp;
+  P.stage_bytes = a.out2 ? 32768u : 16384u;
+  const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 34 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
   P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= 100 * 1024) ? 1 : 0;
-  if (getenv("LEDB200_TC_NO_RESIDENT")) P.b_resident = 0;
+  static const bool no_resident = getenv("LEDB200_TC_NO_RESIDENT") != nullptr;
+  if (no_resident) P.b_resident = 0;
   uint32_t left = SMEM_BUDGET - bar_bytes - 1024;
   if (P.b_resident) {
     left -= b_res_bytes;
@@ -512,7 +585,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     P.SB = (int)std::min<uint32_t>(8, std::max<uint32_t>(2, (left * 6 / 10) / P.b_tile_bytes));
     left -= P.SB * P.b_tile_bytes;
   }
-  P.SA = (int)std::min<uint32_t>(6, left / P.a_stage_bytes);
+  P.SA = (int)std::min<uint32_t>(8, left / P.a_stage_bytes);
   if (P.SA < 2) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
   const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
                       (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
@@ -548,13 +621,16 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (rc) return rc;
 
   const int grid = (int)std::min<int64_t>(P.total_tiles, num_sms());
-  if (s2) {
-    LEDB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
-  } else {
-    LEDB_CUDA_OK(cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    conv_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
-  }
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
+    if (attr_err == cudaSuccess)
+      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
+  });
+  if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
+  if (s2) conv_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+  else    conv_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
   LEDB_LAUNCH_OK("conv_tc_kernel");
   return LEDB200_OK;
 }

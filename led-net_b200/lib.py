@@ -72,7 +72,7 @@ def get():
     lib.ledb200_ohem_workspace_bytes.argtypes = [i64]
     lib.ledb200_ohem_workspace_bytes.restype = i64
     lib.ledb200_ohem_ce.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, i64, f32, vp, vp, vp, vp, vp]
-    lib.ledb200_conv2d.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, vp, vp, vp, i32, vp]
+    lib.ledb200_conv2d.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):

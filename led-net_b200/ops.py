@@ -86,11 +86,16 @@ def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, residual=None, 
     Cout, _, k, _ = w.shape
     pad = k // 2
     Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
-    out = torch.empty((N, Ho, Wo, Cout), dtype=x.dtype, device=x.device)
+    # 16-byte pixels for the tensor-core path: Cout 19 -> pixel stride 24, like the engine's buffers
+    ld = (Cout + 7) // 8 * 8
+    out_full = torch.empty((N, Ho, Wo, ld), dtype=x.dtype, device=x.device)
     host = [None if t is None else t.detach().to('cpu', torch.float32).contiguous()
             for t in (bias, pre_scale, pre_shift)]
-    res = residual.contiguous() if residual is not None else None
-    L.check(L.get().ledb200_conv2d(_p(x), _p(out), _p(res), L.torch_dtype_code(x), N, H, W, Cin, Cout, k,
+    res = None
+    if residual is not None:
+        res = residual.new_zeros((N, Ho, Wo, ld))
+        res[..., :Cout] = residual
+    L.check(L.get().ledb200_conv2d(_p(x), _p(out_full), _p(res), L.torch_dtype_code(x), N, H, W, Cin, Cout, k,
                                    stride, int(relu), _p(w), _p(host[0]), _p(host[1]), _p(host[2]),
-                                   backend, L.stream_ptr(x.device)), 'ledb200_conv2d')
-    return out
+                                   backend, Cin, ld, ld, L.stream_ptr(x.device)), 'ledb200_conv2d')
+    return out_full[..., :Cout]
