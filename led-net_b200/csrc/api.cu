@@ -50,9 +50,9 @@ int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtyp
   if (res_ld == 0) res_ld = Cout;
   if (in_ld < Cin || out_ld < Cout || res_ld < Cout) return fail(LEDB200_EINVAL, "conv2d: pixel stride smaller than the channel count");
   cudaStream_t st = (cudaStream_t)stream;
-  const int taps = ksize * ksize, cp16 = (Cout + 15) / 16 * 16;
-  std::vector<float> wd((size_t)taps * Cin * cp16, 0.f), bz(cp16, 0.f);
-  std::vector<__nv_bfloat16> wt((size_t)cp16 * taps * Cin, __float2bfloat16(0.f));
+  const int taps = ksize * ksize, cp16 = (Cout + 15) / 16 * 16, cptc = conv_tc_pad(Cout);
+  std::vector<float> wd((size_t)taps * Cin * cp16, 0.f), bz(cptc > cp16 ? cptc : cp16, 0.f);
+  std::vector<__nv_bfloat16> wt((size_t)cptc * taps * Cin, __float2bfloat16(0.f));
   for (int o = 0; o < Cout; ++o)
     for (int c = 0; c < Cin; ++c)
       for (int t = 0; t < taps; ++t) {
@@ -80,7 +80,7 @@ int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtyp
     a.in = in; a.in_dtype = dtype; a.in_sc = 1; a.in_sw = in_ld; a.in_sh = (int64_t)W * in_ld; a.in_sn = (int64_t)H * W * in_ld;
     a.out = out; a.out_dtype = dtype; a.out_ld = out_ld; a.res = residual; a.res_ld = res_ld;
     a.bias = d_b; a.pre_scale = d_ps; a.pre_shift = d_pb; a.pre_relu = 1;
-    a.w_direct = d_wd; a.w_tc = d_wt; a.cout_pad16 = cp16; a.cout_pad_tc = cp16;
+    a.w_direct = d_wd; a.w_tc = d_wt; a.cout_pad16 = cp16; a.cout_pad_tc = cptc;
     a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = ksize; a.stride = stride; a.pad = pad; a.dil = 1;
     a.Ho = (H + 2 * pad - ksize) / stride + 1; a.Wo = (W + 2 * pad - ksize) / stride + 1; a.relu = relu;
     if (backend == 2) {

@@ -31,12 +31,12 @@
 #include <vector>
 #include <cstdlib>
 
-#include "kernels.h"
+#include "tc_common.cuh"
 
 namespace ledb {
 namespace {
 
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;            // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int TH = 16, TW = 8;            // output tile: 16 rows x 8 cols = 128 pixels = UMMA M
 constexpr int MAX_SLABS = 6, MAX_TAPS = 9;
 constexpr uint32_t SMEM_BUDGET = 220 * 1024;
@@ -64,7 +64,8 @@ struct TcParams {
   uint32_t a_box_bytes, b_box_bytes;      // bytes one TMA box actually writes (expect_tx)
   int SA, SB, b_resident;
   int cp;                            // Cout padded to the N tiling (ntiles_n * NT)
-  uint32_t stage_bytes;              // epilogue staging: 16 KB (+16 KB with a second output)
+  uint32_t stage_bytes;              // epilogue staging: 32 KB (+32 KB with a second output)
+  int step2[4];                      // 2*grid tiles as digits (n-tile, tile col, tile row, image)
   uint32_t tmem_cols;
   // epilogue
   __nv_bfloat16* out; int out_ld;
@@ -75,102 +76,24 @@ struct TcParams {
   int relu;
 };
 
-// ------------------------------------------------------------------ PTX wrappers
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+using namespace tc;   // PTX wrappers: tc_common.cuh
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+// Tap tables, compile-time so the MMA issue loop unrolls into immediate-offset descriptor adds
+// (a single thread issues every MMA: any dependent address arithmetic there is on the critical path).
+//   MODE 0: 3x3 stride 1, one halo slab, 9 taps      MODE 1: 1x1 (stride 1 or 2), one slab, one tap
+//   MODE 2: 3x3 stride 2, six parity slabs: slab 2*kw -> taps (kh=0, kh=2), slab 2*kw+1 -> tap kh=1
+template <int MODE> __device__ __forceinline__ constexpr int mode_slabs() { return MODE == 2 ? 6 : 1; }
+template <int MODE> __device__ __forceinline__ constexpr int mode_taps(int s) {
+  return MODE == 0 ? 9 : (MODE == 1 ? 1 : ((s & 1) ? 1 : 2));
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+template <int MODE> __device__ __forceinline__ constexpr int mode_tap_pix(int s, int t) {
+  return MODE == 0 ? (t / 3) * (TW + 2) + (t % 3) : (MODE == 1 ? 0 : (((s & 1) == 0 && t == 1) ? TW : 0));
 }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-  return ok != 0;
-}
-// Bounded wait: a protocol bug traps (visible as a launch failure) instead of hanging the GPU.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if (++spins > (1u << 28)) __trap();
-  }
-}
-__device__ __forceinline__ bool elect_one() {
-  uint32_t pred;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "elect.sync _|p, 0xffffffff;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(pred));
-  return pred != 0;
-}
-__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
-  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1) : "memory");
-}
-__device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3) {
-  asm volatile("cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
-}
-__device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2, int c3, int c4) {
-  asm volatile("cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-               ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
-}
-__device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr) : "memory");
-}
-__device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
-
-// UMMA shared-memory descriptor, K-major operand, rows of KC*2 bytes (128B or 64B swizzle).
-// Layout per cute/arch/mma_sm100_desc.hpp (SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
-// SBO>>4 [32,46), version=1 [46,48), base_offset [49,52), layout type [61,64).  The high word is
-// constant per operand; the MMA loop only rebuilds the low word (start address).
-__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
-  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
-}
-__device__ __forceinline__ uint64_t make_desc(uint32_t hi, uint32_t saddr) {
-  const uint32_t lo = ((saddr >> 4) & 0x3FFFu) | (1u << 16);   // LBO (unused for swizzled K-major) = 1
-  return ((uint64_t)hi << 32) | lo;
+template <int MODE> __device__ __forceinline__ constexpr int mode_tap_id(int s, int t) {
+  return MODE == 0 ? t : (MODE == 1 ? 0 : ((s & 1) ? 3 + (s >> 1) : (t ? 6 + (s >> 1) : (s >> 1))));
 }
 
-// 128B XOR swizzle of a linear byte offset (bank-conflict-free epilogue staging)
-__device__ __forceinline__ uint32_t swz(uint32_t a) { return a ^ (((a >> 7) & 7u) << 4); }
-
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&h);
-}
-__device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&u);
-#pragma unroll
-  for (int i = 0; i < 4; ++i) { float2 t = __bfloat1622float2(h[i]); f[2 * i] = t.x; f[2 * i + 1] = t.y; }
-}
-
-template <bool S2>
+template <int MODE, int KSTEPS, bool S2>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
@@ -200,11 +123,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    mbar_fence_init();
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(P.tmem_cols) : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    tmem_alloc(tmem_slot, P.tmem_cols);
   }
   // per-channel epilogue constants, zero padded to cp so no channel guard is needed later
   for (int c = threadIdx.x; c < P.cp; c += kThreads) {
@@ -220,7 +142,6 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   const uint32_t row_bytes = P.KC * 2;
   const uint32_t layout_type = (P.KC == 64) ? 2u : (P.KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
-  const int ksteps = P.KC / 16;
 
   if (warp == 0) {
     // =========================== TMA producer (whole warp loops, one elected lane issues) =========
@@ -269,10 +190,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
     const bool leader = elect_one();
-    const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(P.NT >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    const uint32_t idesc = make_idesc_bf16_m128(P.NT);
     const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
     const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+    constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
     int sa = 0, pa = 0, sb = 0, pb = 0;
     int ts = 0, tp = 0;
     if (P.b_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
@@ -282,31 +204,35 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
       uint32_t acc = 0;
       for (int ch = 0; ch < P.nchunks; ++ch) {
-        for (int s = 0; s < P.nslabs; ++s) {
-          const Slab& sl = P.slabs[s];
+        const uint32_t b_chunk = sB_u + (uint32_t)(ch * 9) * P.b_tile_bytes;   // resident weights of this chunk
+#pragma unroll
+        for (int s = 0; s < mode_slabs<MODE>(); ++s) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_base = sA_u + (uint32_t)sa * P.a_stage_bytes;
-          for (int t = 0; t < sl.ntaps; ++t) {
-            uint32_t b_base;
-            if (P.b_resident) {
-              b_base = sB_u + (uint32_t)(ch * 9 + sl.tap_id[t]) * P.b_tile_bytes;
-            } else {
-              mbar_wait(&b_full[sb], pb);
-              tc_fence_after();
-              b_base = sB_u + (uint32_t)sb * P.b_tile_bytes;
-            }
-            const uint32_t a_tap = a_base + (uint32_t)sl.tap_pix[t] * row_bytes;
-            if (leader) {
-#pragma unroll 4
-              for (int k = 0; k < ksteps; ++k) {
-                tc_mma(d_tmem, make_desc(a_hi, a_tap + k * 32), make_desc(b_hi, b_base + k * 32), idesc, acc);
-                acc = 1;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            if (t < mode_taps<MODE>(s)) {
+              uint32_t b_base;
+              if (P.b_resident) {
+                b_base = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * P.b_tile_bytes;
+              } else {
+                mbar_wait(&b_full[sb], pb);
+                tc_fence_after();
+                b_base = sB_u + (uint32_t)sb * P.b_tile_bytes;
               }
-            }
-            if (!P.b_resident) {
-              if (leader) tc_commit(&b_empty[sb]);          // frees the B stage when these MMAs retire
-              if (++sb == P.SB) { sb = 0; pb ^= 1; }
+              if (leader) {
+#pragma unroll
+                for (int k = 0; k < KSTEPS; ++k) {
+                  tc_mma(d_tmem, make_desc(a_hi, a_base + (uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32),
+                         make_desc(b_hi, b_base + k * 32), idesc, acc);
+                  acc = 1;
+                }
+              }
+              if (!P.b_resident) {
+                if (leader) tc_commit(&b_empty[sb]);        // frees the B stage when these MMAs retire
+                if (++sb == P.SB) { sb = 0; pb ^= 1; }
+              }
             }
           }
           if (leader) tc_commit(&a_empty[sa]);              // frees the A slab
@@ -318,52 +244,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++ts == 2) { ts = 0; tp ^= 1; }
     }
   } else {
-    // =========================== epilogue warps ===========================
+    // =========================== epilogue: two groups of 4 warps ===========================
+    // Group g owns TMEM accumulator stage g and every second tile of this CTA, so the epilogue of tile i
+    // overlaps the epilogue of tile i+1 as well as its MMAs.  Per tile:
     // TMEM -> registers (thread = output pixel) -> +bias (+residual) -> ReLU -> bf16 -> warp-private
     // swizzled staging tile -> 16 B stores with consecutive lanes on consecutive addresses.
+    const int ew = warp - 2;                      // 0..7
+    const int grp = ew >> 2;                      // accumulator stage / tile parity
     const int q = warp & 3;                       // TMEM lane quadrant this warp may access
     const int m = q * 32 + lane;                  // tile row = output pixel within the tile
-    const int ph = m / TW, pw = m % TW;
-    uint8_t* st1 = sStage + (size_t)q * 4096;
-    uint8_t* st2 = sStage + 16384 + (size_t)q * 4096;
+    const int ph = m >> 3, pw = m & 7;            // TW == 8
+    uint8_t* st1 = sStage + (size_t)ew * 4096;
+    uint8_t* st2 = sStage + 32768 + (size_t)ew * 4096;
     const int cout8 = (P.Cout + 7) & ~7;          // stores cover whole 8-channel groups (buffers are padded)
-    int ts = 0, tp = 0;
-    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % P.ntiles_n);
-      int64_t r = tile / P.ntiles_n;
-      const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
-      const int th = (int)(r % P.tiles_h);
-      const int n = (int)(r / P.tiles_h);
+    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * P.NT);
+    uint32_t tp = 0;
+    // tile coordinates, advanced incrementally by 2*gridDim.x tiles (mixed-radix digits from the host)
+    uint32_t t0 = blockIdx.x + (uint32_t)grp * gridDim.x;
+    int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
+    int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+    int th = (int)(t0 % (uint32_t)P.tiles_h);
+    int n = (int)(t0 / (uint32_t)P.tiles_h);
+    for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < (uint32_t)P.total_tiles; tile += 2 * gridDim.x) {
       const int oh = th * TH + ph, ow = tw * TW + pw;
       const bool pvalid = (oh < P.Ho) && (ow < P.Wo);
-      const int64_t pix = ((int64_t)n * P.Ho + oh) * P.Wo + ow;
-      const int64_t pix_w0 = ((int64_t)n * P.Ho + th * TH + q * 4) * P.Wo + tw * TW;   // first pixel of this warp's 4 rows
-      mbar_wait(&t_full[ts], tp);
+      const int64_t pix0 = ((int64_t)n * P.Ho + th * TH) * P.Wo + tw * TW;   // first pixel of the tile
+      const int poff = ph * P.Wo + pw;                                        // this thread's pixel, relative
+      const int cgt = nt * P.NT;
+      const __nv_bfloat16* res_px = P.res ? P.res + (pix0 + poff) * P.res_ld + cgt : nullptr;
+      __nv_bfloat16* out_t = P.out ? P.out + pix0 * P.out_ld + cgt : nullptr;
+      __nv_bfloat16* out2_t = P.out2 ? P.out2 + pix0 * P.out2_ld + cgt : nullptr;
+      const int rows_ok = P.Ho - th * TH - q * 4, cols_ok = P.Wo - tw * TW;   // valid rows (of this warp's 4) / cols
+      mbar_wait(&t_full[grp], tp);
+      tp ^= 1;
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(ts * P.NT);
       for (int c0 = 0; c0 < P.NT; c0 += 32) {
         const int ncol = min(32, P.NT - c0);       // 16 or 32
-        const int cg0 = nt * P.NT + c0;            // first global output channel of this block
         uint32_t v[32];
-        tc_ld16(taddr + c0, v);
-        if (ncol == 32) tc_ld16(taddr + c0 + 16, v + 16);
+        tc_ld16(taddr0 + c0, v);
+        if (ncol == 32) tc_ld16(taddr0 + c0 + 16, v + 16);
         uint4 rr[4];
         bool rv[4];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
-          rv[g] = P.res && pvalid && (8 * g < ncol) && (cg0 + 8 * g < cout8);
-          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(P.res + pix * P.res_ld + cg0 + 8 * g));
+          rv[g] = res_px && pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < cout8);
+          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 8 * g));
         }
         tc_wait_ld();
         const int slice_c = c0 & 63;               // column of this block inside the 64-channel staging slice
-        const int slice_cols = min(64, P.NT - (c0 - slice_c));
-        const uint32_t row_off = (uint32_t)lane * (uint32_t)(slice_cols * 2);
+        const int slice_cols = min(64, P.NT - (c0 - slice_c));   // 16, 32 or 64 (host guarantees a power of two)
+        const int sh = 31 - __clz(slice_cols * 2); // log2(bytes per staged pixel)
+        const uint32_t row_off = (uint32_t)lane << sh;
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           if (8 * g < ncol) {
             float f[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cg0 + 8 * g);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cg0 + 8 * g + 4);
+            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cgt + c0 + 8 * g);
+            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cgt + c0 + 8 * g + 4);
             f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
             f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
             f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
@@ -379,40 +316,40 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
             }
             const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
-            if (P.out)
+            if (out_t)
               *reinterpret_cast<uint4*>(st1 + so) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
                                                                pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            if (P.out2) {
-              const float4 s0 = *reinterpret_cast<const float4*>(s_o2s + cg0 + 8 * g);
-              const float4 s1 = *reinterpret_cast<const float4*>(s_o2s + cg0 + 8 * g + 4);
-              const float4 h0 = *reinterpret_cast<const float4*>(s_o2b + cg0 + 8 * g);
-              const float4 h1 = *reinterpret_cast<const float4*>(s_o2b + cg0 + 8 * g + 4);
-              float o[8];
-              o[0] = fmaxf(fmaf(f[0], s0.x, h0.x), 0.f); o[1] = fmaxf(fmaf(f[1], s0.y, h0.y), 0.f);
-              o[2] = fmaxf(fmaf(f[2], s0.z, h0.z), 0.f); o[3] = fmaxf(fmaf(f[3], s0.w, h0.w), 0.f);
-              o[4] = fmaxf(fmaf(f[4], s1.x, h1.x), 0.f); o[5] = fmaxf(fmaf(f[5], s1.y, h1.y), 0.f);
-              o[6] = fmaxf(fmaf(f[6], s1.z, h1.z), 0.f); o[7] = fmaxf(fmaf(f[7], s1.w, h1.w), 0.f);
-              *reinterpret_cast<uint4*>(st2 + so) = make_uint4(pack_bf16x2(o[0], o[1]), pack_bf16x2(o[2], o[3]),
-                                                               pack_bf16x2(o[4], o[5]), pack_bf16x2(o[6], o[7]));
+            if (out2_t) {
+              const float4 s0 = *reinterpret_cast<const float4*>(s_o2s + cgt + c0 + 8 * g);
+              const float4 s1 = *reinterpret_cast<const float4*>(s_o2s + cgt + c0 + 8 * g + 4);
+              const float4 h0 = *reinterpret_cast<const float4*>(s_o2b + cgt + c0 + 8 * g);
+              const float4 h1 = *reinterpret_cast<const float4*>(s_o2b + cgt + c0 + 8 * g + 4);
+              *reinterpret_cast<uint4*>(st2 + so) = make_uint4(
+                  pack_bf16x2(fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), fmaxf(fmaf(f[1], s0.y, h0.y), 0.f)),
+                  pack_bf16x2(fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), fmaxf(fmaf(f[3], s0.w, h0.w), 0.f)),
+                  pack_bf16x2(fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), fmaxf(fmaf(f[5], s1.y, h1.y), 0.f)),
+                  pack_bf16x2(fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), fmaxf(fmaf(f[7], s1.w, h1.w), 0.f)));
             }
           }
         }
-        // ---- flush a completed staging slice (up to 64 channels x 32 pixels) with coalesced stores
+        // ---- flush a completed staging slice (up to 64 channels x 32 pixels) with coalesced stores:
+        //      lane l of store i covers staged bytes [i*512 + 16 l, +16), i.e. 8 lanes per 128 B pixel row
         if (slice_c + ncol == slice_cols) {
           __syncwarp();
-          const int sc0 = nt * P.NT + (c0 - slice_c);          // first global channel of the slice
-          const uint32_t sbytes = (uint32_t)slice_cols * 2;    // bytes per pixel in the slice
-          const uint32_t total = 32u * sbytes;
-          for (uint32_t L = (uint32_t)lane * 16; L < total; L += 512) {
-            const uint32_t p = L / sbytes, b = L - p * sbytes; // staged pixel (0..31), byte inside its slice
-            const int prow = (int)(p >> 3), pcol = (int)(p & 7);
-            const int c = sc0 + (int)(b >> 1);
-            const bool ok = (th * TH + q * 4 + prow < P.Ho) && (tw * TW + pcol < P.Wo) && (c < cout8);
-            if (ok) {
-              const int64_t gp = pix_w0 + (int64_t)prow * P.Wo + pcol;
+          const int sc0 = c0 - slice_c;                        // first channel of the slice inside this N tile
+          const int niter = slice_cols >> 3;                   // (32 px * slice_cols * 2 B) / 512 B
+          const uint32_t bmask = (1u << sh) - 1;
+#pragma unroll 4
+          for (int i = 0; i < niter; ++i) {
+            const uint32_t L = (uint32_t)i * 512 + (uint32_t)lane * 16;
+            const int p = (int)(L >> sh);                      // staged pixel 0..31
+            const int c = sc0 + (int)((L & bmask) >> 1);
+            const int prow = q * 4 + (p >> 3), pcol = p & 7;
+            if ((p >> 3) < rows_ok && pcol < cols_ok && cgt + c < cout8) {
               const uint32_t so = swz(L);
-              if (P.out) *reinterpret_cast<uint4*>(P.out + gp * P.out_ld + c) = *reinterpret_cast<const uint4*>(st1 + so);
-              if (P.out2) *reinterpret_cast<uint4*>(P.out2 + gp * P.out2_ld + c) = *reinterpret_cast<const uint4*>(st2 + so);
+              const int po = prow * P.Wo + pcol;
+              if (out_t) *reinterpret_cast<uint4*>(out_t + (int64_t)po * P.out_ld + c) = *reinterpret_cast<const uint4*>(st1 + so);
+              if (out2_t) *reinterpret_cast<uint4*>(out2_t + (int64_t)po * P.out2_ld + c) = *reinterpret_cast<const uint4*>(st2 + so);
             }
           }
           __syncwarp();
@@ -420,8 +357,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[ts]);
-      if (++ts == 2) { ts = 0; tp ^= 1; }
+      if (lane == 0) mbar_arrive(&t_empty[grp]);
+      // advance the tile coordinates by 2*gridDim.x
+      nt += P.step2[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+      tw += P.step2[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+      th += P.step2[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+      n += P.step2[3];
     }
   }
 
@@ -429,7 +370,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(P.tmem_cols) : "memory");
+    tmem_dealloc(tmem_base, P.tmem_cols);
   }
 }
 
@@ -466,22 +407,15 @@ int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, con
   return LEDB200_OK;
 }
 
-int pick_kc(int cin) { return cin % 64 == 0 ? 64 : (cin % 32 == 0 ? 32 : 16); }
+int pick_kc(int cin) { return cin % 64 == 0 ? 64 : 32; }
 int num_sms() {
   static int n = 0;
   if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
   return n;
 }
-int layout_mode() {   // 1 = single halo slab per Cin chunk (default); LEDB200_TC_LAYOUT=E -> three column slabs
-  static int mode = -1;
-  if (mode < 0) {
-    const char* e = getenv("LEDB200_TC_LAYOUT");
-    mode = (e && e[0] == 'E') ? 0 : 1;
-  }
-  return mode;
-}
-
 }  // namespace
+
+int conv_tc_pad(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : (cout + 63) / 64 * 64); }
 
 bool conv_tc_eligible(const ConvArgs& a) {
   if (a.in_dtype != LEDB200_BF16 || a.out_dtype != LEDB200_BF16) return false;
@@ -489,22 +423,23 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.ksize != 1 && a.ksize != 3) return false;
   if (a.stride != 1 && a.stride != 2) return false;
   if (a.dil != 1 && a.ksize == 3) return false;
-  if (a.Cin < 16 || a.Cin % 16) return false;
+  if (a.Cin < 32 || a.Cin % 32) return false;                        // K blocks of 32 or 64 channels
   if (a.in_sc != 1 || a.in_sw % 8) return false;                     // NHWC, 16 B aligned pixels
   if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;       // parity-split view needs even H, W
   const int c8 = (a.Cout + 7) / 8 * 8;                               // stores cover whole 8-channel groups
   if (a.out && (a.out_ld % 8 || a.out_ld < c8)) return false;
   if (a.out2 && (a.out2_ld % 8 || a.out2_ld < c8)) return false;
   if (a.res && (a.res_ld % 8 || a.res_ld < c8)) return false;
-  const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : (a.Cout + 15) / 16 * 16;
+  const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
   if (cp > 256 && cp % 256) return false;
+  if (cp != 16 && cp != 32 && cp % 64) return false;                 // epilogue staging slices are 16/32/64 channels
+  if ((int64_t)a.N * ceil_div(a.Ho, TH) * ceil_div(a.Wo, TW) * (cp > 256 ? cp / 256 : 1) >= (1ll << 31)) return false;
   return true;
 }
 
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (!conv_tc_eligible(a)) return fail(LEDB200_EINVAL, "conv_tc: shape not eligible");
   TcParams P{};
-  const int lm = (a.ksize == 3 && a.stride == 1) ? layout_mode() : 0;
   const bool s2 = a.stride == 2;
   P.Cin = a.Cin; P.Cout = a.Cout;
   const int cp = a.cout_pad_tc;
@@ -521,25 +456,17 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   P.sbo_bytes = 8 * row_bytes;
   // ---- slab tables
   if (a.ksize == 3 && !s2) {
-    if (lm == 0) {
-      P.nslabs = 3; box_rows = TH + 2;
-      for (int kw = 0; kw < 3; ++kw) {
-        Slab& s = P.slabs[kw];
-        s.c_mul = 0; s.dw = kw - 1; s.dh = -1; s.ph = 0; s.ntaps = 3;
-        for (int kh = 0; kh < 3; ++kh) { s.tap_pix[kh] = kh * TW; s.tap_id[kh] = kh * 3 + kw; }
-      }
-    } else {   // ONE halo slab (TH+2) x (TW+2) per Cin chunk; every tap is a row- AND column-shifted window
-               // of it: the descriptor start address is not swizzle-atom aligned and SBO = (TW+2) rows.
-               // The hardware applies the swizzle XOR on absolute shared-memory address bits (probed on
-               // B200: tests/probe_tc_layout.py, profiles/r1_notes.md), so this reads exactly what TMA
-               // wrote.  Input fetch 1.4x instead of 3.4x, one TMA per chunk instead of three.
-      P.nslabs = 1; box_rows = TH + 2; box_w = TW + 2;
-      P.sbo_bytes = box_w * row_bytes;
-      Slab& s = P.slabs[0];
-      s.c_mul = 0; s.dw = -1; s.dh = -1; s.ph = 0; s.ntaps = 9;
-      for (int kh = 0; kh < 3; ++kh)
-        for (int kw = 0; kw < 3; ++kw) { s.tap_pix[kh * 3 + kw] = kh * box_w + kw; s.tap_id[kh * 3 + kw] = kh * 3 + kw; }
-    }
+    // ONE halo slab (TH+2) x (TW+2) per Cin chunk; every tap is a row- AND column-shifted window of it:
+    // the descriptor start address is not swizzle-atom aligned and SBO = (TW+2) rows.  The hardware
+    // applies the swizzle XOR on absolute shared-memory address bits (probed on B200, see
+    // profiles/r1_notes.md), so this reads exactly what TMA wrote.  Input fetch 1.4x instead of the
+    // 3.4x of three column-shifted slabs, one TMA per chunk instead of three.
+    P.nslabs = 1; box_rows = TH + 2; box_w = TW + 2;
+    P.sbo_bytes = box_w * row_bytes;
+    Slab& s = P.slabs[0];
+    s.c_mul = 0; s.dw = -1; s.dh = -1; s.ph = 0; s.ntaps = 9;
+    for (int kh = 0; kh < 3; ++kh)
+      for (int kw = 0; kw < 3; ++kw) { s.tap_pix[kh * 3 + kw] = kh * box_w + kw; s.tap_id[kh * 3 + kw] = kh * 3 + kw; }
   } else if (a.ksize == 1 && !s2) {
     P.nslabs = 1;
     Slab& s = P.slabs[0];
@@ -571,7 +498,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   P.ntaps_total = taps;
   // ---- shared-memory plan
   P.cp = cp;
-  P.stage_bytes = a.out2 ? 32768u : 16384u;
+  P.stage_bytes = a.out2 ? 65536u : 32768u;
   const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 34 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
   P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= 100 * 1024) ? 1 : 0;
@@ -621,16 +548,35 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (rc) return rc;
 
   const int grid = (int)std::min<int64_t>(P.total_tiles, num_sms());
+  {
+    uint32_t st2 = 2u * (uint32_t)grid;
+    P.step2[0] = (int)(st2 % (uint32_t)P.ntiles_n); st2 /= (uint32_t)P.ntiles_n;
+    P.step2[1] = (int)(st2 % (uint32_t)P.tiles_w); st2 /= (uint32_t)P.tiles_w;
+    P.step2[2] = (int)(st2 % (uint32_t)P.tiles_h);
+    P.step2[3] = (int)(st2 / (uint32_t)P.tiles_h);
+  }
+  const int mode = (a.ksize == 1) ? 1 : (s2 ? 2 : 0);
+  const int ksteps = P.KC / 16;
+  using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
+  static const KernelFn kernels[3][2] = {
+      {conv_tc_kernel<0, 2, false>, conv_tc_kernel<0, 4, false>},
+      {nullptr, nullptr},   // 1x1: stride decides the tensor-map rank, filled below
+      {conv_tc_kernel<2, 2, true>, conv_tc_kernel<2, 4, true>}};
+  static const KernelFn kernels_1x1[2][2] = {{conv_tc_kernel<1, 2, false>, conv_tc_kernel<1, 4, false>},
+                                             {conv_tc_kernel<1, 2, true>, conv_tc_kernel<1, 4, true>}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    attr_err = cudaFuncSetAttribute(conv_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
-    if (attr_err == cudaSuccess)
-      attr_err = cudaFuncSetAttribute(conv_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
+    const KernelFn all[] = {kernels[0][0], kernels[0][1], kernels[2][0], kernels[2][1], kernels_1x1[0][0],
+                            kernels_1x1[0][1], kernels_1x1[1][0], kernels_1x1[1][1]};
+    for (KernelFn f : all) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
+      if (e != cudaSuccess) attr_err = e;
+    }
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
-  if (s2) conv_tc_kernel<true><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
-  else    conv_tc_kernel<false><<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+  const KernelFn fn = (mode == 1) ? kernels_1x1[s2 ? 1 : 0][ksteps == 4] : kernels[mode][ksteps == 4];
+  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
   LEDB_LAUNCH_OK("conv_tc_kernel");
   return LEDB200_OK;
 }

@@ -219,10 +219,7 @@ int bn_affine(const ledb200_handle& e, const std::string& bn, int c, std::vector
   return LEDB200_OK;
 }
 
-int tc_pad(int cout) {   // UMMA N: multiple of 16 in [16,256]; larger Cout is split in tiles of 256
-  int p = (cout + 15) / 16 * 16;
-  return p;
-}
+int tc_pad(int cout) { return conv_tc_pad(cout); }   // UMMA N tile: 16, 32 or a multiple of 64 (<= 256 per tile)
 
 // Fold BN into OIHW weights and repack for both conv back ends.
 int pack_conv(ledb200_handle& e, ConvDef& d, const float* w_oihw, const float* bias_in, const float* scale,
@@ -457,6 +454,8 @@ void add_stem0(Builder& B, int out_x1, int out_x1h) {
   const int ci = e0.conv_by_name.at("backbone.stem.0");
   const int a2 = aff(e0, "decode_head.head_x1.0.bn");
   const int n = B.p.n, H = B.p.h, W = B.p.w;
+  const int c0 = e0.convs[ci].cout;
+  const bool use_tc = e0.cfg.conv_backend != 1 && dtype == LEDB200_BF16 && (c0 == 16 || c0 == 32);
   B.p.ops.push_back({"backbone.stem.0", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
     const ConvDef& d = e.convs[ci];
     ConvArgs a;
@@ -477,11 +476,12 @@ void add_stem0(Builder& B, int out_x1, int out_x1h) {
       a.out2 = Builder::ptr(e, p, out_x1h); a.out2_ld = p.bufs[out_x1h].ld;
       a.o2_scale = e.affs[a2].scale; a.o2_shift = e.affs[a2].shift;
     }
-    a.bias = d.bias; a.w_direct = d.w_direct; a.cout_pad16 = d.cout_pad16;
+    a.bias = d.bias; a.w_direct = d.w_direct; a.w_tc = d.w_tc; a.cout_pad16 = d.cout_pad16; a.cout_pad_tc = d.cout_pad_tc;
     a.N = n; a.H = H; a.W = W; a.Cin = d.cin; a.Ho = p.bufs[out_x1].h; a.Wo = p.bufs[out_x1].w; a.Cout = d.cout;
     a.ksize = 3; a.stride = 2; a.pad = 1; a.dil = 1; a.relu = 1;
+    if (use_tc && stem_tc_eligible(a)) return launch_stem_tc(a, st);
     return launch_conv_direct(a, st);
-  }, K_CONV_DIRECT, 0.0, 0.0});
+  }, use_tc ? K_CONV_TC : K_CONV_DIRECT, 0.0, 0.0});
   {
     const Buf& bo = B.p.bufs[out_x1];
     const double npo = (double)bo.n * bo.h * bo.w;

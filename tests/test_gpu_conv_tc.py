@@ -59,3 +59,25 @@ def test_conv_tc_many_tiles_persistent():
     ref = F.conv2d(x, w, None, 1, 1)
     out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16), w, None, 1, backend=2)
     assert rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) < 6e-3
+
+
+@pytest.mark.parametrize('hw', [(64, 96), (70, 94), (34, 50)])
+@pytest.mark.parametrize('raw_u8', [False, True])
+def test_stem_tc_matches_oracle(hw, raw_u8):
+    """csrc/stem_tc.cu (thread-built im2col + tcgen05) against the oracle's stem[0] ConvModule and the
+    head_x1 pre-activation BN+ReLU of it (second output), for float and raw-uint8 input."""
+    import oracle
+    from lednet_b200 import synth
+    from util import build_pair
+    o, m = build_pair(19, dtype='bf16')
+    img = synth.make_images_u8(2, *hw, seed=3)
+    x = oracle.preprocess(img)
+    with torch.no_grad():
+        ref_x1 = o.backbone.stem[0](x)
+        ref_x1h = o.decode_head.head_x1[0].activate(o.decode_head.head_x1[0].bn(ref_x1))
+    eng = m.engine()
+    eng.forward_infer(img.to(DEV) if raw_u8 else x.to(DEV))
+    assert eng.op_info()[0][1] == 'conv_tc'            # the stem ran on the tensor-core kernel
+    got_x1, got_x1h = eng.debug_fetch('x1'), eng.debug_fetch('x1h')
+    assert rel_err(got_x1, ref_x1) < 1.5e-2
+    assert rel_err(got_x1h, ref_x1h) < 1.5e-2
