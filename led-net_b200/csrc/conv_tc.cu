@@ -93,7 +93,7 @@ template <int MODE> __device__ __forceinline__ constexpr int mode_tap_id(int s, 
   return MODE == 0 ? t : (MODE == 1 ? 0 : ((s & 1) ? 3 + (s >> 1) : (t ? 6 + (s >> 1) : (s >> 1))));
 }
 
-template <int MODE, int KSTEPS, bool S2>
+template <int MODE, int KSTEPS, bool S2, bool BRES>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
@@ -147,7 +147,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== TMA producer (whole warp loops, one elected lane issues) =========
     const bool leader = elect_one();
     int sa = 0, pa = 0, sb = 0, pb = 0;
-    if (P.b_resident && leader) {
+    if (BRES && leader) {
       // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
       mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
       for (int ch = 0; ch < P.nchunks; ++ch)
@@ -173,7 +173,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             else    tma_load_4d(dst, &tmA, smem_u32(&a_full[sa]), ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
           }
           if (++sa == P.SA) { sa = 0; pa ^= 1; }
-          if (!P.b_resident) {
+          if (!BRES) {
             for (int t = 0; t < sl.ntaps; ++t) {
               mbar_wait(&b_empty[sb], pb ^ 1);
               if (leader) {
@@ -189,58 +189,58 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
-    const bool leader = elect_one();
+    const uint32_t leader = elect_one() ? 1u : 0u;
     const uint32_t idesc = make_idesc_bf16_m128(P.NT);
     const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
     const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
     const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
     constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
+    // descriptor low words advance by (bytes >> 4); the 14-bit address field cannot overflow (smem < 256 KB)
+    const uint32_t a_lo0 = ((sA_u >> 4) & 0x3FFFu) | (1u << 16), b_lo0 = ((sB_u >> 4) & 0x3FFFu) | (1u << 16);
+    const uint32_t a_stage16 = P.a_stage_bytes >> 4, b_tile16 = P.b_tile_bytes >> 4;
     int sa = 0, pa = 0, sb = 0, pb = 0;
     int ts = 0, tp = 0;
-    if (P.b_resident) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+    if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
     for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
       mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
       uint32_t acc = 0;
       for (int ch = 0; ch < P.nchunks; ++ch) {
-        const uint32_t b_chunk = sB_u + (uint32_t)(ch * 9) * P.b_tile_bytes;   // resident weights of this chunk
+        const uint32_t b_chunk = b_lo0 + (uint32_t)(ch * 9) * b_tile16;   // resident weights of this chunk
 #pragma unroll
         for (int s = 0; s < mode_slabs<MODE>(); ++s) {
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
-          const uint32_t a_base = sA_u + (uint32_t)sa * P.a_stage_bytes;
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             if (t < mode_taps<MODE>(s)) {
-              uint32_t b_base;
-              if (P.b_resident) {
-                b_base = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * P.b_tile_bytes;
+              uint32_t b_lo;
+              if (BRES) {
+                b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
               } else {
                 mbar_wait(&b_full[sb], pb);
                 tc_fence_after();
-                b_base = sB_u + (uint32_t)sb * P.b_tile_bytes;
+                b_lo = b_lo0 + (uint32_t)sb * b_tile16;
               }
-              if (leader) {
 #pragma unroll
-                for (int k = 0; k < KSTEPS; ++k) {
-                  tc_mma(d_tmem, make_desc(a_hi, a_base + (uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32),
-                         make_desc(b_hi, b_base + k * 32), idesc, acc);
-                  acc = 1;
-                }
+              for (int k = 0; k < KSTEPS; ++k) {
+                const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                tc_mma_if(d_tmem, ((uint64_t)a_hi << 32) | al, ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc, leader);
+                acc = 1;
               }
-              if (!P.b_resident) {
-                if (leader) tc_commit(&b_empty[sb]);        // frees the B stage when these MMAs retire
+              if (!BRES) {
+                tc_commit_if(&b_empty[sb], leader);         // frees the B stage when these MMAs retire
                 if (++sb == P.SB) { sb = 0; pb ^= 1; }
               }
             }
           }
-          if (leader) tc_commit(&a_empty[sa]);              // frees the A slab
+          tc_commit_if(&a_empty[sa], leader);               // frees the A slab
           if (++sa == P.SA) { sa = 0; pa ^= 1; }
         }
       }
-      if (leader) tc_commit(&t_full[ts]);                   // accumulator complete -> epilogue
-      __syncwarp();
+      tc_commit_if(&t_full[ts], leader);                    // accumulator complete -> epilogue
       if (++ts == 2) { ts = 0; tp ^= 1; }
     }
   } else {
@@ -558,24 +558,33 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   const int mode = (a.ksize == 1) ? 1 : (s2 ? 2 : 0);
   const int ksteps = P.KC / 16;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
-  static const KernelFn kernels[3][2] = {
-      {conv_tc_kernel<0, 2, false>, conv_tc_kernel<0, 4, false>},
-      {nullptr, nullptr},   // 1x1: stride decides the tensor-map rank, filled below
-      {conv_tc_kernel<2, 2, true>, conv_tc_kernel<2, 4, true>}};
-  static const KernelFn kernels_1x1[2][2] = {{conv_tc_kernel<1, 2, false>, conv_tc_kernel<1, 4, false>},
-                                             {conv_tc_kernel<1, 2, true>, conv_tc_kernel<1, 4, true>}};
+  // [mode][stride 2][KC == 64][weights resident]
+  static const KernelFn kernels[3][2][2][2] = {
+      {{{conv_tc_kernel<0, 2, false, false>, conv_tc_kernel<0, 2, false, true>},
+        {conv_tc_kernel<0, 4, false, false>, conv_tc_kernel<0, 4, false, true>}},
+       {{nullptr, nullptr}, {nullptr, nullptr}}},
+      {{{conv_tc_kernel<1, 2, false, false>, conv_tc_kernel<1, 2, false, true>},
+        {conv_tc_kernel<1, 4, false, false>, conv_tc_kernel<1, 4, false, true>}},
+       {{conv_tc_kernel<1, 2, true, false>, conv_tc_kernel<1, 2, true, true>},
+        {conv_tc_kernel<1, 4, true, false>, conv_tc_kernel<1, 4, true, true>}}},
+      {{{nullptr, nullptr}, {nullptr, nullptr}},
+       {{conv_tc_kernel<2, 2, true, false>, conv_tc_kernel<2, 2, true, true>},
+        {conv_tc_kernel<2, 4, true, false>, conv_tc_kernel<2, 4, true, true>}}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    const KernelFn all[] = {kernels[0][0], kernels[0][1], kernels[2][0], kernels[2][1], kernels_1x1[0][0],
-                            kernels_1x1[0][1], kernels_1x1[1][0], kernels_1x1[1][1]};
-    for (KernelFn f : all) {
-      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_BUDGET + 2048);
-      if (e != cudaSuccess) attr_err = e;
-    }
+    for (int m = 0; m < 3; ++m)
+      for (int s = 0; s < 2; ++s)
+        for (int k = 0; k < 2; ++k)
+          for (int r = 0; r < 2; ++r)
+            if (kernels[m][s][k][r]) {
+              cudaError_t e = cudaFuncSetAttribute(kernels[m][s][k][r], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)SMEM_BUDGET + 2048);
+              if (e != cudaSuccess) attr_err = e;
+            }
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
-  const KernelFn fn = (mode == 1) ? kernels_1x1[s2 ? 1 : 0][ksteps == 4] : kernels[mode][ksteps == 4];
+  const KernelFn fn = kernels[mode][s2 ? 1 : 0][ksteps == 4][P.b_resident ? 1 : 0];
   fn<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
   LEDB_LAUNCH_OK("conv_tc_kernel");
   return LEDB200_OK;
