@@ -78,6 +78,152 @@ struct TcParams {
 
 using namespace tc;   // PTX wrappers: tc_common.cuh
 
+__device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+
+// Epilogue of the persistent conv kernel, run by warps 2..9 as two groups of four.  Group g owns TMEM
+// accumulator stage g and every second tile of this CTA, so the epilogue of tile i overlaps the
+// epilogue of tile i+1 as well as its MMAs.  Per tile and 32-column block:
+//   tcgen05.ld (thread = output pixel) -> +bias (+residual) -> ReLU -> bf16 -> warp-private XOR-swizzled
+//   staging (up to 64 channels x 32 pixels) -> 16 B global stores with consecutive lanes on consecutive
+//   addresses (full 32 B sectors; 8 lanes cover one 128 B pixel row of a 64-channel slice).
+// The second output relu(s*y + b) (pre-activation BN+ReLU of the consumer) goes through its own
+// staging tile.  Templated on which tensors exist so the hot loop has no per-element branches; ReLU is
+// a max against 0 or -inf.
+template <bool HAS_RES, bool HAS_OUT, bool HAS_OUT2>
+__device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int lane, uint32_t tmem_base,
+                                              uint64_t* t_full, uint64_t* t_empty, uint32_t st_u, uint32_t bias_u,
+                                              uint32_t o2s_u, uint32_t o2b_u) {
+  const int ew = warp - 2;                      // 0..7
+  const int grp = ew >> 2;                      // accumulator stage / tile parity
+  const int q = warp & 3;                       // TMEM lane quadrant this warp may access
+  const int m = q * 32 + lane;                  // tile row = output pixel within the tile
+  const int ph = m >> 3, pw = m & 7;            // TW == 8
+  const uint32_t st1 = st_u + (uint32_t)ew * 4096, st2 = st_u + 32768 + (uint32_t)ew * 4096;
+  const int NT = P.NT, Ho = P.Ho, Wo = P.Wo;
+  const int cout8 = (P.Cout + 7) & ~7;          // stores cover whole 8-channel groups (buffers are padded)
+  const float relu_lo = P.relu ? 0.f : -INFINITY;
+  const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * NT);
+  // staging slice geometry (constant per launch: NT is 16, 32 or a multiple of 64)
+  const int slice_cols = min(64, NT);
+  const int sh = 31 - __clz(slice_cols * 2);    // log2(bytes per staged pixel): 5, 6 or 7
+  const int ppi = 512 >> sh;                    // pixels covered by one warp-wide 16 B store
+  const int niter = slice_cols >> 3;            // stores per slice = 32 px * slice bytes / 512
+  const int pl = lane >> (sh - 4);              // pixel of this lane inside a store
+  const int cl = (lane & ((1 << (sh - 4)) - 1)) * 8;   // channel of this lane inside the slice
+  const uint32_t row_off = (uint32_t)lane << sh;
+  uint32_t tp = 0;
+  // tile coordinates, advanced incrementally by 2*gridDim.x tiles (mixed-radix digits from the host)
+  uint32_t t0 = blockIdx.x + (uint32_t)grp * gridDim.x;
+  int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
+  int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+  int th = (int)(t0 % (uint32_t)P.tiles_h);
+  int n = (int)(t0 / (uint32_t)P.tiles_h);
+  const uint32_t total = (uint32_t)P.total_tiles, step = 2 * gridDim.x;
+  for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < total; tile += step) {
+    const bool pvalid = (th * TH + ph < Ho) && (tw * TW + pw < Wo);
+    const int64_t pix0 = ((int64_t)n * Ho + th * TH) * Wo + tw * TW;       // first pixel of the tile
+    const int cgt = nt * NT;                                               // first output channel of this N tile
+    const __nv_bfloat16* res_px = HAS_RES ? P.res + (pix0 + ph * Wo + pw) * P.res_ld + cgt : nullptr;
+    __nv_bfloat16* out_t = HAS_OUT ? P.out + pix0 * P.out_ld + cgt : nullptr;
+    __nv_bfloat16* out2_t = HAS_OUT2 ? P.out2 + pix0 * P.out2_ld + cgt : nullptr;
+    const int rows_ok = Ho - th * TH - q * 4, cols_ok = Wo - tw * TW;      // valid rows (of this warp's 4) / cols
+    mbar_wait(&t_full[grp], tp);
+    tp ^= 1;
+    tc_fence_after();
+    for (int c0 = 0; c0 < NT; c0 += 32) {
+      const int ncol = min(32, NT - c0);         // 16 or 32
+      uint32_t v[32];
+      tc_ld16(taddr0 + c0, v);
+      if (ncol == 32) tc_ld16(taddr0 + c0 + 16, v + 16);
+      uint4 rr[4];
+      bool rv[4];
+      if (HAS_RES) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rv[g] = pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < cout8);
+          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 8 * g));
+        }
+      }
+      tc_wait_ld();
+      const int slice_c = c0 & 63;               // column of this block inside the staging slice
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        if (8 * g < ncol) {
+          float f[8];
+          const float4 b0 = lds128f(bias_u + (uint32_t)(cgt + c0 + 8 * g) * 4);
+          const float4 b1 = lds128f(bias_u + (uint32_t)(cgt + c0 + 8 * g + 4) * 4);
+          f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+          f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+          f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+          f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+          if (HAS_RES) {
+            if (rv[g]) {
+              float t[8];
+              unpack8(rr[g], t);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) f[j] += t[j];
+            }
+          }
+#pragma unroll
+          for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], relu_lo);
+          const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
+          if (HAS_OUT)
+            sts128(st1 + so, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          if (HAS_OUT2) {
+            const float4 s0 = lds128f(o2s_u + (uint32_t)(cgt + c0 + 8 * g) * 4);
+            const float4 s1 = lds128f(o2s_u + (uint32_t)(cgt + c0 + 8 * g + 4) * 4);
+            const float4 h0 = lds128f(o2b_u + (uint32_t)(cgt + c0 + 8 * g) * 4);
+            const float4 h1 = lds128f(o2b_u + (uint32_t)(cgt + c0 + 8 * g + 4) * 4);
+            sts128(st2 + so,
+                   pack_bf16x2(fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), fmaxf(fmaf(f[1], s0.y, h0.y), 0.f)),
+                   pack_bf16x2(fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), fmaxf(fmaf(f[3], s0.w, h0.w), 0.f)),
+                   pack_bf16x2(fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), fmaxf(fmaf(f[5], s1.y, h1.y), 0.f)),
+                   pack_bf16x2(fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), fmaxf(fmaf(f[7], s1.w, h1.w), 0.f)));
+          }
+        }
+      }
+      // ---- flush a completed staging slice with coalesced stores
+      if (slice_c + ncol == slice_cols) {
+        __syncwarp();
+        const int c = c0 - slice_c + cl;                       // this lane's channel inside the N tile
+        const bool c_ok = cgt + c < cout8;
+#pragma unroll 4
+        for (int i = 0; i < niter; ++i) {
+          const int p = i * ppi + pl;                          // staged pixel 0..31
+          const int prow = p >> 3, pcol = p & 7;
+          if (c_ok && prow < rows_ok && pcol < cols_ok) {
+            const uint32_t so = swz((uint32_t)i * 512 + (uint32_t)lane * 16);
+            const int po = (q * 4 + prow) * Wo + pcol;
+            if (HAS_OUT) *reinterpret_cast<uint4*>(out_t + (int64_t)po * P.out_ld + c) = lds128(st1 + so);
+            if (HAS_OUT2) *reinterpret_cast<uint4*>(out2_t + (int64_t)po * P.out2_ld + c) = lds128(st2 + so);
+          }
+        }
+        __syncwarp();
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t_empty[grp]);
+    // advance the tile coordinates by 2*gridDim.x
+    nt += P.step2[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+    tw += P.step2[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+    th += P.step2[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+    n += P.step2[3];
+  }
+}
+
 // Tap tables, compile-time so the MMA issue loop unrolls into immediate-offset descriptor adds
 // (a single thread issues every MMA: any dependent address arithmetic there is on the critical path).
 //   MODE 0: 3x3 stride 1, one halo slab, 9 taps      MODE 1: 1x1 (stride 1 or 2), one slab, one tap
@@ -244,125 +390,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       if (++ts == 2) { ts = 0; tp ^= 1; }
     }
   } else {
-    // =========================== epilogue: two groups of 4 warps ===========================
-    // Group g owns TMEM accumulator stage g and every second tile of this CTA, so the epilogue of tile i
-    // overlaps the epilogue of tile i+1 as well as its MMAs.  Per tile:
-    // TMEM -> registers (thread = output pixel) -> +bias (+residual) -> ReLU -> bf16 -> warp-private
-    // swizzled staging tile -> 16 B stores with consecutive lanes on consecutive addresses.
-    const int ew = warp - 2;                      // 0..7
-    const int grp = ew >> 2;                      // accumulator stage / tile parity
-    const int q = warp & 3;                       // TMEM lane quadrant this warp may access
-    const int m = q * 32 + lane;                  // tile row = output pixel within the tile
-    const int ph = m >> 3, pw = m & 7;            // TW == 8
-    uint8_t* st1 = sStage + (size_t)ew * 4096;
-    uint8_t* st2 = sStage + 32768 + (size_t)ew * 4096;
-    const int cout8 = (P.Cout + 7) & ~7;          // stores cover whole 8-channel groups (buffers are padded)
-    const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * P.NT);
-    uint32_t tp = 0;
-    // tile coordinates, advanced incrementally by 2*gridDim.x tiles (mixed-radix digits from the host)
-    uint32_t t0 = blockIdx.x + (uint32_t)grp * gridDim.x;
-    int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
-    int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
-    int th = (int)(t0 % (uint32_t)P.tiles_h);
-    int n = (int)(t0 / (uint32_t)P.tiles_h);
-    for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < (uint32_t)P.total_tiles; tile += 2 * gridDim.x) {
-      const int oh = th * TH + ph, ow = tw * TW + pw;
-      const bool pvalid = (oh < P.Ho) && (ow < P.Wo);
-      const int64_t pix0 = ((int64_t)n * P.Ho + th * TH) * P.Wo + tw * TW;   // first pixel of the tile
-      const int poff = ph * P.Wo + pw;                                        // this thread's pixel, relative
-      const int cgt = nt * P.NT;
-      const __nv_bfloat16* res_px = P.res ? P.res + (pix0 + poff) * P.res_ld + cgt : nullptr;
-      __nv_bfloat16* out_t = P.out ? P.out + pix0 * P.out_ld + cgt : nullptr;
-      __nv_bfloat16* out2_t = P.out2 ? P.out2 + pix0 * P.out2_ld + cgt : nullptr;
-      const int rows_ok = P.Ho - th * TH - q * 4, cols_ok = P.Wo - tw * TW;   // valid rows (of this warp's 4) / cols
-      mbar_wait(&t_full[grp], tp);
-      tp ^= 1;
-      tc_fence_after();
-      for (int c0 = 0; c0 < P.NT; c0 += 32) {
-        const int ncol = min(32, P.NT - c0);       // 16 or 32
-        uint32_t v[32];
-        tc_ld16(taddr0 + c0, v);
-        if (ncol == 32) tc_ld16(taddr0 + c0 + 16, v + 16);
-        uint4 rr[4];
-        bool rv[4];
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          rv[g] = res_px && pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < cout8);
-          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 8 * g));
-        }
-        tc_wait_ld();
-        const int slice_c = c0 & 63;               // column of this block inside the 64-channel staging slice
-        const int slice_cols = min(64, P.NT - (c0 - slice_c));   // 16, 32 or 64 (host guarantees a power of two)
-        const int sh = 31 - __clz(slice_cols * 2); // log2(bytes per staged pixel)
-        const uint32_t row_off = (uint32_t)lane << sh;
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          if (8 * g < ncol) {
-            float f[8];
-            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + cgt + c0 + 8 * g);
-            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + cgt + c0 + 8 * g + 4);
-            f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
-            f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
-            f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
-            f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
-            if (rv[g]) {
-              float t[8];
-              unpack8(rr[g], t);
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] += t[j];
-            }
-            if (P.relu) {
-#pragma unroll
-              for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], 0.f);
-            }
-            const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
-            if (out_t)
-              *reinterpret_cast<uint4*>(st1 + so) = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]),
-                                                               pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
-            if (out2_t) {
-              const float4 s0 = *reinterpret_cast<const float4*>(s_o2s + cgt + c0 + 8 * g);
-              const float4 s1 = *reinterpret_cast<const float4*>(s_o2s + cgt + c0 + 8 * g + 4);
-              const float4 h0 = *reinterpret_cast<const float4*>(s_o2b + cgt + c0 + 8 * g);
-              const float4 h1 = *reinterpret_cast<const float4*>(s_o2b + cgt + c0 + 8 * g + 4);
-              *reinterpret_cast<uint4*>(st2 + so) = make_uint4(
-                  pack_bf16x2(fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), fmaxf(fmaf(f[1], s0.y, h0.y), 0.f)),
-                  pack_bf16x2(fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), fmaxf(fmaf(f[3], s0.w, h0.w), 0.f)),
-                  pack_bf16x2(fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), fmaxf(fmaf(f[5], s1.y, h1.y), 0.f)),
-                  pack_bf16x2(fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), fmaxf(fmaf(f[7], s1.w, h1.w), 0.f)));
-            }
-          }
-        }
-        // ---- flush a completed staging slice (up to 64 channels x 32 pixels) with coalesced stores:
-        //      lane l of store i covers staged bytes [i*512 + 16 l, +16), i.e. 8 lanes per 128 B pixel row
-        if (slice_c + ncol == slice_cols) {
-          __syncwarp();
-          const int sc0 = c0 - slice_c;                        // first channel of the slice inside this N tile
-          const int niter = slice_cols >> 3;                   // (32 px * slice_cols * 2 B) / 512 B
-          const uint32_t bmask = (1u << sh) - 1;
-#pragma unroll 4
-          for (int i = 0; i < niter; ++i) {
-            const uint32_t L = (uint32_t)i * 512 + (uint32_t)lane * 16;
-            const int p = (int)(L >> sh);                      // staged pixel 0..31
-            const int c = sc0 + (int)((L & bmask) >> 1);
-            const int prow = q * 4 + (p >> 3), pcol = p & 7;
-            if ((p >> 3) < rows_ok && pcol < cols_ok && cgt + c < cout8) {
-              const uint32_t so = swz(L);
-              const int po = prow * P.Wo + pcol;
-              if (out_t) *reinterpret_cast<uint4*>(out_t + (int64_t)po * P.out_ld + c) = *reinterpret_cast<const uint4*>(st1 + so);
-              if (out2_t) *reinterpret_cast<uint4*>(out2_t + (int64_t)po * P.out2_ld + c) = *reinterpret_cast<const uint4*>(st2 + so);
-            }
-          }
-          __syncwarp();
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[grp]);
-      // advance the tile coordinates by 2*gridDim.x
-      nt += P.step2[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
-      tw += P.step2[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
-      th += P.step2[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
-      n += P.step2[3];
+    // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
+    const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);
+    const int variant = (P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0);
+    switch (variant) {
+      case 2: epilogue_loop<false, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 3: epilogue_loop<true, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 4: epilogue_loop<false, false, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 5: epilogue_loop<true, false, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 6: epilogue_loop<false, true, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      default: epilogue_loop<true, true, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
     }
   }
 
