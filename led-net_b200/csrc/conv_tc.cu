@@ -373,7 +373,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
                 const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                tc_mma_if(d_tmem, ((uint64_t)a_hi << 32) | al, ((uint64_t)b_hi << 32) | (b_lo + 2 * k), idesc, acc, leader);
+                tc_mma_if2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc, leader);
                 acc = 1;
               }
               if (!BRES) {
