@@ -18,6 +18,7 @@
 //   * `x += resize(...)` is one upsample+add(+ReLU) kernel; DAPPM pooling carries its BN+ReLU.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 #include <map>
@@ -60,10 +61,16 @@ namespace {
 using OpFn = std::function<int(ledb200_handle&, Plan&, cudaStream_t)>;
 enum OpKind { K_CONV_DIRECT = 0, K_CONV_TC = 1, K_UPADD = 2, K_POOL = 3, K_AFFINE = 4, K_TAIL = 5, K_LAYOUT = 6 };
 // flops / bytes are ALGORITHMIC (what the layer must move or compute), see DESIGN.md section 4
-struct Op { std::string name; OpFn fn; int kind = 0; double flops = 0, bytes = 0; };
+struct Op {
+  std::string name; OpFn fn; int kind = 0; double flops = 0, bytes = 0;
+  int lane = 0;            // 0 = detail/spatial stream, 1 = context stream (bilateral branches run concurrently)
+  bool wait_other = false; // this op consumes something the OTHER lane produced: join before launching
+};
 
+struct GraphEntry { std::vector<const void*> key; cudaGraphExec_t exec = nullptr; };
 struct Plan {
   int kind = 0, n = 0, h = 0, w = 0;
+  std::vector<GraphEntry> graphs;   // captured CUDA graphs, keyed by the caller's buffer pointers
   std::vector<Buf> bufs;
   std::vector<Op> ops;
   size_t arena = 0;
@@ -91,6 +98,9 @@ struct ledb200_handle {
   size_t arena_cap = 0;
   std::map<std::string, std::unique_ptr<Plan>> plans;
   Plan* last_plan = nullptr;
+  cudaStream_t cap[2] = {nullptr, nullptr};   // engine-owned streams: graph capture / eager two-lane execution
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_x[2] = {nullptr, nullptr};
+  int use_graph = 1, use_lanes = 1;
   // per-call externals
   const void* ext_img = nullptr; int ext_layout = 0;
   void* ext_pred = nullptr; int ext_pred_dtype = LEDB200_U8; float* ext_logits = nullptr;
@@ -296,7 +306,12 @@ struct Builder {
   ledb200_handle& e;
   Plan& p;
   int dt;
+  int cur_lane = 0;
+  bool pending_wait = false;
   Builder(ledb200_handle& e_, Plan& p_) : e(e_), p(p_), dt(e_.cfg.dtype) {}
+  // following ops go to `l`; wait = the next op consumes a tensor produced on the other lane
+  void lane(int l, bool wait = false) { cur_lane = l; pending_wait = pending_wait || wait; }
+  void tag() { p.ops.back().lane = cur_lane; p.ops.back().wait_other = pending_wait; pending_wait = false; }
 
   int buf(const std::string& name, int n, int h, int w, int c, int ld = 0) {
     Buf b{name, n, h, w, c, ld ? ld : c, p.arena};
@@ -350,6 +365,7 @@ struct Builder {
       if (use_tc) return launch_conv_tc(a, st);
       return launch_conv_direct(a, st);
     }, use_tc ? K_CONV_TC : K_CONV_DIRECT, flops, bytes});
+    tag();
     return out;
   }
   void out_hw(const std::string& cname, int in, int& Ho, int& Wo) {
@@ -409,6 +425,7 @@ struct Builder {
       a.dtype = dtype; a.N = bo.n; a.H = bo.h; a.W = bo.w; a.C = bs.c; a.h = bs.h; a.w = bs.w; a.relu = relu;
       return launch_upsample_add(a, st);
     }, K_UPADD, 0.0, 0.0});
+    tag();
     {
       const Buf& bs = p.bufs[src];
       const Buf& bo = p.bufs[out >= 0 ? out : out2];
@@ -426,6 +443,7 @@ struct Builder {
       a.dtype = dtype; a.N = bi.n; a.H = bi.h; a.W = bi.w; a.C = bi.c; a.Ho = bo.h; a.Wo = bo.w; a.k = k; a.s = s; a.p = pd;
       return launch_avgpool_bnrelu(a, st);
     }, K_POOL, 0.0, 0.0});
+    tag();
     p.ops.back().bytes = esize(e) * ((double)p.bufs[in].n * p.bufs[in].h * p.bufs[in].w * p.bufs[in].c +
                                      (double)p.bufs[out].n * p.bufs[out].h * p.bufs[out].w * p.bufs[out].c);
   }
@@ -440,6 +458,7 @@ struct Builder {
       a.dtype = dtype; a.npix = (int64_t)bi.n * bi.h * bi.w; a.C = bi.c;
       return launch_affine_relu(a, st);
     }, K_AFFINE, 0.0, 0.0});
+    tag();
     p.ops.back().bytes = esize(e) * (double)p.bufs[in].n * p.bufs[in].h * p.bufs[in].w * p.bufs[in].c * (1 + (oa >= 0) + (ob >= 0));
   }
 };
@@ -512,36 +531,50 @@ void build_trunk(Builder& B, bool raw_c5, bool head_inputs) {
   t = B.basic_block(b + "stem.2.1", t, true, false);
   t = B.basic_block(b + "stem.4.0", t, true, false);
   const int x = B.basic_block(b + "stem.4.1", t, true, false);
-  // ---- stage 3 (ddrnet.py:190-201)
+  // ---- stage 3 (ddrnet.py:190-201).  The context (lane 1) and spatial (lane 0) branches are independent
+  //      between the bilateral fusion points, so they are issued on two streams: the low-resolution
+  //      context convolutions have too few tiles to fill 148 SMs and overlap with the HBM-bound
+  //      spatial ones.
   int xc_r = -1, xs_r = -1;
+  B.lane(1, true);
   t = B.basic_block(b + "context_branch_layers.0.0", x, true, false);
   int xc = B.basic_block(b + "context_branch_layers.0.1", t, false, true, &xc_r);
+  B.lane(0);
   t = B.basic_block(b + "spatial_branch_layers.0.0", x, true, false);
   int xs = B.basic_block(b + "spatial_branch_layers.0.1", t, false, true, &xs_r);
+  B.lane(1);
   int comp = B.buf("comp1", n, p.bufs[xc].h, p.bufs[xc].w, 2 * C);
   B.conv(b + "compression_1", xc_r, comp);
-  int xc_in = B.buf("xc4in", n, p.bufs[xc].h, p.bufs[xc].w, 4 * C);
-  B.conv(b + "down_1", xs_r, xc_in, xc, true);                       // relu(x_c + down_1(relu(x_s)))
+  B.lane(0, true);
   int xs_in = B.buf("xs4in", n, p.bufs[xs].h, p.bufs[xs].w, 2 * C);
   B.upadd("fuse3.up_add", xs, comp, xs_in, true);                    // relu(x_s + up(comp_c))
+  B.lane(1, true);
+  int xc_in = B.buf("xc4in", n, p.bufs[xc].h, p.bufs[xc].w, 4 * C);
+  B.conv(b + "down_1", xs_r, xc_in, xc, true);                       // relu(x_c + down_1(relu(x_s)))
   // ---- stage 4 (ddrnet.py:203-212)
   t = B.basic_block(b + "context_branch_layers.1.0", xc_in, true, false);
   xc = B.basic_block(b + "context_branch_layers.1.1", t, false, true, &xc_r);
+  B.lane(0);
   t = B.basic_block(b + "spatial_branch_layers.1.0", xs_in, true, false);
   xs = B.basic_block(b + "spatial_branch_layers.1.1", t, false, true, &xs_r);
+  B.lane(1);
   comp = B.buf("comp2", n, p.bufs[xc].h, p.bufs[xc].w, 2 * C);
   B.conv(b + "compression_2", xc_r, comp);
+  B.lane(0, true);
+  xs_in = B.buf("xs5in", n, p.bufs[xs].h, p.bufs[xs].w, 2 * C);
+  B.upadd("fuse4.up_add", xs, comp, xs_in, true);
+  B.lane(1, true);
   int Hd, Wd;
   B.out_hw(b + "down_2.0", xs_r, Hd, Wd);
   const int d2a = B.buf("down_2.0", n, Hd, Wd, 4 * C);
   B.conv(b + "down_2.0", xs_r, d2a, -1, true);
   xc_in = B.buf("xc5in", n, p.bufs[xc].h, p.bufs[xc].w, 8 * C);
   B.conv(b + "down_2.1", d2a, xc_in, xc, true);
-  xs_in = B.buf("xs5in", n, p.bufs[xs].h, p.bufs[xs].w, 2 * C);
-  B.upadd("fuse4.up_add", xs, comp, xs_in, true);
-  // ---- stage 5 (ddrnet.py:214-224)
-  const int xs5 = B.bottleneck(b + "spatial_branch_layers.2.0", xs_in);
+  // ---- stage 5 (ddrnet.py:214-224): context bottleneck + DAPPM on lane 1, spatial bottleneck on lane 0
   const int xc5 = B.bottleneck(b + "context_branch_layers.2.0", xc_in);
+  B.lane(0);
+  const int xs5 = B.bottleneck(b + "spatial_branch_layers.2.0", xs_in);
+  B.lane(1);
   // DAPPM (ppm.py:119-130)
   const int P = e.cfg.ppm_channels;
   const int hh = p.bufs[xc5].h, ww = p.bufs[xc5].w, cc = p.bufs[xc5].c;
@@ -576,6 +609,7 @@ void build_trunk(Builder& B, bool raw_c5, bool head_inputs) {
   // c5 = x_s + up(spp)  (ddrnet.py:218-224); head prologue BN+ReLU fused as 2nd output
   const int c5 = raw_c5 ? B.buf("c5", n, p.bufs[xs5].h, p.bufs[xs5].w, 4 * C) : -1;
   const int c5h = head_inputs ? B.buf("c5h", n, p.bufs[xs5].h, p.bufs[xs5].w, 4 * C) : -1;
+  B.lane(0, true);
   B.upadd("final.up_add", xs5, spp, c5, false, c5h, head_inputs ? aff(e, "decode_head.head.0.bn") : -1);
 }
 
@@ -661,6 +695,8 @@ void build_head_standalone(Builder& B, int h8, int w8, int h2, int w2, int h4, i
   add_export(B, "hx2", &ledb200_handle::ext_hx2);
 }
 
+void drop_graphs(ledb200_handle& e);
+
 int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Plan** out) {
   std::string key = std::to_string(kind) + ":" + std::to_string(n) + ":" + std::to_string(h) + ":" + std::to_string(w);
   if (extra) for (int i = 0; i < 6; ++i) key += ":" + std::to_string(extra[i]);
@@ -687,6 +723,7 @@ int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Pla
   Plan* p = it->second.get();
   if (p->arena > e.arena_cap) {
     LEDB_CUDA_OK(cudaDeviceSynchronize());
+    drop_graphs(e);
     if (e.arena) LEDB_CUDA_OK(cudaFree(e.arena));
     e.arena = nullptr; e.arena_cap = 0;
     void* q = nullptr;
@@ -700,12 +737,82 @@ int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Pla
   return LEDB200_OK;
 }
 
-int run_plan(ledb200_handle& e, Plan& p, cudaStream_t st) {
+void drop_graphs(ledb200_handle& e) {
+  for (auto& kv : e.plans)
+    for (auto& g : kv.second->graphs) if (g.exec) cudaGraphExecDestroy(g.exec);
+  for (auto& kv : e.plans) kv.second->graphs.clear();
+}
+
+int ensure_streams(ledb200_handle& e) {
+  if (e.cap[0]) return LEDB200_OK;
+  for (int i = 0; i < 2; ++i) LEDB_CUDA_OK(cudaStreamCreateWithFlags(&e.cap[i], cudaStreamNonBlocking));
+  LEDB_CUDA_OK(cudaEventCreateWithFlags(&e.ev_fork, cudaEventDisableTiming));
+  LEDB_CUDA_OK(cudaEventCreateWithFlags(&e.ev_join, cudaEventDisableTiming));
+  for (int i = 0; i < 2; ++i) LEDB_CUDA_OK(cudaEventCreateWithFlags(&e.ev_x[i], cudaEventDisableTiming));
+  return LEDB200_OK;
+}
+
+// Issue every op of the plan on two streams: lane 0 = s0, lane 1 = s1.  s1 forks from s0 at the start
+// and joins back at the end; an op flagged wait_other first makes its stream wait for the other
+// stream's tail.  Works both eagerly and under stream capture (the events become graph edges).
+int issue_ops(ledb200_handle& e, Plan& p, cudaStream_t s0, cudaStream_t s1) {
+  const bool lanes = e.use_lanes && s1 != nullptr;
+  cudaStream_t ss[2] = {s0, lanes ? s1 : s0};
+  if (lanes) {
+    LEDB_CUDA_OK(cudaEventRecord(e.ev_fork, s0));
+    LEDB_CUDA_OK(cudaStreamWaitEvent(s1, e.ev_fork, 0));
+  }
   for (auto& op : p.ops) {
-    int rc = op.fn(e, p, st);
+    const int l = lanes ? op.lane : 0;
+    if (lanes && op.wait_other) {
+      LEDB_CUDA_OK(cudaEventRecord(e.ev_x[1 - l], ss[1 - l]));
+      LEDB_CUDA_OK(cudaStreamWaitEvent(ss[l], e.ev_x[1 - l], 0));
+    }
+    int rc = op.fn(e, p, ss[l]);
     if (rc) { set_error("op '" + op.name + "': " + g_err); return rc; }
   }
+  if (lanes) {
+    LEDB_CUDA_OK(cudaEventRecord(e.ev_join, s1));
+    LEDB_CUDA_OK(cudaStreamWaitEvent(s0, e.ev_join, 0));
+  }
+  return LEDB200_OK;
+}
+
+std::vector<const void*> ext_key(const ledb200_handle& e) {
+  return {e.ext_img, (const void*)(intptr_t)e.ext_layout, e.ext_pred, (const void*)(intptr_t)e.ext_pred_dtype,
+          e.ext_logits, e.ext_c5, e.ext_x1, e.ext_x2, e.in_c5, e.in_x1, e.in_x2, e.ext_xc, e.ext_hx1, e.ext_hx2,
+          e.arena};
+}
+
+int run_plan(ledb200_handle& e, Plan& p, cudaStream_t st) {
   e.last_plan = &p;
+  int rc = ensure_streams(e);
+  if (rc) return rc;
+  if (!e.use_graph) {
+    // eager: lane 0 is the caller's stream, lane 1 the engine's side stream
+    return issue_ops(e, p, st, e.cap[1]);
+  }
+  // one CUDA graph per (plan, caller buffers): kernel arguments, tensor maps and the two-lane
+  // dependency structure are baked at capture; replay is a single launch on the caller's stream
+  const std::vector<const void*> key = ext_key(e);
+  for (auto& g : p.graphs)
+    if (g.key == key) { LEDB_CUDA_OK(cudaGraphLaunch(g.exec, st)); return LEDB200_OK; }
+  if (p.graphs.size() >= 8) {   // callers that allocate fresh outputs every call: keep the cache bounded
+    if (p.graphs.front().exec) cudaGraphExecDestroy(p.graphs.front().exec);
+    p.graphs.erase(p.graphs.begin());
+  }
+  LEDB_CUDA_OK(cudaStreamBeginCapture(e.cap[0], cudaStreamCaptureModeRelaxed));
+  rc = issue_ops(e, p, e.cap[0], e.cap[1]);
+  cudaGraph_t graph = nullptr;
+  cudaError_t ce = cudaStreamEndCapture(e.cap[0], &graph);
+  if (rc) { if (graph) cudaGraphDestroy(graph); cudaGetLastError(); return rc; }
+  if (ce != cudaSuccess) { cudaGetLastError(); return fail(LEDB200_ECUDA, std::string("graph capture: ") + cudaGetErrorString(ce)); }
+  GraphEntry ge; ge.key = key;
+  ce = cudaGraphInstantiate(&ge.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (ce != cudaSuccess) return fail(LEDB200_ECUDA, std::string("graph instantiate: ") + cudaGetErrorString(ce));
+  p.graphs.push_back(ge);
+  LEDB_CUDA_OK(cudaGraphLaunch(ge.exec, st));
   return LEDB200_OK;
 }
 
@@ -740,6 +847,8 @@ int ledb200_create(const ledb200_cfg* cfg, ledb200_handle** out) {
   auto* h = new (std::nothrow) ledb200_handle();
   if (!h) return fail(LEDB200_ENOMEM, "out of host memory");
   h->cfg = *cfg;
+  h->use_graph = getenv("LEDB200_NO_GRAPH") ? 0 : 1;
+  h->use_lanes = getenv("LEDB200_NO_LANES") ? 0 : 1;
   try { define_model(*h); } catch (const std::exception& ex) { delete h; return fail(LEDB200_EINVAL, ex.what()); }
   *out = h;
   return LEDB200_OK;
@@ -749,6 +858,10 @@ int ledb200_destroy(ledb200_handle* h) {
   if (!h) return LEDB200_OK;
   cudaSetDevice(h->cfg.device);
   cudaDeviceSynchronize();
+  drop_graphs(*h);
+  for (int i = 0; i < 2; ++i) { if (h->cap[i]) cudaStreamDestroy(h->cap[i]); if (h->ev_x[i]) cudaEventDestroy(h->ev_x[i]); }
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
   for (void* p : h->dev_allocs) cudaFree(p);
   if (h->arena) cudaFree(h->arena);
   delete h;
