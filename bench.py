@@ -210,35 +210,55 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
     launches_per_step = eng.plan_launches() + 1
 
-    # ---- end-to-end through the public API with HOST buffers: pinned uint8 images + labels in,
-    #      (fused-preprocess) forward, confusion matrix, matrix read back to the host
-    cm_host = torch.empty((K + 1, K), dtype=torch.int64).pin_memory()
-    img_dev = torch.empty_like(img_u8)
-    lab_dev = torch.empty_like(lab)
+    # ---- end-to-end through the public API with HOST buffers: every step copies ITS OWN pinned uint8
+    #      images + labels to the device, runs the fused-preprocess forward + confusion matrix and reads
+    #      the matrix back to the host.  Two buffer sets and a copy stream let step i+1's upload overlap
+    #      step i's kernels (what a real eval loop with a prefetching loader does); every upload, kernel
+    #      and read-back still happens inside the timed region.
+    copy_stream = torch.cuda.Stream(device=dev)
+    bufs = [dict(img=torch.empty_like(img_u8), lab=torch.empty_like(lab), pred=torch.empty_like(pred),
+                 cm_host=torch.empty((K + 1, K), dtype=torch.int64).pin_memory(),
+                 up=torch.cuda.Event(), done=torch.cuda.Event()) for _ in range(2)]
+    cur = torch.cuda.current_stream(dev)
 
-    def e2e_step():
-        img_dev.copy_(img_u8_host, non_blocking=True)
-        lab_dev.copy_(lab_host, non_blocking=True)
-        p = m.predict_labels(img_dev, pred=pred)
-        c = ops.confusion_accumulate(p, lab_dev, K, 255)
+    def e2e_upload(b):
+        with torch.cuda.stream(copy_stream):
+            copy_stream.wait_event(b['done'])            # the previous user of this buffer set has finished
+            b['img'].copy_(img_u8_host, non_blocking=True)
+            b['lab'].copy_(lab_host, non_blocking=True)
+            b['up'].record(copy_stream)
+
+    def e2e_compute(b):
+        cur.wait_event(b['up'])
+        p = m.predict_labels(b['img'], pred=b['pred'])
+        c = ops.confusion_accumulate(p, b['lab'], K, 255)
         if dist is not None:
             dist.all_reduce(c)
-        cm_host.copy_(c, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
+        b['cm_host'].copy_(c, non_blocking=True)
+        b['done'].record(cur)
 
-    for _ in range(2):
-        e2e_step()
+    def e2e_run(nsteps):
+        e2e_upload(bufs[0])
+        for i in range(nsteps):
+            if i + 1 < nsteps:
+                e2e_upload(bufs[(i + 1) % 2])
+            e2e_compute(bufs[i % 2])
+        cur.synchronize()
+
+    for b in bufs:
+        b['done'].record(cur)
+    e2e_run(3)
     barrier()
-    e2e_steps = max(3, args.steps // 2)
+    e2e_steps = max(4, args.steps)
     e0.record()
-    for _ in range(e2e_steps):
-        e2e_step()
+    e2e_run(e2e_steps)
     e1.record()
     barrier()
     t2 = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if dist is not None:
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_ms = t2.item() / e2e_steps
+    cm_host = bufs[0]['cm_host']
 
     if rank != 0:
         if dist is not None:

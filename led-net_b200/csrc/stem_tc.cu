@@ -96,25 +96,40 @@ __global__ void __launch_bounds__(ST_THREADS, 6) stem_tc_kernel(const __grid_con
     // ---- gather 27 inputs (zero outside the image: padding is applied after normalisation)
     float x[27];
     {
-      const Tin* base = in + (int64_t)n * P.in_sn;
       const int ih0 = 2 * oh - 1, iw0 = 2 * ow - 1;
-      const bool pv = oh < P.Ho && ow < P.Wo;
+      const Tin* base = in + (int64_t)n * P.in_sn + (int64_t)ih0 * P.in_sh + (int64_t)iw0 * P.in_sw;
+      const bool interior = ih0 >= 0 && iw0 >= 0 && ih0 + 2 < P.H && iw0 + 2 < P.W;   // implies oh < Ho, ow < Wo
+      if (interior) {
+        // nine (channel, row) pointers, three taps each: no per-tap bounds or address arithmetic
 #pragma unroll
-      for (int kh = 0; kh < 3; ++kh) {
-        const int ih = ih0 + kh;
-        const bool rok = pv && ih >= 0 && ih < P.H;
+        for (int ci = 0; ci < 3; ++ci) {
+          const float sc = ci == 0 ? ps0 : (ci == 1 ? ps1 : ps2), sb = ci == 0 ? pb0 : (ci == 1 ? pb1 : pb2);
 #pragma unroll
-        for (int kw = 0; kw < 3; ++kw) {
-          const int iw = iw0 + kw;
-          const bool ok = rok && iw >= 0 && iw < P.W;
-          const Tin* p = base + (int64_t)ih * P.in_sh + (int64_t)iw * P.in_sw;
-          float v0 = 0.f, v1 = 0.f, v2 = 0.f;
-          if (ok) {
-            v0 = fmaf(to_f32(__ldg(p)), ps0, pb0);
-            v1 = fmaf(to_f32(__ldg(p + P.in_sc)), ps1, pb1);
-            v2 = fmaf(to_f32(__ldg(p + 2 * P.in_sc)), ps2, pb2);
+          for (int kh = 0; kh < 3; ++kh) {
+            const Tin* rp = base + ci * P.in_sc + kh * P.in_sh;
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) x[(kh * 3 + kw) * 3 + ci] = fmaf(to_f32(__ldg(rp + kw * P.in_sw)), sc, sb);
           }
-          x[(kh * 3 + kw) * 3 + 0] = v0; x[(kh * 3 + kw) * 3 + 1] = v1; x[(kh * 3 + kw) * 3 + 2] = v2;
+        }
+      } else {
+        const bool pv = oh < P.Ho && ow < P.Wo;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const int ih = ih0 + kh;
+          const bool rok = pv && ih >= 0 && ih < P.H;
+#pragma unroll
+          for (int kw = 0; kw < 3; ++kw) {
+            const int iw = iw0 + kw;
+            const bool ok = rok && iw >= 0 && iw < P.W;
+            const Tin* p = base + (int64_t)kh * P.in_sh + (int64_t)kw * P.in_sw;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+            if (ok) {
+              v0 = fmaf(to_f32(__ldg(p)), ps0, pb0);
+              v1 = fmaf(to_f32(__ldg(p + P.in_sc)), ps1, pb1);
+              v2 = fmaf(to_f32(__ldg(p + 2 * P.in_sc)), ps2, pb2);
+            }
+            x[(kh * 3 + kw) * 3 + 0] = v0; x[(kh * 3 + kw) * 3 + 1] = v1; x[(kh * 3 + kw) * 3 + 2] = v2;
+          }
         }
       }
     }
