@@ -65,7 +65,7 @@ struct TcParams {
   int SA, SB, b_resident;
   int cp;                            // Cout padded to the N tiling (ntiles_n * NT)
   uint32_t stage_bytes;              // epilogue staging: 32 KB (+32 KB with a second output)
-  int step2[4];                      // 2*grid tiles as digits (n-tile, tile col, tile row, image)
+  int step1[4], step2[4];            // grid and 2*grid tiles as digits (n-tile, tile col, tile row, image)
   uint32_t tmem_cols;
   // epilogue
   __nv_bfloat16* out; int out_ld;
@@ -92,9 +92,12 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   return v;
 }
 
-// Epilogue of the persistent conv kernel, run by warps 2..9 as two groups of four.  Group g owns TMEM
-// accumulator stage g and every second tile of this CTA, so the epilogue of tile i overlaps the
-// epilogue of tile i+1 as well as its MMAs.  Per tile and 32-column block:
+// Epilogue of the persistent conv kernel, run by warps 2..9 as two groups of four.
+//   N tile >= 64: both groups work on EVERY tile, group g drains column half g of the accumulator (all
+//     128 lanes), so a tile's epilogue takes half as long and the epilogue warps never idle waiting for
+//     "their" accumulator stage while the MMAs of the next tile run into the other TMEM stage;
+//   N tile < 64: group g owns accumulator stage g and every second tile (per-tile fixed costs dominate).
+// Per tile and block of up to 32 columns:
 //   tcgen05.ld (thread = output pixel) -> +bias (+residual) -> ReLU -> bf16 -> warp-private XOR-swizzled
 //   staging (up to 64 channels x 32 pixels) -> 16 B global stores with consecutive lanes on consecutive
 //   addresses (full 32 B sectors; 8 lanes cover one 128 B pixel row of a 64-channel slice).
@@ -106,7 +109,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
                                               uint64_t* t_full, uint64_t* t_empty, uint32_t st_u, uint32_t bias_u,
                                               uint32_t o2s_u, uint32_t o2b_u) {
   const int ew = warp - 2;                      // 0..7
-  const int grp = ew >> 2;                      // accumulator stage / tile parity
+  const int grp = ew >> 2;                      // column half of every accumulator
   const int q = warp & 3;                       // TMEM lane quadrant this warp may access
   const int m = q * 32 + lane;                  // tile row = output pixel within the tile
   const int ph = m >> 3, pw = m & 7;            // TW == 8
@@ -114,24 +117,29 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
   const int NT = P.NT, Ho = P.Ho, Wo = P.Wo;
   const int cout8 = (P.Cout + 7) & ~7;          // stores cover whole 8-channel groups (buffers are padded)
   const float relu_lo = P.relu ? 0.f : -INFINITY;
-  const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(grp * NT);
-  // staging slice geometry (constant per launch: NT is 16, 32 or a multiple of 64)
-  const int slice_cols = min(64, NT);
+  const uint32_t taddr_q = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool split = NT >= 64;                  // split columns between the groups, else alternate tiles
+  const int ncols_g = split ? NT / 2 : NT;
+  const int cbeg = split ? grp * ncols_g : 0, cend = cbeg + ncols_g;
+  // staging slice geometry (constant per launch: ncols_g is 16, 32, 64 or a multiple of 64)
+  const int slice_cols = max(16, min(64, ncols_g));
   const int sh = 31 - __clz(slice_cols * 2);    // log2(bytes per staged pixel): 5, 6 or 7
   const int ppi = 512 >> sh;                    // pixels covered by one warp-wide 16 B store
   const int niter = slice_cols >> 3;            // stores per slice = 32 px * slice bytes / 512
   const int pl = lane >> (sh - 4);              // pixel of this lane inside a store
   const int cl = (lane & ((1 << (sh - 4)) - 1)) * 8;   // channel of this lane inside the slice
   const uint32_t row_off = (uint32_t)lane << sh;
-  uint32_t tp = 0;
-  // tile coordinates, advanced incrementally by 2*gridDim.x tiles (mixed-radix digits from the host)
-  uint32_t t0 = blockIdx.x + (uint32_t)grp * gridDim.x;
+  uint32_t tp = 0, ts = split ? 0u : (uint32_t)grp;
+  // tile coordinates, advanced incrementally by the tile step (mixed-radix digits from the host)
+  const uint32_t first = blockIdx.x + (split ? 0u : (uint32_t)grp * gridDim.x);
+  const int* stepd = split ? P.step1 : P.step2;
+  uint32_t t0 = first;
   int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
   int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
   int th = (int)(t0 % (uint32_t)P.tiles_h);
   int n = (int)(t0 / (uint32_t)P.tiles_h);
-  const uint32_t total = (uint32_t)P.total_tiles, step = 2 * gridDim.x;
-  for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < total; tile += step) {
+  const uint32_t total = (uint32_t)P.total_tiles, step = split ? gridDim.x : 2 * gridDim.x;
+  for (uint32_t tile = first; tile < total; tile += step) {
     const bool pvalid = (th * TH + ph < Ho) && (tw * TW + pw < Wo);
     const int64_t pix0 = ((int64_t)n * Ho + th * TH) * Wo + tw * TW;       // first pixel of the tile
     const int cgt = nt * NT;                                               // first output channel of this N tile
@@ -139,11 +147,11 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
     __nv_bfloat16* out_t = HAS_OUT ? P.out + pix0 * P.out_ld + cgt : nullptr;
     __nv_bfloat16* out2_t = HAS_OUT2 ? P.out2 + pix0 * P.out2_ld + cgt : nullptr;
     const int rows_ok = Ho - th * TH - q * 4, cols_ok = Wo - tw * TW;      // valid rows (of this warp's 4) / cols
-    mbar_wait(&t_full[grp], tp);
-    tp ^= 1;
+    mbar_wait(&t_full[ts], tp);
     tc_fence_after();
-    for (int c0 = 0; c0 < NT; c0 += 32) {
-      const int ncol = min(32, NT - c0);         // 16 or 32
+    const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      const int ncol = min(32, cend - c0);       // 16 or 32
       uint32_t v[32];
       tc_ld16(taddr0 + c0, v);
       if (ncol == 32) tc_ld16(taddr0 + c0 + 16, v + 16);
@@ -157,7 +165,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         }
       }
       tc_wait_ld();
-      const int slice_c = c0 & 63;               // column of this block inside the staging slice
+      const int slice_c = (c0 - cbeg) & 63;      // column of this block inside the staging slice
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
         if (8 * g < ncol) {
@@ -215,12 +223,13 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
     }
     tc_fence_before();
     __syncwarp();
-    if (lane == 0) mbar_arrive(&t_empty[grp]);
-    // advance the tile coordinates by 2*gridDim.x
-    nt += P.step2[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
-    tw += P.step2[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
-    th += P.step2[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
-    n += P.step2[3];
+    if (lane == 0) mbar_arrive(&t_empty[ts]);
+    if (split) { if (++ts == 2) { ts = 0; tp ^= 1; } } else { tp ^= 1; }
+    // advance the tile coordinates by the tile step
+    nt += stepd[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+    tw += stepd[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+    th += stepd[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+    n += stepd[3];
   }
 }
 
@@ -268,7 +277,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], P.NT >= 64 ? 8 : 4); }
     mbar_fence_init();
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
@@ -586,11 +595,14 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 
   const int grid = (int)std::min<int64_t>(P.total_tiles, num_sms());
   {
-    uint32_t st2 = 2u * (uint32_t)grid;
-    P.step2[0] = (int)(st2 % (uint32_t)P.ntiles_n); st2 /= (uint32_t)P.ntiles_n;
-    P.step2[1] = (int)(st2 % (uint32_t)P.tiles_w); st2 /= (uint32_t)P.tiles_w;
-    P.step2[2] = (int)(st2 % (uint32_t)P.tiles_h);
-    P.step2[3] = (int)(st2 / (uint32_t)P.tiles_h);
+    for (int k = 1; k <= 2; ++k) {
+      int* d = k == 1 ? P.step1 : P.step2;
+      uint32_t stp = (uint32_t)(k * grid);
+      d[0] = (int)(stp % (uint32_t)P.ntiles_n); stp /= (uint32_t)P.ntiles_n;
+      d[1] = (int)(stp % (uint32_t)P.tiles_w); stp /= (uint32_t)P.tiles_w;
+      d[2] = (int)(stp % (uint32_t)P.tiles_h);
+      d[3] = (int)(stp / (uint32_t)P.tiles_h);
+    }
   }
   const int mode = (a.ksize == 1) ? 1 : (s2 ? 2 : 0);
   const int ksteps = P.KC / 16;
