@@ -192,6 +192,67 @@ int ledb200_conv2d(const void* in, void* out, const void* residual, int32_t dtyp
                    const float* pre_scale, const float* pre_shift, int32_t backend,
                    int32_t in_ld, int32_t out_ld, int32_t res_ld, void* stream);
 
+/* ---- training step (north_star kernel 6) -----------------------------
+ * The reference trains through autograd over ATen/cuDNN (encoder_decoder.py:161-185 -> led_head.py:101-146,
+ * SGD per configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:64-65).  These entry points are the forward
+ * and backward kernels of every op on that path; led-net_b200/train_ops.py wraps them as
+ * torch.autograd.Function so PyTorch supplies only the tape.  All tensors are DEVICE fp32 NHWC, dense. */
+
+/* Weights stay in the reference's OIHW fp32 state-dict layout; each step repacks them on the device.
+ * mode 0 -> forward layout [tap][Cin][Cout16]; mode 1 -> data-gradient layout [tap flipped][Cout][Cin16]. */
+int64_t ledb200_train_packed_weight_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode);
+int ledb200_train_pack_weight(const float* w_oihw, float* out, int32_t Cout, int32_t Cin, int32_t k,
+                              int32_t mode, void* stream);
+/* nn.Conv2d(k in {1,3}, padding k/2, stride in {1,2}) forward: y[N,Ho,Wo,Cout] (bias_opt [Cout] or NULL). */
+int ledb200_train_conv_fwd(const float* x, const float* w_packed, const float* bias_opt, float* y,
+                           int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                           int32_t stride, void* stream);
+/* d(loss)/dx [N,H,W,Cin] from dy [N,Ho,Wo,Cout] (H, W are the conv INPUT extents). */
+int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float* dx, int32_t N,
+                             int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
+                             void* stream);
+/* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias; workspace >= 2*Cout doubles if dbias. */
+int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, float* dbias_opt, int32_t N,
+                             int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
+                             void* workspace, void* stream);
+/* nn.BatchNorm2d in training mode fused with the block's residual add and ReLU
+ * (basic_block.py:62-75): out = [relu](bn(y) [+ res]); saves batch mean / inverse std for backward and
+ * updates the running statistics (momentum, unbiased variance) in place.  workspace >= 2*C doubles. */
+int ledb200_train_bn_fwd(const float* y, const float* gamma, const float* beta, const float* res_opt,
+                         float* out, float* save_mean, float* save_invstd, float* running_mean_opt,
+                         float* running_var_opt, float momentum, float eps, int32_t relu, int64_t npix,
+                         int32_t C, void* workspace, void* stream);
+/* backward of the above: dy, dres_opt (= masked dout), dgamma, dbeta. */
+int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, const float* gamma,
+                         const float* save_mean, const float* save_invstd, float* dy, float* dres_opt,
+                         float* dgamma, float* dbeta, int32_t relu, int64_t npix, int32_t C, void* workspace,
+                         void* stream);
+/* resize(mode='bilinear', align_corners=False) (utils/wrappers.py:8-27) and its backward (dsrc overwritten). */
+int ledb200_train_resize_fwd(const float* src, float* out, int32_t N, int32_t h, int32_t w, int32_t H,
+                             int32_t W, int32_t C, void* stream);
+int ledb200_train_resize_bwd(const float* dout, float* dsrc, int32_t N, int32_t h, int32_t w, int32_t H,
+                             int32_t W, int32_t C, void* stream);
+/* out = [relu](a [+ b_opt]); relu backward dx = dout * (out > 0). */
+int ledb200_train_add_relu(const float* a, const float* b_opt, float* out, int32_t relu, int64_t n,
+                           void* stream);
+int ledb200_train_relu_bwd(const float* dout, const float* out, float* dx, int64_t n, void* stream);
+/* nn.AvgPool2d(k,s,p) (count_include_pad=True) or AdaptiveAvgPool2d(1) when k == 0 (ppm.py:66-90). */
+int ledb200_train_avgpool_fwd(const float* in, float* out, int32_t N, int32_t H, int32_t W, int32_t C,
+                              int32_t Ho, int32_t Wo, int32_t k, int32_t s, int32_t p, void* stream);
+int ledb200_train_avgpool_bwd(const float* dout, float* din, int32_t N, int32_t H, int32_t W, int32_t C,
+                              int32_t Ho, int32_t Wo, int32_t k, int32_t s, int32_t p, void* stream);
+/* channel slice copy (torch.cat(dim=1) of ppm.py:128 and its backward). */
+int ledb200_train_copy_channels(const float* src, int32_t src_ld, int32_t src_off, float* dst,
+                                int32_t dst_ld, int32_t dst_off, int64_t npix, int32_t C, void* stream);
+/* NCHW <-> NHWC fp32 (the boundary to the reference's tensors). */
+int ledb200_train_layout(const float* in, float* out, int32_t N, int32_t C, int32_t H, int32_t W,
+                         int32_t to_nhwc, void* stream);
+/* torch.optim.SGD(momentum, weight_decay) over one flat parameter arena; grad is multiplied by
+ * grad_scale first (1/world_size after a sum all-reduce). */
+int ledb200_train_sgd_step(float* param, const float* grad, float* momentum_buf, int64_t n, float lr,
+                           float momentum, float weight_decay, int32_t first_step, float grad_scale,
+                           void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -60,8 +60,14 @@ conv_direct_kernel(ConvArgs a) {
     for (int idx = t; idx < IT * IT; idx += 128) {
       const int y = idx / IT, x = idx % IT;
       const int gy = iy0 + y, gx = ix0 + x;
-      const bool ok = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W);
-      const Tin* p = in + (int64_t)gy * a.in_sh + (int64_t)gx * a.in_sw;
+      bool ok = (gy >= 0 && gy < a.H && gx >= 0 && gx < a.W);
+      int ry = gy, rx = gx;
+      if (a.in_up > 1) {   // virtual zero insertion (dgrad of a strided conv): only multiples of in_up are real
+        ok = ok && (gy % a.in_up == 0) && (gx % a.in_up == 0);
+        ry = gy / a.in_up; rx = gx / a.in_up;
+        ok = ok && ry < a.Hr && rx < a.Wr;
+      }
+      const Tin* p = in + (int64_t)ry * a.in_sh + (int64_t)rx * a.in_sw;
 #pragma unroll
       for (int c = 0; c < CK; ++c) {
         float v = 0.f;

@@ -20,6 +20,11 @@ SYMBOLS = [
     'ledb200_debug_fetch', 'ledb200_profile_ops', 'ledb200_op_info', 'ledb200_op_name', 'ledb200_plan_launches',
     'ledb200_head_fuse_argmax', 'ledb200_confusion_accumulate', 'ledb200_ohem_workspace_bytes',
     'ledb200_ohem_ce', 'ledb200_conv2d',
+    'ledb200_train_packed_weight_floats', 'ledb200_train_pack_weight', 'ledb200_train_conv_fwd',
+    'ledb200_train_conv_dgrad', 'ledb200_train_conv_wgrad', 'ledb200_train_bn_fwd', 'ledb200_train_bn_bwd',
+    'ledb200_train_resize_fwd', 'ledb200_train_resize_bwd', 'ledb200_train_add_relu', 'ledb200_train_relu_bwd',
+    'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
+    'ledb200_train_layout', 'ledb200_train_sgd_step',
 ]
 
 
@@ -73,6 +78,23 @@ def get():
     lib.ledb200_ohem_workspace_bytes.restype = i64
     lib.ledb200_ohem_ce.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, i64, f32, vp, vp, vp, vp, vp]
     lib.ledb200_conv2d.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, vp, vp, vp, i32, i32, i32, i32, vp]
+    lib.ledb200_train_packed_weight_floats.argtypes = [i32] * 4
+    lib.ledb200_train_packed_weight_floats.restype = i64
+    lib.ledb200_train_pack_weight.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.ledb200_train_conv_fwd.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp]
+    lib.ledb200_train_conv_dgrad.argtypes = [vp, vp, vp] + [i32] * 7 + [vp]
+    lib.ledb200_train_conv_wgrad.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp]
+    lib.ledb200_train_bn_fwd.argtypes = [vp] * 9 + [f32, f32, i32, i64, i32, vp, vp]
+    lib.ledb200_train_bn_bwd.argtypes = [vp] * 10 + [i32, i64, i32, vp, vp]
+    lib.ledb200_train_resize_fwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
+    lib.ledb200_train_resize_bwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
+    lib.ledb200_train_add_relu.argtypes = [vp, vp, vp, i32, i64, vp]
+    lib.ledb200_train_relu_bwd.argtypes = [vp, vp, vp, i64, vp]
+    lib.ledb200_train_avgpool_fwd.argtypes = [vp, vp] + [i32] * 9 + [vp]
+    lib.ledb200_train_avgpool_bwd.argtypes = [vp, vp] + [i32] * 9 + [vp]
+    lib.ledb200_train_copy_channels.argtypes = [vp, i32, i32, vp, i32, i32, i64, i32, vp]
+    lib.ledb200_train_layout.argtypes = [vp, vp] + [i32] * 5 + [vp]
+    lib.ledb200_train_sgd_step.argtypes = [vp, vp, vp, i64, f32, f32, f32, i32, f32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):

@@ -86,6 +86,61 @@ class DAPPM(nn.Module):
         self.shortcut = ConvModule(cin, cout, 1, pre_act=True)
 
 
+def _as_nhwc(x):
+    """[N,C,H,W] tensor (any memory format) -> NHWC-contiguous [N,H,W,C] (a view when the tensor is
+    already channels_last, otherwise one layout kernel)."""
+    from . import train_ops as T
+    if x.dim() != 4:
+        raise ValueError(f'expected a 4-D NCHW tensor, got shape {tuple(x.shape)}')
+    v = x.permute(0, 2, 3, 1)
+    if v.is_contiguous():
+        return v
+    return T.to_nhwc(x.contiguous())
+
+
+def _as_nchw_view(x_nhwc):
+    return x_nhwc.permute(0, 3, 1, 2)
+
+
+def _block_train(x, blk, out_relu):
+    """BasicBlock / Bottleneck forward (basic_block.py:62-75, 206-221) on the training kernels."""
+    from . import train_ops as T
+    res = x
+    if blk.downsample is not None:
+        ds = blk.downsample
+        res = T.bn_act(T.conv2d(x, ds[0].weight, None, ds[0].stride[0]), ds[1])
+    y = T.conv_module(x, blk.conv1, relu=True)
+    if isinstance(blk, Bottleneck):
+        y = T.conv_module(y, blk.conv2, relu=True)
+        return T.conv_module(y, blk.conv3, relu=out_relu, res=res)
+    return T.conv_module(y, blk.conv2, relu=out_relu, res=res)
+
+
+def _layer_train(x, layer):
+    """ddrnet.py:151-180: the first BasicBlock of a layer ends in ReLU, the last block of a layer and
+    every Bottleneck do not."""
+    n = len(layer)
+    for i, blk in enumerate(layer):
+        out_relu = isinstance(blk, BasicBlock) and i == 0 and n > 1
+        x = _block_train(x, blk, out_relu)
+    return x
+
+
+_DAPPM_POOLS = ((5, 2, 2), (9, 4, 4), (17, 8, 8), (0, 1, 0))     # ppm.py:66-90; k == 0: global average
+
+
+def _dappm_train(x, spp):
+    """DAPPM.forward (ppm.py:119-130); every ConvModule is pre-activation (norm, act, conv)."""
+    from . import train_ops as T
+    hw = x.shape[1:3]
+    feats = [T.pre_conv_module(x, spp.scales[0])]
+    for i, (k, s, p) in enumerate(_DAPPM_POOLS, start=1):
+        pooled = T.avg_pool(x, k, s, p)
+        up = T.resize(T.pre_conv_module(pooled, spp.scales[i][1]), hw)
+        feats.append(T.pre_conv_module(T.add(up, feats[i - 1]), spp.processes[i - 1]))
+    return T.add(T.pre_conv_module(T.cat_channels(feats), spp.compression), T.pre_conv_module(x, spp.shortcut))
+
+
 class _EngineOwner(nn.Module):
     """Lazily (re)builds the CUDA engine from the current parameters."""
     _prefix = ''
@@ -161,10 +216,41 @@ class LEDNet(_EngineOwner):
 
     def forward(self, x):
         if self.training:
-            raise NotImplementedError(
-                'train-mode LEDNet.forward needs the dgrad/wgrad kernels (SURVEY section 8a row T4); '
-                'not built yet - call .eval() for inference')
+            return self._forward_train(x)
         return self.engine().backbone_forward(x)
+
+    def _forward_train(self, x):
+        """Train-mode forward (batch-statistics BatchNorm, autograd tape over the kernels of
+        csrc/train.cu).  Wiring = ddrnet.py:182-224 with the two stem taps; returns
+        ``(c3, c5, x1, x2)`` as led_head.py:66-75 consumes them: NCHW-shaped tensors (channels_last
+        memory, so no copy is made on either side of the boundary)."""
+        from . import train_ops as T
+        self.reset_engine()                      # parameters are about to change
+        x = _as_nhwc(x)
+        size8 = (math.ceil(x.shape[1] / 8), math.ceil(x.shape[2] / 8))       # ddrnet.py:185
+        x1 = T.conv_module(x, self.stem[0], relu=True)
+        x2 = T.conv_module(x1, self.stem[1], relu=True)
+        x = T.relu(_layer_train(x2, self.stem[2]))
+        x = T.relu(_layer_train(x, self.stem[4]))
+        # stage 3 (ddrnet.py:190-201)
+        x_c = _layer_train(x, self.context_branch_layers[0])
+        x_s = _layer_train(x, self.spatial_branch_layers[0])
+        comp = T.conv_module(T.relu(x_c), self.compression_1)
+        x_c = T.add(x_c, T.conv_module(T.relu(x_s), self.down_1))
+        x_s = T.add(x_s, T.resize(comp, size8))
+        c3 = x_s
+        # stage 4 (ddrnet.py:203-212)
+        x_c = _layer_train(T.relu(x_c), self.context_branch_layers[1])
+        x_s = _layer_train(T.relu(x_s), self.spatial_branch_layers[1])
+        comp = T.conv_module(T.relu(x_c), self.compression_2)
+        d = T.conv_module(T.conv_module(T.relu(x_s), self.down_2[0], relu=True), self.down_2[1])
+        x_c = T.add(x_c, d)
+        x_s = T.add(x_s, T.resize(comp, size8))
+        # stage 5 (ddrnet.py:214-224)
+        x_s = _layer_train(T.relu(x_s), self.spatial_branch_layers[2])
+        x_c = _dappm_train(_layer_train(T.relu(x_c), self.context_branch_layers[2]), self.spp)
+        c5 = T.add(x_s, T.resize(x_c, size8))
+        return tuple(_as_nchw_view(t) for t in (c3, c5, x1, x2))
 
 
 @MODELS.register_module()
@@ -242,11 +328,30 @@ class LEDHead(_EngineOwner):
 
     def forward(self, inputs):
         if self.training:
-            raise NotImplementedError(
-                'train-mode LEDHead.forward needs the dgrad/wgrad kernels (SURVEY section 8a row T4); '
-                'loss_by_feat() on given logits is available')
+            return self._forward_train(inputs)
         c5, x1, x2 = inputs
         return self.engine().head_forward(c5, x1, x2)
+
+    def _base_head_train(self, x, head):
+        from . import train_ops as T
+        return T.bn_act(T.pre_conv_module(x, head[0]), head[1], relu=True)      # led_head.py:84-99
+
+    def _forward_train(self, inputs):
+        """led_head.py:66-75: (context logits, spatial/aux logits, head_x1, head_x2)."""
+        from . import train_ops as T
+        self.reset_engine()
+        c3, c5, x1, x2 = (_as_nhwc(t) for t in inputs)
+        ctx = self._base_head_train(c5, self.head)
+        ctx = T.conv2d(ctx, self.conv_seg.weight, self.conv_seg.bias)           # cls_seg, decode_head.py:241-246
+        spa = self._base_head_train(c3, self.aux_head)
+        spa = T.conv2d(spa, self.aux_cls_seg.weight, self.aux_cls_seg.bias)
+        h1 = self._base_head_train(x1, self.head_x1)
+        h2 = self._base_head_train(x2, self.head_x2)
+        return tuple(_as_nchw_view(t) for t in (ctx, spa, h1, h2))
+
+    def loss(self, inputs, batch_data_samples, train_cfg=None):
+        """BaseDecodeHead.loss (decode_head.py:248-265)."""
+        return self.loss_by_feat(self.forward(inputs), batch_data_samples)
 
     def predict(self, inputs, batch_img_metas=None, test_cfg=None):
         return self.predict_by_feat(self.forward(inputs), batch_img_metas)
@@ -262,19 +367,20 @@ class LEDHead(_EngineOwner):
                             for s in batch_data_samples], dim=0)
 
     def loss_by_feat(self, seg_logits, batch_data_samples):
-        """led_head.py:101-146.  The OHEM loss + accuracy run in the CUDA kernel; the train-time
-        resize ladder still uses ATen's differentiable interpolate (its backward kernel is a
-        'next' row)."""
-        import torch.nn.functional as F
+        """led_head.py:101-146: two fused full-resolution logit maps (context, spatial), one OHEM loss
+        each plus the accuracy of the context map.  Resize ladder, adds, OHEM CE and accuracy all run
+        in the library's kernels (forward and backward)."""
+        from . import train_ops as T
         from .losses import accuracy
-        ctx, spa, h1, h2 = seg_logits
+        ctx, spa, h1, h2 = (_as_nhwc(t) for t in seg_logits)
         label = self._stack_batch_gt(batch_data_samples)
-        hw = label.shape[2:]
+        hw = tuple(label.shape[2:])
+        hw4, hw2 = tuple(s // 4 for s in hw), tuple(s // 2 for s in hw)
 
         def ladder(t):
-            t = h2 + F.interpolate(t, size=tuple(s // 4 for s in hw), mode='bilinear', align_corners=False)
-            t = h1 + F.interpolate(t, size=tuple(s // 2 for s in hw), mode='bilinear', align_corners=False)
-            return F.interpolate(t, size=tuple(hw), mode='bilinear', align_corners=False)
+            t = T.add(h2, T.resize(t, hw4))
+            t = T.add(h1, T.resize(t, hw2))
+            return T.to_nchw(T.resize(t, hw))
         ctx, spa = ladder(ctx), ladder(spa)
         label = label.squeeze(1)
         return dict(loss_context=self.loss_decode[0](ctx, label),

@@ -88,7 +88,40 @@ class EncoderDecoder(nn.Module):
 
     # -- reference API --------------------------------------------------------------------
     def extract_feat(self, inputs):
+        if self.training:
+            return self.backbone(inputs)            # train-mode tape over csrc/train.cu
         return self.engine().backbone_forward(inputs)
+
+    def train(self, mode=True):
+        if mode:
+            self.reset_engine()                     # folded eval weights go stale once training resumes
+        return super().train(mode)
+
+    def loss(self, inputs, data_samples):
+        """encoder_decoder.py:161-185: decode-head losses under the 'decode.' prefix."""
+        x = self.extract_feat(inputs)
+        out = self.decode_head.loss(x, data_samples, self.train_cfg)
+        return {'decode.' + k: v for k, v in out.items()}
+
+    @staticmethod
+    def parse_losses(losses):
+        """mmengine BaseModel.parse_losses: total = sum of every entry whose key contains 'loss'."""
+        log = {k: (v.mean() if isinstance(v, torch.Tensor) else sum(x.mean() for x in v))
+               for k, v in losses.items()}
+        total = sum(v for k, v in log.items() if 'loss' in k)
+        log['loss'] = total
+        return total, log
+
+    def train_step(self, data, optimizer):
+        """mmengine BaseModel.train_step: preprocess -> loss -> backward -> optimiser step.
+        `optimizer` is a lednet_b200.optim.FlatSGD (or any object with zero_grad()/step())."""
+        if self.data_preprocessor is not None and isinstance(data, dict) and 'inputs' in data:
+            data = self.data_preprocessor(data, training=True)
+        total, log = self.parse_losses(self.loss(data['inputs'], data['data_samples']))
+        optimizer.zero_grad()
+        total.backward()
+        optimizer.step()
+        return log
 
     def encode_decode(self, inputs, batch_img_metas=None):
         """encoder_decoder.py:124-132: full-resolution logits [N,K,H,W] (fused, one call)."""
@@ -157,4 +190,6 @@ class EncoderDecoder(nn.Module):
             return self.predict(inputs, data_samples)
         if mode == 'tensor':
             return self.decode_head.forward(self.extract_feat(inputs))
-        raise NotImplementedError("mode='loss' needs the backward kernels (SURVEY section 8a row T4)")
+        if mode == 'loss':
+            return self.loss(inputs, data_samples)
+        raise RuntimeError(f'Invalid mode "{mode}". Only supports loss, predict and tensor mode')

@@ -1,0 +1,299 @@
+"""torch.autograd.Function wrappers over the training kernels of libledb200 (csrc/train.cu).
+
+The reference trains through autograd over ATen/cuDNN ops (``EncoderDecoder.loss``,
+``mmseg/models/segmentors/encoder_decoder.py:161-185`` -> ``LEDHead.loss``,
+``decode_heads/led_head.py:101-146``).  Here every op of that graph is a hand-written kernel pair
+(forward, backward); PyTorch only records the tape, owns the memory and runs NCCL.
+
+Layout: activations are NHWC fp32 CUDA tensors ``[N,H,W,C]`` between these functions
+(``to_nhwc`` / ``to_nchw`` convert at the boundary to the reference's NCHW tensors);
+weights stay in the reference's OIHW state-dict layout.  There is no CPU fallback.
+"""
+import ctypes as C
+
+import torch
+
+from . import lib as L
+
+
+def _p(t):
+    return C.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def _chk(t, name='tensor'):
+    if not t.is_cuda:
+        raise L.LedB200Error(f'{name}: LED-Net B200 training ops need CUDA tensors (no CPU fallback)')
+    if t.dtype != torch.float32:
+        raise L.LedB200Error(f'{name}: training ops are fp32, got {t.dtype}')
+    return t.contiguous()
+
+
+def _st(t):
+    return L.stream_ptr(t.device)
+
+
+def _ws(dev, c):
+    return torch.empty(2 * c, dtype=torch.float64, device=dev)
+
+
+def _out_hw(h, w, k, s):
+    p = k // 2
+    return (h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1
+
+
+class _Layout(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, to_nhwc):
+        x = _chk(x, 'layout')
+        ctx.to_nhwc = to_nhwc
+        if to_nhwc:
+            n, c, h, w = x.shape
+            out = torch.empty((n, h, w, c), dtype=x.dtype, device=x.device)
+        else:
+            n, h, w, c = x.shape
+            out = torch.empty((n, c, h, w), dtype=x.dtype, device=x.device)
+        L.check(L.get().ledb200_train_layout(_p(x), _p(out), n, c, h, w, int(to_nhwc), _st(x)), 'train_layout')
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        return _Layout.apply(g, not ctx.to_nhwc), None
+
+
+def to_nhwc(x):
+    return _Layout.apply(x, True)
+
+
+def to_nchw(x):
+    return _Layout.apply(x, False)
+
+
+class _Conv(torch.autograd.Function):
+    """nn.Conv2d(k, stride, padding=k//2[, bias]) on NHWC activations."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride):
+        x, weight = _chk(x, 'conv input'), _chk(weight, 'conv weight')
+        lib = L.get()
+        n, h, w, cin = x.shape
+        cout, cin_w, k, _ = weight.shape
+        assert cin_w == cin, f'conv: input has {cin} channels, weight expects {cin_w}'
+        ho, wo = _out_hw(h, w, k, stride)
+        wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 0), dtype=torch.float32,
+                         device=x.device)
+        L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 0, _st(x)), 'train_pack_weight')
+        y = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device)
+        b = _chk(bias, 'conv bias') if bias is not None else None
+        L.check(lib.ledb200_train_conv_fwd(_p(x), _p(wp), _p(b), _p(y), n, h, w, cin, cout, k, stride, _st(x)),
+                'train_conv_fwd')
+        ctx.save_for_backward(x, weight)
+        ctx.stride, ctx.has_bias = stride, bias is not None
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = _chk(dy, 'conv grad')
+        lib = L.get()
+        n, h, w, cin = x.shape
+        cout, _, k, _ = weight.shape
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 1), dtype=torch.float32,
+                             device=x.device)
+            L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 1, _st(x)), 'train_pack_weight')
+            dx = torch.empty_like(x)
+            L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride, _st(x)),
+                    'train_conv_dgrad')
+        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(weight)
+            ws = None
+            if ctx.has_bias:
+                db = torch.empty(cout, dtype=torch.float32, device=x.device)
+                ws = _ws(x.device, cout)
+            L.check(lib.ledb200_train_conv_wgrad(_p(x), _p(dy), _p(dw), _p(db), n, h, w, cin, cout, k, ctx.stride,
+                                                 _p(ws), _st(x)), 'train_conv_wgrad')
+        return dx, dw, db, None
+
+
+def conv2d(x, weight, bias=None, stride=1):
+    return _Conv.apply(x, weight, bias, stride)
+
+
+class _BNAct(torch.autograd.Function):
+    """out = [relu](BatchNorm2d_train(y) [+ res]); running stats updated in place."""
+
+    @staticmethod
+    def forward(ctx, y, gamma, beta, res, running_mean, running_var, momentum, eps, relu):
+        y = _chk(y, 'bn input')
+        c = y.shape[-1]
+        npix = y.numel() // c
+        out = torch.empty_like(y)
+        mean = torch.empty(c, dtype=torch.float32, device=y.device)
+        invstd = torch.empty_like(mean)
+        r = _chk(res, 'bn residual') if res is not None else None
+        L.check(L.get().ledb200_train_bn_fwd(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
+                                             _p(running_mean), _p(running_var), float(momentum), float(eps),
+                                             int(relu), npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_fwd')
+        ctx.save_for_backward(y, out, gamma, mean, invstd)
+        ctx.relu, ctx.has_res = relu, res is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        y, out, gamma, mean, invstd = ctx.saved_tensors
+        dout = _chk(dout, 'bn grad')
+        c = y.shape[-1]
+        npix = y.numel() // c
+        dy = torch.empty_like(y)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        dres = None
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = torch.empty_like(y) if ctx.relu else dout
+        L.check(L.get().ledb200_train_bn_bwd(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
+                                             _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta), int(ctx.relu),
+                                             npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_bwd')
+        return dy, dgamma, dbeta, dres, None, None, None, None, None
+
+
+def bn_act(y, bn, res=None, relu=False):
+    """`bn`: an nn.BatchNorm2d in training mode (its running stats are updated like PyTorch does)."""
+    if bn.num_batches_tracked is not None:
+        bn.num_batches_tracked.add_(1)
+    return _BNAct.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+
+
+class _Resize(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, size):
+        x = _chk(x, 'resize input')
+        n, h, w, c = x.shape
+        H, W = int(size[0]), int(size[1])
+        out = torch.empty((n, H, W, c), dtype=torch.float32, device=x.device)
+        L.check(L.get().ledb200_train_resize_fwd(_p(x), _p(out), n, h, w, H, W, c, _st(x)), 'train_resize_fwd')
+        ctx.shape = (n, h, w, c, H, W)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, h, w, c, H, W = ctx.shape
+        dout = _chk(dout, 'resize grad')
+        dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
+        L.check(L.get().ledb200_train_resize_bwd(_p(dout), _p(dx), n, h, w, H, W, c, _st(dout)), 'train_resize_bwd')
+        return dx, None
+
+
+def resize(x, size):
+    """resize(mode='bilinear', align_corners=False) (mmseg/models/utils/wrappers.py:8-27)."""
+    return _Resize.apply(x, tuple(size))
+
+
+class _AddRelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b, relu):
+        a = _chk(a, 'add input')
+        bb = _chk(b, 'add input') if b is not None else None
+        if bb is not None:
+            assert a.shape == bb.shape, f'add: {tuple(a.shape)} vs {tuple(bb.shape)}'
+        out = torch.empty_like(a)
+        L.check(L.get().ledb200_train_add_relu(_p(a), _p(bb), _p(out), int(relu), a.numel(), _st(a)),
+                'train_add_relu')
+        ctx.relu, ctx.has_b = relu, b is not None
+        if relu:
+            ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _chk(dout, 'add grad')
+        if ctx.relu:
+            (out,) = ctx.saved_tensors
+            dx = torch.empty_like(out)
+            L.check(L.get().ledb200_train_relu_bwd(_p(dout), _p(out), _p(dx), out.numel(), _st(out)),
+                    'train_relu_bwd')
+        else:
+            dx = dout
+        return dx, (dx if ctx.has_b else None), None
+
+
+def add(a, b, relu=False):
+    return _AddRelu.apply(a, b, relu)
+
+
+def relu(x):
+    return _AddRelu.apply(x, None, True)
+
+
+class _AvgPool(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, k, s, p):
+        x = _chk(x, 'pool input')
+        n, h, w, c = x.shape
+        ho, wo = (1, 1) if k == 0 else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
+        out = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+        L.check(L.get().ledb200_train_avgpool_fwd(_p(x), _p(out), n, h, w, c, ho, wo, k, s, p, _st(x)),
+                'train_avgpool_fwd')
+        ctx.cfg = (n, h, w, c, ho, wo, k, s, p)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        n, h, w, c, ho, wo, k, s, p = ctx.cfg
+        dout = _chk(dout, 'pool grad')
+        dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
+        L.check(L.get().ledb200_train_avgpool_bwd(_p(dout), _p(dx), n, h, w, c, ho, wo, k, s, p, _st(dout)),
+                'train_avgpool_bwd')
+        return dx, None, None, None
+
+
+def avg_pool(x, k, s, p):
+    """nn.AvgPool2d(k, s, p); k == 0 means nn.AdaptiveAvgPool2d((1, 1))."""
+    return _AvgPool.apply(x, k, s, p)
+
+
+class _Cat(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, *xs):
+        xs = [_chk(x, 'cat input') for x in xs]
+        n, h, w, _ = xs[0].shape
+        cs = [x.shape[-1] for x in xs]
+        out = torch.empty((n, h, w, sum(cs)), dtype=torch.float32, device=xs[0].device)
+        off = 0
+        for x, c in zip(xs, cs):
+            L.check(L.get().ledb200_train_copy_channels(_p(x), c, 0, _p(out), sum(cs), off, n * h * w, c, _st(x)),
+                    'train_copy_channels')
+            off += c
+        ctx.cs = cs
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        dout = _chk(dout, 'cat grad')
+        n, h, w, ct = dout.shape
+        outs, off = [], 0
+        for c in ctx.cs:
+            d = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
+            L.check(L.get().ledb200_train_copy_channels(_p(dout), ct, off, _p(d), c, 0, n * h * w, c, _st(dout)),
+                    'train_copy_channels')
+            outs.append(d)
+            off += c
+        return tuple(outs)
+
+
+def cat_channels(xs):
+    """torch.cat(xs, dim=1) of the reference (channels are the last axis here)."""
+    return _Cat.apply(*xs)
+
+
+# ---- module-level helpers mirroring mmcv's ConvModule orders ---------------------------------------
+def conv_module(x, m, relu=False, res=None):
+    """ConvModule order ('conv','norm','act'): conv -> BN (+ residual) -> optional ReLU.
+    `m` holds `.conv` (nn.Conv2d) and `.bn` (nn.BatchNorm2d)."""
+    y = conv2d(x, m.conv.weight, m.conv.bias, m.conv.stride[0])
+    return bn_act(y, m.bn, res=res, relu=relu)
+
+
+def pre_conv_module(x, m):
+    """ConvModule order ('norm','act','conv') (led_head.py:94, ppm.py:42-43): BN -> ReLU -> conv."""
+    return conv2d(bn_act(x, m.bn, relu=True), m.conv.weight, m.conv.bias, m.conv.stride[0])

@@ -1,0 +1,228 @@
+"""GPU parity of the training step: every forward/backward kernel of
+csrc/train.cu against ATen's CPU autograd, then the whole step (loss dict, every parameter gradient,
+BatchNorm running statistics, SGD update) against the CPU oracle in train mode.
+Gate (north_star): loss and gradients within 1e-2 relative error; the fp32 kernels are held to 1e-3."""
+import warnings
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import oracle
+import lednet_b200 as L
+from lednet_b200 import synth, train_ops as T
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def nhwc(t):
+    return t.permute(0, 2, 3, 1).contiguous().to(DEV)
+
+
+def nchw(t):
+    return t.permute(0, 3, 1, 2).cpu()
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,hw,bias', [
+    (3, 32, 3, 2, (34, 50), False), (32, 32, 3, 1, (20, 36), False), (32, 64, 3, 2, (24, 40), False),
+    (32, 64, 3, 2, (23, 41), False), (64, 19, 1, 1, (9, 13), True), (64, 128, 1, 2, (16, 24), False),
+    (64, 128, 1, 2, (15, 25), False), (32, 19, 3, 1, (17, 33), False), (128, 64, 3, 1, (8, 16), False),
+    (640, 128, 1, 1, (4, 8), False), (512, 128, 1, 1, (1, 1), False)])
+def test_conv_fwd_bwd(cin, cout, k, stride, hw, bias):
+    g = torch.Generator().manual_seed(cin * 131 + cout + k)
+    x = torch.randn(2, cin, *hw, generator=g, requires_grad=True)
+    w = (torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5).requires_grad_()
+    b = (torch.randn(cout, generator=g) * 0.1).requires_grad_() if bias else None
+    ref = F.conv2d(x, w, b, stride, k // 2)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    xd = nhwc(x.detach()).requires_grad_()
+    wd = w.detach().to(DEV).requires_grad_()
+    bd = b.detach().to(DEV).requires_grad_() if bias else None
+    out = T.conv2d(xd, wd, bd, stride)
+    out.backward(nhwc(dy))
+    assert rel_err(nchw(out.detach()), ref.detach()) < 1e-5
+    assert rel_err(nchw(xd.grad), x.grad) < 1e-5
+    assert rel_err(wd.grad.cpu(), w.grad) < 1e-4
+    if bias:
+        assert rel_err(bd.grad.cpu(), b.grad) < 1e-5
+
+
+@pytest.mark.parametrize('c,hw,relu,res', [(32, (20, 36), True, True), (19, (17, 9), True, False),
+                                            (64, (8, 8), False, True), (640, (2, 3), True, False),
+                                            (128, (1, 1), True, False)])
+def test_bn_act(c, hw, relu, res):
+    g = torch.Generator().manual_seed(c)
+    bn = torch.nn.BatchNorm2d(c)
+    with torch.no_grad():
+        bn.weight.copy_(torch.rand(c, generator=g) + 0.5)
+        bn.bias.copy_(torch.randn(c, generator=g) * 0.1)
+        bn.running_mean.copy_(torch.randn(c, generator=g) * 0.1)
+        bn.running_var.copy_(torch.rand(c, generator=g) + 0.5)
+    import copy
+    bnd = copy.deepcopy(bn).to(DEV)
+    y = (torch.randn(3, c, *hw, generator=g) * 2 + 0.5).requires_grad_()
+    r = torch.randn(3, c, *hw, generator=g).requires_grad_() if res else None
+    ref = bn(y)
+    if res:
+        ref = ref + r
+    if relu:
+        ref = F.relu(ref)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    yd = nhwc(y.detach()).requires_grad_()
+    rd = nhwc(r.detach()).requires_grad_() if res else None
+    out = T.bn_act(yd, bnd, res=rd, relu=relu)
+    out.backward(nhwc(dout))
+    assert rel_err(nchw(out.detach()), ref.detach()) < 1e-5
+    assert rel_err(nchw(yd.grad), y.grad) < 2e-4
+    assert rel_err(bnd.weight.grad.cpu(), bn.weight.grad) < 1e-4
+    assert rel_err(bnd.bias.grad.cpu(), bn.bias.grad) < 1e-4
+    if res:
+        assert rel_err(nchw(rd.grad), r.grad) < 1e-6
+    assert rel_err(bnd.running_mean.cpu(), bn.running_mean) < 1e-5
+    assert rel_err(bnd.running_var.cpu(), bn.running_var) < 1e-5
+    assert int(bnd.num_batches_tracked) == int(bn.num_batches_tracked)
+
+
+@pytest.mark.parametrize('c,src,dst', [(19, (8, 16), (16, 32)), (64, (4, 8), (32, 64)), (128, (2, 4), (16, 32)),
+                                       (19, (13, 7), (50, 27)), (128, (1, 1), (2, 4)), (3, (9, 9), (5, 4))])
+def test_resize(c, src, dst):
+    g = torch.Generator().manual_seed(c + src[0])
+    x = torch.randn(2, c, *src, generator=g, requires_grad=True)
+    ref = F.interpolate(x, size=dst, mode='bilinear', align_corners=False)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    xd = nhwc(x.detach()).requires_grad_()
+    out = T.resize(xd, dst)
+    out.backward(nhwc(dout))
+    assert rel_err(nchw(out.detach()), ref.detach()) < 1e-6
+    assert rel_err(nchw(xd.grad), x.grad) < 1e-5
+
+
+@pytest.mark.parametrize('k,s,p,hw', [(5, 2, 2, (16, 32)), (9, 4, 4, (16, 32)), (17, 8, 8, (16, 32)),
+                                      (0, 1, 0, (16, 32)), (5, 2, 2, (7, 9)), (17, 8, 8, (3, 5)), (9, 4, 4, (2, 2))])
+def test_avgpool(k, s, p, hw):
+    g = torch.Generator().manual_seed(k + hw[0])
+    x = torch.randn(2, 24, *hw, generator=g, requires_grad=True)
+    ref = F.adaptive_avg_pool2d(x, 1) if k == 0 else F.avg_pool2d(x, k, s, p)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    xd = nhwc(x.detach()).requires_grad_()
+    out = T.avg_pool(xd, k, s, p)
+    out.backward(nhwc(dout))
+    assert rel_err(nchw(out.detach()), ref.detach()) < 1e-5
+    assert rel_err(nchw(xd.grad), x.grad) < 1e-5
+
+
+def test_add_relu_cat_layout():
+    g = torch.Generator().manual_seed(5)
+    a = torch.randn(2, 19, 5, 7, generator=g, requires_grad=True)
+    b = torch.randn(2, 19, 5, 7, generator=g, requires_grad=True)
+    c = torch.randn(2, 8, 5, 7, generator=g, requires_grad=True)
+    ref = torch.cat([F.relu(a + b), a + b, F.relu(c)], 1)
+    dout = torch.randn(ref.shape, generator=g)
+    ref.backward(dout)
+    ad, bd, cd = (t.detach().to(DEV).requires_grad_() for t in (a, b, c))
+    an, bn_, cn = T.to_nhwc(ad), T.to_nhwc(bd), T.to_nhwc(cd)
+    out = T.to_nchw(T.cat_channels([T.add(an, bn_, relu=True), T.add(an, bn_), T.relu(cn)]))
+    out.backward(dout.to(DEV))
+    assert torch.equal(out.detach().cpu(), ref.detach())
+    for got, want in ((ad, a), (bd, b), (cd, c)):
+        assert rel_err(got.grad.cpu(), want.grad) < 1e-6
+
+
+def _train_pair(K, channels=32, seed=2):
+    torch.manual_seed(0)
+    loss_cfg = [dict(thres=0.9, min_kept=4096, loss_weight=1.0), dict(thres=0.9, min_kept=4096, loss_weight=0.4)]
+    o = oracle.OracleSegmentor(num_classes=K, channels=channels)
+    o.decode_head.loss_decode = loss_cfg
+    sd = synth.make_state_dict(o.state_dict(), seed=seed)
+    o.load_state_dict(sd)
+    o.train()
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(
+            dict(type='LEDNet', channels=channels),
+            dict(type='LEDHead', in_channels=4 * channels, channels=64, num_classes=K, dropout_ratio=0.,
+                 tap_channels=channels,
+                 loss_decode=[dict(type='OhemCrossEntropy', **c) for c in loss_cfg]),
+            data_preprocessor=None, compute_dtype='fp32')
+    m.load_state_dict(sd, strict=True)
+    m.to(DEV).train()
+    return o, m
+
+
+@pytest.mark.parametrize('K,hw', [(19, (128, 256)), (2, (96, 160))])
+def test_train_step_vs_oracle(K, hw):
+    o, m = _train_pair(K)
+    N = 2
+    x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0))
+    lab = synth.make_labels(N, *hw, K, seed=1)
+    # ---- oracle: loss, gradients, two SGD steps
+    opt_o = torch.optim.SGD(o.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    ref = o.loss(x, lab)
+    total_ref = ref['loss_context'] + ref['loss_spatial']
+    opt_o.zero_grad()
+    total_ref.backward()
+    ref_grads = {k: p.grad.clone() for k, p in o.named_parameters()}
+    # ---- product
+    opt = L.FlatSGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(N)]
+    losses = m.loss(x.to(DEV), samples)
+    total, log = m.parse_losses(losses)
+    opt.zero_grad()
+    total.backward()
+    torch.cuda.synchronize()
+    assert abs(float(losses['decode.loss_context']) - float(ref['loss_context'])) < 1e-3 * abs(float(ref['loss_context']))
+    assert abs(float(losses['decode.loss_spatial']) - float(ref['loss_spatial'])) < 1e-3 * abs(float(ref['loss_spatial']))
+    assert abs(float(losses['decode.acc_seg']) - float(ref['acc_seg'])) < 1e-2
+    worst = 0.0
+    got = dict(m.named_parameters())
+    assert set(got) == set(ref_grads)
+    for k, gr in ref_grads.items():
+        e = rel_err(got[k].grad.cpu(), gr)
+        worst = max(worst, e)
+        assert e < 1e-2, (k, e)
+    print(f'worst parameter-gradient rel err {worst:.2e}')
+    # BatchNorm running statistics moved identically
+    bufs_o = dict(o.named_buffers())
+    for k, b in m.named_buffers():
+        if k.endswith('running_mean') or k.endswith('running_var'):
+            assert rel_err(b.cpu(), bufs_o[k]) < 1e-4, k
+    # ---- SGD update parity over two steps (second step exercises the momentum buffer)
+    opt_o.step()
+    opt.step()
+    for _ in range(1):
+        ref = o.loss(x, lab)
+        opt_o.zero_grad()
+        (ref['loss_context'] + ref['loss_spatial']).backward()
+        opt_o.step()
+        log = m.train_step(dict(inputs=x.to(DEV), data_samples=samples), opt)
+    torch.cuda.synchronize()
+    po = dict(o.named_parameters())
+    for k, p in m.named_parameters():
+        assert rel_err(p.detach().cpu(), po[k].detach()) < 1e-3, k
+    assert abs(float(log['loss']) - float(ref['loss_context'] + ref['loss_spatial'])) < 1e-2 * abs(float(log['loss']))
+
+
+def test_eval_after_train_uses_updated_weights():
+    """the folded inference engine must be rebuilt from the trained parameters."""
+    o, m = _train_pair(3)
+    x = oracle.preprocess(synth.make_images_u8(2, 64, 128, seed=3))
+    lab = synth.make_labels(2, 64, 128, 3, seed=4)
+    samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(2)]
+    opt = L.FlatSGD(m.parameters(), lr=0.05)
+    m.eval()
+    before = m.encode_decode(x.to(DEV)).clone()
+    m.train()
+    m.train_step(dict(inputs=x.to(DEV), data_samples=samples), opt)
+    m.eval()
+    after = m.encode_decode(x.to(DEV))
+    assert not torch.allclose(before, after)
+    o.load_state_dict({k: v.cpu() for k, v in m.state_dict().items()})
+    o.eval()
+    ref, _ = o.predict(x)
+    assert rel_err(after.cpu(), ref) < 1e-4

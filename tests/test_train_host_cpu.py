@@ -1,0 +1,84 @@
+"""CPU-side checks of the training host logic: flat parameter arena, the DDP gradient all-reduce over
+gloo (world_size 2), PolyLR against mmengine's closed form, and that training ops refuse CPU tensors."""
+import os
+import warnings
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import lednet_b200 as L
+from lednet_b200 import train_ops as T
+
+
+def test_train_ops_refuse_cpu_tensors():
+    with pytest.raises(L.LedB200Error):
+        T.conv2d(torch.zeros(1, 4, 4, 3), torch.zeros(8, 3, 3, 3))
+    with pytest.raises(L.LedB200Error):
+        T.resize(torch.zeros(1, 4, 4, 3), (8, 8))
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64,
+                                                       num_classes=2, dropout_ratio=0.)).train()
+    with pytest.raises(L.LedB200Error):
+        m.loss(torch.zeros(1, 3, 64, 64), [dict(gt_sem_seg=dict(data=torch.zeros(1, 64, 64, dtype=torch.int64)))])
+
+
+def test_flat_arena_views_and_zero_grad():
+    lin = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+    before = [p.detach().clone() for p in lin.parameters()]
+    opt = L.FlatSGD(lin.parameters(), lr=0.1, world_size=1)
+    assert opt.flat.numel() == sum(p.numel() for p in lin.parameters())
+    for p, b in zip(lin.parameters(), before):
+        assert torch.equal(p.detach(), b)
+        assert p.data_ptr() >= opt.flat.data_ptr() and p.grad.data_ptr() >= opt.flat_grad.data_ptr()
+    lin(torch.randn(2, 3, 8, 8)).sum().backward()          # autograd accumulates INTO the flat buffer
+    assert float(opt.flat_grad.abs().sum()) > 0
+    opt.zero_grad()
+    assert float(opt.flat_grad.abs().sum()) == 0
+    with pytest.raises(L.LedB200Error):                     # the update kernel is CUDA only
+        opt.step()
+
+
+def test_poly_lr_closed_form():
+    class O:
+        lr = 0.01
+    s = L.PolyLR(O(), power=0.9, eta_min=1e-4, begin=0, end=80000)
+    assert abs(s.lr_at(0) - 0.01) < 1e-12
+    assert abs(s.lr_at(80000) - 1e-4) < 1e-12
+    assert abs(s.lr_at(40000) - ((0.01 - 1e-4) * 0.5 ** 0.9 + 1e-4)) < 1e-12
+    s.step()
+    assert abs(s.opt.lr - s.lr_at(1)) < 1e-15
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    torch.manual_seed(0)
+    net = torch.nn.Conv2d(2, 3, 3)
+    opt = L.FlatSGD(net.parameters(), lr=0.1)
+    assert opt.world_size == world
+    opt.zero_grad()
+    x = torch.full((1, 2, 5, 5), float(rank + 1))
+    net(x).sum().backward()
+    local = opt.flat_grad.clone()
+    opt.all_reduce_grads()
+    q.put((rank, local, opt.flat_grad.clone()))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_flat_gradient_allreduce_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    total = got[0][1] + got[1][1]
+    assert torch.allclose(got[0][2], total) and torch.allclose(got[1][2], total)
