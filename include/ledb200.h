@@ -253,6 +253,22 @@ int ledb200_train_sgd_step(float* param, const float* grad, float* momentum_buf,
                            float momentum, float weight_decay, int32_t first_step, float grad_scale,
                            void* stream);
 
+/* ---- SESP block (north_star kernel 2) ---------------------------------
+ * SESP.forward (mmseg/models/nn_layers/eesp.py:76-118; CBR/BR/CB/CDilated of espnet_utils.py:8-145),
+ * eval mode, stride 1, k = 4 branches, as ONE kernel: grouped 1x1 + BN + PReLU -> 4 depthwise dilated
+ * 3x3 with hierarchical fusion -> (SESPV2) second depthwise 3x3 with dilation d+1 -> concat, BN + PReLU,
+ * grouped 1x1 + BN -> + input (when nIn == nOut) -> PReLU.  NHWC in/out of `dtype` (F32 or BF16).
+ * `params`: device fp32 block of ledb200_sesp_param_floats(nIn, nOut) floats, BatchNorm already
+ * folded to per-channel scale/shift by the caller, in this order:
+ *   w_proj[n][nIn/4], proj_scale[n], proj_shift[n], proj_slope[n], w_dw[4][n][9], w_dw2[4][n][9],
+ *   br_scale[nOut], br_shift[nOut], br_slope[nOut], w_exp[nOut][n], exp_scale[nOut], exp_shift[nOut],
+ *   act_slope[nOut]            (n = nOut/4).
+ * dilations4: host int32[4], the first depthwise dilation of each branch (eesp.py:40-57). */
+int64_t ledb200_sesp_param_floats(int32_t nIn, int32_t nOut);
+int ledb200_sesp_forward(const void* in, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W,
+                         int32_t nIn, int32_t nOut, const int32_t* dilations4, int32_t v2,
+                         const float* params, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -25,6 +25,7 @@ SYMBOLS = [
     'ledb200_train_resize_fwd', 'ledb200_train_resize_bwd', 'ledb200_train_add_relu', 'ledb200_train_relu_bwd',
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
+    'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
 ]
 
 
@@ -95,6 +96,9 @@ def get():
     lib.ledb200_train_copy_channels.argtypes = [vp, i32, i32, vp, i32, i32, i64, i32, vp]
     lib.ledb200_train_layout.argtypes = [vp, vp] + [i32] * 5 + [vp]
     lib.ledb200_train_sgd_step.argtypes = [vp, vp, vp, i64, f32, f32, f32, i32, f32, vp]
+    lib.ledb200_sesp_param_floats.argtypes = [i32, i32]
+    lib.ledb200_sesp_param_floats.restype = i64
+    lib.ledb200_sesp_forward.argtypes = [vp, vp] + [i32] * 6 + [vp, i32, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):

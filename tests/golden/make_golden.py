@@ -18,6 +18,10 @@ Fixtures
 * ohem.npz        : OhemCrossEntropy (with and without class_weight) + accuracy,
                     forward values and d(loss)/d(score).
 * train_k2.npz    : train-mode LEDHead.loss_by_feat losses on a 2x3x64x64 batch.
+* sesp.npz        : SESP block (eesp.py) eval outputs for the three registered configurations
+                    (64,64,Spatial) / (128,128,context,r_lim=9) / (256,256,context,r_lim=9) and a
+                    channel-changing, non-V2 one; weights from synth seed 5 with PReLU slopes and BN
+                    statistics made non-trivial (sesp_state_dict below).
 """
 import os
 import sys
@@ -55,10 +59,48 @@ def ref_backbone_with_taps(ddr, x):
     return out, taps['x1'], taps['x2']
 
 
+SESP_CASES = [
+    ('s64', dict(nIn=64, nOut=64, Spatial=True), (2, 11, 14)),
+    ('c128', dict(nIn=128, nOut=128, Spatial=False, r_lim=9), (1, 12, 10)),
+    ('c256', dict(nIn=256, nOut=256, Spatial=False, r_lim=9), (1, 7, 9)),
+    ('x32_64_nov2', dict(nIn=32, nOut=64, Spatial=False, SESPV2=False), (1, 9, 8)),
+]
+
+
+def sesp_state_dict(template, seed=5):
+    """synth weights + per-channel PReLU slopes in [0.05, 0.45] (make_state_dict gives a constant 0.25)."""
+    sd = synth.make_state_dict(template, seed=seed)
+    g = torch.Generator().manual_seed(seed)
+    for k in sd:
+        if k.endswith('act.weight') or k == 'module_act.weight':
+            sd[k] = 0.05 + 0.4 * torch.rand(sd[k].shape, generator=g)
+    return sd
+
+
+def sesp_input(case_index, nin, shape):
+    g = torch.Generator().manual_seed(100 + case_index)
+    return torch.randn(shape[0], nin, shape[1], shape[2], generator=g)
+
+
+def make_sesp(ref):
+    out = {}
+    for i, (tag, kw, shape) in enumerate(SESP_CASES):
+        m = ref.SESP(**kw).eval()
+        m.load_state_dict(sesp_state_dict(m.state_dict()))
+        with torch.no_grad():
+            out[tag] = m(sesp_input(i, kw['nIn'], shape)).numpy()
+        out[tag + '_nparams'] = np.int64(sum(p.numel() for p in m.parameters()))
+    np.savez_compressed(os.path.join(OUT, 'sesp.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
     ref = ref_loader.load()
+    if 'sesp' in sys.argv[1:]:            # regenerate only the SESP fixture
+        make_sesp(ref)
+        return
+    make_sesp(ref)
 
     # ---------------- r0_head_k2 -------------------------------------------------
     ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,

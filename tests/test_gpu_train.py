@@ -155,19 +155,30 @@ def _train_pair(K, channels=32, seed=2):
     return o, m
 
 
-@pytest.mark.parametrize('K,hw', [(19, (128, 256)), (2, (96, 160))])
-def test_train_step_vs_oracle(K, hw):
+def _oracle_grads(o, x, lab):
+    ref = o.loss(x, lab)
+    o.zero_grad()
+    (ref['loss_context'] + ref['loss_spatial']).backward()
+    return ref, {k: p.grad.detach().clone() for k, p in o.named_parameters()}
+
+
+@pytest.mark.parametrize('K,hw,N', [(19, (128, 256), 2), (2, (192, 320), 3)])
+def test_train_step_vs_oracle(K, hw, N):
+    """Loss and every parameter gradient against the oracle in train mode.
+
+    Conditioning: train-mode BatchNorm backward subtracts per-channel means of the incoming gradient
+    (catastrophic cancellation), so on this network the reference's OWN fp32 run deviates from its
+    float64 run by up to 3e-2 on a few tensors (measured: tools/debug_train_grads.py).  The gate is
+    therefore taken against the float64 oracle: per tensor, err <= max(1e-2, 3 x the fp32 oracle's own
+    error against float64), plus an absolute floor for gradients that are analytically zero (a BN bias
+    directly in front of another train-mode BN)."""
     o, m = _train_pair(K)
-    N = 2
     x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0))
     lab = synth.make_labels(N, *hw, K, seed=1)
-    # ---- oracle: loss, gradients, two SGD steps
-    opt_o = torch.optim.SGD(o.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-    ref = o.loss(x, lab)
-    total_ref = ref['loss_context'] + ref['loss_spatial']
-    opt_o.zero_grad()
-    total_ref.backward()
-    ref_grads = {k: p.grad.clone() for k, p in o.named_parameters()}
+    ref, ref_grads = _oracle_grads(o, x, lab)                       # fp32 reference path
+    o64, _ = _train_pair(K)
+    o64 = o64.double()
+    ref64, ref_grads64 = _oracle_grads(o64, x.double(), lab)        # float64 reference path
     # ---- product
     opt = L.FlatSGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
     samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(N)]
@@ -176,36 +187,45 @@ def test_train_step_vs_oracle(K, hw):
     opt.zero_grad()
     total.backward()
     torch.cuda.synchronize()
-    assert abs(float(losses['decode.loss_context']) - float(ref['loss_context'])) < 1e-3 * abs(float(ref['loss_context']))
-    assert abs(float(losses['decode.loss_spatial']) - float(ref['loss_spatial'])) < 1e-3 * abs(float(ref['loss_spatial']))
+    for k in ('loss_context', 'loss_spatial'):
+        assert abs(float(losses['decode.' + k].detach()) - float(ref64[k])) < 1e-4 * abs(float(ref64[k])), k
     assert abs(float(losses['decode.acc_seg']) - float(ref['acc_seg'])) < 1e-2
-    worst = 0.0
     got = dict(m.named_parameters())
     assert set(got) == set(ref_grads)
-    for k, gr in ref_grads.items():
-        e = rel_err(got[k].grad.cpu(), gr)
-        worst = max(worst, e)
-        assert e < 1e-2, (k, e)
-    print(f'worst parameter-gradient rel err {worst:.2e}')
+    gscale = max(float(g.abs().max()) for g in ref_grads64.values())
+    worst, worst_ref, n_loose = 0.0, 0.0, 0
+    for k, g64 in ref_grads64.items():
+        floor = 1e-6 * gscale
+        mine = float((got[k].grad.cpu().double() - g64).abs().max())
+        theirs = float((ref_grads[k].double() - g64).abs().max())
+        den = max(float(g64.abs().max()), 1e-30)
+        if mine <= floor:
+            continue
+        worst, worst_ref = max(worst, mine / den), max(worst_ref, theirs / den)
+        bound = max(1e-2, 3 * theirs / den)
+        n_loose += bound > 1e-2
+        assert mine / den <= bound, (k, mine / den, theirs / den)
+    print(f'worst gradient rel err vs float64 oracle: ours {worst:.2e}, fp32 oracle {worst_ref:.2e}; '
+          f'{n_loose} tensors needed the conditioning allowance')
+    assert n_loose <= 8
     # BatchNorm running statistics moved identically
     bufs_o = dict(o.named_buffers())
     for k, b in m.named_buffers():
         if k.endswith('running_mean') or k.endswith('running_var'):
             assert rel_err(b.cpu(), bufs_o[k]) < 1e-4, k
-    # ---- SGD update parity over two steps (second step exercises the momentum buffer)
+    # ---- SGD update parity over two steps (the second exercises the momentum buffer)
+    opt_o = torch.optim.SGD(o.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
     opt_o.step()
     opt.step()
-    for _ in range(1):
-        ref = o.loss(x, lab)
-        opt_o.zero_grad()
-        (ref['loss_context'] + ref['loss_spatial']).backward()
-        opt_o.step()
-        log = m.train_step(dict(inputs=x.to(DEV), data_samples=samples), opt)
+    ref2, _ = _oracle_grads(o, x, lab)
+    opt_o.step()
+    log = m.train_step(dict(inputs=x.to(DEV), data_samples=samples), opt)
     torch.cuda.synchronize()
     po = dict(o.named_parameters())
     for k, p in m.named_parameters():
-        assert rel_err(p.detach().cpu(), po[k].detach()) < 1e-3, k
-    assert abs(float(log['loss']) - float(ref['loss_context'] + ref['loss_spatial'])) < 1e-2 * abs(float(log['loss']))
+        assert rel_err(p.detach().cpu(), po[k].detach()) < 2e-3, k
+    tot2 = float(ref2['loss_context'] + ref2['loss_spatial'])
+    assert abs(float(log['loss'].detach()) - tot2) < 1e-2 * abs(tot2)
 
 
 def test_eval_after_train_uses_updated_weights():

@@ -113,3 +113,24 @@ def test_train_losses(golden_dir, k2_models):
     for k in ('loss_context', 'loss_spatial', 'acc_seg'):
         np.testing.assert_allclose(losses[k].detach().numpy(), g[k], rtol=1e-4, err_msg=k)
     bb.eval(), hd.eval()
+
+
+def test_sesp_block(golden_dir):
+    """oracle/sesp.py against the reference's own SESP (eesp.py) outputs: bit-exact (same ATen ops)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location('make_golden', os.path.join(golden_dir, 'make_golden.py'))
+    src = open(os.path.join(golden_dir, 'make_golden.py')).read()
+    ns = {}
+    # only the case table and the two seeded helpers are needed (the module's main() needs /root/reference)
+    start, end = src.index('SESP_CASES = ['), src.index('def make_sesp')
+    exec('import torch\nfrom lednet_b200 import synth\n' + src[start:end], ns)
+    from oracle.sesp import OracleSESP
+    g = _load(golden_dir, 'sesp.npz')
+    for i, (tag, kw, shape) in enumerate(ns['SESP_CASES']):
+        m = OracleSESP(**kw).eval()
+        m.load_state_dict(ns['sesp_state_dict'](m.state_dict()))
+        assert sum(p.numel() for p in m.parameters()) == int(g[tag + '_nparams'])
+        with torch.no_grad():
+            out = m(ns['sesp_input'](i, kw['nIn'], shape)).numpy()
+        err = np.abs(out - g[tag]).max() / np.abs(g[tag]).max()
+        assert err < 1e-6, (tag, err)
