@@ -1,6 +1,7 @@
 // Shared helpers for libledb200 (sm_100a only).
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -52,6 +53,15 @@ __device__ __forceinline__ void load8(const __nv_bfloat16* p, float v[8]) {
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     float2 f = __bfloat1622float2(h[i]);
+    v[2 * i] = f.x; v[2 * i + 1] = f.y;
+  }
+}
+__device__ __forceinline__ void load8(const __half* p, float v[8]) {
+  uint4 u = __ldg(reinterpret_cast<const uint4*>(p));
+  const __half2* h = reinterpret_cast<const __half2*>(&u);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = __half22float2(h[i]);
     v[2 * i] = f.x; v[2 * i + 1] = f.y;
   }
 }

@@ -67,6 +67,7 @@ struct TcParams {
   uint32_t stage_bytes;              // epilogue staging: 32 KB (+32 KB with a second output)
   int step1[4], step2[4];            // grid and 2*grid tiles as digits (n-tile, tile col, tile row, image)
   uint32_t tmem_cols;
+  int nst;                           // accumulator stages in TMEM: 4 when 4*NT <= 512 columns, else 2
   // epilogue
   __nv_bfloat16* out; int out_ld;
   __nv_bfloat16* out2; int out2_ld;
@@ -74,6 +75,10 @@ struct TcParams {
   const __nv_bfloat16* res; int res_ld;
   const float* bias;
   int relu;
+  // optional: out += bilinear x2 upsample (align_corners=False) of `up` [N, up_h, up_w, up_ld], added AFTER the ReLU
+  const __nv_bfloat16* up; int up_ld, up_h, up_w;
+  int up_f16, out_f16;               // ladder rungs are kept in fp16 (11-bit mantissa; logits are far inside its range)
+  int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads
 };
 
 using namespace tc;   // PTX wrappers: tc_common.cuh
@@ -104,7 +109,7 @@ __device__ __forceinline__ float4 lds128f(uint32_t addr) {
 // The second output relu(s*y + b) (pre-activation BN+ReLU of the consumer) goes through its own
 // staging tile.  Templated on which tensors exist so the hot loop has no per-element branches; ReLU is
 // a max against 0 or -inf.
-template <bool HAS_RES, bool HAS_OUT, bool HAS_OUT2>
+template <bool HAS_RES, bool HAS_OUT, bool HAS_OUT2, bool HAS_UP>
 __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int lane, uint32_t tmem_base,
                                               uint64_t* t_full, uint64_t* t_empty, uint32_t st_u, uint32_t bias_u,
                                               uint32_t o2s_u, uint32_t o2b_u) {
@@ -147,6 +152,46 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
     __nv_bfloat16* out_t = HAS_OUT ? P.out + pix0 * P.out_ld + cgt : nullptr;
     __nv_bfloat16* out2_t = HAS_OUT2 ? P.out2 + pix0 * P.out2_ld + cgt : nullptr;
     const int rows_ok = Ho - th * TH - q * 4, cols_ok = Wo - tw * TW;      // valid rows (of this warp's 4) / cols
+    // operand prefetch (residual / up-add corners) for one 32-column block; issued BEFORE the accumulator
+    // wait for the first block and one block ahead afterwards, so the L2 latency hides behind the MMAs
+    uint4 rr[4];
+    bool rv[4];
+    uint4 uu[HAS_UP ? 3 : 1][4];
+    bool uv[3];
+    float uwx = 0.f, uwy = 0.f;
+    const __nv_bfloat16 *u00 = nullptr, *u01 = nullptr, *u10 = nullptr, *u11 = nullptr;
+    if (HAS_UP) {
+      int y0, y1, x0, x1;
+      float l0;
+      bilinear_coord(min(th * TH + ph, Ho - 1), 0.5f, P.up_h, y0, y1, l0, uwy);
+      bilinear_coord(min(tw * TW + pw, Wo - 1), 0.5f, P.up_w, x0, x1, l0, uwx);
+      const __nv_bfloat16* ub = P.up + (int64_t)n * P.up_h * P.up_w * P.up_ld + cgt;
+      u00 = ub + (y0 * P.up_w + x0) * P.up_ld; u01 = ub + (y0 * P.up_w + x1) * P.up_ld;
+      u10 = ub + (y1 * P.up_w + x0) * P.up_ld; u11 = ub + (y1 * P.up_w + x1) * P.up_ld;
+    }
+    auto prefetch = [&](int c0) {
+      const int ncol = min(32, cend - c0);
+      if (HAS_RES) {
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          rv[g] = pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < cout8) && !(P.dbg & 8);
+          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 8 * g));
+        }
+      }
+      if (HAS_UP) {
+#pragma unroll
+        for (int g = 0; g < 3; ++g) {
+          uv[g] = pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < P.up_ld);
+          if (uv[g]) {
+            uu[g][0] = __ldg(reinterpret_cast<const uint4*>(u00 + c0 + 8 * g));
+            uu[g][1] = __ldg(reinterpret_cast<const uint4*>(u01 + c0 + 8 * g));
+            uu[g][2] = __ldg(reinterpret_cast<const uint4*>(u10 + c0 + 8 * g));
+            uu[g][3] = __ldg(reinterpret_cast<const uint4*>(u11 + c0 + 8 * g));
+          }
+        }
+      }
+    };
+    prefetch(cbeg);
     mbar_wait(&t_full[ts], tp);
     tc_fence_after();
     const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
@@ -155,15 +200,6 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
       uint32_t v[32];
       tc_ld16(taddr0 + c0, v);
       if (ncol == 32) tc_ld16(taddr0 + c0 + 16, v + 16);
-      uint4 rr[4];
-      bool rv[4];
-      if (HAS_RES) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          rv[g] = pvalid && (8 * g < ncol) && (cgt + c0 + 8 * g < cout8);
-          if (rv[g]) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 8 * g));
-        }
-      }
       tc_wait_ld();
       const int slice_c = (c0 - cbeg) & 63;      // column of this block inside the staging slice
 #pragma unroll
@@ -186,8 +222,30 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
           }
 #pragma unroll
           for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], relu_lo);
+          if (HAS_UP) {
+            if (g < 3 && uv[g < 3 ? g : 0]) {
+              float a[8], b[8], c[8], d[8];
+              const int gg = g < 3 ? g : 0;
+              if (P.up_f16) {
+                unpack8h(uu[gg][0], a); unpack8h(uu[gg][1], b); unpack8h(uu[gg][2], c); unpack8h(uu[gg][3], d);
+              } else {
+                unpack8(uu[gg][0], a); unpack8(uu[gg][1], b); unpack8(uu[gg][2], c); unpack8(uu[gg][3], d);
+              }
+              const float ux = 1.f - uwx, uy = 1.f - uwy;
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float r0 = fmaf(b[j], uwx, a[j] * ux);
+                const float r1 = fmaf(d[j], uwx, c[j] * ux);
+                f[j] += fmaf(r1, uwy, r0 * uy);
+              }
+            }
+          }
           const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
-          if (HAS_OUT)
+          if (HAS_UP && P.out_f16) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);   // saturate, never inf
+            sts128(st1 + so, pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+          } else if (HAS_OUT)
             sts128(st1 + so, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
           if (HAS_OUT2) {
             const float4 s0 = lds128f(o2s_u + (uint32_t)(cgt + c0 + 8 * g) * 4);
@@ -202,11 +260,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
           }
         }
       }
+      if ((HAS_RES || HAS_UP) && c0 + 32 < cend) prefetch(c0 + 32);
       // ---- flush a completed staging slice with coalesced stores
       if (slice_c + ncol == slice_cols) {
         __syncwarp();
         const int c = c0 - slice_c + cl;                       // this lane's channel inside the N tile
-        const bool c_ok = cgt + c < cout8;
+        const bool c_ok = (cgt + c < cout8) && !(P.dbg & 1);
 #pragma unroll 4
         for (int i = 0; i < niter; ++i) {
           const int p = i * ppi + pl;                          // staged pixel 0..31
@@ -224,7 +283,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&t_empty[ts]);
-    if (split) { if (++ts == 2) { ts = 0; tp ^= 1; } } else { tp ^= 1; }
+    ts += split ? 1u : 2u;
+    if (ts >= (uint32_t)P.nst) { ts -= (uint32_t)P.nst; tp ^= 1; }
     // advance the tile coordinates by the tile step
     nt += stepd[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
     tw += stepd[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
@@ -267,9 +327,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* a_empty = a_full + 8;          // [8]
   uint64_t* b_full = a_empty + 8;          // [8] (resident: [0] only)
   uint64_t* b_empty = b_full + 8;          // [8]
-  uint64_t* t_full = b_empty + 8;          // [2]
-  uint64_t* t_empty = t_full + 2;          // [2]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+  uint64_t* t_full = b_empty + 8;          // [4]
+  uint64_t* t_empty = t_full + 4;          // [4]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -277,7 +337,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
-    for (int i = 0; i < 2; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], P.NT >= 64 ? 8 : 4); }
+    for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], P.NT >= 64 ? 8 : 4); }
     mbar_fence_init();
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
@@ -310,18 +370,23 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
                       t * P.Cin + ch * P.KC, 0);
     }
-    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
-      const int nt = (int)(tile % P.ntiles_n);
-      int64_t r = tile / P.ntiles_n;
-      const int tw = (int)(r % P.tiles_w); r /= P.tiles_w;
-      const int th = (int)(r % P.tiles_h);
-      const int n = (int)(r / P.tiles_h);
+    // tile coordinates as mixed-radix digits advanced by the grid step (no per-tile divisions: this
+    // single warp's instruction chain is the per-tile critical path of the small-channel layers)
+    uint32_t t0 = blockIdx.x;
+    int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
+    int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+    int th = (int)(t0 % (uint32_t)P.tiles_h);
+    int n = (int)(t0 / (uint32_t)P.tiles_h);
+    const uint32_t total = (uint32_t)P.total_tiles;
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
       const int h0 = th * TH, w0 = tw * TW;
       for (int ch = 0; ch < P.nchunks; ++ch) {
         for (int s = 0; s < P.nslabs; ++s) {
           const Slab& sl = P.slabs[s];
           mbar_wait(&a_empty[sa], pa ^ 1);
-          if (leader) {
+          if (leader && (P.dbg & 4)) {
+            mbar_arrive(&a_full[sa]);
+          } else if (leader) {
             mbar_expect_tx(&a_full[sa], P.a_box_bytes);
             const uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
             if (S2) tma_load_5d(dst, &tmA, smem_u32(&a_full[sa]), sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
@@ -341,10 +406,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
       }
+      nt += P.step1[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+      tw += P.step1[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+      th += P.step1[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+      n += P.step1[3];
     }
   } else if (warp == 1) {
     // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
     const uint32_t leader = elect_one() ? 1u : 0u;
+    const uint32_t mma_on = (P.dbg & 2) ? 0u : leader;
     const uint32_t idesc = make_idesc_bf16_m128(P.NT);
     const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
     const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
@@ -356,7 +426,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int sa = 0, pa = 0, sb = 0, pb = 0;
     int ts = 0, tp = 0;
     if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
-    for (int64_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
+    const uint32_t total = (uint32_t)P.total_tiles;
+    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
       mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
@@ -382,7 +453,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
               for (int k = 0; k < KSTEPS; ++k) {
                 const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                tc_mma_if2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc, leader);
+                tc_mma_if2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc, mma_on);
                 acc = 1;
               }
               if (!BRES) {
@@ -396,19 +467,20 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
       }
       tc_commit_if(&t_full[ts], leader);                    // accumulator complete -> epilogue
-      if (++ts == 2) { ts = 0; tp ^= 1; }
+      if (++ts == P.nst) { ts = 0; tp ^= 1; }
     }
   } else {
     // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
     const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);
-    const int variant = (P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0);
+    const int variant = P.up ? 8 : ((P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0));
     switch (variant) {
-      case 2: epilogue_loop<false, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
-      case 3: epilogue_loop<true, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
-      case 4: epilogue_loop<false, false, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
-      case 5: epilogue_loop<true, false, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
-      case 6: epilogue_loop<false, true, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
-      default: epilogue_loop<true, true, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 2: epilogue_loop<false, true, false, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 3: epilogue_loop<true, true, false, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 4: epilogue_loop<false, false, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 5: epilogue_loop<true, false, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 6: epilogue_loop<false, true, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      case 8: epilogue_loop<false, true, false, true>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
+      default: epilogue_loop<true, true, true, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
     }
   }
 
@@ -477,6 +549,11 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.out2 && (a.out2_ld % 8 || a.out2_ld < c8)) return false;
   if (a.res && (a.res_ld % 8 || a.res_ld < c8)) return false;
   const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
+  if (a.out_f16 && !a.up) return false;                             // fp16 storage exists for the ladder rungs only
+  if (a.up) {   // fused x2 upsample-add: one 32-column block, <= 24 source channels, exact x2, no residual / 2nd output
+    if (cp > 32 || a.up_ld > 24 || a.up_ld % 8 || a.up_ld < c8 || a.res || a.out2 || !a.out) return false;
+    if (a.Ho != 2 * a.up_h || a.Wo != 2 * a.up_w) return false;
+  }
   if (cp > 256 && cp % 256) return false;
   if (cp != 16 && cp != 32 && cp % 64) return false;                 // epilogue staging slices are 16/32/64 channels
   if ((int64_t)a.N * ceil_div(a.Ho, TH) * ceil_div(a.Wo, TW) * (cp > 256 ? cp / 256 : 1) >= (1ll << 31)) return false;
@@ -545,7 +622,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   // ---- shared-memory plan
   P.cp = cp;
   P.stage_bytes = a.out2 ? 65536u : 32768u;
-  const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 34 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
+  const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
   P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= 100 * 1024) ? 1 : 0;
   static const bool no_resident = getenv("LEDB200_TC_NO_RESIDENT") != nullptr;
@@ -562,12 +639,16 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (P.SA < 2) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
   const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
                       (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
+  P.nst = (4 * P.NT <= 512) ? 4 : 2;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * P.NT)) cols <<= 1;
+  while (cols < (uint32_t)(P.nst * P.NT)) cols <<= 1;
   P.tmem_cols = cols;
   P.out = (__nv_bfloat16*)a.out; P.out_ld = a.out_ld;
   P.out2 = (__nv_bfloat16*)a.out2; P.out2_ld = a.out2_ld; P.o2_scale = a.o2_scale; P.o2_shift = a.o2_shift;
   P.res = (const __nv_bfloat16*)a.res; P.res_ld = a.res_ld; P.bias = a.bias; P.relu = a.relu;
+  { const char* e = getenv("LEDB200_TC_DBG"); P.dbg = e ? atoi(e) : 0; }
+  P.up = (const __nv_bfloat16*)a.up; P.up_ld = a.up_ld; P.up_h = a.up_h; P.up_w = a.up_w;
+  P.up_f16 = a.up_f16; P.out_f16 = a.out_f16;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;

@@ -323,27 +323,42 @@ struct Builder {
   static void* ptr(ledb200_handle& e, Plan& p, int id) { return id < 0 ? nullptr : e.arena + p.bufs[id].off; }
 
   // generic conv op on arena buffers.  aff2: affine id for the second output (-1 = plain ReLU copy)
+  // would this conv run on the tensor-core kernel?  (up: buffer whose x2 upsample is added in the epilogue)
+  bool conv_uses_tc(const std::string& cname, int in, int out, int res = -1, int out2 = -1, int up = -1) {
+    const ConvDef& d = e.convs[e.conv_by_name.at(cname)];
+    const Buf bi = p.bufs[in];
+    const int pad = d.k / 2;
+    const int Ho = (bi.h + 2 * pad - d.k) / d.stride + 1, Wo = (bi.w + 2 * pad - d.k) / d.stride + 1;
+    ConvArgs s;
+    s.in_dtype = s.out_dtype = dt; s.N = bi.n; s.H = bi.h; s.W = bi.w; s.Cin = d.cin; s.Ho = Ho; s.Wo = Wo;
+    s.Cout = d.cout; s.ksize = d.k; s.stride = d.stride; s.pad = pad; s.in_sw = bi.ld; s.in_sc = 1;
+    s.out_ld = out >= 0 ? p.bufs[out].ld : 0; s.out2_ld = out2 >= 0 ? p.bufs[out2].ld : 0;
+    s.res_ld = res >= 0 ? p.bufs[res].ld : 0; s.cout_pad_tc = d.cout_pad_tc ? d.cout_pad_tc : tc_pad(d.cout);
+    // eligibility only looks at which optional tensors exist, not at their addresses
+    static const char dummy = 0;
+    if (out >= 0) s.out = const_cast<char*>(&dummy);
+    if (out2 >= 0) s.out2 = const_cast<char*>(&dummy);
+    if (res >= 0) s.res = &dummy;
+    if (up >= 0) { s.up = &dummy; s.up_ld = p.bufs[up].ld; s.up_h = p.bufs[up].h; s.up_w = p.bufs[up].w; }
+    return e.cfg.conv_backend != 1 && dt == LEDB200_BF16 && conv_tc_eligible(s);
+  }
+
+  // generic conv op on arena buffers.  aff2: affine id for the second output (-1 = plain ReLU copy)
   int conv(const std::string& cname, int in, int out, int res = -1, bool relu = false, int out2 = -1,
-           int aff2 = -1, int out_coff = 0, int out2_coff = 0) {
+           int aff2 = -1, int out_coff = 0, int out2_coff = 0, int up = -1, bool up_f16 = false,
+           bool out_f16 = false) {
     const int ci = e.conv_by_name.at(cname);
     const Buf bi = p.bufs[in];
     const ConvDef& d = e.convs[ci];
     const int pad = d.k / 2;
     const int Ho = (bi.h + 2 * pad - d.k) / d.stride + 1, Wo = (bi.w + 2 * pad - d.k) / d.stride + 1;
     const int dtype = dt;
-    bool use_tc = false;
-    {
-      ConvArgs s;
-      s.in_dtype = s.out_dtype = dtype; s.N = bi.n; s.H = bi.h; s.W = bi.w; s.Cin = d.cin; s.Ho = Ho; s.Wo = Wo;
-      s.Cout = d.cout; s.ksize = d.k; s.stride = d.stride; s.pad = pad; s.in_sw = bi.ld; s.in_sc = 1;
-      s.out_ld = out >= 0 ? p.bufs[out].ld : 0; s.out2_ld = out2 >= 0 ? p.bufs[out2].ld : 0;
-      s.res_ld = res >= 0 ? p.bufs[res].ld : 0; s.cout_pad_tc = d.cout_pad_tc ? d.cout_pad_tc : tc_pad(d.cout);
-      use_tc = e.cfg.conv_backend != 1 && dtype == LEDB200_BF16 && conv_tc_eligible(s);
-    }
+    const bool use_tc = conv_uses_tc(cname, in, out, res, out2, up);
     const double es_ = (double)esize(e), npo = (double)bi.n * Ho * Wo;
     const double flops = 2.0 * npo * d.cout * d.cin * d.k * d.k;
     const double bytes = es_ * ((double)bi.n * bi.h * bi.w * d.cin + npo * d.cout * ((out >= 0) + (out2 >= 0) + (res >= 0))) +
-                         es_ * (double)d.cout * d.cin * d.k * d.k;
+                         es_ * (double)d.cout * d.cin * d.k * d.k +
+                         (up >= 0 ? es_ * (double)p.bufs[up].n * p.bufs[up].h * p.bufs[up].w * d.cout : 0.0);
     p.ops.push_back({cname, [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
       const ConvDef& d = e.convs[ci];
       const Buf& bi = p.bufs[in];
@@ -358,6 +373,8 @@ struct Builder {
         if (aff2 >= 0) { a.o2_scale = e.affs[aff2].scale + out2_coff; a.o2_shift = e.affs[aff2].shift + out2_coff; }
       }
       if (res >= 0) { a.res = ptr(e, p, res); a.res_ld = p.bufs[res].ld; }
+      if (up >= 0) { a.up = ptr(e, p, up); a.up_ld = p.bufs[up].ld; a.up_h = p.bufs[up].h; a.up_w = p.bufs[up].w; }
+      a.up_f16 = up_f16 ? 1 : 0; a.out_f16 = out_f16 ? 1 : 0;
       a.bias = d.bias; a.w_direct = d.w_direct; a.w_tc = d.w_tc;
       a.cout_pad16 = d.cout_pad16; a.cout_pad_tc = d.cout_pad_tc;
       a.N = bi.n; a.H = bi.h; a.W = bi.w; a.Cin = d.cin; a.Ho = Ho; a.Wo = Wo; a.Cout = d.cout;
@@ -626,11 +643,38 @@ void build_head_fused(Builder& B) {
   const int xc = B.buf("xc", n, p.bufs[c5h].h, p.bufs[c5h].w, K, kpad(K));
   B.conv(h + "conv_seg", hf, xc);
   const int hx1 = B.buf("hx1", n, p.bufs[x1h].h, p.bufs[x1h].w, K, kpad(K));
-  B.conv(h + "head_x1", x1h, hx1, -1, true);
   const int hx2 = B.buf("hx2", n, p.bufs[x2h].h, p.bufs[x2h].w, K, kpad(K));
-  B.conv(h + "head_x2", x2h, hx2, -1, true);
   p.ho = 2 * p.bufs[hx1].h; p.wo = 2 * p.bufs[hx1].w;
   const int dtype = B.dt;
+  // Ladder in the epilogues: when every rung is an exact x2 (all BASELINE sizes) and the head convs run on
+  // the tensor-core kernel, r2 = head_x2 + up(x_c) and r1 = head_x1 + up(r2) are formed in the convolutions'
+  // epilogues from the fp32 accumulators (conv_tc.cu `up` operand), and the tail only does the last x2
+  // upsample + argmax.  Otherwise (fp32 parity mode, odd sizes, K > 24) the three-level tail kernel runs.
+  static const bool no_ladder = getenv("LEDB200_NO_LADDER") != nullptr;
+  const bool exact2 = p.bufs[hx1].h == 2 * p.bufs[hx2].h && p.bufs[hx1].w == 2 * p.bufs[hx2].w &&
+                      p.bufs[hx2].h == 2 * p.bufs[xc].h && p.bufs[hx2].w == 2 * p.bufs[xc].w;
+  const bool ladder = !no_ladder && exact2 && B.conv_uses_tc(h + "head_x2", x2h, hx2, -1, -1, xc) &&
+                      B.conv_uses_tc(h + "head_x1", x1h, hx1, -1, -1, hx2);
+  if (ladder) {
+    // the rungs are stored as IEEE fp16 (same 2 bytes, 11-bit mantissa): tighter than the bf16 hx1/hx2 of
+    // the three-level path, and class logits are far inside fp16's range (stores saturate at +-65504)
+    B.conv(h + "head_x2", x2h, hx2, -1, true, -1, -1, 0, 0, xc, false, true);     // hx2 buffer now holds r2 (fp16)
+    B.conv(h + "head_x1", x1h, hx1, -1, true, -1, -1, 0, 0, hx2, true, true);     // hx1 buffer now holds r1 (fp16)
+    p.ops.push_back({"tail.up2_argmax", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
+      Tail2Args a;
+      const Buf& b1 = p.bufs[hx1];
+      a.r1 = Builder::ptr(e, p, hx1); a.f16 = 1; a.ld = b1.ld; a.N = b1.n; a.K = K; a.h2 = b1.h; a.w2 = b1.w;
+      a.pred = e.ext_pred; a.pred_dtype = e.ext_pred_dtype; a.logits = e.ext_logits;
+      return launch_tail2(a, st);
+    }, K_TAIL, 0.0, 0.0});
+    B.tag();
+    const Buf& b1 = p.bufs[hx1];
+    p.ops.back().bytes = esize(e) * (double)n * b1.h * b1.w * K + (double)n * p.ho * p.wo;   // r1 in, 1 B label out
+    p.ops.back().flops = (double)n * p.ho * p.wo * K * 8.0;
+    return;
+  }
+  B.conv(h + "head_x1", x1h, hx1, -1, true);
+  B.conv(h + "head_x2", x2h, hx2, -1, true);
   p.ops.push_back({"tail.fuse_argmax", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
     TailArgs a;
     const Buf &bc = p.bufs[xc], &b2 = p.bufs[hx2], &b1 = p.bufs[hx1];
@@ -640,6 +684,7 @@ void build_head_fused(Builder& B) {
     a.pred = e.ext_pred; a.pred_dtype = e.ext_pred_dtype; a.logits = e.ext_logits;
     return launch_tail(a, st);
   }, K_TAIL, 0.0, 0.0});
+  B.tag();
   {
     const Buf &bc = p.bufs[xc], &b2 = p.bufs[hx2], &b1 = p.bufs[hx1];
     const double px = (double)n * (bc.h * bc.w + b2.h * b2.w + b1.h * b1.w);

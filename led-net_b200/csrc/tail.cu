@@ -269,6 +269,146 @@ tail_kernel(TailArgs a, float s2h, float s2w, float sch, float scw, int vec, int
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// tail2: the LAST stage only.  Used when the two lower rungs of the ladder were already folded into the
+// head convolutions' epilogues (conv_tc.cu, `up` operand): the input is r1 = head_x1 + up(head_x2 + up(x_c))
+// at half resolution (fp16 or bf16, NHWC, pixel stride `ld`), the output is argmax_k of its exact x2 bilinear
+// upsample (decode_head.py:373-378 + base.py:187-188).
+//
+// CTA = 128 threads = 8 x 16 thread grid, 32 x 64 output tile, 18 x 34 r1 patch (clamped halo) staged in
+// shared memory as fp32 CLASS PAIRS: plane[kp][row][col] = float2(class 2kp, class 2kp+1), so one LDS.128
+// brings two columns of two classes and the interpolation runs on packed f32x2 FMAs (FMUL2/FFMA2: two
+// classes per instruction, each lane an IEEE fp32 op - same rounding as the scalar formula of tail_kernel).
+// Per thread and class pair: 8 LDS.128, 16 + 16 packed ops for a 4 x 4 output block, then the running
+// (max, index) update per class in ascending order with strict `>` (torch.argmax's first-max rule).
+constexpr int T2_PAIRS = 12;                // class pairs per pass (24 classes)
+constexpr int T2_PLANE = R1_H * R1_W;       // float2 elements per pair plane
+
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 w0, float2 w1) {
+  return __ffma2_rn(b, w1, __fmul2_rn(a, w0));   // b*w1 + a*w0 per lane: fmaf(b, w1, a*w0)
+}
+
+template <typename T, typename TP>
+__global__ void __launch_bounds__(TAIL_THREADS, 4)
+tail2_kernel(const T* __restrict__ r1, int ld, int K, int h2, int w2, TP* __restrict__ pred_base,
+             float* __restrict__ logits, int planes) {
+  extern __shared__ __align__(16) float2 sp[];          // [pairs][R1_H][R1_W]
+  const int Ho = 2 * h2, Wo = 2 * w2;
+  const int tiles_x = (Wo + OT_W - 1) / OT_W;
+  const int n = blockIdx.y;
+  const int a0 = (blockIdx.x / tiles_x) * TROWS, b0 = (blockIdx.x % tiles_x) * TCOLS;
+  const int t = threadIdx.x;
+  const int tr = t / TCOLS, tc = t % TCOLS;
+  const T* src = r1 + (int64_t)n * h2 * w2 * ld;
+
+  const int oy0 = 4 * (a0 + tr), ox0 = 4 * (b0 + tc);
+  float2 wy1[4], wx1[4], wy0[4], wx0[4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    int i0, i1; float l0, l1;
+    bilinear_coord(min(oy0 + r, Ho - 1), 0.5f, h2, i0, i1, l0, l1);
+    wy1[r] = make_float2(l1, l1); wy0[r] = make_float2(1.f - l1, 1.f - l1);
+    bilinear_coord(min(ox0 + r, Wo - 1), 0.5f, w2, i0, i1, l0, l1);
+    wx1[r] = make_float2(l1, l1); wx0[r] = make_float2(1.f - l1, 1.f - l1);
+  }
+  float best[4][4];
+  int bidx[4][4];
+#pragma unroll
+  for (int r = 0; r < 4; ++r)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { best[r][c] = -INFINITY; bidx[r][c] = 0; }
+
+  for (int k0 = 0; k0 < K; k0 += 2 * T2_PAIRS) {
+    const int kc = min(2 * T2_PAIRS, K - k0);
+    const int ng = (kc + 7) >> 3;                 // 8-class groups in this pass (source is padded to 8)
+    if (k0) __syncthreads();
+    // ---- stage the patch: item = (pixel, 8-class group); consecutive lanes read consecutive 16 B
+    for (int i = t; i < T2_PLANE * ng; i += TAIL_THREADS) {
+      const int p = i / ng, g = i - p * ng;
+      const int pi = p / R1_W, pj = p - pi * R1_W;
+      const int gy = clampi(2 * a0 - 1 + pi, 0, h2 - 1), gx = clampi(2 * b0 - 1 + pj, 0, w2 - 1);
+      float v[8];
+      load8(src + ((int64_t)gy * w2 + gx) * ld + k0 + 8 * g, v);
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (4 * g + j < planes) sp[(4 * g + j) * T2_PLANE + p] = make_float2(v[2 * j], v[2 * j + 1]);
+    }
+    __syncthreads();
+    const int npair = (kc + 1) >> 1;
+    for (int kp = 0; kp < npair; ++kp) {
+      const float2* base = sp + kp * T2_PLANE + (2 * tr) * R1_W + 2 * tc;
+      float2 hrow[4][4];   // [window row][output col], lanes = (class k, class k+1)
+#pragma unroll
+      for (int wi = 0; wi < 4; ++wi) {
+        const float4 pq = *reinterpret_cast<const float4*>(base + wi * R1_W);       // window cols 0, 1
+        const float4 rs = *reinterpret_cast<const float4*>(base + wi * R1_W + 2);   // window cols 2, 3
+        const float2 c0 = make_float2(pq.x, pq.y), c1 = make_float2(pq.z, pq.w);
+        const float2 c2 = make_float2(rs.x, rs.y), c3 = make_float2(rs.z, rs.w);
+        // output col c uses window cols (0,1),(1,2),(1,2),(2,3)
+        hrow[wi][0] = lerp2(c0, c1, wx0[0], wx1[0]);
+        hrow[wi][1] = lerp2(c1, c2, wx0[1], wx1[1]);
+        hrow[wi][2] = lerp2(c1, c2, wx0[2], wx1[2]);
+        hrow[wi][3] = lerp2(c2, c3, wx0[3], wx1[3]);
+      }
+      const int k = k0 + 2 * kp;
+      const bool two = (2 * kp + 1) < kc;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        float2 o[4];
+        o[0] = lerp2(hrow[0][c], hrow[1][c], wy0[0], wy1[0]);
+        o[1] = lerp2(hrow[1][c], hrow[2][c], wy0[1], wy1[1]);
+        o[2] = lerp2(hrow[1][c], hrow[2][c], wy0[2], wy1[2]);
+        o[3] = lerp2(hrow[2][c], hrow[3][c], wy0[3], wy1[3]);
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+          if (o[r].x > best[r][c]) { best[r][c] = o[r].x; bidx[r][c] = k; }        // strict > : first max wins
+          if (two && o[r].y > best[r][c]) { best[r][c] = o[r].y; bidx[r][c] = k + 1; }
+          hrow[r][c] = o[r];          // staging for the optional logits store
+        }
+      }
+      if (logits) {
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half && !two) break;
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int oy = oy0 + r;
+            if (oy < Ho) {
+              float* lp = logits + (((int64_t)n * K + k + half) * Ho + oy) * Wo + ox0;
+              float vv[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) vv[c] = half ? hrow[r][c].y : hrow[r][c].x;
+              if (ox0 + 3 < Wo && (Wo & 3) == 0) {
+                *reinterpret_cast<float4*>(lp) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+              } else {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) if (ox0 + c < Wo) lp[c] = vv[c];
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+
+  TP* pred = pred_base + (int64_t)n * Ho * Wo;
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int oy = oy0 + r;
+    if (oy >= Ho) continue;
+    if (sizeof(TP) == 1 && ox0 + 3 < Wo && (Wo & 3) == 0) {
+      uchar4 u = make_uchar4((unsigned char)bidx[r][0], (unsigned char)bidx[r][1], (unsigned char)bidx[r][2],
+                             (unsigned char)bidx[r][3]);
+      *reinterpret_cast<uchar4*>(reinterpret_cast<uint8_t*>(pred) + (int64_t)oy * Wo + ox0) = u;
+    } else {
+#pragma unroll
+      for (int c = 0; c < 4; ++c)
+        if (ox0 + c < Wo) pred[(int64_t)oy * Wo + ox0 + c] = (TP)bidx[r][c];
+    }
+  }
+}
+
 }  // namespace
 
 int launch_tail(const TailArgs& a, cudaStream_t st) {
@@ -312,6 +452,34 @@ int launch_tail(const TailArgs& a, cudaStream_t st) {
   else return fail(LEDB200_EINVAL, "tail: dtype must be F32/BF16 and pred dtype U8/I64");
 #undef LEDB_TAIL
   LEDB_LAUNCH_OK("tail_kernel");
+  return LEDB200_OK;
+}
+
+int launch_tail2(const Tail2Args& a, cudaStream_t st) {
+  if (a.K < 1 || a.K > 255) return fail(LEDB200_EINVAL, "tail2: K must be in [1,255]");
+  if (a.N < 1 || a.h2 < 1 || a.w2 < 1) return fail(LEDB200_EINVAL, "tail2: empty input");
+  if (a.ld % 8 || a.ld < (a.K + 7) / 8 * 8 || ((uintptr_t)a.r1 & 15))
+    return fail(LEDB200_EINVAL, "tail2: r1 must be bf16 NHWC with a 16-byte aligned pixel stride covering K rounded up to 8");
+  const int Ho = 2 * a.h2, Wo = 2 * a.w2;
+  dim3 grid(ceil_div(Wo, OT_W) * ceil_div(Ho, OT_H), a.N);
+  const int pairs = std::min(T2_PAIRS, (a.K + 1) / 2);
+  const size_t smem = (size_t)pairs * T2_PLANE * sizeof(float2);
+#define LEDB_TAIL2(T, TP)                                                                                \
+  do {                                                                                                   \
+    LEDB_CUDA_OK(cudaFuncSetAttribute(tail2_kernel<T, TP>, cudaFuncAttributeMaxDynamicSharedMemorySize,  \
+                                      (int)smem));                                                       \
+    tail2_kernel<T, TP><<<grid, TAIL_THREADS, smem, st>>>(reinterpret_cast<const T*>(a.r1), a.ld, a.K, a.h2, \
+                                                          a.w2, (TP*)a.pred, a.logits, pairs);           \
+  } while (0)
+  if (a.pred_dtype != LEDB200_U8 && a.pred_dtype != LEDB200_I64)
+    return fail(LEDB200_EINVAL, "tail2: pred dtype must be U8 or I64");
+  if (a.f16) {
+    if (a.pred_dtype == LEDB200_U8) LEDB_TAIL2(__half, uint8_t); else LEDB_TAIL2(__half, int64_t);
+  } else {
+    if (a.pred_dtype == LEDB200_U8) LEDB_TAIL2(__nv_bfloat16, uint8_t); else LEDB_TAIL2(__nv_bfloat16, int64_t);
+  }
+#undef LEDB_TAIL2
+  LEDB_LAUNCH_OK("tail2_kernel");
   return LEDB200_OK;
 }
 
