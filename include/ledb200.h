@@ -269,6 +269,21 @@ int ledb200_sesp_forward(const void* in, void* out, int32_t dtype, int32_t N, in
                          int32_t nIn, int32_t nOut, const int32_t* dilations4, int32_t v2,
                          const float* params, void* stream);
 
+/* ---- MFAF gate ---------------------------------------------------------
+ * Replaces Muti_AFF.forward (mmseg/models/classification/model_utils.py:410-429), eval mode:
+ *   xa = x + residual;  att = local(xa) + global(avgpool(xa)) + sum_{L=4,8,16} nearest_up(ctx_L(adaptive_avgpool_L(xa)));
+ *   out = 2 x sigmoid(att) + 2 residual (1 - sigmoid(att)).
+ * NHWC x / residual / out of `dtype` (F32 or BF16), C channels (multiple of 8, <= 256), CI = C // r in
+ * {8, 16, 32, 64}.  `params`: device fp32 block of ledb200_mfaf_param_floats(C, CI) floats, five paths in the
+ * order local_att, context1 (4x4), context2 (8x8), context3 (16x16), global_att, each as
+ *   w1[CI][C], a1[CI], b1[CI], w2[C][CI], a2[C], b2[C]
+ * with the conv bias and BatchNorm folded by the caller to y = a * (W x) + b.
+ * `workspace`: device scratch of ledb200_mfaf_workspace_bytes(N, C) bytes (pooled sums + context table). */
+int64_t ledb200_mfaf_param_floats(int32_t C, int32_t CI);
+int64_t ledb200_mfaf_workspace_bytes(int32_t N, int32_t C);
+int ledb200_mfaf_forward(const void* x, const void* residual, void* out, int32_t dtype, int32_t N, int32_t H,
+                         int32_t W, int32_t C, int32_t CI, const float* params, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -359,116 +359,123 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const uint32_t layout_type = (P.KC == 64) ? 2u : (P.KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
 
   if (warp == 0) {
-    // =========================== TMA producer (whole warp loops, one elected lane issues) =========
-    const bool leader = elect_one();
-    int sa = 0, pa = 0, sb = 0, pb = 0;
-    if (BRES && leader) {
-      // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
-      mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
-      for (int ch = 0; ch < P.nchunks; ++ch)
-        for (int t = 0; t < P.ntaps_total; ++t)
-          tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
-                      t * P.Cin + ch * P.KC, 0);
-    }
-    // tile coordinates as mixed-radix digits advanced by the grid step (no per-tile divisions: this
-    // single warp's instruction chain is the per-tile critical path of the small-channel layers)
-    uint32_t t0 = blockIdx.x;
-    int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
-    int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
-    int th = (int)(t0 % (uint32_t)P.tiles_h);
-    int n = (int)(t0 / (uint32_t)P.tiles_h);
-    const uint32_t total = (uint32_t)P.total_tiles;
-    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      const int h0 = th * TH, w0 = tw * TW;
-      for (int ch = 0; ch < P.nchunks; ++ch) {
-        for (int s = 0; s < P.nslabs; ++s) {
-          const Slab& sl = P.slabs[s];
-          mbar_wait(&a_empty[sa], pa ^ 1);
-          if (leader && (P.dbg & 4)) {
-            mbar_arrive(&a_full[sa]);
-          } else if (leader) {
-            mbar_expect_tx(&a_full[sa], P.a_box_bytes);
-            const uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
-            if (S2) tma_load_5d(dst, &tmA, smem_u32(&a_full[sa]), sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
-            else    tma_load_4d(dst, &tmA, smem_u32(&a_full[sa]), ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
-          }
-          if (++sa == P.SA) { sa = 0; pa ^= 1; }
-          if (!BRES) {
-            for (int t = 0; t < sl.ntaps; ++t) {
-              mbar_wait(&b_empty[sb], pb ^ 1);
-              if (leader) {
+    // =========================== TMA producer: ONE elected lane runs the whole role ================
+    if (elect_one()) {
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      if (BRES) {
+        // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
+        mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
+        for (int ch = 0; ch < P.nchunks; ++ch)
+          for (int t = 0; t < P.ntaps_total; ++t)
+            tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
+                        t * P.Cin + ch * P.KC, 0);
+      }
+      // tile coordinates as mixed-radix digits advanced by the grid step (no per-tile divisions)
+      uint32_t t0 = blockIdx.x;
+      int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
+      int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+      int th = (int)(t0 % (uint32_t)P.tiles_h);
+      int n = (int)(t0 / (uint32_t)P.tiles_h);
+      const uint32_t total = (uint32_t)P.total_tiles;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int h0 = th * TH, w0 = tw * TW;
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          for (int s = 0; s < P.nslabs; ++s) {
+            const Slab& sl = P.slabs[s];
+            mbar_wait(&a_empty[sa], pa ^ 1);
+            if (P.dbg & 4) {
+              mbar_arrive(&a_full[sa]);
+            } else {
+              mbar_expect_tx(&a_full[sa], P.a_box_bytes);
+              const uint32_t dst = smem_u32(sA + (size_t)sa * P.a_stage_bytes);
+              if (S2) tma_load_5d(dst, &tmA, smem_u32(&a_full[sa]), sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
+              else    tma_load_4d(dst, &tmA, smem_u32(&a_full[sa]), ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
+            }
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+            if (!BRES) {
+              for (int t = 0; t < sl.ntaps; ++t) {
+                mbar_wait(&b_empty[sb], pb ^ 1);
                 mbar_expect_tx(&b_full[sb], P.b_box_bytes);
                 tma_load_2d(smem_u32(sB + (size_t)sb * P.b_tile_bytes), &tmB, smem_u32(&b_full[sb]),
                             sl.tap_id[t] * P.Cin + ch * P.KC, nt * P.NT);
-              }
-              if (++sb == P.SB) { sb = 0; pb ^= 1; }
-            }
-          }
-        }
-      }
-      nt += P.step1[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
-      tw += P.step1[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
-      th += P.step1[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
-      n += P.step1[3];
-    }
-  } else if (warp == 1) {
-    // =========================== MMA issuer (whole warp loops, one elected lane issues) ============
-    const uint32_t leader = elect_one() ? 1u : 0u;
-    const uint32_t mma_on = (P.dbg & 2) ? 0u : leader;
-    const uint32_t idesc = make_idesc_bf16_m128(P.NT);
-    const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
-    const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
-    const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
-    constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
-    // descriptor low words advance by (bytes >> 4); the 14-bit address field cannot overflow (smem < 256 KB)
-    const uint32_t a_lo0 = ((sA_u >> 4) & 0x3FFFu) | (1u << 16), b_lo0 = ((sB_u >> 4) & 0x3FFFu) | (1u << 16);
-    const uint32_t a_stage16 = P.a_stage_bytes >> 4, b_tile16 = P.b_tile_bytes >> 4;
-    int sa = 0, pa = 0, sb = 0, pb = 0;
-    int ts = 0, tp = 0;
-    if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
-    const uint32_t total = (uint32_t)P.total_tiles;
-    for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-      mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
-      tc_fence_after();
-      const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
-      uint32_t acc = 0;
-      for (int ch = 0; ch < P.nchunks; ++ch) {
-        const uint32_t b_chunk = b_lo0 + (uint32_t)(ch * 9) * b_tile16;   // resident weights of this chunk
-#pragma unroll
-        for (int s = 0; s < mode_slabs<MODE>(); ++s) {
-          mbar_wait(&a_full[sa], pa);
-          tc_fence_after();
-          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
-#pragma unroll
-          for (int t = 0; t < 9; ++t) {
-            if (t < mode_taps<MODE>(s)) {
-              uint32_t b_lo;
-              if (BRES) {
-                b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
-              } else {
-                mbar_wait(&b_full[sb], pb);
-                tc_fence_after();
-                b_lo = b_lo0 + (uint32_t)sb * b_tile16;
-              }
-#pragma unroll
-              for (int k = 0; k < KSTEPS; ++k) {
-                const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                tc_mma_if2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc, mma_on);
-                acc = 1;
-              }
-              if (!BRES) {
-                tc_commit_if(&b_empty[sb], leader);         // frees the B stage when these MMAs retire
                 if (++sb == P.SB) { sb = 0; pb ^= 1; }
               }
             }
           }
-          tc_commit_if(&a_empty[sa], leader);               // frees the A slab
-          if (++sa == P.SA) { sa = 0; pa ^= 1; }
         }
+        nt += P.step1[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+        tw += P.step1[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+        th += P.step1[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+        n += P.step1[3];
       }
-      tc_commit_if(&t_full[ts], leader);                    // accumulator complete -> epilogue
-      if (++ts == P.nst) { ts = 0; tp ^= 1; }
     }
+    __syncwarp();
+  } else if (warp == 1) {
+    // =========================== MMA issuer: ONE elected lane runs the whole role ==================
+    // (a branch on elect.sync, not a per-lane predicate on each MMA: ptxas then knows a single thread is
+    // active and issues each tcgen05.mma straight from uniform registers; the predicated form cost an
+    // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall of 17 instructions per MMA, and this thread's issue
+    // rate is the per-tile critical path of every 3x3 layer - ncu r1b: producer and epilogue both wait on it)
+    if (elect_one()) {
+      const bool mma_on = !(P.dbg & 2);
+      const uint32_t idesc = make_idesc_bf16_m128(P.NT);
+      const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
+      const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
+      const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
+      constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
+      // descriptor low words advance by (bytes >> 4); the 14-bit address field cannot overflow (smem < 256 KB)
+      const uint32_t a_lo0 = ((sA_u >> 4) & 0x3FFFu) | (1u << 16), b_lo0 = ((sB_u >> 4) & 0x3FFFu) | (1u << 16);
+      const uint32_t a_stage16 = P.a_stage_bytes >> 4, b_tile16 = P.b_tile_bytes >> 4;
+      int sa = 0, pa = 0, sb = 0, pb = 0;
+      int ts = 0, tp = 0;
+      if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+      const uint32_t total = (uint32_t)P.total_tiles;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
+        uint32_t acc = 0;
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          const uint32_t b_chunk = b_lo0 + (uint32_t)(ch * 9) * b_tile16;   // resident weights of this chunk
+#pragma unroll
+          for (int s = 0; s < mode_slabs<MODE>(); ++s) {
+            mbar_wait(&a_full[sa], pa);
+            tc_fence_after();
+            const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
+#pragma unroll
+            for (int t = 0; t < 9; ++t) {
+              if (t < mode_taps<MODE>(s)) {
+                uint32_t b_lo;
+                if (BRES) {
+                  b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+                } else {
+                  mbar_wait(&b_full[sb], pb);
+                  tc_fence_after();
+                  b_lo = b_lo0 + (uint32_t)sb * b_tile16;
+                }
+                if (mma_on) {
+#pragma unroll
+                  for (int k = 0; k < KSTEPS; ++k) {
+                    const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                    tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc);
+                    acc = 1;
+                  }
+                }
+                if (!BRES) {
+                  tc_commit(&b_empty[sb]);                  // frees the B stage when these MMAs retire
+                  if (++sb == P.SB) { sb = 0; pb ^= 1; }
+                }
+              }
+            }
+            tc_commit(&a_empty[sa]);                        // frees the A slab
+            if (++sa == P.SA) { sa = 0; pa ^= 1; }
+          }
+        }
+        tc_commit(&t_full[ts]);                             // accumulator complete -> epilogue
+        if (++ts == P.nst) { ts = 0; tp ^= 1; }
+      }
+    }
+    __syncwarp();
   } else {
     // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
     const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);

@@ -26,6 +26,7 @@ SYMBOLS = [
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
+    'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
 ]
 
 
@@ -99,6 +100,11 @@ def get():
     lib.ledb200_sesp_param_floats.argtypes = [i32, i32]
     lib.ledb200_sesp_param_floats.restype = i64
     lib.ledb200_sesp_forward.argtypes = [vp, vp] + [i32] * 6 + [vp, i32, vp, vp]
+    lib.ledb200_mfaf_param_floats.argtypes = [i32, i32]
+    lib.ledb200_mfaf_param_floats.restype = i64
+    lib.ledb200_mfaf_workspace_bytes.argtypes = [i32, i32]
+    lib.ledb200_mfaf_workspace_bytes.restype = i64
+    lib.ledb200_mfaf_forward.argtypes = [vp, vp, vp] + [i32] * 6 + [vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):

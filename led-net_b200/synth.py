@@ -38,6 +38,10 @@ def make_state_dict(template, seed=2):
         is_bn = (prefix + '.running_mean') in keyset
         if leaf == 'num_batches_tracked':
             v = np.zeros(shape, dtype=np.int64)
+        elif not t.dtype.is_floating_point:           # index buffers (GETB relative_position_index): structural
+            v = t.detach().cpu().numpy()
+        elif leaf == 'relative_position_bias_table':  # GETB: made non-trivial (reference init is N(0, 0.02))
+            v = r.normal(0.0, 0.5, shape)
         elif is_bn:
             if leaf == 'weight':
                 v = r.uniform(0.5, 1.5, shape)

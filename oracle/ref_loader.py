@@ -75,7 +75,7 @@ def load():
     from . import mmcv_shim
 
     saved = {k: sys.modules.get(k) for k in list(sys.modules)
-             if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg', 'prettytable')}
+             if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg', 'prettytable', 'timm')}
 
     class BaseModule(nn.Module):
         def __init__(self, init_cfg=None):
@@ -154,10 +154,20 @@ def load():
             eesp = _load('mmseg.models.nn_layers.eesp', 'mmseg/models/nn_layers/eesp.py')
         except Exception:           # pragma: no cover - optional block
             eesp = None
+        # MFAF gate (Muti_AFF, pure torch) and GETB (needs timm only for DropPath / trunc_normal_)
+        mu = _load('mmseg.models.classification.model_utils',
+                   'mmseg/models/classification/model_utils.py')
+        import torch.nn.init as _init
+        _pkg('timm')
+        _pkg('timm.models')
+        _mod('timm.models.layers', DropPath=nn.Identity, to_2tuple=lambda v: (v, v),
+             trunc_normal_=_init.trunc_normal_)
+        getb = _load('mmseg.models.backbones.UNetFormer_GETB',
+                     'mmseg/models/backbones/UNetFormer_GETB.py')
     finally:
         # drop the stubs again so nothing else in the process sees a fake mmseg/mmcv
         for k in [k for k in sys.modules
-                  if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg', 'prettytable')]:
+                  if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg', 'prettytable', 'timm')]:
             del sys.modules[k]
         for k, v in saved.items():
             if v is not None:
@@ -168,6 +178,7 @@ def load():
         IoUMetric=iou.IoUMetric, OhemCrossEntropy=ohem.OhemCrossEntropy,
         accuracy=acc.accuracy, resize=wr.resize, BasicBlock=bb.BasicBlock,
         Bottleneck=bb.Bottleneck, DAPPM=ppm.DAPPM,
-        SESP=getattr(eesp, 'SESP', None) if eesp else None, MODELS=models, METRICS=metrics)
+        SESP=getattr(eesp, 'SESP', None) if eesp else None, Muti_AFF=mu.Muti_AFF,
+        GETBBlock=getb.GETBBlock, MODELS=models, METRICS=metrics)
     _cache['ns'] = ns
     return ns

@@ -22,6 +22,8 @@ Fixtures
                     (64,64,Spatial) / (128,128,context,r_lim=9) / (256,256,context,r_lim=9) and a
                     channel-changing, non-V2 one; weights from synth seed 5 with PReLU slopes and BN
                     statistics made non-trivial (sesp_state_dict below).
+* mfaf.npz        : Muti_AFF (classification/model_utils.py) eval outputs on tests/block_cases.MFAF_CASES.
+* getb.npz        : GETBBlock (backbones/UNetFormer_GETB.py) eval outputs on tests/block_cases.GETB_CASES.
 """
 import os
 import sys
@@ -93,6 +95,28 @@ def make_sesp(ref):
     np.savez_compressed(os.path.join(OUT, 'sesp.npz'), **out)
 
 
+def make_blocks(ref):
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import block_cases as bc
+    out = {}
+    for i, (tag, kw, shape) in enumerate(bc.MFAF_CASES):
+        m = ref.Muti_AFF(**kw).eval()
+        m.load_state_dict(bc.block_state_dict(m.state_dict(), seed=31))
+        x, r = bc.block_input(i, kw['channels'], shape, 300, n_inputs=2)
+        with torch.no_grad():
+            out[tag] = m(x, r).numpy()
+        out[tag + '_nparams'] = np.int64(sum(p.numel() for p in m.parameters()))
+    np.savez_compressed(os.path.join(OUT, 'mfaf.npz'), **out)
+    out = {}
+    for i, (tag, kw, shape) in enumerate(bc.GETB_CASES):
+        m = ref.GETBBlock(**kw).eval()
+        m.load_state_dict(bc.block_state_dict(m.state_dict(), seed=41))
+        with torch.no_grad():
+            out[tag] = m(bc.block_input(i, kw['dim'], shape, 400)).numpy()
+        out[tag + '_nparams'] = np.int64(sum(p.numel() for p in m.parameters()))
+    np.savez_compressed(os.path.join(OUT, 'getb.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -100,7 +124,11 @@ def main():
     if 'sesp' in sys.argv[1:]:            # regenerate only the SESP fixture
         make_sesp(ref)
         return
+    if 'blocks' in sys.argv[1:]:          # regenerate only the MFAF / GETB fixtures
+        make_blocks(ref)
+        return
     make_sesp(ref)
+    make_blocks(ref)
 
     # ---------------- r0_head_k2 -------------------------------------------------
     ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,

@@ -162,6 +162,33 @@ def _oracle_grads(o, x, lab):
     return ref, {k: p.grad.detach().clone() for k, p in o.named_parameters()}
 
 
+def _check_grads(mine_grads, ref_grads, ref_grads64, tag):
+    """per-tensor gate against the float64 oracle, relative to the fp32 oracle's own error (see the docstring
+    of test_train_step_vs_oracle)."""
+    gscale = max(float(g.abs().max()) for g in ref_grads64.values())
+    floor = 1e-6 * gscale
+
+    def _err(grads, k, g64):
+        return float((grads[k].double() - g64).abs().max()) / max(float(g64.abs().max()), 1e-30)
+
+    # conditioning of the whole problem = the fp32 reference's own worst tensor (a single rounding
+    # sample per tensor is a noisy estimate of that tensor's conditioning; scatter/atomic summation
+    # order makes ours vary from run to run, so no tensor is held to better than the reference's worst)
+    worst_ref = max(_err(ref_grads, k, g64) for k, g64 in ref_grads64.items()
+                    if float((ref_grads[k].double() - g64).abs().max()) > floor)
+    worst, n_loose = 0.0, 0
+    for k, g64 in ref_grads64.items():
+        if float((mine_grads[k].double() - g64).abs().max()) <= floor:
+            continue
+        mine, theirs = _err(mine_grads, k, g64), _err(ref_grads, k, g64)
+        worst = max(worst, mine)
+        n_loose += mine > max(1e-2, 3 * theirs)
+        assert mine <= max(1e-2, 3 * theirs, 1.5 * worst_ref), (tag, k, mine, theirs, worst_ref)
+    print(f'{tag}: worst gradient rel err vs float64 oracle: ours {worst:.2e}, fp32 oracle {worst_ref:.2e}; '
+          f'{n_loose} tensors needed the conditioning allowance')
+    assert n_loose <= 4          # tensors that needed the whole-problem allowance
+
+
 @pytest.mark.parametrize('K,hw,N', [(19, (128, 256), 2), (2, (192, 320), 3)])
 def test_train_step_vs_oracle(K, hw, N):
     """Loss and every parameter gradient against the oracle in train mode.
@@ -193,29 +220,8 @@ def test_train_step_vs_oracle(K, hw, N):
     assert abs(float(losses['decode.acc_seg']) - float(ref['acc_seg'])) < 1e-2
     got = dict(m.named_parameters())
     assert set(got) == set(ref_grads)
-    gscale = max(float(g.abs().max()) for g in ref_grads64.values())
-    floor = 1e-6 * gscale
-
-    def _err(grads, k, g64):
-        return float((grads[k].double() - g64).abs().max()) / max(float(g64.abs().max()), 1e-30)
-
     mine_grads = {k: got[k].grad.cpu() for k in ref_grads64}
-    # conditioning of the whole problem = the fp32 reference's own worst tensor (a single rounding
-    # sample per tensor is a noisy estimate of that tensor's conditioning; scatter/atomic summation
-    # order makes ours vary from run to run, so no tensor is held to better than the reference's worst)
-    worst_ref = max(_err(ref_grads, k, g64) for k, g64 in ref_grads64.items()
-                    if float((ref_grads[k].double() - g64).abs().max()) > floor)
-    worst, n_loose = 0.0, 0
-    for k, g64 in ref_grads64.items():
-        if float((mine_grads[k].double() - g64).abs().max()) <= floor:
-            continue
-        mine, theirs = _err(mine_grads, k, g64), _err(ref_grads, k, g64)
-        worst = max(worst, mine)
-        n_loose += mine > max(1e-2, 3 * theirs)
-        assert mine <= max(1e-2, 3 * theirs, 1.5 * worst_ref), (k, mine, theirs, worst_ref)
-    print(f'worst gradient rel err vs float64 oracle: ours {worst:.2e}, fp32 oracle {worst_ref:.2e}; '
-          f'{n_loose} tensors needed the conditioning allowance')
-    assert n_loose <= 4          # tensors that needed the whole-problem allowance
+    _check_grads(mine_grads, ref_grads, ref_grads64, 'step 1')
     # BatchNorm running statistics moved identically
     bufs_o = dict(o.named_buffers())
     for k, b in m.named_buffers():
@@ -228,29 +234,37 @@ def test_train_step_vs_oracle(K, hw, N):
     # above, scaled by lr: the fp32 oracle itself is off by up to 1e-1 on some tensors of this net.)
     shadow = {k: torch.nn.Parameter(p.detach().cpu().clone()) for k, p in m.named_parameters()}
     opt_s = torch.optim.SGD(shadow.values(), lr=0.01, momentum=0.9, weight_decay=5e-4)
-    opt_o = torch.optim.SGD(o.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
     for k in shadow:
         shadow[k].grad = mine_grads[k].clone()
     opt_s.step()
-    opt_o.step()
     opt.step()
     for k, p in m.named_parameters():
         assert rel_err(p.detach().cpu(), shadow[k].detach()) < 1e-6, k
-    ref2, _ = _oracle_grads(o, x, lab)
-    opt_o.step()
+    # Step 2 is checked where it is well posed: the oracle (fp32 and float64) is loaded with the PRODUCT's
+    # parameters after step 1, and the product's step-2 loss and gradients are gated against it exactly like
+    # step 1.  (Free-running both for two steps and comparing parameters re-measures the conditioning above
+    # amplified by lr x |g| / |w|: the fp32 oracle itself drifts 5-20 % from its float64 run that way.)
+    state1 = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    ob, _ = _train_pair(K)
+    ob.load_state_dict(state1)
+    ob.train()
+    ref2, ref2_grads = _oracle_grads(ob, x, lab)
+    ob64, _ = _train_pair(K)
+    ob64.load_state_dict(state1)
+    ob64 = ob64.double().train()
+    ref2_64, ref2_grads64 = _oracle_grads(ob64, x.double(), lab)
     log = m.train_step(dict(inputs=x.to(DEV), data_samples=samples), opt)
     torch.cuda.synchronize()
     # train_step = zero_grad, backward, step: the step-2 gradients are still in .grad
-    for k, p in m.named_parameters():
-        shadow[k].grad = p.grad.detach().cpu().clone()
-    opt_s.step()
-    po = dict(o.named_parameters())
+    grads2 = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
+    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2')
+    for k in shadow:
+        shadow[k].grad = grads2[k].clone()
+    opt_s.step()                                                    # second step exercises the momentum buffer
     for k, p in m.named_parameters():
         assert rel_err(p.detach().cpu(), shadow[k].detach()) < 1e-6, k
-        # and the trajectory stays with the oracle's (loose: lr x the gradient conditioning above)
-        assert rel_err(p.detach().cpu(), po[k].detach()) < 5e-2, k
-    tot2 = float(ref2['loss_context'] + ref2['loss_spatial'])
-    assert abs(float(log['loss'].detach()) - tot2) < 1e-2 * abs(tot2)
+    tot2, tot2_64 = (float(r['loss_context'] + r['loss_spatial']) for r in (ref2, ref2_64))
+    assert abs(float(log['loss'].detach()) - tot2_64) < max(1e-4 * abs(tot2_64), 3 * abs(tot2 - tot2_64))
 
 
 def test_eval_after_train_uses_updated_weights():

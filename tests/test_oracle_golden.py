@@ -134,3 +134,34 @@ def test_sesp_block(golden_dir):
             out = m(ns['sesp_input'](i, kw['nIn'], shape)).numpy()
         err = np.abs(out - g[tag]).max() / np.abs(g[tag]).max()
         assert err < 1e-6, (tag, err)
+
+
+def test_mfaf_block(golden_dir):
+    """oracle/mfaf.py against the reference's own Muti_AFF (classification/model_utils.py) outputs: bit-exact."""
+    import block_cases as bc
+    from oracle.mfaf import OracleMutiAFF
+    g = _load(golden_dir, 'mfaf.npz')
+    for i, (tag, kw, shape) in enumerate(bc.MFAF_CASES):
+        m = OracleMutiAFF(**kw).eval()
+        m.load_state_dict(bc.block_state_dict(m.state_dict(), seed=31))
+        assert sum(p.numel() for p in m.parameters()) == int(g[tag + '_nparams'])
+        x, r = bc.block_input(i, kw['channels'], shape, 300, n_inputs=2)
+        with torch.no_grad():
+            out = m(x, r).numpy()
+        assert np.array_equal(out, g[tag]), tag
+
+
+def test_getb_block(golden_dir):
+    """oracle/getb.py against the reference's own GETBBlock (backbones/UNetFormer_GETB.py) outputs.  The oracle
+    writes einops' rearranges as view/permute, so matmul operand strides may differ: 1e-6, not bit-exact."""
+    import block_cases as bc
+    from oracle.getb import OracleGETBBlock
+    g = _load(golden_dir, 'getb.npz')
+    for i, (tag, kw, shape) in enumerate(bc.GETB_CASES):
+        m = OracleGETBBlock(**kw).eval()
+        m.load_state_dict(bc.block_state_dict(m.state_dict(), seed=41))
+        assert sum(p.numel() for p in m.parameters()) == int(g[tag + '_nparams'])
+        with torch.no_grad():
+            out = m(bc.block_input(i, kw['dim'], shape, 400)).numpy()
+        assert out.shape == g[tag].shape
+        assert np.abs(out - g[tag]).max() <= 1e-6 * np.abs(g[tag]).max(), tag

@@ -48,3 +48,27 @@ def test_sesp_block_loads():
         pytest.skip('SESP not loadable')
     m = ref.SESP(64, 64)
     assert sum(p.numel() for p in m.parameters()) == 2864
+
+
+def test_mfaf_and_getb_equal_verbatim_reference():
+    """fresh seeded inputs (not the committed goldens), including sizes that are not multiples of the pooling
+    grids / attention window."""
+    from oracle.mfaf import OracleMutiAFF
+    from oracle.getb import OracleGETBBlock
+    ref = ref_loader.load()
+    g = torch.Generator().manual_seed(77)
+    for kw, hw in ((dict(channels=64), (23, 41)), (dict(channels=128, r=4), (16, 32))):
+        a, b = ref.Muti_AFF(**kw).eval(), OracleMutiAFF(**kw).eval()
+        sd = synth.make_state_dict(a.state_dict(), seed=51)
+        a.load_state_dict(sd), b.load_state_dict(sd)
+        x, r = (torch.randn(2, kw['channels'], *hw, generator=g) for _ in range(2))
+        with torch.no_grad():
+            assert torch.equal(a(x, r), b(x, r))
+    for kw, hw in ((dict(dim=128, num_heads=8, window_size=8), (11, 19)), (dict(dim=64, num_heads=8, window_size=4), (8, 12))):
+        a, b = ref.GETBBlock(**kw).eval(), OracleGETBBlock(**kw).eval()
+        sd = synth.make_state_dict(a.state_dict(), seed=52)
+        a.load_state_dict(sd), b.load_state_dict(sd)
+        x = torch.randn(1, kw['dim'], *hw, generator=g)
+        with torch.no_grad():
+            ya, yb = a(x), b(x)
+        assert float((ya - yb).abs().max()) <= 1e-6 * float(ya.abs().max())
