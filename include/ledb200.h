@@ -284,6 +284,24 @@ int64_t ledb200_mfaf_workspace_bytes(int32_t N, int32_t C);
 int ledb200_mfaf_forward(const void* x, const void* residual, void* out, int32_t dtype, int32_t N, int32_t H,
                          int32_t W, int32_t C, int32_t CI, const float* params, void* workspace, void* stream);
 
+/* ---- GETB block ---------------------------------------------------------
+ * Replaces GETBBlock.forward (mmseg/models/backbones/UNetFormer_GETB.py:221-226; GlobalLocalAttention :97-206,
+ * Mlp :79-94), eval mode, window_size 8: out = y + fc2(ReLU6(fc1(BN2(y)))), y = x + attn(BN1(x)).
+ * A handle owns the device copies of the weights (both conv layouts) and a workspace that grows only when a
+ * larger shape arrives.  `params`: HOST fp32 block of ledb200_getb_param_floats(dim, heads, hidden) floats:
+ *   w_qkv[3C][C] (BN1 folded in), b_qkv[3C], n1_scale[C], n1_shift[C] (BN1 as y = s x + t),
+ *   rel_bias[heads][64][64] (relative_position_bias_table gathered by relative_position_index),
+ *   w_dw[C][64] (depthwise 8x8), dw_scale[C], dw_shift[C] (proj BN), w_proj[C][C],
+ *   w_fc1[hidden][C] (BN2 folded in), b_fc1[hidden], w_fc2[C][hidden], b_fc2[C].
+ * x / out: NHWC [N,H,W,dim] of the handle's dtype (F32 or BF16); H, W >= 2 and the reflect padding to a multiple
+ * of 8 must be smaller than the input (PyTorch's own F.pad rule). */
+typedef struct ledb200_getb ledb200_getb;
+int64_t ledb200_getb_param_floats(int32_t dim, int32_t heads, int32_t hidden);
+int ledb200_getb_create(int32_t dim, int32_t heads, int32_t hidden, int32_t window, int32_t dtype,
+                        const float* params, ledb200_getb** out);
+int ledb200_getb_destroy(ledb200_getb* g);
+int ledb200_getb_forward(ledb200_getb* g, const void* x, void* out, int32_t N, int32_t H, int32_t W, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -138,6 +138,7 @@ conv_direct_kernel(ConvArgs a) {
         float t = acc[i][j] + (a.bias ? a.bias[co0 + j] : 0.f);
         if (r) t += rr[j];
         v[j] = a.relu ? fmaxf(t, 0.f) : t;
+        if (a.relu == 2) v[j] = fminf(v[j], 6.f);
       }
       if (a.out) { store8(o + co0, v); store8(o + co0 + 8, v + 8); }
       if (o2) {
@@ -157,7 +158,8 @@ conv_direct_kernel(ConvArgs a) {
       if (co >= a.Cout) break;
       float v = acc[i][j] + (a.bias ? a.bias[co] : 0.f);
       if (r) v += to_f32(r[co]);
-      const float vr = a.relu ? fmaxf(v, 0.f) : v;
+      float vr = a.relu ? fmaxf(v, 0.f) : v;
+      if (a.relu == 2) vr = fminf(vr, 6.f);
       if (a.out) o[co] = from_f32<Tout>(vr);
       if (o2) {
         float v2 = a.o2_scale ? fmaf(vr, a.o2_scale[co], a.o2_shift[co]) : vr;

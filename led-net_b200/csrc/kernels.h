@@ -33,7 +33,7 @@ struct ConvArgs {
   int cout_pad_tc = 0;
   int N = 0, H = 0, W = 0, Cin = 0, Ho = 0, Wo = 0, Cout = 0;
   int ksize = 3, stride = 1, pad = 1, dil = 1;
-  int relu = 0;
+  int relu = 0;                  // 0 none, 1 ReLU, 2 ReLU6 (GETB Mlp, UNetFormer_GETB.py:80)
   // CUDA-core path only: the input is a zero-inserted view (factor in_up) of a real [Hr x Wr] tensor;
   // H/W are then the VIRTUAL extents.  Used for the data gradient of stride-2 convolutions (train.cu).
   int in_up = 1, Hr = 0, Wr = 0;

@@ -27,6 +27,7 @@ SYMBOLS = [
     'ledb200_train_layout', 'ledb200_train_sgd_step',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
+    'ledb200_getb_param_floats', 'ledb200_getb_create', 'ledb200_getb_destroy', 'ledb200_getb_forward',
 ]
 
 
@@ -105,6 +106,11 @@ def get():
     lib.ledb200_mfaf_workspace_bytes.argtypes = [i32, i32]
     lib.ledb200_mfaf_workspace_bytes.restype = i64
     lib.ledb200_mfaf_forward.argtypes = [vp, vp, vp] + [i32] * 6 + [vp, vp, vp]
+    lib.ledb200_getb_param_floats.argtypes = [i32, i32, i32]
+    lib.ledb200_getb_param_floats.restype = i64
+    lib.ledb200_getb_create.argtypes = [i32, i32, i32, i32, i32, vp, C.POINTER(vp)]
+    lib.ledb200_getb_destroy.argtypes = [vp]
+    lib.ledb200_getb_forward.argtypes = [vp, vp, vp, i32, i32, i32, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):
