@@ -79,7 +79,7 @@ struct TcParams {
   // optional: out += bilinear x2 upsample (align_corners=False) of `up` [N, up_h, up_w, up_ld], added AFTER the ReLU
   const __nv_bfloat16* up; int up_ld, up_h, up_w;
   int up_f16, out_f16;               // ladder rungs are kept in fp16 (11-bit mantissa; logits are far inside its range)
-  int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads
+  int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 16/32 aligned A windows
 };
 
 using namespace tc;   // PTX wrappers: tc_common.cuh
@@ -91,6 +91,15 @@ __device__ __forceinline__ uint4 lds128(uint32_t addr) {
   uint4 v;
   asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
   return v;
+}
+// 256-bit global accesses (sm_100): one full 32 B sector per thread and instruction
+__device__ __forceinline__ void ldg256(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
 }
 __device__ __forceinline__ float4 lds128f(uint32_t addr) {
   float4 v;
@@ -145,40 +154,39 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
   int th = (int)(t0 % (uint32_t)P.tiles_h);
   int n = (int)(t0 / (uint32_t)P.tiles_h);
   const uint32_t total = (uint32_t)P.total_tiles, step = split ? gridDim.x : 2 * gridDim.x;
-  // ---- fast path (interior tiles, 32-column blocks, every predicate and address hoisted out of the tile loop).
-  // ncu r1b: the generic body below executes ~520 SASS instructions per warp and tile, ~190 of them useful;
-  // with two epilogue warps per scheduler that instruction count - not HBM, not the MMAs - bounded every
-  // layer with Cout <= 64 (probe: 25 us for a 64->64 layer with stores, MMAs and TMA all switched off).
+  // ---- fast path: interior tiles, 32-column blocks, registers -> global directly.
+  // Measured on B200 (profiles/r1c_notes.md): with N tile <= 64 every tcgen05.mma re-reads its 4 KB A window
+  // from shared memory (6 KB per MMA at 128 B/clk = 48 clk against a 32 clk tensor floor), so the 3x3 layers
+  // are bound by the shared-memory port; the staged epilogue of the generic path below adds another
+  // 32-64 KB of st.shared/ld.shared per tile on the same port plus ~520 instructions per warp.  Here each
+  // thread owns one output pixel: 32 channels = 64 contiguous bytes = two 256-bit stores (full 32 B sectors),
+  // the residual comes in as two 256-bit loads issued before the accumulator wait, and nothing touches shared
+  // memory except the bias broadcast.
   const bool cout_all = (cout8 == P.cp);
-  const bool fast_launch = (ncols_g % 32 == 0) && (!HAS_RES || cout_all) && P.relu != 2 &&
-                           (!HAS_UP || (P.up_ld == 24 && P.cp == 32 && cout8 == 24));
-  const uint32_t base_x = swz(row_off);                                    // this lane's staging row, swizzled
-  const uint32_t f0 = ((uint32_t)lane * 16) ^ (((uint32_t)lane >> 3) << 4);         // flush reads, even / odd i
-  const uint32_t f1 = ((uint32_t)lane * 16) ^ ((4u + ((uint32_t)lane >> 3)) << 4);
-  const int row_out = Wo * P.out_ld, row_out2 = Wo * P.out2_ld;            // elements per output image row
-  const int lane_out = (q * 4 * Wo + pl) * P.out_ld + cl, lane_out2 = (q * 4 * Wo + pl) * P.out2_ld + cl;
-  const int lane_res = (ph * Wo + pw) * P.res_ld;
+  const bool al32 = ((P.out_ld | P.out2_ld | P.res_ld) % 16 == 0) &&
+                    (((uintptr_t)P.out | (uintptr_t)P.out2 | (uintptr_t)P.res) % 32 == 0);
+  const bool fast_launch = (ncols_g % 32 == 0) && P.relu != 2 &&
+                           (HAS_UP ? (P.up_ld == 24 && P.cp == 32 && cout8 == 24 && P.out_ld % 8 == 0)
+                                   : (cout_all && al32));
+  const int lane_px = ph * Wo + pw;                                         // this thread's pixel inside the tile
   for (uint32_t tile = first; tile < total; tile += step) {
     if (fast_launch && th * TH + TH <= Ho && tw * TW + TW <= Wo) {
-      const int64_t pix0 = ((int64_t)n * Ho + th * TH) * Wo + tw * TW;
+      const int64_t pix = ((int64_t)n * Ho + th * TH) * Wo + tw * TW + lane_px;
       const int cgt = nt * NT;
-      const __nv_bfloat16* res_px = HAS_RES ? P.res + pix0 * P.res_ld + lane_res + cgt : nullptr;
-      __nv_bfloat16* out_l = HAS_OUT ? P.out + pix0 * P.out_ld + lane_out + cgt : nullptr;
-      __nv_bfloat16* out2_l = HAS_OUT2 ? P.out2 + pix0 * P.out2_ld + lane_out2 + cgt : nullptr;
+      const __nv_bfloat16* res_px = HAS_RES ? P.res + pix * P.res_ld + cgt : nullptr;
+      __nv_bfloat16* out_px = HAS_OUT ? P.out + pix * P.out_ld + cgt : nullptr;
+      __nv_bfloat16* out2_px = HAS_OUT2 ? P.out2 + pix * P.out2_ld + cgt : nullptr;
       uint4 rr[HAS_RES ? 4 : 1];
       uint4 uu[HAS_UP ? 3 : 1][4];
       __half2 hwx0, hwx1, hwy0, hwy1;
       float uwx = 0.f, uwy = 0.f;
-      if (HAS_RES) {
-#pragma unroll
-        for (int g = 0; g < 4; ++g) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + cbeg + 8 * g));
-      }
+      if (HAS_RES) { ldg256(res_px + cbeg, rr[0], rr[1]); ldg256(res_px + cbeg + 16, rr[2], rr[3]); }
       if (HAS_UP) {
         int y0, y1, x0, x1;
         float l0;
         bilinear_coord(th * TH + ph, 0.5f, P.up_h, y0, y1, l0, uwy);
         bilinear_coord(tw * TW + pw, 0.5f, P.up_w, x0, x1, l0, uwx);
-        hwx1 = __float2half2_rn(uwx); hwx0 = __float2half2_rn(1.f - uwx);   // 0.25 / 0.75 / 0 / 1: exact in fp16
+        hwx1 = __float2half2_rn(uwx); hwx0 = __float2half2_rn(1.f - uwx);   // 0, 1/4, 3/4, 1: exact in fp16
         hwy1 = __float2half2_rn(uwy); hwy0 = __float2half2_rn(1.f - uwy);
         const __nv_bfloat16* ub = P.up + (int64_t)n * P.up_h * P.up_w * P.up_ld;
         const __nv_bfloat16 *u00 = ub + (y0 * P.up_w + x0) * P.up_ld, *u01 = ub + (y0 * P.up_w + x1) * P.up_ld;
@@ -199,9 +207,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         tc_ld16(taddr0 + c0, v);
         tc_ld16(taddr0 + c0 + 16, v + 16);
         tc_wait_ld();
-        const int slice_c = (c0 - cbeg) & (slice_cols - 1);          // 0, or 0 / 32 inside a 64-column slice
-        const uint32_t bx = base_x ^ (uint32_t)(slice_c * 2);
         const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
+        uint4 o[4], o2[HAS_OUT2 ? 4 : 1];
 #pragma unroll
         for (int g = 0; g < 4; ++g) {
           float f[8];
@@ -222,8 +229,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
           if (HAS_UP && g < 3) {
             const int gg = g < 3 ? g : 0;
             if (P.up_f16) {
-              // rung stored in fp16: interpolate in packed half2 (weights 0, 1/4, 3/4, 1 are exact; two
-              // roundings of 2^-11 on a term that is itself an fp16-rounded value), widen once
+              // rung stored in fp16: interpolate in packed half2 (the weights are exact; two roundings of 2^-11
+              // on a term that is itself an fp16-rounded value), widen once
               const __half2* a = reinterpret_cast<const __half2*>(&uu[gg][0]);
               const __half2* b = reinterpret_cast<const __half2*>(&uu[gg][1]);
               const __half2* c = reinterpret_cast<const __half2*>(&uu[gg][2]);
@@ -247,52 +254,33 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
               }
             }
           }
-          const uint32_t so = bx ^ (uint32_t)(16 * g);
           if (HAS_UP && P.out_f16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);   // saturate, never inf
-            sts128(st1 + so, pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
-          } else if (HAS_OUT)
-            sts128(st1 + so, pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+            o[g] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+          } else if (HAS_OUT) {
+            o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          }
           if (HAS_OUT2) {
-            const uint32_t o2 = (uint32_t)(cgt + c0) * 4 + 32 * g;
-            const float4 s0 = lds128f(o2s_u + o2), s1 = lds128f(o2s_u + o2 + 16);
-            const float4 h0 = lds128f(o2b_u + o2), h1 = lds128f(o2b_u + o2 + 16);
-            sts128(st2 + so,
-                   pack_bf16x2(fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), fmaxf(fmaf(f[1], s0.y, h0.y), 0.f)),
-                   pack_bf16x2(fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), fmaxf(fmaf(f[3], s0.w, h0.w), 0.f)),
-                   pack_bf16x2(fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), fmaxf(fmaf(f[5], s1.y, h1.y), 0.f)),
-                   pack_bf16x2(fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), fmaxf(fmaf(f[7], s1.w, h1.w), 0.f)));
+            const uint32_t q2 = (uint32_t)(cgt + c0) * 4 + 32 * g;
+            const float4 s0 = lds128f(o2s_u + q2), s1 = lds128f(o2s_u + q2 + 16);
+            const float4 h0 = lds128f(o2b_u + q2), h1 = lds128f(o2b_u + q2 + 16);
+            o2[g] = make_uint4(
+                pack_bf16x2(fmaxf(fmaf(f[0], s0.x, h0.x), 0.f), fmaxf(fmaf(f[1], s0.y, h0.y), 0.f)),
+                pack_bf16x2(fmaxf(fmaf(f[2], s0.z, h0.z), 0.f), fmaxf(fmaf(f[3], s0.w, h0.w), 0.f)),
+                pack_bf16x2(fmaxf(fmaf(f[4], s1.x, h1.x), 0.f), fmaxf(fmaf(f[5], s1.y, h1.y), 0.f)),
+                pack_bf16x2(fmaxf(fmaf(f[6], s1.z, h1.z), 0.f), fmaxf(fmaf(f[7], s1.w, h1.w), 0.f)));
           }
         }
-        if (HAS_RES && c0 + 32 < cend) {
+        if (HAS_RES && c0 + 32 < cend) { ldg256(res_px + c0 + 32, rr[0], rr[1]); ldg256(res_px + c0 + 48, rr[2], rr[3]); }
+        if (!(P.dbg & 1)) {
+          if (HAS_UP) {                               // 24 stored channels, 48 B pixels: three 128-bit stores
 #pragma unroll
-          for (int g = 0; g < 4; ++g) rr[g] = __ldg(reinterpret_cast<const uint4*>(res_px + c0 + 32 + 8 * g));
-        }
-        if (slice_c + 32 == slice_cols) {            // flush the completed staging slice, coalesced
-          __syncwarp();
-          const int sc0 = c0 - slice_c;
-          const bool c_ok = (cout_all || cgt + sc0 + cl < cout8) && !(P.dbg & 1);
-          auto flush = [&](auto check_tag) {         // CHECK = false: every lane stores (no per-store branch)
-            constexpr bool CHECK = decltype(check_tag)::value;
-            if (sh == 6) {                           // 32-column slice: 8 pixels per store, image row i
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const uint32_t so = (uint32_t)i * 512 + ((i & 1) ? f1 : f0);
-                if (HAS_OUT) { const uint4 w = lds128(st1 + so); if (!CHECK || c_ok) *reinterpret_cast<uint4*>(out_l + (sc0 + i * row_out)) = w; }
-                if (HAS_OUT2) { const uint4 w = lds128(st2 + so); if (!CHECK || c_ok) *reinterpret_cast<uint4*>(out2_l + (sc0 + i * row_out2)) = w; }
-              }
-            } else {                                 // 64-column slice: 4 pixels per store, image row i / 2
-#pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                const uint32_t so = (uint32_t)i * 512 + ((i & 1) ? f1 : f0);
-                if (HAS_OUT) { const uint4 w = lds128(st1 + so); if (!CHECK || c_ok) *reinterpret_cast<uint4*>(out_l + (sc0 + (i >> 1) * row_out + (i & 1) * 4 * P.out_ld)) = w; }
-                if (HAS_OUT2) { const uint4 w = lds128(st2 + so); if (!CHECK || c_ok) *reinterpret_cast<uint4*>(out2_l + (sc0 + (i >> 1) * row_out2 + (i & 1) * 4 * P.out2_ld)) = w; }
-              }
-            }
-          };
-          if (cout_all && !(P.dbg & 1)) flush(std::false_type{}); else flush(std::true_type{});
-          __syncwarp();
+            for (int g = 0; g < 3; ++g) *reinterpret_cast<uint4*>(out_px + 8 * g) = o[g];
+          } else {
+            if (HAS_OUT) { stg256(out_px + c0, o[0], o[1]); stg256(out_px + c0 + 16, o[2], o[3]); }
+            if (HAS_OUT2) { stg256(out2_px + c0, o2[0], o2[1]); stg256(out2_px + c0 + 16, o2[2], o2[3]); }
+          }
         }
       }
     } else {
@@ -575,7 +563,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (elect_one()) {
       const bool mma_on = !(P.dbg & 2);
       const uint32_t idesc = make_idesc_bf16_m128(P.NT);
-      const uint32_t a_hi = desc_hi((uint32_t)P.sbo_bytes, layout_type);
+      // probe bits (timing only, results wrong): 16 = every tap window starts at the slab base (atom aligned),
+      // 32 = 8-row groups 1024 B apart (atom aligned) instead of one slab row apart
+      const uint32_t a_hi = desc_hi((P.dbg & 32) ? 8 * row_bytes : (uint32_t)P.sbo_bytes, layout_type);
+      const uint32_t tap_mul = (P.dbg & 16) ? 0u : 1u;
       const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
@@ -612,7 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (mma_on) {
 #pragma unroll
                   for (int k = 0; k < KSTEPS; ++k) {
-                    const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                    const uint32_t al = a_lo + tap_mul * (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB) >> 4) + ((k * 32) >> 4);
                     tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc);
                     acc = 1;
                   }
@@ -729,7 +720,9 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   const bool s2 = a.stride == 2;
   P.Cin = a.Cin; P.Cout = a.Cout;
   const int cp = a.cout_pad_tc;
-  P.NT = cp > 256 ? 256 : cp;
+  // N tile: the whole (padded) Cout when it is 16 / 32 / 64 / 128 / 256, 256 for multiples of 256, else 64-column
+  // tiles (e.g. 192 = GETB qkv of a 64-channel block): the epilogue's column split needs a power-of-two tile
+  P.NT = cp > 256 ? 256 : ((cp & (cp - 1)) == 0 ? cp : 64);
   P.ntiles_n = cp / P.NT;
   P.KC = pick_kc(a.Cin);
   P.nchunks = a.Cin / P.KC;

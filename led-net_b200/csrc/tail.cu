@@ -303,15 +303,10 @@ tail2_kernel(const T* __restrict__ r1, int ld, int K, int h2, int w2, TP* __rest
   const T* src = r1 + (int64_t)n * h2 * w2 * ld;
 
   const int oy0 = 4 * (a0 + tr), ox0 = 4 * (b0 + tc);
-  float2 wy1[4], wx1[4], wy0[4], wx0[4];
-#pragma unroll
-  for (int r = 0; r < 4; ++r) {
-    int i0, i1; float l0, l1;
-    bilinear_coord(min(oy0 + r, Ho - 1), 0.5f, h2, i0, i1, l0, l1);
-    wy1[r] = make_float2(l1, l1); wy0[r] = make_float2(1.f - l1, 1.f - l1);
-    bilinear_coord(min(ox0 + r, Wo - 1), 0.5f, w2, i0, i1, l0, l1);
-    wx1[r] = make_float2(l1, l1); wx0[r] = make_float2(1.f - l1, 1.f - l1);
-  }
+  // exact x2, align_corners=False: even outputs take (1/4, 3/4) of window (i-1, i), odd ones (3/4, 1/4) of
+  // (i, i+1).  At the image border ATen clamps the source index (weights 1/0); the patch below replicates the
+  // border pixel instead, and fma(a, 3/4, a/4) == a exactly, so constant weights give the same bits.
+  const float2 q14 = make_float2(0.25f, 0.25f), q34 = make_float2(0.75f, 0.75f);
   float best[4][4];
   int bidx[4][4];
 #pragma unroll
@@ -346,20 +341,20 @@ tail2_kernel(const T* __restrict__ r1, int ld, int K, int h2, int w2, TP* __rest
         const float2 c0 = make_float2(pq.x, pq.y), c1 = make_float2(pq.z, pq.w);
         const float2 c2 = make_float2(rs.x, rs.y), c3 = make_float2(rs.z, rs.w);
         // output col c uses window cols (0,1),(1,2),(1,2),(2,3)
-        hrow[wi][0] = lerp2(c0, c1, wx0[0], wx1[0]);
-        hrow[wi][1] = lerp2(c1, c2, wx0[1], wx1[1]);
-        hrow[wi][2] = lerp2(c1, c2, wx0[2], wx1[2]);
-        hrow[wi][3] = lerp2(c2, c3, wx0[3], wx1[3]);
+        hrow[wi][0] = lerp2(c0, c1, q14, q34);
+        hrow[wi][1] = lerp2(c1, c2, q34, q14);
+        hrow[wi][2] = lerp2(c1, c2, q14, q34);
+        hrow[wi][3] = lerp2(c2, c3, q34, q14);
       }
       const int k = k0 + 2 * kp;
       const bool two = (2 * kp + 1) < kc;
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         float2 o[4];
-        o[0] = lerp2(hrow[0][c], hrow[1][c], wy0[0], wy1[0]);
-        o[1] = lerp2(hrow[1][c], hrow[2][c], wy0[1], wy1[1]);
-        o[2] = lerp2(hrow[1][c], hrow[2][c], wy0[2], wy1[2]);
-        o[3] = lerp2(hrow[2][c], hrow[3][c], wy0[3], wy1[3]);
+        o[0] = lerp2(hrow[0][c], hrow[1][c], q14, q34);
+        o[1] = lerp2(hrow[1][c], hrow[2][c], q34, q14);
+        o[2] = lerp2(hrow[1][c], hrow[2][c], q14, q34);
+        o[3] = lerp2(hrow[2][c], hrow[3][c], q34, q14);
 #pragma unroll
         for (int r = 0; r < 4; ++r) {
           if (o[r].x > best[r][c]) { best[r][c] = o[r].x; bidx[r][c] = k; }        // strict > : first max wins

@@ -162,20 +162,30 @@ def _oracle_grads(o, x, lab):
     return ref, {k: p.grad.detach().clone() for k, p in o.named_parameters()}
 
 
-def _check_grads(mine_grads, ref_grads, ref_grads64, tag):
-    """per-tensor gate against the float64 oracle, relative to the fp32 oracle's own error (see the docstring
-    of test_train_step_vs_oracle)."""
+def _check_grads(mine_grads, ref_grads, ref_grads64, tag, cond_floor=0.0):
+    """Gates against the float64 oracle, relative to the fp32 oracle's own error (see the docstring of
+    test_train_step_vs_oracle):
+      * whole gradient vector: ||ours - g64|| / ||g64|| <= max(1e-2, 3 x the fp32 oracle's) - the 1e-2 of north_star;
+      * per tensor (max-norm): <= max(1e-2, 3 x the fp32 oracle's error on that tensor, 3 x the conditioning of the
+        problem) where the conditioning is the fp32 oracle's own worst tensor, taken over this and earlier steps
+        (`cond_floor`): one rounding sample per tensor is a noisy estimate, and scatter / atomic summation order makes
+        ours vary from run to run.
+    Returns the conditioning estimate for later steps."""
     gscale = max(float(g.abs().max()) for g in ref_grads64.values())
     floor = 1e-6 * gscale
 
     def _err(grads, k, g64):
         return float((grads[k].double() - g64).abs().max()) / max(float(g64.abs().max()), 1e-30)
 
-    # conditioning of the whole problem = the fp32 reference's own worst tensor (a single rounding
-    # sample per tensor is a noisy estimate of that tensor's conditioning; scatter/atomic summation
-    # order makes ours vary from run to run, so no tensor is held to better than the reference's worst)
+    def _global(grads):
+        num = sum(float((grads[k].double() - g64).pow(2).sum()) for k, g64 in ref_grads64.items())
+        den = sum(float(g64.pow(2).sum()) for g64 in ref_grads64.values())
+        return (num / den) ** 0.5
+
+    g_mine, g_ref = _global(mine_grads), _global(ref_grads)
     worst_ref = max(_err(ref_grads, k, g64) for k, g64 in ref_grads64.items()
                     if float((ref_grads[k].double() - g64).abs().max()) > floor)
+    cond = max(worst_ref, cond_floor)
     worst, n_loose = 0.0, 0
     for k, g64 in ref_grads64.items():
         if float((mine_grads[k].double() - g64).abs().max()) <= floor:
@@ -183,10 +193,11 @@ def _check_grads(mine_grads, ref_grads, ref_grads64, tag):
         mine, theirs = _err(mine_grads, k, g64), _err(ref_grads, k, g64)
         worst = max(worst, mine)
         n_loose += mine > max(1e-2, 3 * theirs)
-        assert mine <= max(1e-2, 3 * theirs, 1.5 * worst_ref), (tag, k, mine, theirs, worst_ref)
-    print(f'{tag}: worst gradient rel err vs float64 oracle: ours {worst:.2e}, fp32 oracle {worst_ref:.2e}; '
-          f'{n_loose} tensors needed the conditioning allowance')
-    assert n_loose <= 4          # tensors that needed the whole-problem allowance
+        assert mine <= max(1e-2, 3 * theirs, 3 * cond), (tag, k, mine, theirs, cond)
+    print(f'{tag}: gradient vs float64 oracle: whole-vector rel err ours {g_mine:.2e} / fp32 oracle {g_ref:.2e}; '
+          f'worst tensor ours {worst:.2e} / fp32 oracle {worst_ref:.2e}; {n_loose} tensors above 3 x their own')
+    assert g_mine <= max(1e-2, 3 * g_ref), (tag, g_mine, g_ref)
+    return cond
 
 
 @pytest.mark.parametrize('K,hw,N', [(19, (128, 256), 2), (2, (192, 320), 3)])
@@ -221,7 +232,7 @@ def test_train_step_vs_oracle(K, hw, N):
     got = dict(m.named_parameters())
     assert set(got) == set(ref_grads)
     mine_grads = {k: got[k].grad.cpu() for k in ref_grads64}
-    _check_grads(mine_grads, ref_grads, ref_grads64, 'step 1')
+    cond = _check_grads(mine_grads, ref_grads, ref_grads64, 'step 1')
     # BatchNorm running statistics moved identically
     bufs_o = dict(o.named_buffers())
     for k, b in m.named_buffers():
@@ -257,7 +268,7 @@ def test_train_step_vs_oracle(K, hw, N):
     torch.cuda.synchronize()
     # train_step = zero_grad, backward, step: the step-2 gradients are still in .grad
     grads2 = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
-    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2')
+    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2', cond_floor=cond)
     for k in shadow:
         shadow[k].grad = grads2[k].clone()
     opt_s.step()                                                    # second step exercises the momentum buffer
