@@ -302,6 +302,23 @@ int ledb200_getb_create(int32_t dim, int32_t heads, int32_t hidden, int32_t wind
 int ledb200_getb_destroy(ledb200_getb* g);
 int ledb200_getb_forward(ledb200_getb* g, const void* x, void* out, int32_t N, int32_t H, int32_t W, void* stream);
 
+/* ---- result post-processing -------------------------------------------
+ * ledb200_postprocess: BaseSegmentor.postprocess_result (mmseg/models/segmentors/base.py:153-198) for ONE image:
+ *   logits fp32 [K,H,W] (NCHW plane layout) -> remove `padding_lrtb` (left, right, top, bottom; NULL = none) -> undo
+ *   `flip` (0 none, 1 horizontal, 2 vertical) -> bilinear resize to [out_h, out_w] (align_corners as the head's) ->
+ *   pred [out_h,out_w] = argmax over K (first max), or sigmoid(v) > threshold when K == 1 (pred dtype U8, I64 or F32);
+ *   `out_logits` (nullable) receives the resized fp32 [K,out_h,out_w] logits (sigmoid applied when K == 1).
+ * ledb200_slide_accumulate / ledb200_slide_finalize: EncoderDecoder.slide_inference (encoder_decoder.py:241-292):
+ *   preds[:, :, y1:y1+hc, x1:x1+wc] += crop_logits; count[:, 0, same window] += 1; then preds /= count in place and,
+ *   when `pred` is given, argmax over K into [N,H,W] (U8 or I64).  preds [N,K,H,W], count [N,1,H,W], fp32. */
+int ledb200_postprocess(const float* logits, int32_t K, int32_t H, int32_t W, const int32_t* padding_lrtb,
+                        int32_t flip, int32_t out_h, int32_t out_w, int32_t align_corners, float threshold,
+                        void* pred, int32_t pred_dtype, float* out_logits, void* stream);
+int ledb200_slide_accumulate(float* preds, float* count, const float* crop_logits, int32_t N, int32_t K, int32_t H,
+                             int32_t W, int32_t hc, int32_t wc, int32_t y1, int32_t x1, void* stream);
+int ledb200_slide_finalize(float* preds, const float* count, int32_t N, int32_t K, int32_t H, int32_t W, void* pred,
+                           int32_t pred_dtype, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

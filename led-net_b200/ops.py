@@ -99,3 +99,47 @@ def conv2d(x_nhwc, weight_oihw, bias=None, stride=1, relu=False, residual=None, 
                                    stride, int(relu), _p(w), _p(host[0]), _p(host[1]), _p(host[2]),
                                    backend, Cin, ld, ld, L.stream_ptr(x.device)), 'ledb200_conv2d')
     return out_full[..., :Cout]
+
+
+def postprocess(seg_logit, padding=None, flip=None, ori_shape=None, align_corners=False, threshold=0.3,
+                pred_dtype=torch.int64, want_logits=True):
+    """BaseSegmentor.postprocess_result for ONE image (base.py:153-198): seg_logit fp32 [K,H,W] -> crop `padding`
+    (left, right, top, bottom), undo `flip` ('horizontal' | 'vertical' | None), bilinear resize to `ori_shape`,
+    argmax (K > 1) or sigmoid > threshold (K == 1).  Returns (pred [1,h,w], logits [K,h,w] or None)."""
+    _need_cuda(seg_logit)
+    x = seg_logit.contiguous().float()
+    K, H, W = x.shape
+    pad = tuple(int(v) for v in (padding if padding is not None else (0, 0, 0, 0)))
+    assert flip in (None, False, 'horizontal', 'vertical'), flip
+    oh, ow = (int(v) for v in ori_shape) if ori_shape is not None else (H - pad[2] - pad[3], W - pad[0] - pad[1])
+    if K == 1:
+        pred_dtype = torch.float32                    # (sigmoid > threshold).to(seg_logits) in the reference
+    pred = torch.empty((1, oh, ow), dtype=pred_dtype, device=x.device)
+    out = torch.empty((K, oh, ow), dtype=torch.float32, device=x.device) if want_logits else None
+    pad_c = (C.c_int32 * 4)(*pad)
+    L.check(L.get().ledb200_postprocess(_p(x), K, H, W, pad_c, {None: 0, False: 0, 'horizontal': 1, 'vertical': 2}[flip],
+                                        oh, ow, int(bool(align_corners)), float(threshold), _p(pred),
+                                        L.torch_dtype_code(pred), _p(out), L.stream_ptr(x.device)), 'ledb200_postprocess')
+    return pred, out
+
+
+def slide_accumulate(preds, count, crop_logits, y1, x1):
+    """preds[:, :, y1:y1+hc, x1:x1+wc] += crop_logits; count[:, :, same] += 1 (encoder_decoder.py:283-287)."""
+    _need_cuda(preds, count, crop_logits)
+    assert preds.is_contiguous() and count.is_contiguous() and preds.dtype == count.dtype == torch.float32
+    crop = crop_logits.contiguous().float()
+    N, K, H, W = preds.shape
+    _, _, hc, wc = crop.shape
+    L.check(L.get().ledb200_slide_accumulate(_p(preds), _p(count), _p(crop), N, K, H, W, hc, wc, int(y1), int(x1),
+                                             L.stream_ptr(preds.device)), 'ledb200_slide_accumulate')
+
+
+def slide_finalize(preds, count, want_pred=False, pred_dtype=torch.int64):
+    """preds /= count in place (encoder_decoder.py:290); optionally also argmax over K -> [N,H,W]."""
+    _need_cuda(preds, count)
+    N, K, H, W = preds.shape
+    pred = torch.empty((N, H, W), dtype=pred_dtype, device=preds.device) if want_pred else None
+    L.check(L.get().ledb200_slide_finalize(_p(preds), _p(count), N, K, H, W, _p(pred),
+                                           L.torch_dtype_code(pred) if want_pred else L.I64,
+                                           L.stream_ptr(preds.device)), 'ledb200_slide_finalize')
+    return preds, pred

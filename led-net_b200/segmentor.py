@@ -12,6 +12,7 @@ import torch.nn.functional as F
 
 from .engine import Engine, MEAN, STD
 from .registry import MODELS
+from . import ops
 
 
 @MODELS.register_module()
@@ -131,24 +132,24 @@ class EncoderDecoder(nn.Module):
         return self.encode_decode(inputs, batch_img_metas)
 
     def slide_inference(self, inputs, batch_img_metas=None):
-        """encoder_decoder.py:241-292; accumulation uses torch ops (a fused scatter is a 'next' row)."""
+        """encoder_decoder.py:241-292.  Every crop runs the fused engine; `preds += F.pad(...)`, the count matrix and
+        the final division are the slide_accumulate / slide_finalize kernels (no padded full-size copy per crop)."""
         h_stride, w_stride = self.test_cfg['stride']
         h_crop, w_crop = self.test_cfg['crop_size']
         n, _, h_img, w_img = inputs.shape
         h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
         w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
-        preds = inputs.new_zeros((n, self.out_channels, h_img, w_img), dtype=torch.float32)
-        count = inputs.new_zeros((n, 1, h_img, w_img), dtype=torch.float32)
+        preds = torch.zeros((n, self.out_channels, h_img, w_img), dtype=torch.float32, device=inputs.device)
+        count = torch.zeros((n, 1, h_img, w_img), dtype=torch.float32, device=inputs.device)
         for hi in range(h_grids):
             for wi in range(w_grids):
                 y1, x1 = hi * h_stride, wi * w_stride
                 y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
                 y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
                 logit = self.encode_decode(inputs[:, :, y1:y2, x1:x2].contiguous())
-                preds += F.pad(logit, (x1, w_img - x2, y1, h_img - y2))
-                count[:, :, y1:y2, x1:x2] += 1
+                ops.slide_accumulate(preds, count, logit, y1, x1)
         assert (count == 0).sum() == 0
-        return preds / count
+        return ops.slide_finalize(preds, count)[0]
 
     def inference(self, inputs, batch_img_metas=None):
         mode = self.test_cfg.get('mode', 'whole')
@@ -158,17 +159,32 @@ class EncoderDecoder(nn.Module):
             else self.whole_inference(inputs, batch_img_metas)
 
     def postprocess_result(self, seg_logits, data_samples=None):
-        """base.py:153-198 for C > 1 with identity un-pad / resize (all benchmark configs)."""
+        """base.py:153-198: per image remove the padding, undo the test-time flip, resize to `ori_shape`, argmax
+        (or sigmoid > threshold for one class) - one kernel per image (ops.postprocess).  `data_samples` are dicts
+        whose 'metainfo' (or the dict itself) carries img_padding_size / padding_size, flip, flip_direction, ori_shape."""
         out = []
         for i in range(seg_logits.shape[0]):
-            lg = seg_logits[i]
-            out.append({'seg_logits': {'data': lg},
-                        'pred_sem_seg': {'data': lg.argmax(dim=0, keepdim=True)}})
+            meta = {}
+            if data_samples is not None and isinstance(data_samples[i], dict):
+                meta = data_samples[i].get('metainfo', data_samples[i])
+            padding = meta.get('img_padding_size', meta.get('padding_size', [0] * 4))
+            flip = None
+            if meta.get('flip', None):
+                flip = meta.get('flip_direction', None)
+                assert flip in ['horizontal', 'vertical']
+            pred, lg = ops.postprocess(seg_logits[i], padding=padding, flip=flip, ori_shape=meta.get('ori_shape'),
+                                       align_corners=self.align_corners,
+                                       threshold=getattr(self.decode_head, 'threshold', None) or 0.3)
+            out.append({'seg_logits': {'data': lg}, 'pred_sem_seg': {'data': pred}})
         return out
 
     def predict(self, inputs, data_samples=None):
         """encoder_decoder.py:187-222: list of {'seg_logits','pred_sem_seg'} per image."""
-        if self.test_cfg.get('mode', 'whole') == 'whole':
+        def _plain(s):                       # no crop / flip / resize requested for this sample
+            m = s.get('metainfo', s) if isinstance(s, dict) else {}
+            return not (m.get('flip') or m.get('ori_shape') is not None and tuple(m['ori_shape']) != tuple(inputs.shape[-2:])
+                        or any(m.get('img_padding_size', m.get('padding_size', [0] * 4))))
+        if self.test_cfg.get('mode', 'whole') == 'whole' and (data_samples is None or all(_plain(s) for s in data_samples)):
             pred, logits = self.engine().forward_infer(inputs, pred_dtype=torch.int64, want_logits=True)
             res = [{'seg_logits': {'data': logits[i]}, 'pred_sem_seg': {'data': pred[i:i + 1]}}
                    for i in range(pred.shape[0])]

@@ -302,3 +302,67 @@ def test_slide_inference_matches_oracle():
     ref = o.inference(x)
     got = m.inference(x.to(DEV))
     assert rel_err(got.cpu(), ref) < 1e-4
+
+
+def _ref_postprocess(lg, padding, flip, ori_shape, align_corners, threshold=0.3):
+    """the reference's postprocess_result body for one image (base.py:153-198) on CPU tensors"""
+    K, H, W = lg.shape
+    l, r, t, b = padding
+    x = lg[None, :, t:H - b, l:W - r]
+    if flip == 'horizontal':
+        x = x.flip(dims=(3,))
+    elif flip == 'vertical':
+        x = x.flip(dims=(2,))
+    x = oracle.resize(x, ori_shape, align_corners).squeeze(0)
+    if K > 1:
+        return x, x.argmax(dim=0, keepdim=True)
+    x = x.sigmoid()
+    return x, (x > threshold).to(x)
+
+
+@pytest.mark.parametrize('K,hw,padding,flip,ori,ac', [
+    (2, (64, 114), (0, 0, 0, 0), None, (90, 160), False),        # Apple-Branch ratio 1.40625 (512x910 -> 720x1280)
+    (19, (40, 56), (0, 3, 0, 5), 'horizontal', (64, 96), False),  # padded + flipped + up
+    (5, (37, 29), (2, 1, 3, 0), 'vertical', (20, 17), True),      # down-sampling, align_corners
+    (3, (16, 24), (0, 0, 0, 0), None, (16, 24), False),           # identity
+    (1, (20, 30), (0, 2, 0, 2), None, (31, 47), False),           # single class: sigmoid > threshold
+])
+def test_postprocess_result_matches_reference_steps(K, hw, padding, flip, ori, ac):
+    g = torch.Generator().manual_seed(K * 100 + hw[0])
+    lg = torch.randn(K, *hw, generator=g) * 3
+    ref_lg, ref_pred = _ref_postprocess(lg, padding, flip, ori, ac)
+    pred, out = L.ops.postprocess(lg.to(DEV), padding=padding, flip=flip, ori_shape=ori, align_corners=ac)
+    assert out.shape == ref_lg.shape and pred.shape == ref_pred.shape
+    assert rel_err(out.cpu(), ref_lg) < 1e-5
+    if K > 1:
+        assert pred.dtype == torch.int64
+        mism = pred.cpu() != ref_pred
+        # labels identical except numerical ties of the two best logits
+        top2 = ref_lg.topk(2, dim=0).values
+        assert not (mism[0] & ((top2[0] - top2[1]) > 1e-5 * ref_lg.abs().max())).any()
+        assert mism.float().mean() < 1e-3
+        assert torch.equal(out.argmax(dim=0, keepdim=True).cpu(), pred.cpu())       # self-consistent
+    else:
+        near = (ref_lg - 0.3).abs() < 1e-6
+        assert torch.equal(pred.cpu()[~near], ref_pred[~near])
+
+
+def test_predict_with_metainfo_uses_postprocess():
+    """EncoderDecoder.predict with ori_shape / padding / flip in the samples' metainfo == oracle whole inference followed
+    by the reference's post-processing steps."""
+    K = 3
+    o, m = build_pair(K, dtype='fp32')
+    img = synth.make_images_u8(2, 64, 96, seed=5)
+    x = oracle.preprocess(img)
+    ref_logits, _ = o.predict(x)
+    metas = [dict(metainfo=dict(ori_shape=(80, 100), img_padding_size=(0, 4, 0, 8))),
+             dict(metainfo=dict(ori_shape=(64, 96), flip=True, flip_direction='horizontal'))]
+    res = m.predict(x.to(DEV), metas)
+    for i, meta in enumerate(metas):
+        mi = meta['metainfo']
+        ref_lg, ref_pred = _ref_postprocess(ref_logits[i], mi.get('img_padding_size', (0, 0, 0, 0)),
+                                            mi.get('flip_direction') if mi.get('flip') else None, mi['ori_shape'], False)
+        got = res[i]['seg_logits']['data'].cpu()
+        assert got.shape == ref_lg.shape
+        assert rel_err(got, ref_lg) < 1e-4
+        assert (res[i]['pred_sem_seg']['data'].cpu() != ref_pred).float().mean() < 1e-3
