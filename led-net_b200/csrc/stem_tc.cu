@@ -25,6 +25,11 @@ namespace {
 
 using namespace tc;
 
+__device__ __forceinline__ void stg256(void* p, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+               ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+}
+
 constexpr int ST_TW = 16, ST_TH = 8;      // output tile (128 pixels = UMMA M)
 constexpr int ST_THREADS = 128;
 constexpr int ST_MAXN = 32;
@@ -86,6 +91,8 @@ __global__ void __launch_bounds__(ST_THREADS, 6) stem_tc_kernel(const __grid_con
   const int cout8 = (P.Cout + 7) & ~7;
   const int sh = 31 - __clz(P.NP * 2);                      // log2(bytes per staged pixel); NP is 16 or 32
   uint32_t phase = 0;
+  const bool direct = P.NP == 32 && P.Cout == 32 && (P.out_ld | P.out2_ld) % 16 == 0 &&
+                      (((uintptr_t)P.out | (uintptr_t)P.out2) % 32 == 0);
 
   for (uint32_t tile = blockIdx.x; tile < P.total_tiles; tile += gridDim.x) {
     const int tw = (int)(tile % (uint32_t)P.tiles_w);
@@ -162,6 +169,37 @@ __global__ void __launch_bounds__(ST_THREADS, 6) stem_tc_kernel(const __grid_con
     tc_fence_after();
     // ---- epilogue: thread t owns accumulator row t (TMEM lane t)
     const uint32_t taddr = tmem_base + ((uint32_t)(warp * 32) << 16);
+    if (direct) {
+      // 32 channels = 64 contiguous bytes per pixel and output: two 256-bit stores each, no staging
+      // (same reasoning as the conv_tc fast path: fewer instructions, no shared-memory round trip)
+      uint32_t v[32];
+      tc_ld16(taddr, v);
+      tc_ld16(taddr + 16, v + 16);
+      tc_wait_ld();
+      if (oh < P.Ho && ow < P.Wo) {
+        const int64_t gp = ((int64_t)n * P.Ho + oh) * P.Wo + ow;
+        uint4 o[4], o2[4];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+          float f[8];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            f[j] = __uint_as_float(v[8 * g + j]) + s_bias[8 * g + j];
+            if (P.relu) f[j] = fmaxf(f[j], 0.f);
+          }
+          o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
+          if (P.out2) {
+            float w[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) w[j] = fmaxf(fmaf(f[j], s_o2s[8 * g + j], s_o2b[8 * g + j]), 0.f);
+            o2[g] = make_uint4(pack_bf16x2(w[0], w[1]), pack_bf16x2(w[2], w[3]), pack_bf16x2(w[4], w[5]), pack_bf16x2(w[6], w[7]));
+          }
+        }
+        if (P.out) { stg256(P.out + gp * P.out_ld, o[0], o[1]); stg256(P.out + gp * P.out_ld + 16, o[2], o[3]); }
+        if (P.out2) { stg256(P.out2 + gp * P.out2_ld, o2[0], o2[1]); stg256(P.out2 + gp * P.out2_ld + 16, o2[2], o2[3]); }
+      }
+      continue;     // the __syncthreads() after the next tile's gather orders these TMEM reads before its MMAs
+    }
     uint8_t* st1 = sStage[0][warp];
     uint8_t* st2 = sStage[1][warp];
     for (int c0 = 0; c0 < P.NP; c0 += 16) {
