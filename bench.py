@@ -289,7 +289,19 @@ def main():
     else:
         ach = dom['bytes'] / (dom['ms'] * 1e-3) / 1e9
         roof = dict(bound='hbm', achieved=ach, peak=pk['hbm'], unit='GB/s', frac=ach / pk['hbm'])
-    roof.update(traffic=None, kernel=dom_kind, launches_per_step=dom['n'], kernel_ms_per_step=dom['ms'],
+    # DRAM bytes per launch of the dominant kernel family, from the committed ncu capture of this workload
+    # (profiles/dominant_kernel_traffic.json, written by tools/ncu_traffic.py from dram__bytes_{read,write}.sum)
+    traffic = None
+    try:
+        with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), 'profiles', 'dominant_kernel_traffic.json')) as f:
+            tj = json.load(f)
+        if tj.get('kernel') == dom_kind and tj.get('batch') == N and (tj.get('height'), tj.get('width')) == (H, W):
+            traffic = tj['dram_bytes_per_launch']
+            roof['traffic_source'] = tj.get('source')
+            roof['algorithmic_bytes_per_launch'] = dom['bytes'] / dom['n']
+    except (OSError, ValueError, KeyError):
+        pass
+    roof.update(traffic=traffic, kernel=dom_kind, launches_per_step=dom['n'], kernel_ms_per_step=dom['ms'],
                 kernel_share_of_step=dom['ms'] / sum(f['ms'] for f in fam.values()),
                 peak_source=pk['source'], step_roofline_ms=roof_ms,
                 step_frac_of_per_layer_roofline=roof_ms / ms_step)

@@ -284,6 +284,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         }
       }
     } else {
+    if (P.stage_bytes == 0) __trap();            // host promised an all-interior fast-path launch
     const bool pvalid = (th * TH + ph < Ho) && (tw * TW + pw < Wo);
     const int64_t pix0 = ((int64_t)n * Ho + th * TH) * Wo + tw * TW;       // first pixel of the tile
     const int cgt = nt * NT;                                               // first output channel of this N tile
@@ -778,9 +779,20 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   // ---- shared-memory plan
   P.cp = cp;
   P.stage_bytes = a.out2 ? 65536u : 32768u;
+  {
+    // When every tile is interior and the launch takes the epilogue fast path (same conditions as in
+    // epilogue_loop), the staging tiles are never touched: give their 32-64 KB to the A ring / resident weights.
+    const int cout8 = (a.Cout + 7) & ~7;
+    const int ncols_g = P.NT >= 64 ? P.NT / 2 : P.NT;
+    const bool al32 = ((a.out_ld | a.out2_ld | a.res_ld) % 16 == 0) &&
+                      (((uintptr_t)a.out | (uintptr_t)a.out2 | (uintptr_t)a.res) % 32 == 0);
+    const bool fast = (ncols_g % 32 == 0) && a.relu != 2 &&
+                      (a.up ? (a.up_ld == 24 && cp == 32 && cout8 == 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
+    if (fast && a.Ho % TH == 0 && a.Wo % TW == 0) P.stage_bytes = 0;
+  }
   const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
-  P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= 100 * 1024) ? 1 : 0;
+  P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= (P.stage_bytes ? 100u : 150u) * 1024) ? 1 : 0;
   static const bool no_resident = getenv("LEDB200_TC_NO_RESIDENT") != nullptr;
   if (no_resident) P.b_resident = 0;
   uint32_t left = SMEM_BUDGET - bar_bytes - 1024;
