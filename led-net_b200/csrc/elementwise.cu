@@ -151,12 +151,18 @@ __global__ void __launch_bounds__(kThreads) upsample_add16_kernel(UpAddArgs a, f
       o[hh] = pack_bf16x8(v);
       if (out2) {
         float w[8];
+        if (a.o2_scale) {                      // per-channel affine as four 16 B loads (arena buffers: 16 B aligned)
+          const float4* sc = reinterpret_cast<const float4*>(a.o2_scale + g * 16 + hh * 8);
+          const float4* sf = reinterpret_cast<const float4*>(a.o2_shift + g * 16 + hh * 8);
+          const float4 s0 = __ldg(sc), s1 = __ldg(sc + 1), b0 = __ldg(sf), b1 = __ldg(sf + 1);
+          w[0] = fmaf(v[0], s0.x, b0.x); w[1] = fmaf(v[1], s0.y, b0.y); w[2] = fmaf(v[2], s0.z, b0.z); w[3] = fmaf(v[3], s0.w, b0.w);
+          w[4] = fmaf(v[4], s1.x, b1.x); w[5] = fmaf(v[5], s1.y, b1.y); w[6] = fmaf(v[6], s1.z, b1.z); w[7] = fmaf(v[7], s1.w, b1.w);
+        } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const int ch = g * 16 + hh * 8 + c;
-          const float tt = a.o2_scale ? fmaf(v[c], a.o2_scale[ch], a.o2_shift[ch]) : v[c];
-          w[c] = fmaxf(tt, 0.f);
+          for (int c = 0; c < 8; ++c) w[c] = v[c];
         }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) w[c] = fmaxf(w[c], 0.f);
         o2[hh] = pack_bf16x8(w);
       }
     }
@@ -342,7 +348,8 @@ int launch_upsample_add(const UpAddArgs& a, cudaStream_t st) {
   const float sh = (float)a.h / (float)a.H, sw = (float)a.w / (float)a.W;
   const int64_t total = (int64_t)a.N * a.H * a.W * (a.C / 8);
   const bool al32 = a.C % 16 == 0 && (!a.out || a.out_ld % 16 == 0) && (!a.out2 || a.out2_ld % 16 == 0) &&
-                    (((uintptr_t)a.base | (uintptr_t)a.src | (uintptr_t)a.out | (uintptr_t)a.out2) % 32 == 0);
+                    (((uintptr_t)a.base | (uintptr_t)a.src | (uintptr_t)a.out | (uintptr_t)a.out2) % 32 == 0) &&
+                    (((uintptr_t)a.o2_scale | (uintptr_t)a.o2_shift) % 16 == 0);
   if (a.dtype == LEDB200_BF16 && al32 && total / 2 < (1ll << 31) && (int64_t)a.h * a.w * a.C < (1ll << 31)) {
     const uint32_t t16 = (uint32_t)(total / 2);
     upsample_add16_kernel<<<grid_for(t16), kThreads, 0, st>>>(a, sh, sw, t16);

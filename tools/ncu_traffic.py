@@ -4,11 +4,14 @@ forward at the bench workload into profiles/dominant_kernel_traffic.json (read b
 
     ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum --clock-control none --csv \
         --log-file gpurun_out/r1c/traffic.csv python tools/prof_forward.py --batch 16 --iters 1
-    python tools/ncu_traffic.py gpurun_out/r1c/traffic.csv conv_tc 16 1024 2048 profiles/r1c_traffic.csv
+    python tools/ncu_traffic.py gpurun_out/r1c/traffic.csv 'conv_tc=conv_tc|stem_tc' 16 1024 2048 profiles/r1c_traffic.csv
+
+(`kind=regex`: the engine's op kind as bench.py names it, and the regex selecting that family's kernels.)
 """
 import csv
 import json
 import os
+import re
 import sys
 from collections import OrderedDict
 
@@ -28,9 +31,11 @@ for r in rows[1:]:
     elif u in ('ms', 'msecond'):
         v *= 1e6
     d[r[mi]] = v
-fam = [d for d in per.values() if family in d['name']]
+kind, _, pattern = family.partition('=')
+pattern = re.compile(pattern or kind)
+fam = [d for d in per.values() if pattern.search(d['name'])]
 tot = sum(d.get('dram__bytes_read.sum', 0) + d.get('dram__bytes_write.sum', 0) for d in fam)
-out = dict(kernel=family, batch=batch, height=height, width=width, launches=len(fam),
+out = dict(kernel=kind, kernel_regex=pattern.pattern, batch=batch, height=height, width=width, launches=len(fam),
            dram_bytes_per_launch=tot / max(len(fam), 1),
            dram_read_bytes_total=sum(d.get('dram__bytes_read.sum', 0) for d in fam),
            dram_write_bytes_total=sum(d.get('dram__bytes_write.sum', 0) for d in fam),
