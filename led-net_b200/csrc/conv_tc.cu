@@ -37,7 +37,7 @@
 namespace ledb {
 namespace {
 
-constexpr int kThreads = 320;            // TMA warp, MMA warp, 2 x 4 epilogue warps
+constexpr int kThreads = 352;            // TMA warp, MMA warp, 2 x 4 epilogue warps, second MMA issuer (warp 10)
 constexpr int TH = 16, TW = 8;            // output tile: 16 rows x 8 cols = 128 pixels = UMMA M
 constexpr int MAX_SLABS = 6, MAX_TAPS = 9;
 constexpr uint32_t SMEM_BUDGET = 220 * 1024;
@@ -69,6 +69,7 @@ struct TcParams {
   int step1[4], step2[4];            // grid and 2*grid tiles as digits (n-tile, tile col, tile row, image)
   uint32_t tmem_cols;
   int nst;                           // accumulator stages in TMEM: 4 when 4*NT <= 512 columns, else 2
+  int nmw;                           // MMA issuer threads: 2 when weights are resident and the A ring allows it
   // epilogue
   __nv_bfloat16* out; int out_ld;
   __nv_bfloat16* out2; int out2_ld;
@@ -79,7 +80,7 @@ struct TcParams {
   // optional: out += bilinear x2 upsample (align_corners=False) of `up` [N, up_h, up_w, up_ld], added AFTER the ReLU
   const __nv_bfloat16* up; int up_ld, up_h, up_w;
   int up_f16, out_f16;               // ladder rungs are kept in fp16 (11-bit mantissa; logits are far inside its range)
-  int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 16/32 aligned A windows
+  int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 32 atom-aligned A row groups, 64 empty epilogue, 128 single MMA issuer
 };
 
 using namespace tc;   // PTX wrappers: tc_common.cuh
@@ -202,7 +203,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
       mbar_wait(&t_full[ts], tp);
       tc_fence_after();
       const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
-      for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      for (int c0 = (P.dbg & 64) ? cend : cbeg; c0 < cend; c0 += 32) {     // probe bit 64: epilogue only hands the stage back
         uint32_t v[32];
         tc_ld16(taddr0 + c0, v);
         tc_ld16(taddr0 + c0 + 16, v + 16);
@@ -555,19 +556,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
-  } else if (warp == 1) {
-    // =========================== MMA issuer: ONE elected lane runs the whole role ==================
+  } else if (warp == 1 || warp == 10) {
+    // =========================== MMA issuers: ONE elected lane of warp 1 (and of warp 10) ==========
+    // Two issuers alternate tiles when the weights are resident.  Measured (ncu r1c, profiles/r1c_notes.md): after
+    // the last tcgen05.mma of a tile the issuing thread rewrites a uniform register the queued MMAs still read
+    // (write-after-read scoreboard), so it sits until the MMA queue has drained and only then runs its ~250
+    // instructions of barrier waits and descriptor set-up for the next tile - the tensor pipe idles ~1250 clk per
+    // tile (83 clk per MMA against 48 in isolation).  With a second issuer that bubble is covered by the other
+    // thread's tile: the two tiles use different accumulator stages and A slabs, so their MMAs may interleave.
     // (a branch on elect.sync, not a per-lane predicate on each MMA: ptxas then knows a single thread is
     // active and issues each tcgen05.mma straight from uniform registers; the predicated form cost an
     // ELECT / R2UR.BROADCAST / BRA.U.ANY waterfall of 17 instructions per MMA, and this thread's issue
     // rate is the per-tile critical path of every 3x3 layer - ncu r1b: producer and epilogue both wait on it)
-    if (elect_one()) {
+    const int nmw = (P.dbg & 128) ? 1 : P.nmw;              // host: 2 only with resident weights and SA % (2 * slabs per tile) == 0
+    const int mw = (warp == 1) ? 0 : 1;
+    if (mw < nmw && elect_one()) {
       const bool mma_on = !(P.dbg & 2);
       const uint32_t idesc = make_idesc_bf16_m128(P.NT);
-      // probe bits (timing only, results wrong): 16 = every tap window starts at the slab base (atom aligned),
-      // 32 = 8-row groups 1024 B apart (atom aligned) instead of one slab row apart
+      // probe bit 32 (timing only, results wrong): 8-row groups 1024 B apart (atom aligned) instead of one slab row
       const uint32_t a_hi = desc_hi((P.dbg & 32) ? 8 * row_bytes : (uint32_t)P.sbo_bytes, layout_type);
-      const uint32_t tap_mul = (P.dbg & 16) ? 0u : 1u;
       const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
       const uint32_t sA_u = smem_u32(sA), sB_u = smem_u32(sB);
       constexpr uint32_t ROWB = KSTEPS * 32;        // bytes per A/B row = KC * 2
@@ -578,38 +585,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int ts = 0, tp = 0;
       if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
       const uint32_t total = (uint32_t)P.total_tiles;
-      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+      // the j-th tile of this CTA owns accumulator stage j % nst and the next nchunks * slabs A stages of the ring
+      const int slabs_per_tile = P.nchunks * mode_slabs<MODE>();
+      auto skip_tile = [&]() {
+        for (int i = 0; i < slabs_per_tile; ++i) if (++sa == P.SA) { sa = 0; pa ^= 1; }
+        if (++ts == P.nst) { ts = 0; tp ^= 1; }
+      };
+      if (mw == 1) skip_tile();
+      for (uint32_t tile = blockIdx.x + (uint32_t)mw * gridDim.x; tile < total; tile += (uint32_t)nmw * gridDim.x) {
         mbar_wait(&t_empty[ts], tp ^ 1);            // epilogue has drained this accumulator stage
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ts * P.NT);
-        uint32_t acc = 0;
         for (int ch = 0; ch < P.nchunks; ++ch) {
+          // accumulate flag: 0 only for the very first MMA of a tile.  It must NOT be a loop-carried register:
+          // ptxas then re-materialises it into the uniform register the in-flight UTCHMMAs still read (R2UR per
+          // tap), and that write-after-read wait drains the MMA queue at every tap (measured: 158 clk stall per
+          // tap, 83 clk per MMA instead of 48 - profiles/r1c_notes.md).  Every MMA but the chunk's first takes a
+          // literal 1.
+          const uint32_t acc_first = ch ? 1u : 0u;
           const uint32_t b_chunk = b_lo0 + (uint32_t)(ch * 9) * b_tile16;   // resident weights of this chunk
 #pragma unroll
           for (int s = 0; s < mode_slabs<MODE>(); ++s) {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
             const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
+            if (BRES) {
+              // resident weights: no per-tap waits, so the slab's MMAs are ONE straight-line block - every
+              // descriptor word is the per-slab base plus an immediate and the uniform registers the in-flight
+              // UTCHMMAs read are not rewritten between taps
+              if (mma_on) {
 #pragma unroll
-            for (int t = 0; t < 9; ++t) {
-              if (t < mode_taps<MODE>(s)) {
-                uint32_t b_lo;
-                if (BRES) {
-                  b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
-                } else {
-                  mbar_wait(&b_full[sb], pb);
-                  tc_fence_after();
-                  b_lo = b_lo0 + (uint32_t)sb * b_tile16;
-                }
-                if (mma_on) {
+                for (int t = 0; t < 9; ++t) {
+                  if (t < mode_taps<MODE>(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
 #pragma unroll
-                  for (int k = 0; k < KSTEPS; ++k) {
-                    const uint32_t al = a_lo + tap_mul * (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB) >> 4) + ((k * 32) >> 4);
-                    tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc);
-                    acc = 1;
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                    }
                   }
                 }
-                if (!BRES) {
+              }
+            } else {
+#pragma unroll
+              for (int t = 0; t < 9; ++t) {
+                if (t < mode_taps<MODE>(s)) {
+                  mbar_wait(&b_full[sb], pb);
+                  tc_fence_after();
+                  const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_tile16;
+                  if (mma_on) {
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                    }
+                  }
                   tc_commit(&b_empty[sb]);                  // frees the B stage when these MMAs retire
                   if (++sb == P.SB) { sb = 0; pb ^= 1; }
                 }
@@ -621,10 +653,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tc_commit(&t_full[ts]);                             // accumulator complete -> epilogue
         if (++ts == P.nst) { ts = 0; tp ^= 1; }
+        if (nmw == 2) skip_tile();                          // the other issuer's tile
       }
     }
     __syncwarp();
-  } else {
+  } else if (warp < 10) {
     // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
     const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);
     const int variant = P.up ? 8 : ((P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0));
@@ -805,6 +838,15 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   }
   P.SA = (int)std::min<uint32_t>(8, left / P.a_stage_bytes);
   if (P.SA < 2) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
+  {
+    // Two MMA issuers alternate tiles (see the kernel).  An mbarrier parity wait is only sound when the waiter is at
+    // most one phase behind, so every A stage must always be consumed by the SAME issuer: the ring length has to be
+    // a multiple of 2 x (slabs per tile).  Trim the ring to that, or fall back to one issuer (stride-2 layers: 6 slabs).
+    const int slabs_per_tile = P.nchunks * P.nslabs;
+    const int sa2 = P.SA / (2 * slabs_per_tile) * (2 * slabs_per_tile);
+    P.nmw = 1;
+    if (P.b_resident && sa2 >= 2 * slabs_per_tile && sa2 >= 2) { P.nmw = 2; P.SA = sa2; }
+  }
   const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
                       (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
   P.nst = (4 * P.NT <= 512) ? 4 : 2;

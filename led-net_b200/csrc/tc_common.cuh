@@ -115,6 +115,17 @@ __device__ __forceinline__ void tc_mma2(uint32_t d_tmem, uint32_t a_lo, uint32_t
       "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
       ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate) : "memory");
 }
+// same, accumulate always on (no predicate operand to materialise)
+__device__ __forceinline__ void tc_mma2_acc(uint32_t d_tmem, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                                            uint32_t idesc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.eq.b32 p, 0, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc) : "memory");
+}
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t* v) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"

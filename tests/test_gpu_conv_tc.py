@@ -51,14 +51,27 @@ def test_conv_tc(cin, cout, k, stride, hw):
     assert rel_err(out.float(), out_d.float()) < 8e-3
 
 
-def test_conv_tc_many_tiles_persistent():
-    # more tiles than SMs: exercises the persistent loop, TMEM double buffering and ring wrap-around
-    g = torch.Generator().manual_seed(7)
-    x = torch.randn(4, 64, 128, 256, generator=g).bfloat16().float()
-    w = (torch.randn(64, 64, 3, 3, generator=g) * (2.0 / 576) ** 0.5).bfloat16().float()
-    ref = F.conv2d(x, w, None, 1, 1)
-    out = ops.conv2d(x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16), w, None, 1, backend=2)
+@pytest.mark.parametrize('cin,cout,stride,nhw', [
+    (64, 64, 1, (4, 128, 256)),      # 7 tiles per CTA, one slab per tile: two MMA issuers alternate tiles
+    (32, 32, 1, (2, 256, 256)),      # 64 B swizzle rows, alternate-tile epilogue groups
+    (128, 64, 1, (4, 128, 128)),     # two Cin chunks per tile, 147 KB of resident weights (head conv)
+    (64, 128, 2, (8, 128, 256)),     # stride 2: six slabs per tile on a shorter ring -> single issuer
+    (128, 128, 1, (4, 64, 128)),     # streamed weights
+])
+def test_conv_tc_many_tiles_persistent(cin, cout, stride, nhw):
+    # more tiles than SMs: exercises the persistent loop, the TMEM accumulator stages, ring wrap-around and the
+    # hand-over between the two MMA issuer threads (with and without a residual)
+    g = torch.Generator().manual_seed(7 + cin + cout)
+    x = torch.randn(nhw[0], cin, nhw[1], nhw[2], generator=g).bfloat16().float()
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (9 * cin)) ** 0.5).bfloat16().float()
+    ref = F.conv2d(x, w, None, stride, 1)
+    res = torch.randn(ref.shape, generator=g).bfloat16().float()
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    out = ops.conv2d(xd, w, None, stride, backend=2)
     assert rel_err(out.float().cpu().permute(0, 3, 1, 2), ref) < 6e-3
+    rd = res.permute(0, 2, 3, 1).contiguous().to(DEV, torch.bfloat16)
+    out = ops.conv2d(xd, w, None, stride, relu=True, residual=rd, backend=2)
+    assert rel_err(out.float().cpu().permute(0, 3, 1, 2), F.relu(ref + res)) < 6e-3
 
 
 @pytest.mark.parametrize('hw', [(64, 96), (70, 94), (34, 50)])
