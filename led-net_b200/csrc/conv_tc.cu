@@ -211,7 +211,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
         uint4 o[4], o2[HAS_OUT2 ? 4 : 1];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < (HAS_UP ? 3 : 4); ++g) {     // ladder rungs: 24 stored channels, the 4th group is padding
           float f[8];
           const float4 b0 = lds128f(bias_b + 32 * g);
           const float4 b1 = lds128f(bias_b + 32 * g + 16);
@@ -255,10 +255,9 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
               }
             }
           }
-          if (HAS_UP && P.out_f16) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);   // saturate, never inf
-            o[g] = make_uint4(pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
+          if (HAS_UP && P.out_f16) {                   // cvt.rn.satfinite: saturates at +-65504, never inf
+            o[g] = make_uint4(pack_f16x2_sat(f[0], f[1]), pack_f16x2_sat(f[2], f[3]), pack_f16x2_sat(f[4], f[5]),
+                              pack_f16x2_sat(f[6], f[7]));
           } else if (HAS_OUT) {
             o[g] = make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7]));
           }

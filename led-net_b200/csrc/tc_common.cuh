@@ -171,6 +171,11 @@ __device__ __forceinline__ uint32_t pack_f16x2(float a, float b) {
   __half2 h = __floats2half2_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&h);
 }
+__device__ __forceinline__ uint32_t pack_f16x2_sat(float a, float b) {   // a -> low half, b -> high half
+  uint32_t r;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
 __device__ __forceinline__ void unpack8h(const uint4& u, float* f) {
   const __half2* h = reinterpret_cast<const __half2*>(&u);
 #pragma unroll
