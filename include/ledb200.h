@@ -319,6 +319,18 @@ int ledb200_slide_accumulate(float* preds, float* count, const float* crop_logit
 int ledb200_slide_finalize(float* preds, const float* count, int32_t N, int32_t K, int32_t H, int32_t W, void* pred,
                            int32_t pred_dtype, void* stream);
 
+/* ---- SEAM edge gate -----------------------------------------------------
+ * The inline edge path of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338, 388-389), eval mode:
+ *   e = minmax_normalise(BN(conv3x3 C->1 (x))) over the whole tensor; b_s = [clamp(laplacian_stride_s(e), 0) > t] for
+ *   s = 1, 2, 4 (strided maps nearest-upsampled); m = [0.6 b_1 + 0.3 b_2 + 0.1 b_4 > t]; out = BN(conv3x3 1->C (m)) * x_s + x_s.
+ * x / x_s / out: NHWC of `dtype` (F32 or BF16), C a multiple of 8.  `params`: device fp32 block of
+ * ledb200_seam_param_floats(C) floats: w1[9][C] (tap major), a1, b1, six pad floats, w2[9][C], a2[C], b2[C] (BatchNorm folded to
+ * y = a * conv + b).  `workspace`: ledb200_seam_workspace_bytes(N, H, W) bytes. */
+int64_t ledb200_seam_param_floats(int32_t C);
+int64_t ledb200_seam_workspace_bytes(int32_t N, int32_t H, int32_t W);
+int ledb200_seam_forward(const void* x, const void* x_s, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W,
+                         int32_t C, float threshold, const float* params, void* workspace, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -14,5 +14,6 @@ from .engine import Engine  # noqa: F401
 from .sesp import SESP  # noqa: F401
 from .mfaf import Muti_AFF  # noqa: F401
 from .getb import GETBBlock  # noqa: F401
+from .seam import SEAM  # noqa: F401
 from .optim import FlatSGD, PolyLR  # noqa: F401
 from . import ops, synth, train_ops  # noqa: F401

@@ -29,6 +29,7 @@ SYMBOLS = [
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
     'ledb200_getb_param_floats', 'ledb200_getb_create', 'ledb200_getb_destroy', 'ledb200_getb_forward',
     'ledb200_postprocess', 'ledb200_slide_accumulate', 'ledb200_slide_finalize',
+    'ledb200_seam_param_floats', 'ledb200_seam_workspace_bytes', 'ledb200_seam_forward',
 ]
 
 
@@ -115,6 +116,11 @@ def get():
     lib.ledb200_postprocess.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, f32, vp, i32, vp, vp]
     lib.ledb200_slide_accumulate.argtypes = [vp, vp, vp] + [i32] * 8 + [vp]
     lib.ledb200_slide_finalize.argtypes = [vp, vp] + [i32] * 4 + [vp, i32, vp]
+    lib.ledb200_seam_param_floats.argtypes = [i32]
+    lib.ledb200_seam_param_floats.restype = i64
+    lib.ledb200_seam_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ledb200_seam_workspace_bytes.restype = i64
+    lib.ledb200_seam_forward.argtypes = [vp, vp, vp] + [i32] * 5 + [f32, vp, vp, vp]
     for name in SYMBOLS:
         fn = getattr(lib, name)
         if fn.restype is C.c_int and name not in ('ledb200_version',):

@@ -126,3 +126,49 @@ def test_getb_errors():
         m(torch.zeros(1, 64, 8, 8))
     with pytest.raises(L.LedB200Error):
         m(torch.zeros(1, 64, 3, 16, device=DEV))        # reflect pad 5 >= height 3: F.pad rejects it too
+
+
+@pytest.mark.parametrize('shape', [(2, 32, 48), (1, 37, 51), (1, 5, 7), (3, 128, 256)])
+@pytest.mark.parametrize('dtype', [torch.float32, torch.bfloat16])
+def test_seam_vs_oracle(shape, dtype):
+    """SEAM edge gate against oracle/seam.py (a restatement of tools/speed/ddrnet_speed.py:282-338, 388-389; upstream has
+    no runnable module or test for it: parity unpinned beyond the restatement).  The mask is a chain of hard thresholds,
+    so pixels whose Laplacians sit within rounding distance of the threshold may legitimately flip: they (and their 3x3
+    neighbourhood, through conv_2) are excluded; everything else must match."""
+    from oracle.seam import OracleSEAM
+    import torch.nn.functional as F
+    o = OracleSEAM(64).eval()
+    sd = bc.block_state_dict(o.state_dict(), seed=23)
+    sd['fusion_kernel'] = o.fusion_kernel.detach().clone()         # a constant (0.6, 0.3, 0.1), not a trained weight
+    o.load_state_dict(sd)
+    m = L.SEAM(64).eval()
+    m.load_state_dict(sd)
+    g = torch.Generator().manual_seed(shape[1] * 5 + shape[2])
+    x = torch.randn(shape[0], 64, shape[1], shape[2], generator=g).to(dtype).float()
+    xs = torch.randn(shape[0], 64, shape[1], shape[2], generator=g).to(dtype).float()
+    with torch.no_grad():
+        ref = o(x, xs)
+        mask, e = o.edge_mask(x)
+        # instability map: any of the three Laplacians within eps of the threshold at the position it is sampled
+        lap = lambda s: F.conv2d(e, o.laplacian_kernel, stride=s, padding=1).clamp(min=0)    # noqa: E731
+        eps = 2e-5       # bf16 mode: x is pre-rounded and the edge response stays fp32, so the mask is as sharp as in fp32
+        unstable = (lap(1) - 0.1).abs() < eps
+        for s in (2, 4):
+            unstable |= F.interpolate(((lap(s) - 0.1).abs() < eps).float(), e.shape[2:], mode='nearest') > 0
+        unstable = F.max_pool2d(unstable.float(), 3, 1, 1) > 0                                 # conv_2's 3x3 reach
+    out = m(x.to(DEV, dtype), xs.to(DEV, dtype)).float().cpu()
+    assert out.shape == ref.shape
+    ok = ~unstable.expand_as(ref)
+    assert ok.float().mean() > 0.9
+    tol = 2e-5 if dtype == torch.float32 else 8e-3
+    err = ((out - ref).abs() * ok).max() / ref.abs().max()
+    assert err < tol, float(err)
+    assert 0.02 < float(mask.mean()) < 0.98            # the gate is exercised on both sides
+
+
+def test_seam_errors():
+    with pytest.raises(NotImplementedError):
+        L.SEAM(channels=60)
+    m = L.SEAM(64).eval()
+    with pytest.raises(L.LedB200Error):
+        m(torch.zeros(1, 64, 4, 4), torch.zeros(1, 64, 4, 4))
