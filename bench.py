@@ -115,6 +115,8 @@ def main():
     ap.add_argument('--batch', type=int, default=WORKLOAD['batch_per_gpu'])
     ap.add_argument('--height', type=int, default=WORKLOAD['height'])
     ap.add_argument('--width', type=int, default=WORKLOAD['width'])
+    ap.add_argument('--classes', type=int, default=WORKLOAD['num_classes'],
+                    help='other BASELINE configs (e.g. config 5: --batch 128 --height 512 --width 512 --classes 2)')
     ap.add_argument('--dtype', default='bf16', choices=['bf16', 'fp32'])
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op table to stderr')
@@ -150,7 +152,7 @@ def main():
         import torch.distributed as dist
         dist.init_process_group('nccl', device_id=dev)
 
-    K, N, H, W = WORKLOAD['num_classes'], args.batch, args.height, args.width
+    K, N, H, W = args.classes, args.batch, args.height, args.width
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
@@ -315,7 +317,7 @@ def main():
         metric=METRIC, value=world * N / (ms_step * 1e-3), unit=UNIT, n_gpus=world, steps=args.steps,
         warmup=max(3, args.warmup), ms_per_step=ms_step, higher_is_better=True, scaling='weak', vs_baseline=None,
         dtype=args.dtype, data='synthetic',
-        config=dict(WORKLOAD, batch_per_gpu=N, height=H, width=W, global_batch=world * N,
+        config=dict(WORKLOAD, batch_per_gpu=N, height=H, width=W, num_classes=K, global_batch=world * N,
                     parallelism=f'dp{world} (batch-sharded, one int64 confusion-matrix all-reduce per step)',
                     l2='inputs larger than L2 (403 MB fp32 images per step vs 126 MB L2)',
                     input='normalised fp32 NCHW resident in HBM; raw uint8 from pinned host memory for e2e'),
