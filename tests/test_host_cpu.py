@@ -119,3 +119,43 @@ def test_engine_param_shapes_cover_engine_expectations():
     shapes = build_param_shapes(32, 128, 64, 19)
     assert shapes['decode_head.head_x1.0.conv.weight'] == (19, 32, 3, 3)
     assert shapes['backbone.spp.compression.conv.weight'] == (128, 640, 1, 1)
+
+
+def test_led_block_modules_mirror_the_reference_surface():
+    """SESP / Muti_AFF / GETBBlock / SEAM: registered under the reference's names, state-dict keys equal the oracle's
+    (= the reference's, see tests/test_oracle_vs_reference.py), packed parameter blocks have the size the C ABI
+    documents, unsupported configurations and CPU tensors fail loudly (no fallback)."""
+    from oracle.sesp import OracleSESP
+    from oracle.mfaf import OracleMutiAFF
+    from oracle.getb import OracleGETBBlock
+    from oracle.seam import OracleSEAM
+    lib = libmod.get()
+    pairs = [
+        (L.MODELS.build(dict(type='SESP', nIn=64, nOut=64)), OracleSESP(64, 64)),
+        (L.MODELS.build(dict(type='Muti_AFF', channels=64)), OracleMutiAFF(64)),
+        (L.MODELS.build(dict(type='GETBBlock', dim=128, num_heads=8, window_size=8)), OracleGETBBlock(128, 8)),
+        (L.MODELS.build(dict(type='SEAM', channels=64)), OracleSEAM(64)),
+    ]
+    for mine, ref in pairs:
+        assert set(mine.state_dict()) == set(ref.state_dict()), type(mine).__name__
+        assert sum(p.numel() for p in mine.parameters()) == sum(p.numel() for p in ref.parameters())
+        mine.load_state_dict(ref.state_dict(), strict=True)
+    cpu = torch.device('cpu')
+    assert pairs[1][0].packed_params(cpu).numel() == lib.ledb200_mfaf_param_floats(64, 16)
+    assert pairs[2][0].packed_params().numel() == lib.ledb200_getb_param_floats(128, 8, 512)
+    assert pairs[3][0].packed_params(cpu).numel() == lib.ledb200_seam_param_floats(64)
+    assert lib.ledb200_mfaf_workspace_bytes(2, 64) > 0 and lib.ledb200_seam_workspace_bytes(2, 8, 8) >= 2 * 64 * 5
+    x = torch.zeros(1, 64, 16, 16)
+    for mod, args in ((pairs[0][0], (x,)), (pairs[1][0], (x, x)), (pairs[3][0], (x, x)),
+                      (pairs[2][0], (torch.zeros(1, 128, 16, 16),))):
+        with pytest.raises(L.LedB200Error):
+            mod.eval()(*args)
+    for bad in (dict(type='Muti_AFF', channels=60), dict(type='GETBBlock', dim=128, num_heads=8, window_size=4),
+                dict(type='SEAM', channels=60), dict(type='SESP', nIn=64, nOut=64, stride=2)):
+        with pytest.raises(NotImplementedError):
+            L.MODELS.build(bad)
+    # C ABI argument checks need no GPU: null buffers / bad shapes are rejected before any launch
+    assert lib.ledb200_postprocess(None, 2, 4, 4, None, 0, 4, 4, 0, 0.3, None, 3, None, None) < 0
+    assert b'null' in lib.ledb200_last_error()
+    assert lib.ledb200_seam_forward(None, None, None, 0, 1, 4, 4, 64, 0.1, None, None, None) < 0
+    assert lib.ledb200_getb_forward(None, None, None, 1, 8, 8, None) < 0
