@@ -82,3 +82,50 @@ def test_flat_gradient_allreduce_gloo_world2():
         assert p.exitcode == 0
     total = got[0][1] + got[1][1]
     assert torch.allclose(got[0][2], total) and torch.allclose(got[1][2], total)
+
+
+def _eval_worker(rank, world, port, q):
+    """the eval path's only collective: each rank holds the int64 (K+1) x K matrix of its own image shard"""
+    import numpy as np
+    import oracle
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    K = 5
+    g = np.random.default_rng(100 + rank)
+    pred = g.integers(0, K, (2, 24, 32))
+    lab = g.integers(0, K, (2, 24, 32))
+    lab[g.random(lab.shape) < 0.1] = 255
+    m = L.IoUMetric(iou_metrics=['mIoU', 'mFscore'])
+    m.dataset_meta = dict(classes=[str(i) for i in range(K)])
+    cm = np.zeros((K + 1, K), dtype=np.int64)
+    cm[:K] = oracle.confusion_matrix(pred, lab, K, 255)[:K]     # host stand-in for the CUDA histogram of this shard
+    m._cm = torch.from_numpy(cm)
+    local = m.total_confusion(reduce_ranks=False).clone()
+    metrics = m.compute_metrics()                                # all-reduces over the two ranks
+    q.put((rank, local, m.total_confusion().clone(), metrics, pred, lab))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_confusion_matrix_allreduce_gloo_world2():
+    import numpy as np
+    import oracle
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_eval_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    total = got[0][1] + got[1][1]
+    assert torch.equal(got[0][2], total) and torch.equal(got[1][2], total)
+    assert got[0][3] == got[1][3]
+    # and the metrics equal the reference's float32-histogram pipeline over all four images
+    res = [oracle.intersect_and_union(torch.from_numpy(g[4][i]), torch.from_numpy(g[5][i]), 5, 255)
+           for g in got for i in range(2)]
+    ref = oracle.compute_metrics(res, ['mIoU', 'mFscore'])
+    for k, v in ref.items():
+        assert abs(float(got[0][3][k]) - float(v)) < 1e-9, k
