@@ -167,7 +167,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
   const bool al32 = ((P.out_ld | P.out2_ld | P.res_ld) % 16 == 0) &&
                     (((uintptr_t)P.out | (uintptr_t)P.out2 | (uintptr_t)P.res) % 32 == 0);
   const bool fast_launch = (ncols_g % 32 == 0) && P.relu != 2 &&
-                           (HAS_UP ? (P.up_ld == 24 && P.cp == 32 && cout8 == 24 && P.out_ld % 8 == 0)
+                           (HAS_UP ? (P.up_ld == cout8 && P.cp == 32 && cout8 <= 24 && P.out_ld % 8 == 0)
                                    : (cout_all && al32));
   const int lane_px = ph * Wo + pw;                                         // this thread's pixel inside the tile
   for (uint32_t tile = first; tile < total; tile += step) {
@@ -194,10 +194,12 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         const __nv_bfloat16 *u10 = ub + (y1 * P.up_w + x0) * P.up_ld, *u11 = ub + (y1 * P.up_w + x1) * P.up_ld;
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-          uu[g][0] = __ldg(reinterpret_cast<const uint4*>(u00 + 8 * g));
-          uu[g][1] = __ldg(reinterpret_cast<const uint4*>(u01 + 8 * g));
-          uu[g][2] = __ldg(reinterpret_cast<const uint4*>(u10 + 8 * g));
-          uu[g][3] = __ldg(reinterpret_cast<const uint4*>(u11 + 8 * g));
+          if (8 * g < cout8) {                        // 8, 16 or 24 stored channels (K = 2 ... 19 classes)
+            uu[g][0] = __ldg(reinterpret_cast<const uint4*>(u00 + 8 * g));
+            uu[g][1] = __ldg(reinterpret_cast<const uint4*>(u01 + 8 * g));
+            uu[g][2] = __ldg(reinterpret_cast<const uint4*>(u10 + 8 * g));
+            uu[g][3] = __ldg(reinterpret_cast<const uint4*>(u11 + 8 * g));
+          }
         }
       }
       mbar_wait(&t_full[ts], tp);
@@ -211,7 +213,8 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
         uint4 o[4], o2[HAS_OUT2 ? 4 : 1];
 #pragma unroll
-        for (int g = 0; g < (HAS_UP ? 3 : 4); ++g) {     // ladder rungs: 24 stored channels, the 4th group is padding
+        for (int g = 0; g < (HAS_UP ? 3 : 4); ++g) {     // ladder rungs: <= 24 stored channels, the rest is padding
+          if (HAS_UP && 8 * g >= cout8) continue;
           float f[8];
           const float4 b0 = lds128f(bias_b + 32 * g);
           const float4 b1 = lds128f(bias_b + 32 * g + 16);
@@ -276,7 +279,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         if (!(P.dbg & 1)) {
           if (HAS_UP) {                               // 24 stored channels, 48 B pixels: three 128-bit stores
 #pragma unroll
-            for (int g = 0; g < 3; ++g) *reinterpret_cast<uint4*>(out_px + 8 * g) = o[g];
+            for (int g = 0; g < 3; ++g) if (8 * g < cout8) *reinterpret_cast<uint4*>(out_px + 8 * g) = o[g];
           } else {
             if (HAS_OUT) { stg256(out_px + c0, o[0], o[1]); stg256(out_px + c0 + 16, o[2], o[3]); }
             if (HAS_OUT2) { stg256(out2_px + c0, o2[0], o2[1]); stg256(out2_px + c0 + 16, o2[2], o2[3]); }
@@ -720,7 +723,8 @@ int num_sms() {
 }
 }  // namespace
 
-int conv_tc_pad(int cout) { return cout <= 16 ? 16 : (cout <= 32 ? 32 : (cout + 63) / 64 * 64); }
+// 32 is the smallest N tile: the epilogue fast path works on 32-column blocks, and an N = 16 MMA costs the same A fetch
+int conv_tc_pad(int cout) { return cout <= 32 ? 32 : (cout + 63) / 64 * 64; }
 
 bool conv_tc_eligible(const ConvArgs& a) {
   if (a.in_dtype != LEDB200_BF16 || a.out_dtype != LEDB200_BF16) return false;
@@ -819,7 +823,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     const bool al32 = ((a.out_ld | a.out2_ld | a.res_ld) % 16 == 0) &&
                       (((uintptr_t)a.out | (uintptr_t)a.out2 | (uintptr_t)a.res) % 32 == 0);
     const bool fast = (ncols_g % 32 == 0) && a.relu != 2 &&
-                      (a.up ? (a.up_ld == 24 && cp == 32 && cout8 == 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
+                      (a.up ? (a.up_ld == cout8 && cp == 32 && cout8 <= 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
     if (fast && a.Ho % TH == 0 && a.Wo % TW == 0) P.stage_bytes = 0;
   }
   const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;

@@ -42,7 +42,7 @@ struct ConvArgs {
 int launch_conv_direct(const ConvArgs& a, cudaStream_t st);
 // tcgen05/TMEM implicit GEMM (conv_tc.cu).  conv_tc_eligible() says whether the shape fits.
 bool conv_tc_eligible(const ConvArgs& a);
-int conv_tc_pad(int cout);   // rows of the K-major bf16 weight matrix: 16, 32 or a multiple of 64
+int conv_tc_pad(int cout);   // rows of the K-major bf16 weight matrix: 32 or a multiple of 64
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 
 // stem conv 0 (3 -> C, 3x3 s2) on the tensor cores with a thread-built im2col tile (stem_tc.cu)
