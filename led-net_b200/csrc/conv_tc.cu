@@ -167,7 +167,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
   const bool al32 = ((P.out_ld | P.out2_ld | P.res_ld) % 16 == 0) &&
                     (((uintptr_t)P.out | (uintptr_t)P.out2 | (uintptr_t)P.res) % 32 == 0);
   const bool fast_launch = (ncols_g % 32 == 0) && P.relu != 2 &&
-                           (HAS_UP ? (P.up_ld == cout8 && P.cp == 32 && cout8 <= 24 && P.out_ld % 8 == 0)
+                           (HAS_UP ? (P.up_ld == 24 && P.cp == 32 && cout8 == 24 && P.out_ld % 8 == 0)
                                    : (cout_all && al32));
   const int lane_px = ph * Wo + pw;                                         // this thread's pixel inside the tile
   for (uint32_t tile = first; tile < total; tile += step) {
@@ -182,6 +182,21 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
       __half2 hwx0, hwx1, hwy0, hwy1;
       float uwx = 0.f, uwy = 0.f;
       if (HAS_RES) { ldg256(res_px + cbeg, rr[0], rr[1]); ldg256(res_px + cbeg + 16, rr[2], rr[3]); }
+      if (HAS_RES && tile + step < total) {
+        // L1 prefetch of the residual row the NEXT tile of this warp will read: the residual epilogue is bound by
+        // that L2 latency (probe r1c: 52 us with the MMAs off against 29 us without a residual), and a register
+        // prefetch does not fit under the 168-register cap (tried: slower)
+        int nt2 = nt + stepd[0], tw2 = tw, th2 = th, n2 = n;
+        if (nt2 >= P.ntiles_n) { nt2 -= P.ntiles_n; ++tw2; }
+        tw2 += stepd[1]; if (tw2 >= P.tiles_w) { tw2 -= P.tiles_w; ++th2; }
+        th2 += stepd[2]; if (th2 >= P.tiles_h) { th2 -= P.tiles_h; ++n2; }
+        n2 += stepd[3];
+        if (th2 * TH + TH <= Ho && tw2 * TW + TW <= Wo) {
+          const __nv_bfloat16* rn = P.res + (((int64_t)n2 * Ho + th2 * TH) * Wo + tw2 * TW + lane_px) * P.res_ld + nt2 * NT + cbeg;
+          prefetch_l1(rn);
+          if (ncols_g > 64) prefetch_l1(rn + 64);
+        }
+      }
       if (HAS_UP) {
         int y0, y1, x0, x1;
         float l0;
@@ -194,12 +209,10 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         const __nv_bfloat16 *u10 = ub + (y1 * P.up_w + x0) * P.up_ld, *u11 = ub + (y1 * P.up_w + x1) * P.up_ld;
 #pragma unroll
         for (int g = 0; g < 3; ++g) {
-          if (8 * g < cout8) {                        // 8, 16 or 24 stored channels (K = 2 ... 19 classes)
-            uu[g][0] = __ldg(reinterpret_cast<const uint4*>(u00 + 8 * g));
-            uu[g][1] = __ldg(reinterpret_cast<const uint4*>(u01 + 8 * g));
-            uu[g][2] = __ldg(reinterpret_cast<const uint4*>(u10 + 8 * g));
-            uu[g][3] = __ldg(reinterpret_cast<const uint4*>(u11 + 8 * g));
-          }
+          uu[g][0] = __ldg(reinterpret_cast<const uint4*>(u00 + 8 * g));
+          uu[g][1] = __ldg(reinterpret_cast<const uint4*>(u01 + 8 * g));
+          uu[g][2] = __ldg(reinterpret_cast<const uint4*>(u10 + 8 * g));
+          uu[g][3] = __ldg(reinterpret_cast<const uint4*>(u11 + 8 * g));
         }
       }
       mbar_wait(&t_full[ts], tp);
@@ -213,8 +226,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
         uint4 o[4], o2[HAS_OUT2 ? 4 : 1];
 #pragma unroll
-        for (int g = 0; g < (HAS_UP ? 3 : 4); ++g) {     // ladder rungs: <= 24 stored channels, the rest is padding
-          if (HAS_UP && 8 * g >= cout8) continue;
+        for (int g = 0; g < (HAS_UP ? 3 : 4); ++g) {     // ladder rungs: 24 stored channels, the 4th group is padding
           float f[8];
           const float4 b0 = lds128f(bias_b + 32 * g);
           const float4 b1 = lds128f(bias_b + 32 * g + 16);
@@ -279,7 +291,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
         if (!(P.dbg & 1)) {
           if (HAS_UP) {                               // 24 stored channels, 48 B pixels: three 128-bit stores
 #pragma unroll
-            for (int g = 0; g < 3; ++g) if (8 * g < cout8) *reinterpret_cast<uint4*>(out_px + 8 * g) = o[g];
+            for (int g = 0; g < 3; ++g) *reinterpret_cast<uint4*>(out_px + 8 * g) = o[g];
           } else {
             if (HAS_OUT) { stg256(out_px + c0, o[0], o[1]); stg256(out_px + c0 + 16, o[2], o[3]); }
             if (HAS_OUT2) { stg256(out2_px + c0, o2[0], o2[1]); stg256(out2_px + c0 + 16, o2[2], o2[3]); }
@@ -823,7 +835,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     const bool al32 = ((a.out_ld | a.out2_ld | a.res_ld) % 16 == 0) &&
                       (((uintptr_t)a.out | (uintptr_t)a.out2 | (uintptr_t)a.res) % 32 == 0);
     const bool fast = (ncols_g % 32 == 0) && a.relu != 2 &&
-                      (a.up ? (a.up_ld == cout8 && cp == 32 && cout8 <= 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
+                      (a.up ? (a.up_ld == 24 && cp == 32 && cout8 == 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
     if (fast && a.Ho % TH == 0 && a.Wo % TW == 0) P.stage_bytes = 0;
   }
   const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
