@@ -25,4 +25,4 @@ timeout 400 ncu --set full --import-source on --clock-control none -k regex:'tai
    -o $O/others python tools/prof_forward.py --batch 16 --iters 1 > $O/ncu_others.log 2>&1
 ls -la $O
 tail -4 $O/pytest_gpu.log; cat $O/smoke.log; cut -c1-600 $O/bench.json; cat $O/bench_ref.json | cut -c1-300; cat $O/bench_train.json | cut -c1-400
-tail -2 $O/launches.log $O/traffic.log $O/ncu_spa.log $O/ncu_head.log $O/ncu_others.log
+for f in launches traffic ncu_spa ncu_head ncu_others; do tail -n 2 $O/$f.log; done
