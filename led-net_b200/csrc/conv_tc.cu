@@ -494,11 +494,24 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
+    // descriptor fetch starts now instead of at the first TMA (part of the fixed cost per launch, r1c_notes.md 3b)
+    prefetch_tensormap(&tmA);
+    prefetch_tensormap(&tmB);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], P.NT >= 64 ? 8 : 4); }
     mbar_fence_init();
+    if (BRES) {
+      // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes.  Issued by
+      // the thread that initialised the barriers, BEFORE the CTA-wide sync: the weight fetch (up to 150 KB, the
+      // longest latency of the ramp) overlaps the TMEM allocation and the bias loads instead of following them
+      mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
+      for (int ch = 0; ch < P.nchunks; ++ch)
+        for (int t = 0; t < P.ntaps_total; ++t)
+          tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
+                      t * P.Cin + ch * P.KC, 0);
+    }
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
     tmem_alloc(tmem_slot, P.tmem_cols);
@@ -522,14 +535,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== TMA producer: ONE elected lane runs the whole role ================
     if (elect_one()) {
       int sa = 0, pa = 0, sb = 0, pb = 0;
-      if (BRES) {
-        // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes
-        mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
-        for (int ch = 0; ch < P.nchunks; ++ch)
-          for (int t = 0; t < P.ntaps_total; ++t)
-            tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
-                        t * P.Cin + ch * P.KC, 0);
-      }
+      // (resident weights were requested by thread 0 before the CTA-wide sync)
       // tile coordinates as mixed-radix digits advanced by the grid step (no per-tile divisions)
       uint32_t t0 = blockIdx.x;
       int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
