@@ -80,10 +80,25 @@ struct TcParams {
   // optional: out += bilinear x2 upsample (align_corners=False) of `up` [N, up_h, up_w, up_ld], added AFTER the ReLU
   const __nv_bfloat16* up; int up_ld, up_h, up_w;
   int up_f16, out_f16;               // ladder rungs are kept in fp16 (11-bit mantissa; logits are far inside its range)
+  int tl_launch;                     // launch ordinal (timeline probe builds only: slot of g_tc_tl)
   int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 32 atom-aligned A row groups, 64 empty epilogue, 128 single MMA issuer
 };
 
 using namespace tc;   // PTX wrappers: tc_common.cuh
+
+// Timeline probe (tools/probes/tc_timeline.sh builds a second library with -DLEDB_TC_TIMELINE; the product build
+// compiles none of it): CTA 0 of every launch stamps clock64 at the points of its ramp into slot `tl_launch`.
+#ifdef LEDB_TC_TIMELINE
+__device__ unsigned long long g_tc_tl[128][16];
+__device__ __forceinline__ unsigned long long gtimer() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
+#define TL(slot, cond) do { if (blockIdx.x == 0 && (cond)) g_tc_tl[P.tl_launch & 127][slot] = clock64(); } while (0)
+#define TLG(slot, cond) do { if (blockIdx.x == 0 && (cond)) g_tc_tl[P.tl_launch & 127][slot] = gtimer(); } while (0)
+#else
+#define TL(slot, cond) do {} while (0)
+#define TLG(slot, cond) do {} while (0)
+#endif
 
 __device__ __forceinline__ void sts128(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -217,6 +232,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
       }
       mbar_wait(&t_full[ts], tp);
       tc_fence_after();
+      TL(7, tile == blockIdx.x && warp == 2 && lane == 0);
       const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
       for (int c0 = (P.dbg & 64) ? cend : cbeg; c0 < cend; c0 += 32) {     // probe bit 64: epilogue only hands the stage back
         uint32_t v[32];
@@ -349,6 +365,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
     prefetch(cbeg);
     mbar_wait(&t_full[ts], tp);
     tc_fence_after();
+    TL(7, tile == blockIdx.x && warp == 2 && lane == 0);
     const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
     for (int c0 = cbeg; c0 < cend; c0 += 32) {
       const int ncol = min(32, cend - c0);       // 16 or 32
@@ -440,6 +457,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
       }
     }
     }   // generic (edge-tile) body
+    TL(8, tile == blockIdx.x && warp == 2 && lane == 0);
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(&t_empty[ts]);
@@ -492,6 +510,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  TL(0, threadIdx.x == 0); TLG(12, threadIdx.x == 0);
 
   if (threadIdx.x == 0) {
     // descriptor fetch starts now instead of at the first TMA (part of the fixed cost per launch, r1c_notes.md 3b)
@@ -512,21 +531,33 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
                       t * P.Cin + ch * P.KC, 0);
     }
+    TL(1, true);
   }
   if (warp == 1) {   // TMEM allocation: one full warp, address lands in shared memory
     tmem_alloc(tmem_slot, P.tmem_cols);
   }
-  // per-channel epilogue constants, zero padded to cp so no channel guard is needed later
-  for (int c = threadIdx.x; c < P.cp; c += kThreads) {
-    const bool in = c < P.Cout;
-    s_bias[c] = (P.bias && in) ? P.bias[c] : 0.f;
-    s_o2s[c] = in ? (P.o2_scale ? P.o2_scale[c] : 1.f) : 0.f;
-    s_o2b[c] = (P.o2_shift && in) ? P.o2_shift[c] : 0.f;
+  // Set-up barrier (named barrier 1).  The producer warp needs neither TMEM nor the epilogue constants: it only
+  // ARRIVES (its barrier initialisation is ordered before the other warps' bar.sync) and requests the first A slabs
+  // while the other warps are still allocating TMEM and waiting for their bias loads - measured with the timeline
+  // probe (tools/probes/tc_timeline.py): first A request 2.0 us after kernel entry when it waited for the sync.
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+  } else {
+    // per-channel epilogue constants, zero padded to cp so no channel guard is needed later
+    for (int c = threadIdx.x - 32; c < P.cp; c += kThreads - 32) {
+      const bool in = c < P.Cout;
+      s_bias[c] = (P.bias && in) ? P.bias[c] : 0.f;
+      s_o2s[c] = in ? (P.o2_scale ? P.o2_scale[c] : 1.f) : 0.f;
+      s_o2b[c] = (P.o2_shift && in) ? P.o2_shift[c] : 0.f;
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    tc_fence_after();
+    TL(2, threadIdx.x == 32);
+    tmem_base = *tmem_slot;
   }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
 
   const uint32_t row_bytes = P.KC * 2;
   const uint32_t layout_type = (P.KC == 64) ? 2u : (P.KC == 32 ? 4u : 6u);   // SW128 / SW64 / SW32
@@ -557,6 +588,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (S2) tma_load_5d(dst, &tmA, smem_u32(&a_full[sa]), sl.c_mul * P.in_ld + ch * P.KC, w0 + sl.dw, sl.ph, h0 + sl.dh, n);
               else    tma_load_4d(dst, &tmA, smem_u32(&a_full[sa]), ch * P.KC, w0 + sl.dw, h0 + sl.dh, n);
             }
+            TL(3, tile == blockIdx.x && ch == 0 && s == 0);
             if (++sa == P.SA) { sa = 0; pa ^= 1; }
             if (!BRES) {
               for (int t = 0; t < sl.ntaps; ++t) {
@@ -604,6 +636,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       int sa = 0, pa = 0, sb = 0, pb = 0;
       int ts = 0, tp = 0;
       if (BRES) { mbar_wait(&b_full[0], 0); tc_fence_after(); }
+      TL(4, mw == 0);
       const uint32_t total = (uint32_t)P.total_tiles;
       // the j-th tile of this CTA owns accumulator stage j % nst and the next nchunks * slabs A stages of the ring
       const int slabs_per_tile = P.nchunks * mode_slabs<MODE>();
@@ -628,6 +661,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           for (int s = 0; s < mode_slabs<MODE>(); ++s) {
             mbar_wait(&a_full[sa], pa);
             tc_fence_after();
+            TL(5, tile == blockIdx.x && ch == 0 && s == 0);
             const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
             if (BRES) {
               // resident weights: no per-tap waits, so the slab's MMAs are ONE straight-line block - every
@@ -672,6 +706,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           }
         }
         tc_commit(&t_full[ts]);                             // accumulator complete -> epilogue
+        TL(6, tile == blockIdx.x);
         if (++ts == P.nst) { ts = 0; tp ^= 1; }
         if (nmw == 2) skip_tile();                          // the other issuer's tile
       }
@@ -692,12 +727,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   }
 
+  TL(9, threadIdx.x == 0);              // producer role finished (its warp reaches the final sync)
+  TL(14, warp == 2 && lane == 0);       // first epilogue warp finished
   tc_fence_before();
   __syncthreads();
+  TL(10, threadIdx.x == 32);
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, P.tmem_cols);
   }
+  TL(11, threadIdx.x == 32); TLG(13, threadIdx.x == 32);
 }
 
 // ------------------------------------------------------------------ host side
@@ -878,6 +917,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   P.out2 = (__nv_bfloat16*)a.out2; P.out2_ld = a.out2_ld; P.o2_scale = a.o2_scale; P.o2_shift = a.o2_shift;
   P.res = (const __nv_bfloat16*)a.res; P.res_ld = a.res_ld; P.bias = a.bias; P.relu = a.relu;
   { const char* e = getenv("LEDB200_TC_DBG"); P.dbg = e ? atoi(e) : 0; }
+  { static int tl_counter = 0; P.tl_launch = tl_counter++; }
   P.up = (const __nv_bfloat16*)a.up; P.up_ld = a.up_ld; P.up_h = a.up_h; P.up_w = a.up_w;
   P.up_f16 = a.up_f16; P.out_f16 = a.out_f16;
 
@@ -952,3 +992,11 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 }
 
 }  // namespace ledb
+
+#ifdef LEDB_TC_TIMELINE
+// probe builds only: copy the 128 x 16 stamp table of the last launches to the host (after a device sync)
+extern "C" int ledb200_probe_tc_timeline(unsigned long long* out) {
+  if (cudaDeviceSynchronize() != cudaSuccess) return 1;
+  return cudaMemcpyFromSymbol(out, ledb::g_tc_tl, sizeof(unsigned long long) * 128 * 16) == cudaSuccess ? 0 : 1;
+}
+#endif

@@ -21,7 +21,7 @@ timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv
    -o $O/conv_tc_spa python tools/prof_forward.py --batch 16 --iters 1 > $O/ncu_spa.log 2>&1
 timeout 400 ncu --set full --import-source on --clock-control none -k regex:conv_tc -s 54 -c 3 \
    -o $O/conv_tc_head python tools/prof_forward.py --batch 16 --iters 1 > $O/ncu_head.log 2>&1
-timeout 400 ncu --set full --import-source on --clock-control none -k regex:'tail2|stem_tc|upsample_add16|confusion' -c 6 \
+timeout 400 ncu --set full --import-source on --clock-control none -k regex:'tail3|tail2|stem_tc|upsample_add16|confusion' -c 6 \
    -o $O/others python tools/prof_forward.py --batch 16 --iters 1 > $O/ncu_others.log 2>&1
 ls -la $O
 tail -4 $O/pytest_gpu.log; cat $O/smoke.log; cut -c1-600 $O/bench.json; cat $O/bench_ref.json | cut -c1-300; cat $O/bench_train.json | cut -c1-400
