@@ -271,8 +271,14 @@ def test_train_step_vs_oracle(K, hw, N):
     # after one lr = 0.01 step from random init the problem is worse conditioned: the fp32 oracle's own whole-vector
     # error against float64 was measured between 3.4e-3 and 1.6e-2 from run to run (it is evaluated at the product's
     # parameters, which carry the atomics' summation-order noise of step 1), ours between 2.5e-3 and 1.7e-2
-    # single tensors (max-norm) scatter more: 0.045-0.11 observed for ours, up to 0.11 for the fp32 oracle itself
-    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2', cond_floor=cond, vec_tol=3e-2, tensor_tol=0.25)
+    # single tensors (max-norm) scatter more: 0.045-0.11 observed for ours, up to 0.11 for the fp32 oracle itself.
+    # Eleven more runs (profiles/r1g_train_step2_scatter.txt): step 1 repeats to three digits (2.04e-3 every run) while
+    # step 2 - evaluated at parameters that differ from run to run only by step 1's atomic summation order - scatters
+    # over two decades for BOTH implementations, independently of each other: whole-vector ours 3.8e-4 ... 3.1e-2, fp32
+    # oracle 5.0e-4 ... 6.0e-3 (1.6e-2 earlier); worst tensor ours 5.7e-4 ... 1.8e-1, fp32 oracle 7.3e-4 ... 1.1e-1.
+    # Step 2 is therefore a PLUMBING gate (stale weights, a missing zero_grad, wrong momentum or BN statistics are O(1)
+    # errors), set one decade above the observed scatter; the precision gate is step 1 (1e-2) and the per-op tests.
+    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2', cond_floor=cond, vec_tol=1e-1, tensor_tol=0.5)
     for k in shadow:
         shadow[k].grad = grads2[k].clone()
     opt_s.step()                                                    # second step exercises the momentum buffer
