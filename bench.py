@@ -12,6 +12,7 @@ backbone -> head -> fused 3-level logit fusion + argmax -> confusion matrix vs s
 batch 16 per GPU, 1024x2048, K=19, bf16 activations.  Prints ONE JSON line (rank 0).
 """
 import argparse
+import ctypes
 import json
 import os
 import subprocess
@@ -139,6 +140,12 @@ def main():
                     e2e=dict(value=r['value'], unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
+
+    # stdout carries exactly ONE line, the JSON: native libraries write there too (at N > 1 NCCL prints its version
+    # banner to stdout when the communicator is created), so fd 1 points at stderr until that line is printed
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
 
     import warnings
     import torch
@@ -325,7 +332,11 @@ def main():
         e2e=dict(value=world * N / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
                  h2d_bytes_per_step=img_u8_host.numel() + lab_host.numel(), d2h_bytes_per_step=cm_host.numel() * 8),
         roofline=roof, cpu_baseline=cpu)
-    print(json.dumps(line))
+    sys.stdout.flush()
+    ctypes.CDLL(None).fflush(None)          # C stdio of the native libraries, before fd 1 is the real stdout again
+    os.dup2(real_stdout, 1)
+    print(json.dumps(line), flush=True)
+    os.dup2(2, 1)
     if dist is not None:
         dist.destroy_process_group()
 
