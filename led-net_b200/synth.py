@@ -82,3 +82,35 @@ def make_labels(n, h, w, num_classes, seed=1, ignore_frac=0.05, ignore_index=255
     ign = r.random((n, h, w)) < ignore_frac
     lab[ign] = ignore_index
     return torch.from_numpy(lab)
+
+
+def class_palette(num_classes):
+    """One BGR colour per class on the 3x3x3 grid {40,127,214}^3 (27 colours; classes beyond wrap with a shade offset)."""
+    lv = np.array([40, 127, 214], dtype=np.int64)
+    pal = np.zeros((num_classes, 3), dtype=np.int64)
+    for k in range(num_classes):
+        j = (k * 7 + 3) % 27          # stride 7 walks the whole grid (gcd(7,27)=1): neighbouring classes differ a lot
+        pal[k] = np.array([lv[j % 3], lv[(j // 3) % 3], lv[j // 9]]) + 12 * (k // 27)
+    return pal
+
+
+def make_scene(n, h, w, num_classes, seed=0, coarse=(32, 32), noise=24, ignore_frac=0.0, ignore_index=255):
+    """A learnable synthetic segmentation scene: a coarse random class map nearest-upsampled to (h, w)
+    ("blocky" labels) and an image whose pixels are the class colour plus uniform noise.
+    A network trained on such scenes for a few hundred steps has TRAINED logit margins (confident inside
+    regions, small only along region borders), which is what north_star's >= 99.9 % bf16 argmax-agreement
+    gate presumes; random-init weights do not (tests/util.py).  Returns (uint8 BGR [n,3,h,w], int64 [n,h,w])."""
+    r = _rng(seed, f'scene{n}x{h}x{w}x{num_classes}')
+    ch, cw = coarse
+    cmap = r.integers(0, num_classes, (n, ch, cw), dtype=np.int64)
+    ys = (np.arange(h) * ch // h)[:, None]
+    xs = (np.arange(w) * cw // w)[None, :]
+    lab = cmap[:, ys, xs]                                             # [n,h,w]
+    pal = class_palette(num_classes)
+    img = pal[lab]                                                    # [n,h,w,3]
+    img = img + r.integers(-noise, noise + 1, img.shape, dtype=np.int64)
+    img = np.clip(img, 0, 255).astype(np.uint8).transpose(0, 3, 1, 2).copy()
+    lab = lab.copy()
+    if ignore_frac > 0:
+        lab[r.random((n, h, w)) < ignore_frac] = ignore_index
+    return torch.from_numpy(img), torch.from_numpy(lab)

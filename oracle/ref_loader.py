@@ -182,3 +182,93 @@ def load():
         GETBBlock=getb.GETBBlock, MODELS=models, METRICS=metrics)
     _cache['ns'] = ns
     return ns
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# SEAM edge gate: inline code of the authors' speed prototype, tools/speed/ddrnet_speed.py (class DDRNet1).
+# The file cannot be imported (it imports `model_utils_speed`, `thop`, mmcv, and its __init__ calls `.cuda()`), and the
+# edge path is not a module of its own.  It IS executed verbatim here: the statements are sliced out of the file's AST
+# (nothing is copied into this repository) and compiled into two functions:
+#   __init__ : the assignments of self.conv_1 / conv_2 / laplacian_kernel / fusion_kernel / boundary_threshold
+#              (ddrnet_speed.py:88-113)
+#   forward  : `seg_label = self.conv_1(x)` ... `seg_labels = boudary_targets_pyramid.float()` (:282-338) followed by
+#              `result = self.conv_2(seg_labels) * x_s` / `x_s = result + x_s` (:388-389)
+# plus the module-level `normalize_tensor` (:24-37).  ConvModule is oracle/mmcv_shim's (third-party restated, as for
+# every other block); `.cuda()` is a no-op while the sliced __init__ runs.
+def load_seam():
+    import ast
+
+    import torch
+    import torch.nn.functional as F
+
+    from . import mmcv_shim
+
+    if 'seam' in _cache:
+        return _cache['seam']
+    path = os.path.join(REF_ROOT, 'tools/speed/ddrnet_speed.py')
+    src = open(path).read()
+    tree = ast.parse(src, filename=path)
+    norm_fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'normalize_tensor')
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'DDRNet1')
+    init = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == '__init__')
+    fwd = next(n for n in cls.body if isinstance(n, ast.FunctionDef) and n.name == 'forward')
+
+    def self_attr_target(st):
+        if isinstance(st, ast.Assign) and len(st.targets) == 1:
+            t = st.targets[0]
+            if isinstance(t, ast.Attribute) and isinstance(t.value, ast.Name) and t.value.id == 'self':
+                return t.attr
+        return None
+
+    def name_target(st):
+        if isinstance(st, ast.Assign) and len(st.targets) == 1 and isinstance(st.targets[0], ast.Name):
+            return st.targets[0].id
+        return None
+
+    wanted = ('conv_1', 'conv_2', 'laplacian_kernel', 'fusion_kernel', 'boundary_threshold')
+    init_stmts = [st for st in init.body if self_attr_target(st) in wanted]
+    assert sorted(self_attr_target(s) for s in init_stmts) == sorted(wanted), 'prototype __init__ changed'
+    body = fwd.body
+    i0 = next(i for i, st in enumerate(body) if name_target(st) == 'seg_label')
+    i1 = next(i for i, st in enumerate(body) if name_target(st) == 'seg_labels')
+    j0 = next(i for i, st in enumerate(body) if name_target(st) == 'result')
+    assert i0 < i1 < j0 and name_target(body[j0 + 1]) == 'x_s'
+    edge_stmts, gate_stmts = body[i0:i1 + 1], body[j0:j0 + 2]
+
+    def make_fn(name, args, stmts, ret_src):
+        fn = ast.parse(f'def {name}({args}):\n    pass\n    return {ret_src}').body[0]
+        fn.body = list(stmts) + [fn.body[-1]]
+        return fn
+
+    mod = ast.Module(body=[norm_fn,
+                           make_fn('seam_init', 'self', init_stmts, 'None'),
+                           make_fn('seam_forward', 'self, x, x_s', edge_stmts + gate_stmts, 'x_s, seg_labels, seg_label')],
+                     type_ignores=[])
+    ast.fix_missing_locations(mod)
+    g = {'torch': torch, 'F': F, 'nn': nn, 'ConvModule': mmcv_shim.ConvModule, 'math': __import__('math')}
+    exec(compile(mod, path, 'exec'), g)
+
+    class RefSEAM(nn.Module):
+        """The prototype's own statements (see load_seam) wrapped as a module: forward(x, x_s) -> gated x_s;
+        `edge` returns (0/1 mask, normalised edge response)."""
+
+        def __init__(self, norm_cfg=None):
+            super().__init__()
+            self.norm_cfg = norm_cfg or dict(type='BN', requires_grad=True)
+            self.act_cfg = dict(type='ReLU', inplace=True)
+            cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda t, *a, **k: t          # ddrnet_speed.py:88 moves the Laplacian to the GPU
+            try:
+                g['seam_init'](self)
+            finally:
+                torch.Tensor.cuda = cuda
+
+        def forward(self, x, x_s):
+            return g['seam_forward'](self, x, x_s)[0]
+
+        def edge(self, x):
+            _, m, e = g['seam_forward'](self, x, torch.zeros_like(x))
+            return m, e
+
+    _cache['seam'] = RefSEAM
+    return RefSEAM

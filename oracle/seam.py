@@ -7,8 +7,11 @@
     m    = [0.6 [b_1 > t] + 0.3 [b_2 > t] + 0.1 [b_4 > t]  >  t]        t = boundary_threshold = 0.1
     out  = conv_2(m) * x_s + x_s                   3x3 conv 1 -> C + BN
 
-PARITY UNPINNED: the prototype cannot be executed here (it needs mmcv and moves a tensor to CUDA in ``__init__``) and
-upstream has no test for it; this restatement follows the source line by line and is the only pin.
+PINNED: the prototype as a whole cannot be executed here (it needs mmcv / thop and moves a tensor to CUDA in
+``__init__``), but its SEAM statements can: ``oracle/ref_loader.load_seam`` slices them out of the file's AST and runs
+them verbatim behind the mmcv ConvModule shim.  ``tests/golden/seam.npz`` holds their outputs (make_golden.py),
+``tests/test_oracle_golden.py::test_seam_gate`` checks this restatement against them on every run and
+``tests/test_oracle_vs_reference.py`` re-checks bit-equality live when ``/root/reference`` is mounted.
 """
 import torch
 import torch.nn as nn

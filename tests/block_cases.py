@@ -18,6 +18,36 @@ GETB_CASES = [
     ('d64_h16', dict(dim=64, num_heads=16, window_size=8, mlp_ratio=2.), (1, 9, 8)),
 ]
 
+# SEAM edge gate (tools/speed/ddrnet_speed.py:282-338, 388-389): (tag, (N, H, W)); 64 channels (the prototype's conv_1/conv_2)
+SEAM_GOLDEN_CHANNELS = [0, 21, 63]
+SEAM_CASES = [('s32x48', (2, 32, 48)), ('s37x51', (1, 37, 51)), ('s5x7', (1, 5, 7)), ('s64x96', (1, 64, 96))]
+
+
+def seam_state_dict(template, seed=23):
+    sd = synth.make_state_dict(template, seed=seed)
+    sd['fusion_kernel'] = template['fusion_kernel'].detach().clone()      # the constant (0.6, 0.3, 0.1), not a weight
+    return sd
+
+
+def seam_inputs(shape):
+    g = torch.Generator().manual_seed(shape[1] * 5 + shape[2])
+    x = torch.randn(shape[0], 64, shape[1], shape[2], generator=g)
+    xs = torch.randn(shape[0], 64, shape[1], shape[2], generator=g)
+    return x, xs
+
+
+def seam_unstable(e, eps=2e-5, threshold=0.1):
+    """[N,1,H,W] bool: pixels whose 0/1 edge mask may legitimately flip under rounding (any of the three Laplacians of
+    the normalised edge response `e` within eps of the threshold at the position it is sampled), dilated by conv_2's
+    3x3 reach - the mask is a chain of hard thresholds."""
+    import torch.nn.functional as F
+    k = torch.tensor([-1, -1, -1, -1, 8, -1, -1, -1, -1], dtype=torch.float32).reshape(1, 1, 3, 3)
+    lap = lambda s: F.conv2d(e, k, stride=s, padding=1).clamp(min=0)    # noqa: E731
+    u = (lap(1) - threshold).abs() < eps
+    for s in (2, 4):
+        u |= F.interpolate(((lap(s) - threshold).abs() < eps).float(), e.shape[2:], mode='nearest') > 0
+    return u, F.max_pool2d(u.float(), 3, 1, 1) > 0
+
 
 def block_state_dict(template, seed):
     """synth weights; the 1x1 / depthwise convs of these blocks are not followed by ReLU chains, so kaiming

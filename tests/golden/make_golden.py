@@ -24,6 +24,9 @@ Fixtures
                     statistics made non-trivial (sesp_state_dict below).
 * mfaf.npz        : Muti_AFF (classification/model_utils.py) eval outputs on tests/block_cases.MFAF_CASES.
 * getb.npz        : GETBBlock (backbones/UNetFormer_GETB.py) eval outputs on tests/block_cases.GETB_CASES.
+* seam.npz        : the SEAM edge gate of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338,388-389),
+                    its own statements executed through oracle.ref_loader.load_seam (AST slice): the 0/1 edge mask
+                    (bit-packed), the normalised edge response and the gated output on tests/block_cases.SEAM_CASES.
 """
 import os
 import sys
@@ -117,9 +120,28 @@ def make_blocks(ref):
     np.savez_compressed(os.path.join(OUT, 'getb.npz'), **out)
 
 
+def make_seam():
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import block_cases as bc
+    m = ref_loader.load_seam()().eval()
+    m.load_state_dict(bc.seam_state_dict(m.state_dict()))
+    out = {}
+    for tag, shape in bc.SEAM_CASES:
+        x, xs = bc.seam_inputs(shape)
+        with torch.no_grad():
+            mask, e = m.edge(x)
+            out[tag] = m(x, xs)[:, bc.SEAM_GOLDEN_CHANNELS].numpy()      # three of the 64 channels keep the fixture small
+            out[tag + '_mask'] = np.packbits(mask.numpy().astype(np.uint8))
+            out[tag + '_edge'] = e.numpy()
+    np.savez_compressed(os.path.join(OUT, 'seam.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
+    if 'seam' in sys.argv[1:]:            # regenerate only the SEAM fixture
+        make_seam()
+        return
     ref = ref_loader.load()
     if 'sesp' in sys.argv[1:]:            # regenerate only the SESP fixture
         make_sesp(ref)
@@ -129,6 +151,7 @@ def main():
         return
     make_sesp(ref)
     make_blocks(ref)
+    make_seam()
 
     # ---------------- r0_head_k2 -------------------------------------------------
     ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,

@@ -165,3 +165,29 @@ def test_getb_block(golden_dir):
             out = m(bc.block_input(i, kw['dim'], shape, 400)).numpy()
         assert out.shape == g[tag].shape
         assert np.abs(out - g[tag]).max() <= 1e-6 * np.abs(g[tag]).max(), tag
+
+
+def test_seam_gate(golden_dir):
+    """oracle/seam.py against the prototype's OWN statements (tools/speed/ddrnet_speed.py:282-338, 388-389, executed
+    through an AST slice when the fixture was generated): edge response, 0/1 mask and gated output."""
+    import block_cases as bc
+    from oracle.seam import OracleSEAM
+    g = np.load(os.path.join(golden_dir, 'seam.npz'))
+    o = OracleSEAM(64).eval()
+    o.load_state_dict(bc.seam_state_dict(o.state_dict()))
+    for tag, shape in bc.SEAM_CASES:
+        x, xs = bc.seam_inputs(shape)
+        with torch.no_grad():
+            mask, e = o.edge_mask(x)
+            out = o(x, xs)
+        # (conv arithmetic order depends on the host's thread count: compare to float rounding, masks outside the
+        #  pixels whose Laplacian sits within rounding distance of the hard threshold)
+        np.testing.assert_allclose(e.numpy(), g[tag + '_edge'], atol=2e-6, rtol=0)
+        unstable, unstable3 = bc.seam_unstable(torch.from_numpy(g[tag + '_edge']))
+        n = mask.numel()
+        gm = torch.from_numpy(np.unpackbits(g[tag + '_mask'])[:n].reshape(mask.shape))
+        assert not ((mask != gm) & ~unstable).any()
+        assert unstable.float().mean() < 0.01
+        ref = torch.from_numpy(g[tag])
+        err = ((out[:, bc.SEAM_GOLDEN_CHANNELS] - ref).abs() * ~unstable3).max() / ref.abs().max()
+        assert err < 2e-6, (tag, float(err))

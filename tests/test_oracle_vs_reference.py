@@ -72,3 +72,22 @@ def test_mfaf_and_getb_equal_verbatim_reference():
         with torch.no_grad():
             ya, yb = a(x), b(x)
         assert float((ya - yb).abs().max()) <= 1e-6 * float(ya.abs().max())
+
+
+def test_seam_equals_prototype_statements():
+    """oracle/seam.py == the SEAM statements of tools/speed/ddrnet_speed.py executed verbatim (AST slice)."""
+    import block_cases as bc
+    from oracle.seam import OracleSEAM
+    r = ref_loader.load_seam()().eval()
+    o = OracleSEAM(64).eval()
+    sd = bc.seam_state_dict(o.state_dict())
+    r.load_state_dict(sd), o.load_state_dict(sd)
+    assert r.boundary_threshold == o.boundary_threshold
+    assert torch.equal(r.laplacian_kernel, o.laplacian_kernel)
+    for tag, shape in bc.SEAM_CASES:
+        x, xs = bc.seam_inputs(shape)
+        with torch.no_grad():
+            assert torch.equal(r(x, xs), o(x, xs)), tag          # same process, same ATen kernels: bit-equal
+            mr, er = r.edge(x)
+            mo, eo = o.edge_mask(x)
+            assert torch.equal(mr, mo) and torch.equal(er, eo)
