@@ -286,7 +286,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
               }
             }
           }
-          if (HAS_UP && P.out_f16) {                   // cvt.rn.satfinite: saturates at +-65504, never inf
+          if (P.out_f16) {                             // cvt.rn.satfinite: saturates at +-65504, never inf
             o[g] = make_uint4(pack_f16x2_sat(f[0], f[1]), pack_f16x2_sat(f[2], f[3]), pack_f16x2_sat(f[4], f[5]),
                               pack_f16x2_sat(f[6], f[7]));
           } else if (HAS_OUT) {
@@ -417,7 +417,7 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
             }
           }
           const uint32_t so = swz(row_off + (uint32_t)(slice_c + 8 * g) * 2);
-          if (HAS_UP && P.out_f16) {
+          if (P.out_f16) {
 #pragma unroll
             for (int j = 0; j < 8; ++j) f[j] = fminf(fmaxf(f[j], -65504.f), 65504.f);   // saturate, never inf
             sts128(st1 + so, pack_f16x2(f[0], f[1]), pack_f16x2(f[2], f[3]), pack_f16x2(f[4], f[5]), pack_f16x2(f[6], f[7]));
@@ -797,7 +797,6 @@ bool conv_tc_eligible(const ConvArgs& a) {
   if (a.out2 && (a.out2_ld % 8 || a.out2_ld < c8)) return false;
   if (a.res && (a.res_ld % 8 || a.res_ld < c8)) return false;
   const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
-  if (a.out_f16 && !a.up) return false;                             // fp16 storage exists for the ladder rungs only
   if (a.up) {   // fused x2 upsample-add: one 32-column block, <= 24 source channels, exact x2, no residual / 2nd output
     if (cp > 32 || a.up_ld > 24 || a.up_ld % 8 || a.up_ld < c8 || a.res || a.out2 || !a.out) return false;
     if (a.Ho != 2 * a.up_h || a.Wo != 2 * a.up_w) return false;

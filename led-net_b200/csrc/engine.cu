@@ -641,26 +641,57 @@ void build_head_fused(Builder& B) {
   const int hf = B.buf("head.feat", n, p.bufs[c5h].h, p.bufs[c5h].w, HC);
   B.conv(h + "head", c5h, hf, -1, true);
   const int xc = B.buf("xc", n, p.bufs[c5h].h, p.bufs[c5h].w, K, kpad(K));
-  B.conv(h + "conv_seg", hf, xc);
   const int hx1 = B.buf("hx1", n, p.bufs[x1h].h, p.bufs[x1h].w, K, kpad(K));
   const int hx2 = B.buf("hx2", n, p.bufs[x2h].h, p.bufs[x2h].w, K, kpad(K));
   p.ho = 2 * p.bufs[hx1].h; p.wo = 2 * p.bufs[hx1].w;
   const int dtype = B.dt;
-  // Ladder in the epilogues: when every rung is an exact x2 (all BASELINE sizes) and the head convs run on
-  // the tensor-core kernel, r2 = head_x2 + up(x_c) and r1 = head_x1 + up(r2) are formed in the convolutions'
-  // epilogues from the fp32 accumulators (conv_tc.cu `up` operand), and the tail only does the last x2
-  // upsample + argmax.  Otherwise (fp32 parity mode, odd sizes, K > 24) the three-level tail kernel runs.
+  // Ladder on the tensor cores (ladder_tc.cu): when every rung is an exact x2 (all BASELINE sizes), K <= 24 and the
+  // engine runs bf16, r2 = head_x2 + up(x_c) is formed in head_x2's epilogue, and head_x1's epilogue forms
+  // r1 = head_x1 + up(r2), exchanges it inside the CTA and does the last x2 upsample + argmax itself: neither r1 nor
+  // the full-resolution logits reach HBM.  When the caller asks for the logits, head_x1 stores r1 (fp16) and
+  // tail2_kernel produces logits + labels.  Otherwise (fp32 parity mode, odd sizes, K > 24) the three-level tail runs.
   static const bool no_ladder = getenv("LEDB200_NO_LADDER") != nullptr;
   const bool exact2 = p.bufs[hx1].h == 2 * p.bufs[hx2].h && p.bufs[hx1].w == 2 * p.bufs[hx2].w &&
                       p.bufs[hx2].h == 2 * p.bufs[xc].h && p.bufs[hx2].w == 2 * p.bufs[xc].w;
-  const bool ladder = !no_ladder && exact2 && B.conv_uses_tc(h + "head_x2", x2h, hx2, -1, -1, xc) &&
-                      B.conv_uses_tc(h + "head_x1", x1h, hx1, -1, -1, hx2);
+  auto rung_args = [&e](Plan& p, const std::string& cname, int in, int up, int out) {
+    const ConvDef& d = e.convs[e.conv_by_name.at(cname)];
+    const Buf &bi = p.bufs[in], &bu = p.bufs[up];
+    LadderArgs a;
+    a.in = e.arena ? Builder::ptr(e, p, in) : (const void*)16; a.in_ld = bi.ld;
+    a.w_tc = d.w_tc; a.cout_pad_tc = d.cout_pad_tc; a.bias = d.bias;
+    a.up = e.arena ? Builder::ptr(e, p, up) : (const void*)16; a.up_ld = bu.ld; a.up_h = bu.h; a.up_w = bu.w;
+    a.out = e.arena ? Builder::ptr(e, p, out) : (void*)16; a.out_ld = p.bufs[out].ld;
+    a.N = bi.n; a.H = bi.h; a.W = bi.w; a.Cin = d.cin; a.K = d.cout;
+    return a;
+  };
+  const bool ladder = !no_ladder && exact2 && dtype == LEDB200_BF16 && e.cfg.conv_backend != 1 &&
+                      ladder_eligible(rung_args(p, h + "head_x2", x2h, xc, hx2)) &&
+                      ladder_eligible(rung_args(p, h + "head_x1", x1h, hx2, hx1)) &&
+                      B.conv_uses_tc(h + "conv_seg", hf, xc);
   if (ladder) {
-    // the rungs are stored as IEEE fp16 (same 2 bytes, 11-bit mantissa): tighter than the bf16 hx1/hx2 of
-    // the three-level path, and class logits are far inside fp16's range (stores saturate at +-65504)
-    B.conv(h + "head_x2", x2h, hx2, -1, true, -1, -1, 0, 0, xc, false, true);     // hx2 buffer now holds r2 (fp16)
-    B.conv(h + "head_x1", x1h, hx1, -1, true, -1, -1, 0, 0, hx2, true, true);     // hx1 buffer now holds r1 (fp16)
+    // the rungs are stored as IEEE fp16 (same 2 bytes, 11-bit mantissa): tighter than bf16, and class logits are far
+    // inside fp16's range (stores saturate at +-65504)
+    B.conv(h + "conv_seg", hf, xc, -1, false, -1, -1, 0, 0, -1, false, true);            // xc (fp16)
+    auto add_rung = [&](const std::string& cname, int in, int up, int out, bool last) {
+      const ConvDef& d = e.convs[e.conv_by_name.at(cname)];
+      const Buf& bi = p.bufs[in];
+      const double npo = (double)bi.n * bi.h * bi.w;
+      p.ops.push_back({cname, [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
+        LadderArgs a = rung_args(p, cname, in, up, out);
+        if (last && !e.ext_logits) { a.final_argmax = 1; a.pred = e.ext_pred; a.pred_i64 = e.ext_pred_dtype == LEDB200_I64; }
+        return launch_ladder(a, st);
+      }, K_CONV_TC, 2.0 * npo * d.cout * d.cin * 9, 0.0});
+      B.tag();
+      // algorithmic bytes: input once, the rung below once, weights; the rung written once - except for the
+      // last rung on the label-only path, which writes 1 B per full-resolution pixel instead
+      const Buf& bu = p.bufs[up];
+      p.ops.back().bytes = 2.0 * (npo * d.cin + (double)bu.n * bu.h * bu.w * d.cout + (double)d.cout * d.cin * 9) +
+                           (last ? 4.0 * npo : 2.0 * npo * d.cout);
+    };
+    add_rung(h + "head_x2", x2h, xc, hx2, false);      // hx2 buffer holds r2 (fp16)
+    add_rung(h + "head_x1", x1h, hx2, hx1, true);      // labels, or r1 (fp16) when the logits are wanted
     p.ops.push_back({"tail.up2_argmax", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
+      if (!e.ext_logits) return LEDB200_OK;            // label-only path: head_x1 already wrote the labels
       Tail2Args a;
       const Buf& b1 = p.bufs[hx1];
       a.r1 = Builder::ptr(e, p, hx1); a.f16 = 1; a.ld = b1.ld; a.N = b1.n; a.K = K; a.h2 = b1.h; a.w2 = b1.w;
@@ -668,11 +699,9 @@ void build_head_fused(Builder& B) {
       return launch_tail2(a, st);
     }, K_TAIL, 0.0, 0.0});
     B.tag();
-    const Buf& b1 = p.bufs[hx1];
-    p.ops.back().bytes = esize(e) * (double)n * b1.h * b1.w * K + (double)n * p.ho * p.wo;   // r1 in, 1 B label out
-    p.ops.back().flops = (double)n * p.ho * p.wo * K * 8.0;
     return;
   }
+  B.conv(h + "conv_seg", hf, xc);
   B.conv(h + "head_x1", x1h, hx1, -1, true);
   B.conv(h + "head_x2", x2h, hx2, -1, true);
   p.ops.push_back({"tail.fuse_argmax", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {

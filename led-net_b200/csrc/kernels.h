@@ -45,6 +45,27 @@ bool conv_tc_eligible(const ConvArgs& a);
 int conv_tc_pad(int cout);   // rows of the K-major bf16 weight matrix: 32 or a multiple of 64
 int launch_conv_tc(const ConvArgs& a, cudaStream_t st);
 
+// One rung of the LEDHead logit ladder on the tensor cores (ladder_tc.cu):
+//   rung : out[N,H,W,24] fp16 = relu(conv3x3(in) + bias) + up2(up)
+//   final: pred[N,2H,2W] = argmax_k up2(relu(conv3x3(in) + bias) + up2(up))      (no rung tensor in HBM)
+struct LadderArgs {
+  const void* in = nullptr;                // [N,H,W,in_ld] bf16, already BN+ReLU pre-activated (Cin = 32 or 64)
+  int in_ld = 0;
+  const __nv_bfloat16* w_tc = nullptr;     // [32][9*Cin] bf16, K-major, BN folded
+  int cout_pad_tc = 0;
+  const float* bias = nullptr;
+  const void* up = nullptr;                // [N,up_h,up_w,24] fp16: the rung below
+  int up_ld = 0, up_h = 0, up_w = 0;
+  void* out = nullptr;                     // rung mode: [N,H,W,24] fp16
+  int out_ld = 0;
+  int final_argmax = 0;
+  void* pred = nullptr;                    // final mode: [N,2H,2W]
+  int pred_i64 = 0;
+  int N = 0, H = 0, W = 0, Cin = 0, K = 0;
+};
+bool ladder_eligible(const LadderArgs& a);
+int launch_ladder(const LadderArgs& a, cudaStream_t st);
+
 // stem conv 0 (3 -> C, 3x3 s2) on the tensor cores with a thread-built im2col tile (stem_tc.cu)
 bool stem_tc_eligible(const ConvArgs& a);
 int launch_stem_tc(const ConvArgs& a, cudaStream_t st);

@@ -1,0 +1,490 @@
+// The logit ladder of LEDHead on the tensor cores (north_star kernels 1 + 3 + 4 fused).
+//
+// Replaces, per rung,
+//   `_make_base_head` 3x3 conv + folded BN + ReLU on a stem tap (mmseg/models/decode_heads/led_head.py:84-99),
+//   the rung of the patched `BaseDecodeHead.predict_by_feat` (mmseg/models/decode_heads/decode_head.py:362-379):
+//        r2 = head_x2(x2) + up2(x_c)        r1 = head_x1(x1) + up2(r2)        out = up2(r1)
+//   and, for the last rung, `postprocess_result`'s argmax(dim=0) (mmseg/models/segmentors/base.py:187-188).
+//
+//   ladder_kernel<false>  (rung):  out[N,H,W,24] fp16 = relu(conv3x3(in) + b) + up2(up)          head_x2 always;
+//                                  head_x1 only when the caller wants the full-resolution logits (tail2 follows)
+//   ladder_kernel<true>   (final): label[N,2H,2W] = argmax_k up2(relu(conv3x3(in) + b) + up2(up))   head_x1 hot path:
+//                                  r1 (402 MB per 16-image batch as fp16) never reaches HBM - round 1 wrote it from
+//                                  the conv epilogue and read it back in tail3 (0.43 + 0.31 ms).
+//
+// GEMM side (same machinery as conv_tc.cu, MODE 0 / KC = 32 / resident weights): M = 128 pixels (16 x 8 tile),
+// N = 32 (K <= 24 classes, zero padded), K = 9 taps x Cin; ONE TMA halo slab (18 x 10 pixels x 32 ch, 64 B swizzle)
+// per Cin block, nine shifted UMMA descriptors into it; fp32 accumulators in TMEM, EIGHT 32-column stages.
+//
+// What is new against conv_tc's ladder epilogue (ncu r1g: issue 35 %, dram 27 %, 168 registers, 2 epilogue warps per
+// scheduler, 12 x 16 B global corner gathers per thread):
+//   * 16 epilogue warps = four groups of four; group g owns every fourth tile of the CTA.  With a per-tile epilogue
+//     of ~700 instructions per thread the warp schedulers are the limiter, so they get 4 warps each instead of 2;
+//   * the `up` corner patch (10 x 6 pixels x 24 ch fp16 = 2.9 KB) arrives by TMA per tile (its own full / empty
+//     barrier ring, loaded with the A slab), so the gather is 12 conflict-free LDS.128 (48 B pixel stride) at 29 clk
+//     instead of L2 round trips, and nothing has to be prefetched into registers across the accumulator wait;
+//   * bilinear border clamps are index clamps at READ time (TMA zero fill outside the image is never consumed),
+//     which is ATen's align_corners=False rule: weights (1/4, 3/4) by parity, fma(v, 3/4, v/4) == v exactly;
+//   * final rung: tiles OVERLAP by one r1 row / column (stride 15 x 7 over a 16 x 8 MMA tile, origin -1).  The group
+//     writes its r1 tile (fp16, 48 B per pixel) to a double-buffered shared exchange tile, one named barrier, then
+//     thread (i, j), i < 15, j < 7, owns the 2 x 2 outputs BETWEEN r1 pixels (i, j) .. (i+1, j+1): four corners,
+//     packed f32x2 lerps (same operation order as tail3_kernel: bit-identical logits), strict `>` running argmax in
+//     ascending class order = torch.argmax's first-max rule.  22 % of the MMA work is recomputed; 0.8 GB per step of
+//     HBM traffic and one launch disappear.
+#include <cuda.h>
+
+#include <algorithm>
+#include <cstdlib>
+#include <mutex>
+
+#include "tc_common.cuh"
+
+namespace ledb {
+namespace {
+
+using namespace tc;
+
+constexpr int LTH = 16, LTW = 8;                 // MMA tile in rung pixels
+constexpr int L_GROUPS = 4;                      // epilogue groups of 4 warps
+constexpr int L_EPI_WARP0 = 4;                   // first epilogue warp (multiple of 4: TMEM lane quadrant = warp & 3)
+constexpr int L_THREADS = 32 * (L_EPI_WARP0 + 4 * L_GROUPS);
+constexpr int L_NST = 8;                         // accumulator stages (32 columns each)
+constexpr int L_NU = 8;                          // `up` patch ring
+constexpr int L_SA = 8;                          // A slab ring
+constexpr int L_NP = 32;                         // UMMA N
+constexpr int L_CH = 24;                         // stored channels per rung pixel (48 B)
+constexpr int UP_H = 10, UP_W = 6;               // `up` patch
+constexpr uint32_t UP_BYTES = UP_H * UP_W * L_CH * 2;          // 2880
+constexpr uint32_t UP_STAGE = 3072;
+constexpr uint32_t A_BOX = (LTH + 2) * (LTW + 2) * 64;          // 11520
+constexpr uint32_t A_STAGE = 12288;
+constexpr uint32_t B_TILE = L_NP * 64;                          // 2048
+constexpr uint32_t X_TILE = 128 * L_CH * 2;                     // 6144: r1 exchange tile of one group
+
+struct LadderParams {
+  int N, H, W;                 // rung size (= conv output = conv input size)
+  int Cin, nchunks;            // Cin = 32 * nchunks
+  int K;                       // classes (<= 24)
+  int up_h, up_w;              // H == 2 up_h, W == 2 up_w
+  int tiles_h, tiles_w;
+  uint32_t total_tiles;
+  int th_step, tw_step, org;   // tile stride (16 x 8, origin 0; final: 15 x 7, origin -1)
+  const float* bias;
+  __half* out;                 // rung: [N,H,W,24] fp16
+  void* pred; int pred_i64;    // final: [N,2H,2W] uint8 or int64
+};
+
+__device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7])
+               : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+__device__ __forceinline__ float4 lds128f(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+// source row of an exact x2 bilinear upsample (align_corners=False): output y reads rows lo(y), lo(y) + 1 with
+// weights (1/4, 3/4) for even y and (3/4, 1/4) for odd y
+__device__ __forceinline__ int lo2(int y) { return (y - 1) >> 1; }
+__device__ __forceinline__ float2 lerp2(float2 a, float2 b, float2 w0, float2 w1) {
+  return __ffma2_rn(b, w1, __fmul2_rn(a, w0));   // b*w1 + a*w0 per lane (tail.cu lerp2: same bits)
+}
+
+template <bool FINAL>
+__global__ void __launch_bounds__(L_THREADS, 1)
+ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+              const __grid_constant__ CUtensorMap tmU, const __grid_constant__ LadderParams P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* sA = smem;                                        // [L_SA][A_STAGE]
+  uint8_t* sB = sA + (size_t)L_SA * A_STAGE;                 // [nchunks * 9][B_TILE]   (resident weights)
+  uint8_t* sU = sB + (size_t)P.nchunks * 9 * B_TILE;         // [L_NU][UP_STAGE]
+  uint8_t* sX = sU + (size_t)L_NU * UP_STAGE;                // [L_GROUPS][2][X_TILE]   (final rung only)
+  float* s_bias = reinterpret_cast<float*>(sX + (FINAL ? (size_t)L_GROUPS * 2 * X_TILE : 0));   // [32]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + L_NP);
+  uint64_t* a_full = bars;                  // [L_SA]
+  uint64_t* a_empty = a_full + L_SA;        // [L_SA]
+  uint64_t* u_full = a_empty + L_SA;        // [L_NU]
+  uint64_t* u_empty = u_full + L_NU;        // [L_NU]
+  uint64_t* t_full = u_empty + L_NU;        // [L_NST]
+  uint64_t* t_empty = t_full + L_NST;       // [L_NST]
+  uint64_t* b_full = t_empty + L_NST;       // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(b_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t total = P.total_tiles;
+
+  if (threadIdx.x == 0) {
+    prefetch_tensormap(&tmA); prefetch_tensormap(&tmB); prefetch_tensormap(&tmU);
+    for (int i = 0; i < L_SA; ++i) { mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); }
+    for (int i = 0; i < L_NU; ++i) { mbar_init(&u_full[i], 1); mbar_init(&u_empty[i], 4); }
+    for (int i = 0; i < L_NST; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], 4); }
+    mbar_init(b_full, 1);
+    mbar_fence_init();
+    // resident weights: one barrier, one expect_tx (requested before the CTA-wide sync, as in conv_tc.cu)
+    mbar_expect_tx(b_full, (uint32_t)(P.nchunks * 9) * B_TILE);
+    for (int ch = 0; ch < P.nchunks; ++ch)
+      for (int t = 0; t < 9; ++t)
+        tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * B_TILE), &tmB, smem_u32(b_full), t * P.Cin + ch * 32, 0);
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, L_NST * L_NP);
+  uint32_t tmem_base = 0;
+  if (warp == 0) {
+    __syncwarp();
+    asm volatile("bar.arrive 1, %0;" ::"n"(L_THREADS) : "memory");
+  } else {
+    if (threadIdx.x >= 32 && threadIdx.x < 32 + L_NP) {
+      const int c = threadIdx.x - 32;
+      s_bias[c] = (P.bias && c < P.K) ? P.bias[c] : 0.f;
+    }
+    tc_fence_before();
+    asm volatile("bar.sync 1, %0;" ::"n"(L_THREADS) : "memory");
+    tc_fence_after();
+    tmem_base = *tmem_slot;
+  }
+
+  if (warp == 0) {
+    // =========================== TMA producer (one elected lane) ===================================
+    if (elect_one()) {
+      int sa = 0, pa = 0, su = 0, pu = 0;
+      uint32_t t0 = blockIdx.x;
+      int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+      int th = (int)(t0 % (uint32_t)P.tiles_h);
+      int n = (int)(t0 / (uint32_t)P.tiles_h);
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int r0 = th * P.th_step + P.org, c0 = tw * P.tw_step + P.org;
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          mbar_wait(&a_empty[sa], pa ^ 1);
+          mbar_expect_tx(&a_full[sa], A_BOX);
+          tma_load_4d(smem_u32(sA + (size_t)sa * A_STAGE), &tmA, smem_u32(&a_full[sa]), ch * 32, c0 - 1, r0 - 1, n);
+          if (++sa == L_SA) { sa = 0; pa ^= 1; }
+        }
+        mbar_wait(&u_empty[su], pu ^ 1);
+        mbar_expect_tx(&u_full[su], UP_BYTES);
+        tma_load_4d(smem_u32(sU + (size_t)su * UP_STAGE), &tmU, smem_u32(&u_full[su]), 0, lo2(c0), lo2(r0), n);
+        if (++su == L_NU) { su = 0; pu ^= 1; }
+        // next tile of this CTA (tile + gridDim.x) as mixed-radix digits
+        uint32_t nx = tile + gridDim.x;
+        tw = (int)(nx % (uint32_t)P.tiles_w); nx /= (uint32_t)P.tiles_w;
+        th = (int)(nx % (uint32_t)P.tiles_h);
+        n = (int)(nx / (uint32_t)P.tiles_h);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1 || warp == 2) {
+    // =========================== MMA issuers: two elected threads alternate tiles =================
+    // (see conv_tc.cu for why two: the issuing thread stalls on its uniform registers until its MMAs have drained)
+    const int mw = warp - 1;
+    if (elect_one()) {
+      const uint32_t idesc = make_idesc_bf16_m128(L_NP);
+      const uint32_t a_hi = desc_hi((LTW + 2) * 64, 4u);          // SBO = one slab row (10 pixels x 64 B), 64 B swizzle
+      const uint32_t b_hi = desc_hi(8 * 64, 4u);
+      const uint32_t a_lo0 = ((smem_u32(sA) >> 4) & 0x3FFFu) | (1u << 16), b_lo0 = ((smem_u32(sB) >> 4) & 0x3FFFu) | (1u << 16);
+      constexpr uint32_t a_stage16 = A_STAGE >> 4, b_tile16 = B_TILE >> 4;
+      int sa = 0, pa = 0, ts = 0, tp = 0;
+      mbar_wait(b_full, 0);
+      tc_fence_after();
+      auto skip_tile = [&]() {
+        for (int i = 0; i < P.nchunks; ++i) if (++sa == L_SA) { sa = 0; pa ^= 1; }
+        if (++ts == L_NST) { ts = 0; tp ^= 1; }
+      };
+      if (mw == 1) skip_tile();
+      for (uint32_t tile = blockIdx.x + (uint32_t)mw * gridDim.x; tile < total; tile += 2 * gridDim.x) {
+        mbar_wait(&t_empty[ts], tp ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(ts * L_NP);
+        for (int ch = 0; ch < P.nchunks; ++ch) {
+          const uint32_t acc_first = ch ? 1u : 0u;
+          const uint32_t b_chunk = b_lo0 + (uint32_t)(ch * 9) * b_tile16;
+          mbar_wait(&a_full[sa], pa);
+          tc_fence_after();
+          const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) {
+            const uint32_t b_lo = b_chunk + (uint32_t)t * b_tile16;
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const uint32_t al = a_lo + (((uint32_t)((t / 3) * (LTW + 2) + (t % 3)) * 64 + k * 32) >> 4);
+              if (t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+              else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+            }
+          }
+          tc_commit(&a_empty[sa]);
+          if (++sa == L_SA) { sa = 0; pa ^= 1; }
+        }
+        tc_commit(&t_full[ts]);
+        if (++ts == L_NST) { ts = 0; tp ^= 1; }
+        skip_tile();                                       // the other issuer's tile
+      }
+    }
+    __syncwarp();
+  } else if (warp >= L_EPI_WARP0) {
+    // =========================== epilogue: four groups of four warps ===============================
+    const int ew = warp - L_EPI_WARP0, grp = ew >> 2, q = warp & 3;
+    const int m = q * 32 + lane, ph = m >> 3, pw = m & 7;        // this thread's pixel of the 16 x 8 tile
+    const uint32_t taddr_q = tmem_base + ((uint32_t)(q * 32) << 16);
+    const uint32_t bias_u = smem_u32(s_bias), sU_u = smem_u32(sU);
+    const uint32_t sX_u = smem_u32(sX) + (uint32_t)grp * 2 * X_TILE;
+    const int H = P.H, W = P.W, K = P.K;
+    uint32_t ts = (uint32_t)grp, tp = 0, su = (uint32_t)grp, pu = 0, xb = 0;     // L_NST, L_NU multiples of L_GROUPS
+    for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < total; tile += (uint32_t)L_GROUPS * gridDim.x) {
+      uint32_t t0 = tile;
+      const int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+      const int th = (int)(t0 % (uint32_t)P.tiles_h);
+      const int n = (int)(t0 / (uint32_t)P.tiles_h);
+      const int r0 = th * P.th_step + P.org, c0 = tw * P.tw_step + P.org;
+      const int y = r0 + ph, x = c0 + pw;
+      // ---- `up` corner addresses in the patch (index clamps = ATen's border rule) and parity weights
+      const int uy0 = lo2(r0), ux0 = lo2(c0);
+      const int ya = clampi(lo2(y), 0, P.up_h - 1) - uy0, yb = clampi(lo2(y) + 1, 0, P.up_h - 1) - uy0;
+      const int xa = clampi(lo2(x), 0, P.up_w - 1) - ux0, xb_ = clampi(lo2(x) + 1, 0, P.up_w - 1) - ux0;
+      // (pixels outside the rung - the origin -1 row / column, the ragged last tiles - may clamp outside the patch:
+      //  keep every read inside it, their values are never consumed)
+      const int ya_c = clampi(ya, 0, UP_H - 1), yb_c = clampi(yb, 0, UP_H - 1);
+      const int xa_c = clampi(xa, 0, UP_W - 1), xb_c = clampi(xb_, 0, UP_W - 1);
+      const uint32_t ub = sU_u + su * UP_STAGE;
+      const uint32_t u00 = ub + (uint32_t)((ya_c * UP_W + xa_c) * (L_CH * 2)), u01 = ub + (uint32_t)((ya_c * UP_W + xb_c) * (L_CH * 2));
+      const uint32_t u10 = ub + (uint32_t)((yb_c * UP_W + xa_c) * (L_CH * 2)), u11 = ub + (uint32_t)((yb_c * UP_W + xb_c) * (L_CH * 2));
+      const __half2 hwx0 = __float2half2_rn((x & 1) ? 0.75f : 0.25f), hwx1 = __float2half2_rn((x & 1) ? 0.25f : 0.75f);
+      const __half2 hwy0 = __float2half2_rn((y & 1) ? 0.75f : 0.25f), hwy1 = __float2half2_rn((y & 1) ? 0.25f : 0.75f);
+
+      mbar_wait(&t_full[ts], tp);
+      tc_fence_after();
+      uint32_t v[24];
+      tc_ld16(taddr_q + ts * (uint32_t)L_NP, v);
+      tc_ld8(taddr_q + ts * (uint32_t)L_NP + 16, v + 16);
+      tc_wait_ld();
+      // the accumulator stage is free as soon as it is in registers
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&t_empty[ts]);
+      mbar_wait(&u_full[su], pu);
+
+      uint4 o[3];                                              // this pixel's rung value, 24 x fp16
+#pragma unroll
+      for (int g = 0; g < 3; ++g) {
+        float f[8];
+        const float4 b0 = lds128f(bias_u + 32 * g), b1 = lds128f(bias_u + 32 * g + 16);
+        f[0] = fmaxf(__uint_as_float(v[8 * g + 0]) + b0.x, 0.f); f[1] = fmaxf(__uint_as_float(v[8 * g + 1]) + b0.y, 0.f);
+        f[2] = fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f); f[3] = fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f);
+        f[4] = fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f); f[5] = fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f);
+        f[6] = fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f); f[7] = fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f);
+        const uint4 ca = lds128(u00 + 16 * g), cb = lds128(u01 + 16 * g), cc = lds128(u10 + 16 * g), cd = lds128(u11 + 16 * g);
+        const __half2* a = reinterpret_cast<const __half2*>(&ca);
+        const __half2* b = reinterpret_cast<const __half2*>(&cb);
+        const __half2* c = reinterpret_cast<const __half2*>(&cc);
+        const __half2* d = reinterpret_cast<const __half2*>(&cd);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          // packed half2 interpolation (the weights are exact; same order as round 1's conv_tc ladder epilogue)
+          const __half2 h0 = __hfma2(b[j], hwx1, __hmul2(a[j], hwx0));
+          const __half2 h1 = __hfma2(d[j], hwx1, __hmul2(c[j], hwx0));
+          const float2 u2 = __half22float2(__hfma2(h1, hwy1, __hmul2(h0, hwy0)));
+          f[2 * j] += u2.x; f[2 * j + 1] += u2.y;
+        }
+        o[g] = make_uint4(pack_f16x2_sat(f[0], f[1]), pack_f16x2_sat(f[2], f[3]), pack_f16x2_sat(f[4], f[5]),
+                          pack_f16x2_sat(f[6], f[7]));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&u_empty[su]);                // patch consumed
+
+      if (!FINAL) {
+        if (y < H && x < W) {
+          __half* op = P.out + (((int64_t)n * H + y) * W + x) * L_CH;
+#pragma unroll
+          for (int g = 0; g < 3; ++g)
+            if (8 * g < K) *reinterpret_cast<uint4*>(op + 8 * g) = o[g];
+        }
+      } else {
+        // ---- exchange the r1 tile inside the group, then the last x2 upsample + argmax
+        const uint32_t xt = sX_u + xb * X_TILE;
+        const uint32_t mine = xt + (uint32_t)m * (L_CH * 2);
+#pragma unroll
+        for (int g = 0; g < 3; ++g) sts128(mine + 16 * g, o[g]);
+        asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
+        const bool act = ph < LTH - 1 && pw < LTW - 1;
+        // outputs Y1 = 2y+1 (3/4 top, 1/4 bottom), Y2 = 2y+2 (1/4, 3/4); same for columns
+        const bool vy1 = y >= 0 && y <= H - 1, vy2 = y >= -1 && y + 1 <= H - 1;
+        const bool vx1 = x >= 0 && x <= W - 1, vx2 = x >= -1 && x + 1 <= W - 1;
+        if (act && (vy1 || vy2) && (vx1 || vx2)) {
+          const int lt = clampi(y, 0, H - 1) - r0, lb = clampi(y + 1, 0, H - 1) - r0;      // tile-local rows, 0..15
+          const int ll = clampi(x, 0, W - 1) - c0, lr = clampi(x + 1, 0, W - 1) - c0;
+          const uint32_t pTL = xt + (uint32_t)((lt * LTW + ll) * (L_CH * 2)), pTR = xt + (uint32_t)((lt * LTW + lr) * (L_CH * 2));
+          const uint32_t pBL = xt + (uint32_t)((lb * LTW + ll) * (L_CH * 2)), pBR = xt + (uint32_t)((lb * LTW + lr) * (L_CH * 2));
+          const float2 q14 = make_float2(0.25f, 0.25f), q34 = make_float2(0.75f, 0.75f);
+          float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // (Y1,X1) (Y1,X2) (Y2,X1) (Y2,X2)
+          int bidx[4] = {0, 0, 0, 0};
+#pragma unroll
+          for (int g = 0; g < 3; ++g) {
+            if (8 * g >= K) break;
+            const uint4 tl = lds128(pTL + 16 * g), tr = lds128(pTR + 16 * g), bl = lds128(pBL + 16 * g), br = lds128(pBR + 16 * g);
+            const __half2* htl = reinterpret_cast<const __half2*>(&tl);
+            const __half2* htr = reinterpret_cast<const __half2*>(&tr);
+            const __half2* hbl = reinterpret_cast<const __half2*>(&bl);
+            const __half2* hbr = reinterpret_cast<const __half2*>(&br);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const int k = 8 * g + 2 * j;
+              if (k >= K) break;
+              const bool two = k + 1 < K;
+              const float2 TL = __half22float2(htl[j]), TR = __half22float2(htr[j]);
+              const float2 BL = __half22float2(hbl[j]), BR = __half22float2(hbr[j]);
+              // horizontal first, then vertical (tail3_kernel's order)
+              const float2 t1 = lerp2(TL, TR, q34, q14), t2 = lerp2(TL, TR, q14, q34);
+              const float2 b1 = lerp2(BL, BR, q34, q14), b2 = lerp2(BL, BR, q14, q34);
+              const float2 o11 = lerp2(t1, b1, q34, q14), o12 = lerp2(t2, b2, q34, q14);
+              const float2 o21 = lerp2(t1, b1, q14, q34), o22 = lerp2(t2, b2, q14, q34);
+              if (o11.x > best[0]) { best[0] = o11.x; bidx[0] = k; }
+              if (o12.x > best[1]) { best[1] = o12.x; bidx[1] = k; }
+              if (o21.x > best[2]) { best[2] = o21.x; bidx[2] = k; }
+              if (o22.x > best[3]) { best[3] = o22.x; bidx[3] = k; }
+              if (two) {
+                if (o11.y > best[0]) { best[0] = o11.y; bidx[0] = k + 1; }
+                if (o12.y > best[1]) { best[1] = o12.y; bidx[1] = k + 1; }
+                if (o21.y > best[2]) { best[2] = o21.y; bidx[2] = k + 1; }
+                if (o22.y > best[3]) { best[3] = o22.y; bidx[3] = k + 1; }
+              }
+            }
+          }
+          const int Ho = 2 * H, Wo = 2 * W;
+          const int64_t base = ((int64_t)n * Ho + (2 * y + 1)) * Wo + (2 * x + 1);
+          if (P.pred_i64) {
+            int64_t* pr = reinterpret_cast<int64_t*>(P.pred);
+            if (vy1 && vx1) pr[base] = bidx[0];
+            if (vy1 && vx2) pr[base + 1] = bidx[1];
+            if (vy2 && vx1) pr[base + Wo] = bidx[2];
+            if (vy2 && vx2) pr[base + Wo + 1] = bidx[3];
+          } else {
+            uint8_t* pr = reinterpret_cast<uint8_t*>(P.pred);
+            if (vy1 && vx1) pr[base] = (uint8_t)bidx[0];
+            if (vy1 && vx2) pr[base + 1] = (uint8_t)bidx[1];
+            if (vy2 && vx1) pr[base + Wo] = (uint8_t)bidx[2];
+            if (vy2 && vx2) pr[base + Wo + 1] = (uint8_t)bidx[3];
+          }
+        }
+        xb ^= 1;
+      }
+      ts += L_GROUPS; if (ts >= (uint32_t)L_NST) { ts -= L_NST; tp ^= 1; }
+      su += L_GROUPS; if (su >= (uint32_t)L_NU) { su -= L_NU; pu ^= 1; }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, L_NST * L_NP);
+  }
+}
+
+typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                             const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                             CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeFn get_encode() {
+  static EncodeFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeFn>(p);
+  });
+  return fn;
+}
+int encode(CUtensorMap* m, CUtensorMapDataType dt, const void* base, int rank, const uint64_t* dims,
+           const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeFn fn = get_encode();
+  if (!fn) return fail(LEDB200_ECUDA, "cuTensorMapEncodeTiled entry point not available");
+  cuuint64_t d[5], s[4];
+  cuuint32_t b[5], es[5];
+  for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
+  CUresult r = fn(m, dt, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(LEDB200_ECUDA, "ladder: cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
+  return LEDB200_OK;
+}
+
+}  // namespace
+
+bool ladder_eligible(const LadderArgs& a) {
+  if (!a.in || !a.up || !a.w_tc) return false;
+  if (a.Cin != 32 && a.Cin != 64) return false;                 // 32-channel K blocks, weights resident
+  if (a.in_ld % 8 || a.in_ld < a.Cin) return false;
+  if (a.K < 1 || a.K > L_CH || a.cout_pad_tc != L_NP) return false;
+  if (a.up_ld != L_CH || a.H != 2 * a.up_h || a.W != 2 * a.up_w) return false;
+  if (((uintptr_t)a.in | (uintptr_t)a.up | (uintptr_t)a.w_tc) & 15) return false;
+  if (a.final_argmax) { if (!a.pred) return false; }
+  else if (!a.out || a.out_ld != L_CH || ((uintptr_t)a.out & 15)) return false;
+  if ((int64_t)a.N * ceil_div(a.H + 1, 15) * ceil_div(a.W + 1, 7) >= (1ll << 31)) return false;
+  return true;
+}
+
+int launch_ladder(const LadderArgs& a, cudaStream_t st) {
+  if (!ladder_eligible(a)) return fail(LEDB200_EINVAL, "ladder: shape not eligible");
+  LadderParams P{};
+  P.N = a.N; P.H = a.H; P.W = a.W; P.Cin = a.Cin; P.nchunks = a.Cin / 32; P.K = a.K;
+  P.up_h = a.up_h; P.up_w = a.up_w; P.bias = a.bias;
+  P.out = (__half*)a.out; P.pred = a.pred; P.pred_i64 = a.pred_i64;
+  if (a.final_argmax) {
+    // overlapping tiles: rung rows -1 .. H-1 in steps of 15 (row i and i+1 of a tile produce outputs 2i+1, 2i+2)
+    P.th_step = LTH - 1; P.tw_step = LTW - 1; P.org = -1;
+    P.tiles_h = ceil_div(a.H + 1, LTH - 1); P.tiles_w = ceil_div(a.W + 1, LTW - 1);
+  } else {
+    P.th_step = LTH; P.tw_step = LTW; P.org = 0;
+    P.tiles_h = ceil_div(a.H, LTH); P.tiles_w = ceil_div(a.W, LTW);
+  }
+  P.total_tiles = (uint32_t)((int64_t)a.N * P.tiles_h * P.tiles_w);
+  CUtensorMap tmA, tmB, tmU;
+  int rc;
+  {
+    const uint64_t ld = (uint64_t)a.in_ld;
+    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t str[3] = {ld * 2, (uint64_t)a.W * ld * 2, (uint64_t)a.H * a.W * ld * 2};
+    const uint32_t box[4] = {32, LTW + 2, LTH + 2, 1};
+    if ((rc = encode(&tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.in, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
+  {
+    const uint64_t dims[2] = {(uint64_t)9 * a.Cin, (uint64_t)L_NP};
+    const uint64_t str[1] = {(uint64_t)9 * a.Cin * 2};
+    const uint32_t box[2] = {32, L_NP};
+    if ((rc = encode(&tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, a.w_tc, 2, dims, str, box, CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+  }
+  {
+    const uint64_t dims[4] = {(uint64_t)L_CH, (uint64_t)a.up_w, (uint64_t)a.up_h, (uint64_t)a.N};
+    const uint64_t str[3] = {(uint64_t)L_CH * 2, (uint64_t)a.up_w * L_CH * 2, (uint64_t)a.up_h * a.up_w * L_CH * 2};
+    const uint32_t box[4] = {L_CH, UP_W, UP_H, 1};
+    if ((rc = encode(&tmU, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, a.up, 4, dims, str, box, CU_TENSOR_MAP_SWIZZLE_NONE))) return rc;
+  }
+  const size_t smem = 1024 + (size_t)L_SA * A_STAGE + (size_t)P.nchunks * 9 * B_TILE + (size_t)L_NU * UP_STAGE +
+                      (a.final_argmax ? (size_t)L_GROUPS * 2 * X_TILE : 0) + L_NP * 4 + (2 * L_SA + 2 * L_NU + 2 * L_NST + 1) * 8 + 16;
+  static std::once_flag attr_once;
+  static cudaError_t attr_err = cudaSuccess;
+  std::call_once(attr_once, [] {
+    cudaError_t e = cudaFuncSetAttribute(ladder_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) attr_err = e;
+    e = cudaFuncSetAttribute(ladder_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+    if (e != cudaSuccess) attr_err = e;
+  });
+  if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("ladder: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
+  static int sms = 0;
+  if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+  const int grid = (int)std::min<uint32_t>(P.total_tiles, (uint32_t)sms);
+  if (a.final_argmax) ladder_kernel<true><<<grid, L_THREADS, smem, st>>>(tmA, tmB, tmU, P);
+  else ladder_kernel<false><<<grid, L_THREADS, smem, st>>>(tmA, tmB, tmU, P);
+  LEDB_LAUNCH_OK("ladder_kernel");
+  return LEDB200_OK;
+}
+
+}  // namespace ledb
