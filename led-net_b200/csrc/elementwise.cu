@@ -405,6 +405,8 @@ int launch_nhwc_to_nchw(const void* in, int in_dtype, float* out, int N, int C, 
   dim3 grid((unsigned)ceil_div64(HW, 32), ceil_div(C, 32), N), block(32, 8);
   if (in_dtype == LEDB200_BF16)
     nhwc_to_nchw_kernel<__nv_bfloat16><<<grid, block, 0, st>>>((const __nv_bfloat16*)in, out, C, HW, in_ld);
+  else if (in_dtype == 5)   // IEEE fp16 (ladder rungs; debug fetch only)
+    nhwc_to_nchw_kernel<__half><<<grid, block, 0, st>>>((const __half*)in, out, C, HW, in_ld);
   else
     nhwc_to_nchw_kernel<float><<<grid, block, 0, st>>>((const float*)in, out, C, HW, in_ld);
   LEDB_LAUNCH_OK("nhwc_to_nchw_kernel");

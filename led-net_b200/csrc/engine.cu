@@ -50,7 +50,7 @@ struct ConvDef {
 };
 struct AffineDef { std::string bn; int c = 0; float* scale = nullptr; float* shift = nullptr; };
 
-struct Buf { std::string name; int n, h, w, c, ld; size_t off; };
+struct Buf { std::string name; int n, h, w, c, ld; size_t off; int f16 = 0; };   // f16: holds IEEE fp16 (ladder rungs)
 
 struct Plan;
 }  // namespace
@@ -314,7 +314,7 @@ struct Builder {
   void tag() { p.ops.back().lane = cur_lane; p.ops.back().wait_other = pending_wait; pending_wait = false; }
 
   int buf(const std::string& name, int n, int h, int w, int c, int ld = 0) {
-    Buf b{name, n, h, w, c, ld ? ld : c, p.arena};
+    Buf b{name, n, h, w, c, ld ? ld : c, p.arena, 0};
     p.arena += ((size_t)n * h * w * b.ld * esize(e) + 255) / 256 * 256;
     p.by_name[name] = (int)p.bufs.size();
     p.bufs.push_back(b);
@@ -669,6 +669,7 @@ void build_head_fused(Builder& B) {
                       ladder_eligible(rung_args(p, h + "head_x1", x1h, hx2, hx1)) &&
                       B.conv_uses_tc(h + "conv_seg", hf, xc);
   if (ladder) {
+    p.bufs[xc].f16 = p.bufs[hx1].f16 = p.bufs[hx2].f16 = 1;
     // the rungs are stored as IEEE fp16 (same 2 bytes, 11-bit mantissa): tighter than bf16, and class logits are far
     // inside fp16's range (stores saturate at +-65504)
     B.conv(h + "conv_seg", hf, xc, -1, false, -1, -1, 0, 0, -1, false, true);            // xc (fp16)
@@ -806,6 +807,8 @@ int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Pla
       return fail(LEDB200_ENOMEM, "cannot allocate " + std::to_string(p->arena >> 20) + " MiB activation workspace");
     }
     e.arena = (char*)q; e.arena_cap = p->arena;
+    // debugging aid: fill the workspace with a NaN pattern so that any read of a never-written byte shows up
+    if (const char* ps = getenv("LEDB200_POISON")) LEDB_CUDA_OK(cudaMemset(q, atoi(ps), p->arena));
   }
   *out = p;
   return LEDB200_OK;
@@ -1028,7 +1031,7 @@ int ledb200_debug_fetch(ledb200_handle* h, const char* buffer_name, float* host_
   float* tmp = nullptr;
   LEDB_CUDA_OK(cudaMalloc(&tmp, n * sizeof(float)));
   cudaStream_t st = (cudaStream_t)stream;
-  rc = launch_nhwc_to_nchw(h->arena + b.off, h->cfg.dtype, tmp, b.n, b.c, b.h, b.w, b.ld, st);
+  rc = launch_nhwc_to_nchw(h->arena + b.off, b.f16 ? 5 /* fp16 */ : h->cfg.dtype, tmp, b.n, b.c, b.h, b.w, b.ld, st);
   if (!rc) {
     cudaError_t ce = cudaMemcpyAsync(host_out, tmp, n * sizeof(float), cudaMemcpyDeviceToHost, st);
     if (ce == cudaSuccess) ce = cudaStreamSynchronize(st);

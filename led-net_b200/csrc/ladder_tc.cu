@@ -25,12 +25,19 @@
 //     instead of L2 round trips, and nothing has to be prefetched into registers across the accumulator wait;
 //   * bilinear border clamps are index clamps at READ time (TMA zero fill outside the image is never consumed),
 //     which is ATen's align_corners=False rule: weights (1/4, 3/4) by parity, fma(v, 3/4, v/4) == v exactly;
-//   * final rung: tiles OVERLAP by one r1 row / column (stride 15 x 7 over a 16 x 8 MMA tile, origin -1).  The group
-//     writes its r1 tile (fp16, 48 B per pixel) to a double-buffered shared exchange tile, one named barrier, then
-//     thread (i, j), i < 15, j < 7, owns the 2 x 2 outputs BETWEEN r1 pixels (i, j) .. (i+1, j+1): four corners,
-//     packed f32x2 lerps (same operation order as tail3_kernel: bit-identical logits), strict `>` running argmax in
-//     ascending class order = torch.argmax's first-max rule.  22 % of the MMA work is recomputed; 0.8 GB per step of
-//     HBM traffic and one launch disappear.
+//   * final rung: tiles OVERLAP by one r1 row / column (stride 15 x 7 over a 16 x 8 MMA tile; the last tile of a row /
+//     column is shifted back so that it ends at the image edge, like every other TMA box of this library it then
+//     leaves the tensor by at most one pixel).  The group writes its r1 tile (fp16, 48 B per pixel) to a
+//     double-buffered shared exchange tile, one named barrier, then thread (i, j) owns the 2 x 2 outputs BETWEEN r1
+//     pixels (i, j) .. (i+1, j+1) - rows 2y+1, 2y+2 - from its own pixel (registers) and three neighbours (LDS), with
+//     packed f32x2 lerps in tail3_kernel's operation order (bit-identical logits) and a strict `>` running argmax in
+//     ascending class order = torch.argmax's first-max rule.  Output row 0 / column 0 (source index clamped: a pure
+//     copy of the first r1 row / column) are written by the threads of r1 row 0 / column 0 in a second, rare pass.
+//     22 % of the MMA work is recomputed (pixels covered by two tiles get bit-identical values, so the duplicate
+//     label stores are benign); 0.8 GB per step of HBM traffic and one launch disappear.
+//   * one producer thread per operand (warp 0: A slabs, warp 3: `up` patches), tile coordinates advanced as
+//     mixed-radix digits: a single thread doing both plus three integer divisions per tile bounded the kernel at
+//     ~800 clk per tile (probe: 239 us with every other role switched off).
 #include <cuda.h>
 
 #include <algorithm>
@@ -68,10 +75,15 @@ struct LadderParams {
   int up_h, up_w;              // H == 2 up_h, W == 2 up_w
   int tiles_h, tiles_w;
   uint32_t total_tiles;
-  int th_step, tw_step, org;   // tile stride (16 x 8, origin 0; final: 15 x 7, origin -1)
+  int th_step, tw_step;        // tile stride (16 x 8; final: 15 x 7)
+  int r_max, c_max;            // largest tile origin (final: H - 16, W - 8: the last tile ends at the image edge)
+  int step[3][3];              // tile-index step of 1, 2 and 4 grids as digits (tile col, tile row, image)
   const float* bias;
   __half* out;                 // rung: [N,H,W,24] fp16
   void* pred; int pred_i64;    // final: [N,2H,2W] uint8 or int64
+  int dbg;                     // LEDB200_LADDER_DBG probe bits (timing / diagnosis only): 1 no output phase, 2 no `up` gather,
+                               // 4 no MMAs, 8 final mode also stores r1 to `out`, 16 single MMA issuer, 32 release the accumulator stage and the
+                               // `up` patch at the END of the tile
 };
 
 __device__ __forceinline__ void tc_ld8(uint32_t taddr, uint32_t* v) {
@@ -153,31 +165,51 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     tmem_base = *tmem_slot;
   }
 
+  // tile coordinates: (tile col, tile row, image) digits advanced by `k` grids at a time (no per-tile divisions)
+  struct TileIt {
+    int tw, th, n;
+    __device__ __forceinline__ void init(uint32_t t, const LadderParams& P) {
+      tw = (int)(t % (uint32_t)P.tiles_w); t /= (uint32_t)P.tiles_w;
+      th = (int)(t % (uint32_t)P.tiles_h);
+      n = (int)(t / (uint32_t)P.tiles_h);
+    }
+    __device__ __forceinline__ void step(const int* d, const LadderParams& P) {
+      tw += d[0]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+      th += d[1]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+      n += d[2];
+    }
+    __device__ __forceinline__ int r0(const LadderParams& P) const { return min(th * P.th_step, P.r_max); }
+    __device__ __forceinline__ int c0(const LadderParams& P) const { return min(tw * P.tw_step, P.c_max); }
+  };
+
   if (warp == 0) {
-    // =========================== TMA producer (one elected lane) ===================================
+    // =========================== TMA producer, A slabs (one elected lane) ==========================
     if (elect_one()) {
-      int sa = 0, pa = 0, su = 0, pu = 0;
-      uint32_t t0 = blockIdx.x;
-      int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
-      int th = (int)(t0 % (uint32_t)P.tiles_h);
-      int n = (int)(t0 / (uint32_t)P.tiles_h);
+      int sa = 0, pa = 0;
+      TileIt it; it.init(blockIdx.x, P);
       for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        const int r0 = th * P.th_step + P.org, c0 = tw * P.tw_step + P.org;
+        const int r0 = it.r0(P), c0 = it.c0(P);
         for (int ch = 0; ch < P.nchunks; ++ch) {
           mbar_wait(&a_empty[sa], pa ^ 1);
           mbar_expect_tx(&a_full[sa], A_BOX);
-          tma_load_4d(smem_u32(sA + (size_t)sa * A_STAGE), &tmA, smem_u32(&a_full[sa]), ch * 32, c0 - 1, r0 - 1, n);
+          tma_load_4d(smem_u32(sA + (size_t)sa * A_STAGE), &tmA, smem_u32(&a_full[sa]), ch * 32, c0 - 1, r0 - 1, it.n);
           if (++sa == L_SA) { sa = 0; pa ^= 1; }
         }
+        it.step(P.step[0], P);
+      }
+    }
+    __syncwarp();
+  } else if (warp == 3) {
+    // =========================== TMA producer, `up` patches (one elected lane) =====================
+    if (elect_one()) {
+      int su = 0, pu = 0;
+      TileIt it; it.init(blockIdx.x, P);
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
         mbar_wait(&u_empty[su], pu ^ 1);
         mbar_expect_tx(&u_full[su], UP_BYTES);
-        tma_load_4d(smem_u32(sU + (size_t)su * UP_STAGE), &tmU, smem_u32(&u_full[su]), 0, lo2(c0), lo2(r0), n);
+        tma_load_4d(smem_u32(sU + (size_t)su * UP_STAGE), &tmU, smem_u32(&u_full[su]), 0, lo2(it.c0(P)), lo2(it.r0(P)), it.n);
         if (++su == L_NU) { su = 0; pu ^= 1; }
-        // next tile of this CTA (tile + gridDim.x) as mixed-radix digits
-        uint32_t nx = tile + gridDim.x;
-        tw = (int)(nx % (uint32_t)P.tiles_w); nx /= (uint32_t)P.tiles_w;
-        th = (int)(nx % (uint32_t)P.tiles_h);
-        n = (int)(nx / (uint32_t)P.tiles_h);
+        it.step(P.step[0], P);
       }
     }
     __syncwarp();
@@ -185,7 +217,8 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     // =========================== MMA issuers: two elected threads alternate tiles =================
     // (see conv_tc.cu for why two: the issuing thread stalls on its uniform registers until its MMAs have drained)
     const int mw = warp - 1;
-    if (elect_one()) {
+    const int nmw = (P.dbg & 16) ? 1 : 2;
+    if (mw < nmw && elect_one()) {
       const uint32_t idesc = make_idesc_bf16_m128(L_NP);
       const uint32_t a_hi = desc_hi((LTW + 2) * 64, 4u);          // SBO = one slab row (10 pixels x 64 B), 64 B swizzle
       const uint32_t b_hi = desc_hi(8 * 64, 4u);
@@ -199,7 +232,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         if (++ts == L_NST) { ts = 0; tp ^= 1; }
       };
       if (mw == 1) skip_tile();
-      for (uint32_t tile = blockIdx.x + (uint32_t)mw * gridDim.x; tile < total; tile += 2 * gridDim.x) {
+      for (uint32_t tile = blockIdx.x + (uint32_t)mw * gridDim.x; tile < total; tile += (uint32_t)nmw * gridDim.x) {
         mbar_wait(&t_empty[ts], tp ^ 1);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(ts * L_NP);
@@ -209,6 +242,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
           mbar_wait(&a_full[sa], pa);
           tc_fence_after();
           const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
+          if (!(P.dbg & 4))
 #pragma unroll
           for (int t = 0; t < 9; ++t) {
             const uint32_t b_lo = b_chunk + (uint32_t)t * b_tile16;
@@ -224,7 +258,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
         tc_commit(&t_full[ts]);
         if (++ts == L_NST) { ts = 0; tp ^= 1; }
-        skip_tile();                                       // the other issuer's tile
+        if (nmw == 2) skip_tile();                         // the other issuer's tile
       }
     }
     __syncwarp();
@@ -237,24 +271,18 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
     const uint32_t sX_u = smem_u32(sX) + (uint32_t)grp * 2 * X_TILE;
     const int H = P.H, W = P.W, K = P.K;
     uint32_t ts = (uint32_t)grp, tp = 0, su = (uint32_t)grp, pu = 0, xb = 0;     // L_NST, L_NU multiples of L_GROUPS
+    TileIt it; it.init(blockIdx.x + (uint32_t)grp * gridDim.x, P);
     for (uint32_t tile = blockIdx.x + (uint32_t)grp * gridDim.x; tile < total; tile += (uint32_t)L_GROUPS * gridDim.x) {
-      uint32_t t0 = tile;
-      const int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
-      const int th = (int)(t0 % (uint32_t)P.tiles_h);
-      const int n = (int)(t0 / (uint32_t)P.tiles_h);
-      const int r0 = th * P.th_step + P.org, c0 = tw * P.tw_step + P.org;
-      const int y = r0 + ph, x = c0 + pw;
+      const int n = it.n, r0 = it.r0(P), c0 = it.c0(P);
+      const int y = r0 + ph, x = c0 + pw;                         // >= 0; may lie beyond the rung in ragged last tiles
       // ---- `up` corner addresses in the patch (index clamps = ATen's border rule) and parity weights
       const int uy0 = lo2(r0), ux0 = lo2(c0);
-      const int ya = clampi(lo2(y), 0, P.up_h - 1) - uy0, yb = clampi(lo2(y) + 1, 0, P.up_h - 1) - uy0;
-      const int xa = clampi(lo2(x), 0, P.up_w - 1) - ux0, xb_ = clampi(lo2(x) + 1, 0, P.up_w - 1) - ux0;
-      // (pixels outside the rung - the origin -1 row / column, the ragged last tiles - may clamp outside the patch:
-      //  keep every read inside it, their values are never consumed)
-      const int ya_c = clampi(ya, 0, UP_H - 1), yb_c = clampi(yb, 0, UP_H - 1);
-      const int xa_c = clampi(xa, 0, UP_W - 1), xb_c = clampi(xb_, 0, UP_W - 1);
+      // (pixels beyond the rung may clamp outside the patch: keep every read inside it, their values are never consumed)
+      const int ya = clampi(clampi(lo2(y), 0, P.up_h - 1) - uy0, 0, UP_H - 1), yb = clampi(clampi(lo2(y) + 1, 0, P.up_h - 1) - uy0, 0, UP_H - 1);
+      const int xa = clampi(clampi(lo2(x), 0, P.up_w - 1) - ux0, 0, UP_W - 1), xb_ = clampi(clampi(lo2(x) + 1, 0, P.up_w - 1) - ux0, 0, UP_W - 1);
       const uint32_t ub = sU_u + su * UP_STAGE;
-      const uint32_t u00 = ub + (uint32_t)((ya_c * UP_W + xa_c) * (L_CH * 2)), u01 = ub + (uint32_t)((ya_c * UP_W + xb_c) * (L_CH * 2));
-      const uint32_t u10 = ub + (uint32_t)((yb_c * UP_W + xa_c) * (L_CH * 2)), u11 = ub + (uint32_t)((yb_c * UP_W + xb_c) * (L_CH * 2));
+      const uint32_t u00 = ub + (uint32_t)((ya * UP_W + xa) * (L_CH * 2)), u01 = ub + (uint32_t)((ya * UP_W + xb_) * (L_CH * 2));
+      const uint32_t u10 = ub + (uint32_t)((yb * UP_W + xa) * (L_CH * 2)), u11 = ub + (uint32_t)((yb * UP_W + xb_) * (L_CH * 2));
       const __half2 hwx0 = __float2half2_rn((x & 1) ? 0.75f : 0.25f), hwx1 = __float2half2_rn((x & 1) ? 0.25f : 0.75f);
       const __half2 hwy0 = __float2half2_rn((y & 1) ? 0.75f : 0.25f), hwy1 = __float2half2_rn((y & 1) ? 0.25f : 0.75f);
 
@@ -267,7 +295,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
       // the accumulator stage is free as soon as it is in registers
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&t_empty[ts]);
+      if (lane == 0 && !(P.dbg & 32)) mbar_arrive(&t_empty[ts]);
       mbar_wait(&u_full[su], pu);
 
       uint4 o[3];                                              // this pixel's rung value, 24 x fp16
@@ -279,6 +307,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         f[2] = fmaxf(__uint_as_float(v[8 * g + 2]) + b0.z, 0.f); f[3] = fmaxf(__uint_as_float(v[8 * g + 3]) + b0.w, 0.f);
         f[4] = fmaxf(__uint_as_float(v[8 * g + 4]) + b1.x, 0.f); f[5] = fmaxf(__uint_as_float(v[8 * g + 5]) + b1.y, 0.f);
         f[6] = fmaxf(__uint_as_float(v[8 * g + 6]) + b1.z, 0.f); f[7] = fmaxf(__uint_as_float(v[8 * g + 7]) + b1.w, 0.f);
+        if (P.dbg & 2) { o[g] = make_uint4(pack_f16x2_sat(f[0], f[1]), pack_f16x2_sat(f[2], f[3]), pack_f16x2_sat(f[4], f[5]), pack_f16x2_sat(f[6], f[7])); continue; }
         const uint4 ca = lds128(u00 + 16 * g), cb = lds128(u01 + 16 * g), cc = lds128(u10 + 16 * g), cd = lds128(u11 + 16 * g);
         const __half2* a = reinterpret_cast<const __half2*>(&ca);
         const __half2* b = reinterpret_cast<const __half2*>(&cb);
@@ -296,7 +325,7 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
                           pack_f16x2_sat(f[6], f[7]));
       }
       __syncwarp();
-      if (lane == 0) mbar_arrive(&u_empty[su]);                // patch consumed
+      if (lane == 0 && !(P.dbg & 32)) mbar_arrive(&u_empty[su]);   // patch consumed
 
       if (!FINAL) {
         if (y < H && x < W) {
@@ -307,28 +336,34 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
         }
       } else {
         // ---- exchange the r1 tile inside the group, then the last x2 upsample + argmax
+        if ((P.dbg & 8) && P.out && y < H && x < W) {
+          __half* op = P.out + (((int64_t)n * H + y) * W + x) * L_CH;
+#pragma unroll
+          for (int g = 0; g < 3; ++g) *reinterpret_cast<uint4*>(op + 8 * g) = o[g];
+        }
         const uint32_t xt = sX_u + xb * X_TILE;
         const uint32_t mine = xt + (uint32_t)m * (L_CH * 2);
 #pragma unroll
         for (int g = 0; g < 3; ++g) sts128(mine + 16 * g, o[g]);
         asm volatile("bar.sync %0, 128;" ::"r"(2 + grp) : "memory");
-        const bool act = ph < LTH - 1 && pw < LTW - 1;
-        // outputs Y1 = 2y+1 (3/4 top, 1/4 bottom), Y2 = 2y+2 (1/4, 3/4); same for columns
-        const bool vy1 = y >= 0 && y <= H - 1, vy2 = y >= -1 && y + 1 <= H - 1;
-        const bool vx1 = x >= 0 && x <= W - 1, vx2 = x >= -1 && x + 1 <= W - 1;
-        if (act && (vy1 || vy2) && (vx1 || vx2)) {
-          const int lt = clampi(y, 0, H - 1) - r0, lb = clampi(y + 1, 0, H - 1) - r0;      // tile-local rows, 0..15
-          const int ll = clampi(x, 0, W - 1) - c0, lr = clampi(x + 1, 0, W - 1) - c0;
-          const uint32_t pTL = xt + (uint32_t)((lt * LTW + ll) * (L_CH * 2)), pTR = xt + (uint32_t)((lt * LTW + lr) * (L_CH * 2));
-          const uint32_t pBL = xt + (uint32_t)((lb * LTW + ll) * (L_CH * 2)), pBR = xt + (uint32_t)((lb * LTW + lr) * (L_CH * 2));
+        // This thread's r1 pixel (y, x) is the TOP-LEFT corner of the outputs it owns: rows 2y+1 (3/4 top, 1/4 bottom)
+        // and 2y+2 (1/4, 3/4), columns 2x+1 and 2x+2.  The bottom / right neighbour is clamped at the rung's edge
+        // (ATen's index clamp); tile row 15 / column 7 have their neighbour in the NEXT tile and only own outputs
+        // when they are the rung's last row / column (neighbour = themselves).
+        const bool has_b = y + 1 <= H - 1, has_r = x + 1 <= W - 1;
+        const bool act = y <= H - 1 && x <= W - 1 && (ph < LTH - 1 || !has_b) && (pw < LTW - 1 || !has_r);
+        if (act && !(P.dbg & 1)) {
+          const uint32_t pTR = mine + (has_r ? (uint32_t)(L_CH * 2) : 0u);
+          const uint32_t pBL = mine + (has_b ? (uint32_t)(LTW * L_CH * 2) : 0u);
+          const uint32_t pBR = pBL + (has_r ? (uint32_t)(L_CH * 2) : 0u);
           const float2 q14 = make_float2(0.25f, 0.25f), q34 = make_float2(0.75f, 0.75f);
           float best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};       // (Y1,X1) (Y1,X2) (Y2,X1) (Y2,X2)
           int bidx[4] = {0, 0, 0, 0};
 #pragma unroll
           for (int g = 0; g < 3; ++g) {
             if (8 * g >= K) break;
-            const uint4 tl = lds128(pTL + 16 * g), tr = lds128(pTR + 16 * g), bl = lds128(pBL + 16 * g), br = lds128(pBR + 16 * g);
-            const __half2* htl = reinterpret_cast<const __half2*>(&tl);
+            const uint4 tr = lds128(pTR + 16 * g), bl = lds128(pBL + 16 * g), br = lds128(pBR + 16 * g);
+            const __half2* htl = reinterpret_cast<const __half2*>(&o[g]);           // own pixel: registers
             const __half2* htr = reinterpret_cast<const __half2*>(&tr);
             const __half2* hbl = reinterpret_cast<const __half2*>(&bl);
             const __half2* hbr = reinterpret_cast<const __half2*>(&br);
@@ -356,26 +391,62 @@ ladder_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ C
               }
             }
           }
-          const int Ho = 2 * H, Wo = 2 * W;
-          const int64_t base = ((int64_t)n * Ho + (2 * y + 1)) * Wo + (2 * x + 1);
+          const int Wo = 2 * W;
+          const int64_t base = ((int64_t)n * (2 * H) + (2 * y + 1)) * Wo + (2 * x + 1);
           if (P.pred_i64) {
             int64_t* pr = reinterpret_cast<int64_t*>(P.pred);
-            if (vy1 && vx1) pr[base] = bidx[0];
-            if (vy1 && vx2) pr[base + 1] = bidx[1];
-            if (vy2 && vx1) pr[base + Wo] = bidx[2];
-            if (vy2 && vx2) pr[base + Wo + 1] = bidx[3];
+            pr[base] = bidx[0];
+            if (has_r) pr[base + 1] = bidx[1];
+            if (has_b) pr[base + Wo] = bidx[2];
+            if (has_b && has_r) pr[base + Wo + 1] = bidx[3];
           } else {
             uint8_t* pr = reinterpret_cast<uint8_t*>(P.pred);
-            if (vy1 && vx1) pr[base] = (uint8_t)bidx[0];
-            if (vy1 && vx2) pr[base + 1] = (uint8_t)bidx[1];
-            if (vy2 && vx1) pr[base + Wo] = (uint8_t)bidx[2];
-            if (vy2 && vx2) pr[base + Wo + 1] = (uint8_t)bidx[3];
+            pr[base] = (uint8_t)bidx[0];
+            if (has_r) pr[base + 1] = (uint8_t)bidx[1];
+            if (has_b) pr[base + Wo] = (uint8_t)bidx[2];
+            if (has_b && has_r) pr[base + Wo + 1] = (uint8_t)bidx[3];
+          }
+          if (y == 0 || x == 0) {
+            // ---- output row 0 / column 0: the source index is clamped there, so they interpolate along the edge only
+            //      (fma(v, 3/4, v/4) == v exactly).  e0 = (0,0), e1 = (0,2x+1), e2 = (0,2x+2), e3 = (2y+1,0), e4 = (2y+2,0)
+            float eb[5] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY, -INFINITY};
+            int ei[5] = {0, 0, 0, 0, 0};
+            for (int g = 0; g < 3; ++g) {
+              if (8 * g >= K) break;
+              const uint4 tl = lds128(mine + 16 * g), tr = lds128(pTR + 16 * g), bl = lds128(pBL + 16 * g);
+              const __half2* htl = reinterpret_cast<const __half2*>(&tl);
+              const __half2* htr = reinterpret_cast<const __half2*>(&tr);
+              const __half2* hbl = reinterpret_cast<const __half2*>(&bl);
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int k = 8 * g + 2 * j;
+                if (k >= K) break;
+                const bool two = k + 1 < K;
+                const float2 TL = __half22float2(htl[j]), TR = __half22float2(htr[j]), BL = __half22float2(hbl[j]);
+                const float2 e[5] = {TL, lerp2(TL, TR, q34, q14), lerp2(TL, TR, q14, q34), lerp2(TL, BL, q34, q14),
+                                     lerp2(TL, BL, q14, q34)};
+#pragma unroll
+                for (int c = 0; c < 5; ++c) {
+                  if (e[c].x > eb[c]) { eb[c] = e[c].x; ei[c] = k; }
+                  if (two && e[c].y > eb[c]) { eb[c] = e[c].y; ei[c] = k + 1; }
+                }
+              }
+            }
+            const int64_t row0 = ((int64_t)n * (2 * H)) * Wo, r1o = row0 + (int64_t)(2 * y + 1) * Wo;
+            auto put = [&](int64_t off, int v) {
+              if (P.pred_i64) reinterpret_cast<int64_t*>(P.pred)[off] = v; else reinterpret_cast<uint8_t*>(P.pred)[off] = (uint8_t)v;
+            };
+            if (y == 0 && x == 0) put(row0, ei[0]);
+            if (y == 0) { put(row0 + 2 * x + 1, ei[1]); if (has_r) put(row0 + 2 * x + 2, ei[2]); }
+            if (x == 0) { put(r1o, ei[3]); if (has_b) put(r1o + Wo, ei[4]); }
           }
         }
         xb ^= 1;
       }
+      if (P.dbg & 32) { __syncwarp(); if (lane == 0) { mbar_arrive(&t_empty[ts]); mbar_arrive(&u_empty[su]); } }
       ts += L_GROUPS; if (ts >= (uint32_t)L_NST) { ts -= L_NST; tp ^= 1; }
       su += L_GROUPS; if (su >= (uint32_t)L_NU) { su -= L_NU; pu ^= 1; }
+      it.step(P.step[2], P);
     }
   }
 
@@ -427,7 +498,7 @@ bool ladder_eligible(const LadderArgs& a) {
   if (((uintptr_t)a.in | (uintptr_t)a.up | (uintptr_t)a.w_tc) & 15) return false;
   if (a.final_argmax) { if (!a.pred) return false; }
   else if (!a.out || a.out_ld != L_CH || ((uintptr_t)a.out & 15)) return false;
-  if ((int64_t)a.N * ceil_div(a.H + 1, 15) * ceil_div(a.W + 1, 7) >= (1ll << 31)) return false;
+  if ((int64_t)a.N * (ceil_div(a.H, 15) + 1) * (ceil_div(a.W, 7) + 1) >= (1ll << 29)) return false;
   return true;
 }
 
@@ -437,13 +508,18 @@ int launch_ladder(const LadderArgs& a, cudaStream_t st) {
   P.N = a.N; P.H = a.H; P.W = a.W; P.Cin = a.Cin; P.nchunks = a.Cin / 32; P.K = a.K;
   P.up_h = a.up_h; P.up_w = a.up_w; P.bias = a.bias;
   P.out = (__half*)a.out; P.pred = a.pred; P.pred_i64 = a.pred_i64;
+  { const char* e = getenv("LEDB200_LADDER_DBG"); P.dbg = e ? atoi(e) : 0; }
   if (a.final_argmax) {
-    // overlapping tiles: rung rows -1 .. H-1 in steps of 15 (row i and i+1 of a tile produce outputs 2i+1, 2i+2)
-    P.th_step = LTH - 1; P.tw_step = LTW - 1; P.org = -1;
-    P.tiles_h = ceil_div(a.H + 1, LTH - 1); P.tiles_w = ceil_div(a.W + 1, LTW - 1);
+    // overlapping tiles: tile row i and i+1 produce output rows 2i+1, 2i+2, so a tile of 16 rung rows advances by 15
+    // (the rung's last row needs no lower neighbour: it may sit in tile row 15); the last tile is shifted back to end
+    // at the edge
+    P.th_step = LTH - 1; P.tw_step = LTW - 1;
+    P.tiles_h = std::max(1, ceil_div(a.H - 1, LTH - 1)); P.tiles_w = std::max(1, ceil_div(a.W - 1, LTW - 1));
+    P.r_max = std::max(0, a.H - LTH); P.c_max = std::max(0, a.W - LTW);
   } else {
-    P.th_step = LTH; P.tw_step = LTW; P.org = 0;
+    P.th_step = LTH; P.tw_step = LTW;
     P.tiles_h = ceil_div(a.H, LTH); P.tiles_w = ceil_div(a.W, LTW);
+    P.r_max = P.c_max = 1 << 30;
   }
   P.total_tiles = (uint32_t)((int64_t)a.N * P.tiles_h * P.tiles_w);
   CUtensorMap tmA, tmB, tmU;
@@ -481,6 +557,12 @@ int launch_ladder(const LadderArgs& a, cudaStream_t st) {
   static int sms = 0;
   if (!sms) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
   const int grid = (int)std::min<uint32_t>(P.total_tiles, (uint32_t)sms);
+  for (int k = 0; k < 3; ++k) {
+    uint32_t stp = (uint32_t)grid << k;
+    P.step[k][0] = (int)(stp % (uint32_t)P.tiles_w); stp /= (uint32_t)P.tiles_w;
+    P.step[k][1] = (int)(stp % (uint32_t)P.tiles_h);
+    P.step[k][2] = (int)(stp / (uint32_t)P.tiles_h);
+  }
   if (a.final_argmax) ladder_kernel<true><<<grid, L_THREADS, smem, st>>>(tmA, tmB, tmU, P);
   else ladder_kernel<false><<<grid, L_THREADS, smem, st>>>(tmA, tmB, tmU, P);
   LEDB_LAUNCH_OK("ladder_kernel");

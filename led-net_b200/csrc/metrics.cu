@@ -16,9 +16,9 @@
 //    (`__match_any_sync`) kernel measured (132 us for 67 MB).  Here every warp owns a private uint16 histogram laid
 //    out [bin][lane]: a thread only ever touches its own column (bank = lane / 2, same-word halves do not
 //    conflict), so an update is a plain ld.shared / add / st.shared.  A thread reads 16 + 16 pixels per pair of
-//    128-bit loads and run-length-merges equal (gt, pred) pairs in registers first (whole 4-pixel words with one
-//    compare when both words are uniform), so blocky label maps cost ~1 update per 16 pixels.  Columns are summed
-//    and merged into the int64 matrix once per warp at the end (and every 4095 vectors: uint16 cannot overflow).
+//    128-bit loads (the next pair prefetched into registers) and run-length-merges equal (gt, pred) pairs
+//    branch-free.  Columns are summed and merged into the int64 matrix once per warp at the end (and every 2047
+//    vectors: uint16 cannot overflow).
 //  * confusion_u8x16_kernel / confusion_kernel: the round-1 warp-aggregated atomic kernels, kept for large K and for
 //    int64 inputs.
 #include <cstdlib>
@@ -111,43 +111,50 @@ template <int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 1)
 confusion_private_kernel(const uint4* __restrict__ pred, const uint4* __restrict__ gt, int64_t nvec, int K, int ignore,
                          unsigned long long* __restrict__ cm) {
-  extern __shared__ __align__(16) unsigned short hcol[];      // [WARPS][bins][32]
-  const int bins = (K + 1) * K;
+  extern __shared__ __align__(16) unsigned short hcol[];      // [WARPS][bins + 1][32]; row `bins` swallows invalid pixels
+  const int bins = (K + 1) * K, rows = bins + 1;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  unsigned short* mine = hcol + (size_t)warp * bins * 32 + lane;          // this thread's column, stride 32
-  uint4* zero = reinterpret_cast<uint4*>(hcol + (size_t)warp * bins * 32);
+  unsigned short* mine = hcol + (size_t)warp * rows * 32 + lane;          // this thread's column, stride 32
+  uint4* zero = reinterpret_cast<uint4*>(hcol + (size_t)warp * rows * 32);
   const int64_t stride = (int64_t)gridDim.x * (WARPS * 32);
-  int64_t i = blockIdx.x * (int64_t)(WARPS * 32) + threadIdx.x;
-  while (i < nvec) {                                          // (outer loop: one pass per 4095 vectors per thread)
-    for (int j = lane; j < bins * 4; j += 32) zero[j] = make_uint4(0, 0, 0, 0);
+  int64_t wi = blockIdx.x * (int64_t)(WARPS * 32) + warp * 32;          // lane 0's vector: the loops are WARP-uniform
+  while (wi < nvec) {                                         // (outer loop: one pass per 2047 vectors per thread)
+    for (int j = lane; j < rows * 4; j += 32) zero[j] = make_uint4(0, 0, 0, 0);
     __syncwarp();
-    int cur = -1;                                             // open run: bin (-1 = none / invalid) and its length
-    unsigned cnt = 0, cur_p4 = 0xffffffffu, cur_g4 = 0xffffffffu;
-    for (int it = 0; it < 4095 && i < nvec; ++it, i += stride) {
-      const uint4 pv = __ldg(pred + i), gv = __ldg(gt + i);
-      const unsigned pw[4] = {pv.x, pv.y, pv.z, pv.w}, gw[4] = {gv.x, gv.y, gv.z, gv.w};
+    // Branch-free run-length merge: `cur` is the open run's row, `cnt` its length.  EVERY pixel does one
+    // read-modify-write of the thread's own column: it adds the finished run's length when the pixel starts a new run
+    // and 0 otherwise (no divergence: with noisy labels some lane of the warp closes a run at almost every pixel, so a
+    // branch would execute both sides every time anyway).
+    int cur = bins;
+    unsigned cnt = 0;
+    uint4 pv = make_uint4(0, 0, 0, 0), gv = make_uint4(0xffffffffu, 0xffffffffu, 0xffffffffu, 0xffffffffu);
+    bool have = wi + lane < nvec;
+    if (have) { pv = __ldg(pred + wi + lane); gv = __ldg(gt + wi + lane); }
+    for (int it = 0; it < 2047 && wi < nvec; ++it, wi += stride) {
+      const uint4 pc = pv, gc = gv;
+      const bool hc = have;
+      const int64_t nx = wi + stride + lane;                  // prefetch the next vector while this one is counted
+      have = nx < nvec;
+      if (have) { pv = __ldg(pred + nx); gv = __ldg(gt + nx); }
+      const unsigned pw[4] = {pc.x, pc.y, pc.z, pc.w}, gw[4] = {gc.x, gc.y, gc.z, gc.w};
 #pragma unroll
-      for (int w = 0; w < 4; ++w) {
-        if (pw[w] == cur_p4 && gw[w] == cur_g4) { cnt += 4; continue; }   // four more pixels of the open run
+      for (int w = 0; w < 4; ++w)
 #pragma unroll
         for (int b = 0; b < 4; ++b) {
           const int p = (pw[w] >> (8 * b)) & 0xff, g = (gw[w] >> (8 * b)) & 0xff;
-          const int bin = (g != ignore && p < K) ? (g >= K ? K : g) * K + p : -1;
-          if (bin == cur) { ++cnt; continue; }
-          if (cur >= 0) mine[cur * 32] += (unsigned short)cnt;
-          cur = bin; cnt = 1;
-          // the word-compare shortcut is only armed for VALID runs (an invalid run counts nothing anyway)
-          cur_p4 = bin >= 0 ? (unsigned)p * 0x01010101u : 0xffffffffu;
-          cur_g4 = bin >= 0 ? (unsigned)g * 0x01010101u : 0xffffffffu;
+          const int bin = (hc && g != ignore && p < K) ? min(g, K) * K + p : bins;
+          const bool same = bin == cur;
+          unsigned short* slot = mine + cur * 32;
+          *slot = (unsigned short)(*slot + (same ? 0u : cnt));
+          cnt = same ? cnt + 1 : 1;
+          cur = bin;
         }
-      }
-      if (cnt > 60000u) { if (cur >= 0) mine[cur * 32] += (unsigned short)cnt; cnt = 0; }   // 16 * 4095 > 65535: flush long runs
     }
-    if (cur >= 0 && cnt) mine[cur * 32] += (unsigned short)cnt;
+    mine[cur * 32] += (unsigned short)cnt;                    // <= 2047 * 16 + 1 per column: no uint16 overflow
     __syncwarp();
     // column sums: lane l adds up bins l, l + 32, ... (64 B per row) and merges them into the global matrix
     for (int b = lane; b < bins; b += 32) {
-      const uint4* row = reinterpret_cast<const uint4*>(hcol + ((size_t)warp * bins + b) * 32);
+      const uint4* row = reinterpret_cast<const uint4*>(hcol + ((size_t)warp * rows + b) * 32);
       unsigned sum = 0;
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -179,7 +186,7 @@ int launch_confusion(const void* pred, const void* gt, int pred_dtype, int gt_dt
       ((uintptr_t)pred % 16 == 0) && ((uintptr_t)gt % 16 == 0) && n >= 16) {
     // atomic-free private-column kernel: as many warps per SM as 200 KB of [bins][32] uint16 columns allow
     const int64_t nvec = n / 16;
-    const size_t per_warp = (size_t)bins * 64;
+    const size_t per_warp = (size_t)(bins + 1) * 64;
     const int warps = per_warp * 16 <= 200 * 1024 ? 16 : (per_warp * 8 <= 200 * 1024 ? 8 : 4);
     const size_t sm = per_warp * warps;
     int sms = 148;
