@@ -227,6 +227,23 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
                          const float* save_mean, const float* save_invstd, float* dy, float* dres_opt,
                          float* dgamma, float* dbeta, int32_t relu, int64_t npix, int32_t C, void* workspace,
                          void* stream);
+/* The same in separate steps, so that the per-channel statistics can be all-reduced between ranks - SyncBN
+ * (configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:20; torch.nn.SyncBatchNorm semantics):
+ *   reduce(mode 0): workspace[0:2C] (double) = (sum y, sum y^2)
+ *   reduce(mode 1): workspace[0:2C]          = (sum dz, sum dz * xhat), dz = dout masked by the ReLU
+ *   fwd_apply     : mean / invstd / running stats from workspace[0:2C] over `total_count` samples, then apply
+ *   bwd_apply     : dgamma / dbeta from workspace[0:2C] (this rank), dy from workspace[2C:4C] (all ranks). */
+int ledb200_train_bn_reduce(const float* a, const float* y_opt, const float* out_opt, const float* mean_opt,
+                            const float* invstd_opt, int32_t mode, int32_t relu, int64_t npix, int32_t C,
+                            void* workspace, void* stream);
+int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* beta, const float* res_opt,
+                               float* out, float* save_mean, float* save_invstd, float* running_mean_opt,
+                               float* running_var_opt, float momentum, float eps, int32_t relu, int64_t npix,
+                               double total_count, int32_t C, const void* workspace, void* stream);
+int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* out, const float* gamma,
+                               const float* save_mean, const float* save_invstd, float* dy, float* dres_opt,
+                               float* dgamma, float* dbeta, int32_t relu, int64_t npix, double total_count,
+                               int32_t C, const void* workspace, void* stream);
 /* resize(mode='bilinear', align_corners=False) (utils/wrappers.py:8-27) and its backward (dsrc overwritten). */
 int ledb200_train_resize_fwd(const float* src, float* out, int32_t N, int32_t h, int32_t w, int32_t H,
                              int32_t W, int32_t C, void* stream);

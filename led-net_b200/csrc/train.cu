@@ -233,8 +233,9 @@ bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ res, cons
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ out,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
-                    const double* __restrict__ acc, float* __restrict__ dy, float* __restrict__ dres,
-                    float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total, int C, float invM) {
+                    const double* __restrict__ acc, const double* __restrict__ acc_local, float* __restrict__ dy,
+                    float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total,
+                    int C, float invM) {
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
     float dz = dout[i];
@@ -244,7 +245,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
     const float xhat = (y[i] - mean[c]) * is;
     dy[i] = gamma[c] * is * (dz - db * invM - xhat * dg * invM);
     if (dres) dres[i] = dz;
-    if (i < C) { dbeta[c] = db; dgamma[c] = dg; }
+    if (i < C) { dbeta[c] = (float)acc_local[c]; dgamma[c] = (float)acc_local[C + c]; }   // parameter gradients stay rank-local (DDP averages them)
   }
 }
 
@@ -492,6 +493,65 @@ int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, fl
   return LEDB200_OK;
 }
 
+// ---- BatchNorm statistics as separate steps, so that a caller can all-reduce them between ranks (SyncBN,
+//      configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:20: torch.nn.SyncBatchNorm semantics).
+// mode 0: workspace[0:2C] = (sum y, sum y^2);  mode 1: workspace[0:2C] = (sum dz, sum dz * xhat), dz = masked dout.
+int ledb200_train_bn_reduce(const float* a, const float* y_opt, const float* out_opt, const float* mean_opt,
+                            const float* invstd_opt, int32_t mode, int32_t relu, int64_t npix, int32_t C,
+                            void* workspace, void* stream) {
+  if (!a || !workspace) return fail(LEDB200_EINVAL, "train_bn_reduce: null buffer");
+  if (npix < 1 || C < 1) return fail(LEDB200_EINVAL, "train_bn_reduce: empty input");
+  if ((size_t)C * 2 * sizeof(double) > 48 * 1024) return fail(LEDB200_EINVAL, "train_bn_reduce: C too large");
+  if (mode == 1 && (!y_opt || !mean_opt || !invstd_opt || (relu && !out_opt)))
+    return fail(LEDB200_EINVAL, "train_bn_reduce: backward statistics need y, mean, invstd (and out for the ReLU mask)");
+  cudaStream_t st = (cudaStream_t)stream;
+  double* acc = (double*)workspace;
+  LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
+  if (mode == 0)
+    chan_reduce_kernel<0><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(a, nullptr, nullptr, nullptr, nullptr,
+                                                                                 0, npix, C, acc);
+  else
+    chan_reduce_kernel<1><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(a, y_opt, out_opt, mean_opt,
+                                                                                 invstd_opt, relu, npix, C, acc);
+  LEDB_LAUNCH_OK("train_bn_reduce");
+  return LEDB200_OK;
+}
+
+// finalize + apply from statistics in workspace[0:2C] taken over `total_count` samples per channel (all ranks)
+int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* beta, const float* res_opt, float* out,
+                               float* save_mean, float* save_invstd, float* running_mean_opt, float* running_var_opt,
+                               float momentum, float eps, int32_t relu, int64_t npix, double total_count, int32_t C,
+                               const void* workspace, void* stream) {
+  if (!y || !gamma || !beta || !out || !save_mean || !save_invstd || !workspace)
+    return fail(LEDB200_EINVAL, "train_bn_fwd_apply: null buffer");
+  if (npix < 1 || C < 1 || total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_fwd_apply: bad sample count");
+  cudaStream_t st = (cudaStream_t)stream;
+  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, C, total_count, eps, momentum, save_mean,
+                                                       save_invstd, running_mean_opt, running_var_opt);
+  bn_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
+                                                   npix * C, C);
+  LEDB_LAUNCH_OK("train_bn_fwd_apply");
+  return LEDB200_OK;
+}
+
+// backward from statistics: workspace[0:2C] = this rank's (sum dz, sum dz*xhat) -> dgamma / dbeta,
+// workspace[2C:4C] = the same summed over all ranks -> dy (1 / total_count)
+int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* out, const float* gamma,
+                               const float* save_mean, const float* save_invstd, float* dy, float* dres_opt,
+                               float* dgamma, float* dbeta, int32_t relu, int64_t npix, double total_count, int32_t C,
+                               const void* workspace, void* stream) {
+  if (!dout || !y || !gamma || !save_mean || !save_invstd || !dy || !dgamma || !dbeta || !workspace)
+    return fail(LEDB200_EINVAL, "train_bn_bwd_apply: null buffer");
+  if (relu && !out) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: the ReLU mask needs the forward output");
+  if (total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: bad sample count");
+  const double* acc = (const double*)workspace;
+  bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(dout, y, out, gamma, save_mean, save_invstd,
+                                                                         acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta,
+                                                                         relu, npix * C, C, (float)(1.0 / total_count));
+  LEDB_LAUNCH_OK("train_bn_bwd_apply");
+  return LEDB200_OK;
+}
+
 // BatchNorm2d in training mode (+ residual add, + ReLU): out = [relu](bn(y) [+ res]).
 // save_mean/save_invstd [C] are outputs (needed by backward); running stats updated in place when given.
 // workspace: >= 2*C doubles.
@@ -501,19 +561,10 @@ int ledb200_train_bn_fwd(const float* y, const float* gamma, const float* beta, 
                          void* stream) {
   if (!y || !gamma || !beta || !out || !save_mean || !save_invstd || !workspace)
     return fail(LEDB200_EINVAL, "train_bn_fwd: null buffer");
-  if (npix < 1 || C < 1) return fail(LEDB200_EINVAL, "train_bn_fwd: empty input");
-  if ((size_t)C * 2 * sizeof(double) > 48 * 1024) return fail(LEDB200_EINVAL, "train_bn_fwd: C too large");
-  cudaStream_t st = (cudaStream_t)stream;
-  double* acc = (double*)workspace;
-  LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
-  chan_reduce_kernel<0><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(y, nullptr, nullptr, nullptr, nullptr,
-                                                                               0, npix, C, acc);
-  bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>(acc, C, (double)npix, eps, momentum, save_mean, save_invstd,
-                                                       running_mean_opt, running_var_opt);
-  bn_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
-                                                   npix * C, C);
-  LEDB_LAUNCH_OK("train_bn_fwd");
-  return LEDB200_OK;
+  int rc = ledb200_train_bn_reduce(y, nullptr, nullptr, nullptr, nullptr, 0, 0, npix, C, workspace, stream);
+  if (rc) return rc;
+  return ledb200_train_bn_fwd_apply(y, gamma, beta, res_opt, out, save_mean, save_invstd, running_mean_opt,
+                                    running_var_opt, momentum, eps, relu, npix, (double)npix, C, workspace, stream);
 }
 
 int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, const float* gamma,
@@ -527,7 +578,7 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
   LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
   chan_reduce_kernel<1><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(dout, y, out, save_mean, save_invstd,
                                                                                relu, npix, C, acc);
-  bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, dy, dres_opt,
+  bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy, dres_opt,
                                                        dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix);
   LEDB_LAUNCH_OK("train_bn_bwd");
   return LEDB200_OK;

@@ -22,6 +22,7 @@ SYMBOLS = [
     'ledb200_ohem_ce', 'ledb200_conv2d',
     'ledb200_train_packed_weight_floats', 'ledb200_train_pack_weight', 'ledb200_train_conv_fwd',
     'ledb200_train_conv_dgrad', 'ledb200_train_conv_wgrad', 'ledb200_train_bn_fwd', 'ledb200_train_bn_bwd',
+    'ledb200_train_bn_reduce', 'ledb200_train_bn_fwd_apply', 'ledb200_train_bn_bwd_apply',
     'ledb200_train_resize_fwd', 'ledb200_train_resize_bwd', 'ledb200_train_add_relu', 'ledb200_train_relu_bwd',
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
@@ -91,6 +92,9 @@ def get():
     lib.ledb200_train_conv_wgrad.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp]
     lib.ledb200_train_bn_fwd.argtypes = [vp] * 9 + [f32, f32, i32, i64, i32, vp, vp]
     lib.ledb200_train_bn_bwd.argtypes = [vp] * 10 + [i32, i64, i32, vp, vp]
+    lib.ledb200_train_bn_reduce.argtypes = [vp] * 5 + [i32, i32, i64, i32, vp, vp]
+    lib.ledb200_train_bn_fwd_apply.argtypes = [vp] * 9 + [f32, f32, i32, i64, C.c_double, i32, vp, vp]
+    lib.ledb200_train_bn_bwd_apply.argtypes = [vp] * 10 + [i32, i64, C.c_double, i32, vp, vp]
     lib.ledb200_train_resize_fwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
     lib.ledb200_train_resize_bwd.argtypes = [vp, vp] + [i32] * 6 + [vp]
     lib.ledb200_train_add_relu.argtypes = [vp, vp, vp, i32, i64, vp]

@@ -38,6 +38,8 @@ class IoUMetric:
         self.results = []
         self.dataset_meta = None
         self._cm = None
+        self._n_samples = 0          # images this rank has processed since the last evaluate()
+        self._last = None            # (pred, label, K) of the most recent image: see evaluate(size)
 
     # -- reference API --------------------------------------------------------------------
     def process(self, data_batch, data_samples):
@@ -47,11 +49,15 @@ class IoUMetric:
             pred = s['pred_sem_seg']['data'].squeeze()
             label = s['gt_sem_seg']['data'].squeeze().to(pred.device)
             self.results.append(ops.confusion_accumulate(pred, label, num_classes, self.ignore_index))
+            self._n_samples += 1
+            self._last = (pred, label, num_classes)
 
     def process_batch(self, pred, label, num_classes=None):
         """Batched fast path: accumulate a whole [N,H,W] prediction/label pair into the running matrix."""
         k = num_classes or len(self.dataset_meta['classes'])
         self._cm = ops.confusion_accumulate(pred, label, k, self.ignore_index, self._cm)
+        self._n_samples += int(pred.shape[0]) if pred.dim() == 3 else 1
+        self._last = (pred[-1] if pred.dim() == 3 else pred, label[-1] if label.dim() == 3 else label, k)
         return self._cm
 
     @staticmethod
@@ -83,6 +89,8 @@ class IoUMetric:
             tot = [sum(c) for c in cols]
         else:
             cm = self.total_confusion(results)
+            if cm is None:
+                raise ValueError('IoUMetric.compute_metrics: no sample has been processed')
             # the reference sums float32 histograms; int64 counts converted once are exact <= 2**24
             tot = [a.to(torch.float32).cpu() for a in _areas_from_cm(cm)]
         ret = self.total_area_to_metrics(*tot, self.metrics, self.nan_to_num, self.beta)
@@ -94,9 +102,22 @@ class IoUMetric:
         return out
 
     def evaluate(self, size=None):
+        """mmengine BaseMetric.evaluate(size): `size` is the dataset length.  A DistributedSampler pads the index list
+        to a multiple of the world size by repeating samples, and `collect_results(results, size)` interleaves the ranks'
+        lists and drops that padded tail - i.e. the LAST sample of every rank >= size % world_size.  The all-reduce here
+        has no per-sample list to truncate, so those ranks subtract their last image's matrix before the sum."""
+        import torch.distributed as dist
+        if (size is not None and dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+                and self._last is not None):
+            world, rank = dist.get_world_size(), dist.get_rank()
+            per_rank = -(-int(size) // world)
+            if int(size) % world and self._n_samples == per_rank and rank >= int(size) % world:
+                pred, label, k = self._last
+                dup = ops.confusion_accumulate(pred, label.to(pred.device), k, self.ignore_index)
+                self.results.append(-dup)
         m = self.compute_metrics(self.results)
         self.results.clear()
-        self._cm = None
+        self._cm, self._n_samples, self._last = None, 0, None
         return m
 
     @staticmethod

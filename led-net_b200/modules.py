@@ -86,6 +86,18 @@ class DAPPM(nn.Module):
         self.shortcut = ConvModule(cin, cout, 1, pre_act=True)
 
 
+def _is_sync(norm_cfg):
+    return isinstance(norm_cfg, dict) and norm_cfg.get('type') == 'SyncBN'
+
+
+def _mark_sync(module, flag=True):
+    """Tag every BatchNorm2d under `module`: train_ops.bn_act all-reduces the batch statistics of tagged layers over
+    the process group (torch.nn.SyncBatchNorm arithmetic)."""
+    for m in module.modules():
+        if isinstance(m, nn.BatchNorm2d):
+            m.sync = flag
+
+
 def _as_nhwc(x):
     """[N,C,H,W] tensor (any memory format) -> NHWC-contiguous [N,H,W,C] (a view when the tensor is
     already channels_last, otherwise one layout kernel)."""
@@ -201,6 +213,18 @@ class LEDNet(_EngineOwner):
             _layer(BasicBlock, 2 * C, 2 * C, 2), _layer(BasicBlock, 2 * C, 2 * C, 2),
             _layer(Bottleneck, 2 * C, 2 * C, 1)])
         self.spp = DAPPM(16 * C, ppm_channels, 4 * C)
+        if _is_sync(norm_cfg):
+            # Which layers are SyncBN in the reference under a SyncBN config (ddrnet.py): the stem convs, compression /
+            # down convs, every downsample BN and every block but the FIRST of a layer get `norm_cfg` (:68-105, 123-138,
+            # 151-180); the first block of each `_make_layer` and the DAPPM are built without it and stay plain BN.
+            _mark_sync(self.stem[0]), _mark_sync(self.stem[1])
+            for mod in (self.compression_1, self.down_1, self.compression_2, self.down_2):
+                _mark_sync(mod)
+            for layer in [self.stem[2], self.stem[4], *self.context_branch_layers, *self.spatial_branch_layers]:
+                if layer[0].downsample is not None:
+                    _mark_sync(layer[0].downsample)
+                for blk in list(layer)[1:]:
+                    _mark_sync(blk)
 
     def init_weights(self):
         for m in self.modules():
@@ -307,6 +331,8 @@ class LEDHead(_EngineOwner):
         self.head_x1 = self._make_base_head(tap_channels, num_classes)
         self.head_x2 = self._make_base_head(tap_channels, num_classes)
         self.aux_cls_seg = nn.Conv2d(channels, out_channels, 1)
+        if _is_sync(norm_cfg):
+            _mark_sync(self)            # every BN of the head is built from norm_cfg (led_head.py:84-99)
         self.init_weights()
 
     @staticmethod

@@ -2,7 +2,7 @@
 data-parallel gradient all-reduce.
 
 Reference: ``configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:64-75`` (SGD lr 0.01, momentum 0.9,
-weight_decay 5e-4; PolyLR power 0.9, eta_min 1e-4, by_epoch=False) driven by mmengine's OptimWrapper
+weight_decay 5e-4; PolyLR power 0.9, eta_min 0, by_epoch=False; the `schedule_80k` base it overrides uses 1e-4) driven by mmengine's OptimWrapper
 and MMDistributedDataParallel (``tools/train.py``).  Here all parameters (and all gradients) live in
 one contiguous fp32 buffer each, so the optimiser step is ONE kernel launch (csrc/train.cu sgd_kernel)
 and the DDP exchange is ONE NCCL all-reduce of the flat gradient - the only collective of the
@@ -60,7 +60,19 @@ class FlatSGD:
             import torch.distributed as dist
             dist.all_reduce(self.flat_grad, op=dist.ReduceOp.SUM, group=self.process_group)
 
+    def _gather_stray_grads(self):
+        """`model.zero_grad()` (set_to_none) between zero_grad() and backward() makes autograd allocate fresh `.grad`
+        tensors: copy them into the flat buffer (and re-attach) instead of silently stepping on zeros."""
+        off = 0
+        for p in self.params:
+            k = p.numel()
+            if p.grad is not None and p.grad.data_ptr() != self.flat_grad.data_ptr() + 4 * off:
+                self.flat_grad[off:off + k].copy_(p.grad.reshape(-1))
+                p.grad = self.flat_grad[off:off + k].view_as(p)
+            off += k
+
     def step(self):
+        self._gather_stray_grads()
         self.all_reduce_grads()
         if not self.flat.is_cuda:
             raise L.LedB200Error('FlatSGD.step needs CUDA parameters (no CPU fallback)')
@@ -75,7 +87,7 @@ class FlatSGD:
 class PolyLR:
     """mmengine PolyLR (by_epoch=False): lr_t = (base - eta_min) * (1 - t/T)^power + eta_min."""
 
-    def __init__(self, optimizer, power=0.9, eta_min=1e-4, begin=0, end=80000):
+    def __init__(self, optimizer, power=0.9, eta_min=0.0, begin=0, end=80000):
         self.opt, self.power, self.eta_min, self.begin, self.end = optimizer, power, eta_min, begin, end
         self.base_lr = optimizer.lr
         self.t = 0

@@ -62,6 +62,9 @@ class EncoderDecoder(nn.Module):
         self.train_cfg, self.test_cfg = train_cfg, dict(test_cfg or dict(mode='whole'))
         self.compute_dtype = compute_dtype
         self._engine = None
+        for part in (self.backbone, self.decode_head):          # stand-alone module engines (mode='tensor') follow
+            if hasattr(part, 'set_compute_dtype'):
+                part.set_compute_dtype(compute_dtype)
         self.register_load_state_dict_post_hook(lambda m, keys: m.reset_engine())
 
     # -- engine ---------------------------------------------------------------------------
@@ -71,6 +74,9 @@ class EncoderDecoder(nn.Module):
     def set_compute_dtype(self, dtype):
         if dtype != self.compute_dtype:
             self.compute_dtype, self._engine = dtype, None
+        for part in (self.backbone, self.decode_head):
+            if hasattr(part, 'set_compute_dtype'):
+                part.set_compute_dtype(dtype)
         return self
 
     def engine(self):

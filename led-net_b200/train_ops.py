@@ -120,11 +120,24 @@ def conv2d(x, weight, bias=None, stride=1):
     return _Conv.apply(x, weight, bias, stride)
 
 
+def _sync_group(sync):
+    """The process group to synchronise BatchNorm statistics over, or None (single process / plain BN)."""
+    if not sync:
+        return None
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size() < 2:
+        return None
+    return dist.group.WORLD
+
+
 class _BNAct(torch.autograd.Function):
-    """out = [relu](BatchNorm2d_train(y) [+ res]); running stats updated in place."""
+    """out = [relu](BatchNorm2d_train(y) [+ res]); running stats updated in place.
+    With `group` (SyncBN) the per-channel (sum, sum of squares, count) - and in backward (sum dz, sum dz*xhat) - are
+    all-reduced over the ranks between the reduction and the apply kernels: torch.nn.SyncBatchNorm's arithmetic
+    (statistics over the GLOBAL batch, parameter gradients rank-local, to be averaged by the DDP all-reduce)."""
 
     @staticmethod
-    def forward(ctx, y, gamma, beta, res, running_mean, running_var, momentum, eps, relu):
+    def forward(ctx, y, gamma, beta, res, running_mean, running_var, momentum, eps, relu, group):
         y = _chk(y, 'bn input')
         c = y.shape[-1]
         npix = y.numel() // c
@@ -132,11 +145,25 @@ class _BNAct(torch.autograd.Function):
         mean = torch.empty(c, dtype=torch.float32, device=y.device)
         invstd = torch.empty_like(mean)
         r = _chk(res, 'bn residual') if res is not None else None
-        L.check(L.get().ledb200_train_bn_fwd(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
+        lib = L.get()
+        total = float(npix)
+        if group is None:
+            L.check(lib.ledb200_train_bn_fwd(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
                                              _p(running_mean), _p(running_var), float(momentum), float(eps),
                                              int(relu), npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_fwd')
+        else:
+            import torch.distributed as dist
+            ws = torch.empty(2 * c + 1, dtype=torch.float64, device=y.device)
+            L.check(lib.ledb200_train_bn_reduce(_p(y), None, None, None, None, 0, 0, npix, c, _p(ws), _st(y)),
+                    'train_bn_reduce')
+            ws[2 * c] = npix
+            dist.all_reduce(ws, group=group)             # one packed message per layer: (sum, sumsq, count)
+            total = float(ws[2 * c].item())
+            L.check(lib.ledb200_train_bn_fwd_apply(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
+                                                   _p(running_mean), _p(running_var), float(momentum), float(eps),
+                                                   int(relu), npix, total, c, _p(ws), _st(y)), 'train_bn_fwd_apply')
         ctx.save_for_backward(y, out, gamma, mean, invstd)
-        ctx.relu, ctx.has_res = relu, res is not None
+        ctx.relu, ctx.has_res, ctx.group, ctx.total = relu, res is not None, group, total
         return out
 
     @staticmethod
@@ -151,17 +178,33 @@ class _BNAct(torch.autograd.Function):
         dres = None
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = torch.empty_like(y) if ctx.relu else dout
-        L.check(L.get().ledb200_train_bn_bwd(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
+        lib = L.get()
+        if ctx.group is None:
+            L.check(lib.ledb200_train_bn_bwd(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
                                              _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta), int(ctx.relu),
                                              npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_bwd')
-        return dy, dgamma, dbeta, dres, None, None, None, None, None
+        else:
+            import torch.distributed as dist
+            ws = torch.empty(4 * c, dtype=torch.float64, device=y.device)
+            L.check(lib.ledb200_train_bn_reduce(_p(dout), _p(y), _p(out), _p(mean), _p(invstd), 1, int(ctx.relu), npix,
+                                                c, _p(ws), _st(y)), 'train_bn_reduce')
+            ws[2 * c:].copy_(ws[:2 * c])
+            dist.all_reduce(ws[2 * c:], group=ctx.group)
+            L.check(lib.ledb200_train_bn_bwd_apply(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
+                                                   _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta),
+                                                   int(ctx.relu), npix, ctx.total, c, _p(ws), _st(y)),
+                    'train_bn_bwd_apply')
+        return dy, dgamma, dbeta, dres, None, None, None, None, None, None
 
 
 def bn_act(y, bn, res=None, relu=False):
-    """`bn`: an nn.BatchNorm2d in training mode (its running stats are updated like PyTorch does)."""
+    """`bn`: an nn.BatchNorm2d in training mode (its running stats are updated like PyTorch does).  When the
+    module carries `sync = True` (built from norm_cfg type 'SyncBN') and a process group of more than one rank is
+    initialised, the batch statistics are those of the GLOBAL batch (torch.nn.SyncBatchNorm)."""
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
-    return _BNAct.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu)
+    return _BNAct.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu,
+                        _sync_group(getattr(bn, 'sync', False)))
 
 
 class _Resize(torch.autograd.Function):

@@ -306,3 +306,18 @@ def test_eval_after_train_uses_updated_weights():
     o.eval()
     ref, _ = o.predict(x)
     assert rel_err(after.cpu(), ref) < 1e-4
+
+
+def test_syncbn_two_ranks_matches_full_batch():
+    """SyncBN (configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:20): two ranks with half a batch each reproduce
+    torch BatchNorm2d on the full batch (forward, backward, running statistics); tools/check_syncbn.py under torchrun
+    (the ranks share this GPU through the gloo backend when fewer than two GPUs are visible)."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', '2',
+                        '--master-addr', '127.0.0.1', '--master-port', '29533', os.path.join(root, 'tools', 'check_syncbn.py')],
+                       capture_output=True, text=True, timeout=600)
+    print(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
