@@ -107,6 +107,123 @@ def cpu_reference_run(steps, warmup, threads=None):
                        f'{warmup} warm-up, {torch.get_num_threads()} threads')
 
 
+def extra_config5(args, rank, world, local, dev, dist, barrier):
+    """BASELINE config 5: Apple-Branch-shaped 2-class 512x512 inference, batch 128 per GPU, same step as the headline
+    (forward + fused argmax + confusion matrix [+ all-reduce]).  Returns a dict (every rank computes it; rank 0 prints)."""
+    import warnings
+    import torch
+    import lednet_b200 as L
+    from lednet_b200 import synth, ops
+    K, N, H, W = 2, 128, 512, 512
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
+                                                       dropout_ratio=0.),
+                             data_preprocessor=dict(type='SegDataPreProcessor', mean=list(L.engine.MEAN),
+                                                    std=list(L.engine.STD), bgr_to_rgb=True),
+                             compute_dtype=args.dtype).eval()
+    m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
+    eng = m.engine()
+    img = synth.make_images_u8(N, H, W, seed=300 + rank).to(dev)
+    mean = torch.tensor(L.engine.MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(L.engine.STD, device=dev).view(1, 3, 1, 1)
+    x = ((img[:, [2, 1, 0]].float() - mean) / std).contiguous()            # 403 MB > L2
+    lab = synth.make_labels(N, H, W, K, seed=400 + rank).to(torch.uint8).to(dev)
+    pred = torch.empty((N, H, W), dtype=torch.uint8, device=dev)
+    cm = torch.zeros((K + 1, K), dtype=torch.int64, device=dev)
+
+    def step():
+        eng.forward_infer(x, pred=pred)
+        ops.confusion_accumulate(pred, lab, K, 255, cm)
+        if dist is not None:
+            dist.all_reduce(cm.clone())
+
+    steps, warm = max(10, args.steps), max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    return dict(metric='LED-Net img/s @512x512 K=2 ' + args.dtype, value=world * N / (ms * 1e-3), unit=UNIT, ms_per_step=ms,
+                steps=steps, warmup=warm, n_gpus=world, gpu_launches=(eng.plan_launches() + 1) * steps,
+                config=dict(workload='BASELINE config 5: 2-class 512x512 whole inference, fused argmax + confusion matrix',
+                            batch_per_gpu=N, height=H, width=W, num_classes=K, l2='inputs larger than L2 (403 MB)'),
+                clocks=sampler.stop() if rank == 0 else None)
+
+
+def extra_train(args, rank, world, local, dev, dist, barrier):
+    """BASELINE config 4: training step on 1024x1024 crops, batch 12 per GPU, K = 19: forward + OHEM CE x2 + backward +
+    flat-gradient all-reduce (N > 1; SyncBN statistics all-reduced per layer as the config's norm_cfg asks) + SGD."""
+    import warnings
+    import torch
+    import lednet_b200 as L
+    from lednet_b200 import synth
+    K, N, S = 19, 12, 1024
+    norm = dict(type='SyncBN', requires_grad=True) if world > 1 else dict(type='BN', requires_grad=True)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(dict(type='LEDNet', norm_cfg=norm),
+                             dict(type='LEDHead', in_channels=128, channels=64, num_classes=K, dropout_ratio=0., norm_cfg=norm),
+                             data_preprocessor=None, compute_dtype='fp32')
+    m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
+    m.to(dev).train()
+    opt = L.FlatSGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+    sched = L.PolyLR(opt, power=0.9, eta_min=0.0, end=80000)
+    img = synth.make_images_u8(N, S, S, seed=500 + rank).to(dev)
+    mean = torch.tensor(L.engine.MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(L.engine.STD, device=dev).view(1, 3, 1, 1)
+    x = ((img[:, [2, 1, 0]].float() - mean) / std).contiguous()
+    lab = synth.make_labels(N, S, S, K, seed=600 + rank).to(dev)
+    samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1])) for i in range(N)]
+
+    def step():
+        total, log = m.parse_losses(m.loss(x, samples))
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        sched.step()
+        return log
+
+    steps, warm = 5, 2
+    for _ in range(warm):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        log = step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    out = dict(metric='LED-Net train img/s @1024x1024', value=world * N / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps,
+               warmup=warm, n_gpus=world, dtype=L.train_ops.COMPUTE if hasattr(L.train_ops, 'COMPUTE') else 'f32',
+               loss=float(log['loss'].detach()),
+               config=dict(workload='BASELINE config 4: fwd + OHEM CE x2 + bwd + gradient all-reduce + SGD', batch_per_gpu=N,
+                           height=S, width=S, num_classes=K, norm=norm['type'],
+                           parallelism=f'dp{world} (flat fp32 gradient all-reduce over NCCL)'),
+               peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, clocks=sampler.stop() if rank == 0 else None)
+    del m, opt, x, lab, samples
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -122,6 +239,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op table to stderr')
     ap.add_argument('--conv-backend', type=int, default=0)
+    ap.add_argument('--no-extras', action='store_true', help='skip the sustained loop and the config-4 / config-5 blocks')
+    ap.add_argument('--sustain-seconds', type=float, default=2.5)
     args = ap.parse_args()
 
     rank = int(os.environ.get('RANK', 0))
@@ -131,7 +250,9 @@ def main():
     if args.impl == 'reference':
         if rank != 0:
             return
-        r = cpu_reference_run(max(1, min(args.steps, 5)), max(1, min(args.warmup, 2)))
+        # the steps / warm-up asked for are the ones run and printed: one step = one 1024x2048 image through the CPU path
+        # (~0.3 s on 16 threads, so the default 10 + 3 and the driver's 20 + 5 finish in seconds)
+        r = cpu_reference_run(max(1, args.steps), max(0, args.warmup))
         line = dict(metric=METRIC, value=r['value'], unit=UNIT, n_gpus=args.gpus, steps=args.steps,
                     warmup=args.warmup, ms_per_step=r['ms_per_step'], higher_is_better=True, scaling='weak',
                     vs_baseline=None, dtype='f32', data='synthetic', impl='reference',
@@ -164,7 +285,7 @@ def main():
         warnings.simplefilter('ignore')
         m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
                                                        dropout_ratio=0.),
-                             data_preprocessor=dict(type='SegDataPreProcessor', bgr_to_rgb=True),
+                             data_preprocessor=dict(type='SegDataPreProcessor', mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True),
                              compute_dtype=args.dtype).eval()
     m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
     if args.conv_backend:
@@ -269,6 +390,30 @@ def main():
     e2e_ms = t2.item() / e2e_steps
     cm_host = bufs[0]['cm_host']
 
+    # ---- sustained: the same device-resident step back to back for >= 2 s (power / thermal behaviour; the headline
+    #      region above lasts ~0.1 s), own clocks record
+    sustained = extra = None
+    if not args.no_extras:
+        n_sus = max(args.steps, int(args.sustain_seconds * 1e3 / ms_step) + 1)
+        s2 = ClockSampler(local)
+        if rank == 0:
+            s2.start()
+        barrier()
+        e0.record()
+        for _ in range(n_sus):
+            step()
+        e1.record()
+        barrier()
+        t3 = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(t3, op=dist.ReduceOp.MAX)
+        sus_ms = t3.item() / n_sus
+        sustained = dict(value=world * N / (sus_ms * 1e-3), unit=UNIT, ms_per_step=sus_ms, steps=n_sus,
+                         seconds=t3.item() * 1e-3, clocks=s2.stop() if rank == 0 else None)
+        # the main workload's buffers are no longer needed by the extras
+        extra = dict(config5=extra_config5(args, rank, world, local, dev, dist, barrier),
+                     train=extra_train(args, rank, world, local, dev, dist, barrier))
+
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
@@ -332,6 +477,9 @@ def main():
         e2e=dict(value=world * N / (e2e_ms * 1e-3), unit=UNIT, ms_per_step=e2e_ms,
                  h2d_bytes_per_step=img_u8_host.numel() + lab_host.numel(), d2h_bytes_per_step=cm_host.numel() * 8),
         roofline=roof, cpu_baseline=cpu)
+    if sustained is not None:
+        line['sustained'] = sustained
+        line['extra'] = extra
     sys.stdout.flush()
     ctypes.CDLL(None).fflush(None)          # C stdio of the native libraries, before fd 1 is the real stdout again
     os.dup2(real_stdout, 1)

@@ -211,13 +211,19 @@ int ledb200_train_conv_fwd(const float* x, const float* w_packed, const float* b
 int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float* dx, int32_t N,
                              int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
                              void* stream);
-/* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias; workspace >= 2*Cout doubles if dbias. */
+/* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias.  Every reduction of the training kernels is order-fixed
+ * (per-CTA / per-block partial sums in `workspace`, added in index order: no floating-point atomics), so a training step
+ * is bit-reproducible run to run.  workspace: device, >= ledb200_train_wgrad_workspace_bytes(Cin, Cout, k) bytes. */
+int64_t ledb200_train_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k);
+int64_t ledb200_train_bn_workspace_bytes(int32_t C);
 int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, float* dbias_opt, int32_t N,
                              int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
                              void* workspace, void* stream);
 /* nn.BatchNorm2d in training mode fused with the block's residual add and ReLU
  * (basic_block.py:62-75): out = [relu](bn(y) [+ res]); saves batch mean / inverse std for backward and
- * updates the running statistics (momentum, unbiased variance) in place.  workspace >= 2*C doubles. */
+ * updates the running statistics (momentum, unbiased variance) in place.  workspace: device, >= ledb200_train_bn_workspace_bytes(C) bytes
+ * (doubles [0,2C) hold the statistics after a reduce step, [2C,4C+8) are free for the caller - SyncBN keeps the all-reduced copy
+ * and the sample count there -, the rest are block partials). */
 int ledb200_train_bn_fwd(const float* y, const float* gamma, const float* beta, const float* res_opt,
                          float* out, float* save_mean, float* save_invstd, float* running_mean_opt,
                          float* running_var_opt, float momentum, float eps, int32_t relu, int64_t npix,
@@ -335,6 +341,23 @@ int ledb200_slide_accumulate(float* preds, float* count, const float* crop_logit
                              int32_t W, int32_t hc, int32_t wc, int32_t y1, int32_t x1, void* stream);
 int ledb200_slide_finalize(float* preds, const float* count, int32_t N, int32_t K, int32_t H, int32_t W, void* pred,
                            int32_t pred_dtype, void* stream);
+
+/* ledb200_slide_merge: slide_inference's accumulation for ALL crop windows in one pass (the crops ran as ONE engine batch):
+ *   crop_logits fp32 [G*N,K,hc,wc] (window g of image n at index g*N+n), window origins y1[g], x1[g] (HOST arrays, G <= 64, in
+ *   the reference's grid order).  Per output pixel the covering windows are summed in that order starting from 0 (bit-identical
+ *   to the sequential `preds += F.pad(crop)`, encoder_decoder.py:283-287), divided by their number (:290) and, when `pred` is
+ *   given, arg-maxed (U8 or I64).  out_logits (nullable) [N,K,H,W].  Windows that leave a row or a column uncovered are an error
+ *   (the reference asserts count_mat != 0, :289).
+ * ledb200_stack_pad: SegDataPreProcessor.forward + stack_batch for ONE sample (mmseg/models/data_preprocessor.py:112-149,
+ *   mmseg/utils/misc.py:30-128): img [3,h,w] (U8 or F32, CHW) -> out [3,Hp,Wp] fp32: channel c reads input channel 2-c when
+ *   swap_rb, (v - mean3[c]) / std3[c] when mean3/std3 (HOST, both or neither) are given, `pad_val` right of / below the image;
+ *   label (nullable, [h,w] U8 or I64) -> label_out [Hp,Wp] int64 padded with seg_pad_val. */
+int ledb200_slide_merge(const float* crop_logits, int32_t G, const int32_t* y1, const int32_t* x1, int32_t N, int32_t K,
+                        int32_t H, int32_t W, int32_t hc, int32_t wc, float* out_logits, void* pred, int32_t pred_dtype,
+                        void* stream);
+int ledb200_stack_pad(const void* img, int32_t img_dtype, int32_t h, int32_t w, int32_t swap_rb, const float* mean3,
+                      const float* std3, float pad_val, float* out, int32_t Hp, int32_t Wp, const void* label,
+                      int32_t label_dtype, int64_t* label_out, int32_t seg_pad_val, void* stream);
 
 /* ---- SEAM edge gate -----------------------------------------------------
  * The inline edge path of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338, 388-389), eval mode:

@@ -10,7 +10,15 @@
 //  * slide_accumulate / slide_finalize : EncoderDecoder.slide_inference (encoder_decoder.py:241-292):
 //      `preds += F.pad(crop_logits, ...)`, `count_mat[..., y1:y2, x1:x2] += 1` without materialising the padded
 //      full-size tensor per crop, then `preds / count_mat` (+ optional argmax) in one pass.
+//  * slide_merge : the same for ALL crops at once (they ran as one batch of the engine): per output pixel the crops that
+//      cover it are summed in the reference's grid order (fp32, starting from 0: bit-identical to the sequential
+//      `preds +=`), divided by their number, and optionally arg-maxed - no full-size read-modify-write per crop.
+//  * stack_pad : SegDataPreProcessor.forward + stack_batch for one sample (mmseg/models/data_preprocessor.py:112-149,
+//      mmseg/utils/misc.py:30-128): BGR<->RGB swap, float, (x - mean) / std, right / bottom padding with `pad_val`
+//      (applied AFTER the normalisation, as the reference does), label map padded with `seg_pad_val`.
 // All tensors are the reference's NCHW fp32; one thread per output pixel, consecutive threads on consecutive x.
+#include <vector>
+
 #include "kernels.h"
 
 namespace ledb {
@@ -105,6 +113,72 @@ __global__ void __launch_bounds__(256) slide_finalize_kernel(float* preds, const
   if (pred) pred[idx] = (TP)bi;
 }
 
+constexpr int kMaxCrops = 64;
+struct MergeArgs {
+  const float* crops;    // [G * N, K, hc, wc], crop g of image n at index g * N + n
+  int G, N, K, H, W, hc, wc;
+  int y1[kMaxCrops], x1[kMaxCrops];
+  float* out;            // optional [N, K, H, W]
+  void* pred;            // optional [N, H, W]
+};
+
+template <typename TP>
+__global__ void __launch_bounds__(256) slide_merge_kernel(const __grid_constant__ MergeArgs a) {
+  const int64_t HW = (int64_t)a.H * a.W;
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)a.N * HW) return;
+  const int n = (int)(idx / HW);
+  const int64_t pix = idx % HW;
+  const int y = (int)(pix / a.W), x = (int)(pix % a.W);
+  const int64_t plane = (int64_t)a.hc * a.wc;
+  float cnt = 0.f;
+  for (int g = 0; g < a.G; ++g)
+    cnt += (y >= a.y1[g] && y < a.y1[g] + a.hc && x >= a.x1[g] && x < a.x1[g] + a.wc) ? 1.f : 0.f;
+  float best = -INFINITY;
+  int bi = 0;
+  for (int k = 0; k < a.K; ++k) {
+    float s = 0.f;                                               // preds = zeros; preds += pad(crop) in grid order
+    for (int g = 0; g < a.G; ++g) {
+      const int yy = y - a.y1[g], xx = x - a.x1[g];
+      if (yy >= 0 && yy < a.hc && xx >= 0 && xx < a.wc)
+        s += __ldg(a.crops + (((int64_t)g * a.N + n) * a.K + k) * plane + (int64_t)yy * a.wc + xx);
+    }
+    const float v = s / cnt;
+    if (a.out) a.out[((int64_t)n * a.K + k) * HW + pix] = v;
+    if (v > best) { best = v; bi = k; }
+  }
+  if (a.pred) reinterpret_cast<TP*>(a.pred)[idx] = (TP)bi;
+}
+
+struct StackPadArgs {
+  const void* img; int h, w, swap_rb, normalize;
+  float mean[3], stdv[3], pad_val;
+  float* out; int Hp, Wp;
+  const void* label; int64_t* label_out; int seg_pad_val;
+};
+
+template <typename TI, typename TL>
+__global__ void __launch_bounds__(256) stack_pad_kernel(const __grid_constant__ StackPadArgs a) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t HWp = (int64_t)a.Hp * a.Wp;
+  if (idx >= HWp) return;
+  const int y = (int)(idx / a.Wp), x = (int)(idx % a.Wp);
+  const bool inside = y < a.h && x < a.w;
+  const int64_t src = (int64_t)y * a.w + x, hw = (int64_t)a.h * a.w;
+  const TI* img = reinterpret_cast<const TI*>(a.img);
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    float v = a.pad_val;
+    if (inside) {
+      v = (float)img[(a.swap_rb ? 2 - c : c) * hw + src];
+      if (a.normalize) v = __fdiv_rn(v - a.mean[c], a.stdv[c]);   // (_input - self.mean) / self.std, channel c AFTER the swap
+    }
+    a.out[c * HWp + idx] = v;
+  }
+  if (a.label_out)
+    a.label_out[idx] = inside ? (int64_t)reinterpret_cast<const TL*>(a.label)[src] : (int64_t)a.seg_pad_val;
+}
+
 }  // namespace
 }  // namespace ledb
 
@@ -167,6 +241,66 @@ int ledb200_slide_finalize(float* preds, const float* count, int32_t N, int32_t 
   if (pred_dtype == LEDB200_I64) slide_finalize_kernel<int64_t><<<grid, 256, 0, st>>>(preds, count, N, K, HW, (int64_t*)pred);
   else slide_finalize_kernel<uint8_t><<<grid, 256, 0, st>>>(preds, count, N, K, HW, (uint8_t*)pred);
   LEDB_LAUNCH_OK("slide_finalize_kernel");
+  return LEDB200_OK;
+}
+
+int ledb200_slide_merge(const float* crop_logits, int32_t G, const int32_t* y1, const int32_t* x1, int32_t N, int32_t K,
+                        int32_t H, int32_t W, int32_t hc, int32_t wc, float* out_logits, void* pred, int32_t pred_dtype,
+                        void* stream) {
+  if (!crop_logits || !y1 || !x1 || (!out_logits && !pred)) return fail(LEDB200_EINVAL, "slide_merge: null buffer");
+  if (G < 1 || G > kMaxCrops) return fail(LEDB200_EINVAL, "slide_merge: between 1 and 64 crops per call");
+  if (N < 1 || K < 1 || hc < 1 || wc < 1 || hc > H || wc > W) return fail(LEDB200_EINVAL, "slide_merge: bad shape");
+  if (pred && pred_dtype != LEDB200_U8 && pred_dtype != LEDB200_I64)
+    return fail(LEDB200_EINVAL, "slide_merge: pred dtype must be U8 or I64");
+  MergeArgs a;
+  a.crops = crop_logits; a.G = G; a.N = N; a.K = K; a.H = H; a.W = W; a.hc = hc; a.wc = wc; a.out = out_logits; a.pred = pred;
+  // encoder_decoder.py:289 asserts count_mat != 0 everywhere.  The reference's windows are a cartesian product of row
+  // and column offsets, so the image is covered iff every row and every column lies in some window: checked here.
+  std::vector<char> rows(H, 0), cols(W, 0);
+  for (int g = 0; g < G; ++g) {
+    if (y1[g] < 0 || x1[g] < 0 || y1[g] + hc > H || x1[g] + wc > W)
+      return fail(LEDB200_EINVAL, "slide_merge: crop window outside the image");
+    a.y1[g] = y1[g]; a.x1[g] = x1[g];
+  }
+  for (int g = 0; g < G; ++g) {
+    for (int y = y1[g]; y < y1[g] + hc; ++y) rows[y] = 1;
+    for (int x = x1[g]; x < x1[g] + wc; ++x) cols[x] = 1;
+  }
+  for (int y = 0; y < H; ++y) if (!rows[y]) return fail(LEDB200_EINVAL, "slide_merge: the crop windows leave rows uncovered");
+  for (int x = 0; x < W; ++x) if (!cols[x]) return fail(LEDB200_EINVAL, "slide_merge: the crop windows leave columns uncovered");
+  const unsigned grid = (unsigned)ceil_div64((int64_t)N * H * W, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (pred_dtype == LEDB200_I64) slide_merge_kernel<int64_t><<<grid, 256, 0, st>>>(a);
+  else slide_merge_kernel<uint8_t><<<grid, 256, 0, st>>>(a);
+  LEDB_LAUNCH_OK("slide_merge_kernel");
+  return LEDB200_OK;
+}
+
+int ledb200_stack_pad(const void* img, int32_t img_dtype, int32_t h, int32_t w, int32_t swap_rb, const float* mean3,
+                      const float* std3, float pad_val, float* out, int32_t Hp, int32_t Wp, const void* label,
+                      int32_t label_dtype, int64_t* label_out, int32_t seg_pad_val, void* stream) {
+  if (!img || !out) return fail(LEDB200_EINVAL, "stack_pad: null buffer");
+  if (h < 1 || w < 1 || Hp < h || Wp < w) return fail(LEDB200_EINVAL, "stack_pad: the padded size is smaller than the image");
+  if (img_dtype != LEDB200_U8 && img_dtype != LEDB200_F32) return fail(LEDB200_EINVAL, "stack_pad: image dtype must be U8 or F32");
+  if ((mean3 == nullptr) != (std3 == nullptr)) return fail(LEDB200_EINVAL, "stack_pad: mean and std come together");
+  if ((label == nullptr) != (label_out == nullptr)) return fail(LEDB200_EINVAL, "stack_pad: label and label_out come together");
+  if (label && label_dtype != LEDB200_U8 && label_dtype != LEDB200_I64)
+    return fail(LEDB200_EINVAL, "stack_pad: label dtype must be U8 or I64");
+  StackPadArgs a;
+  a.img = img; a.h = h; a.w = w; a.swap_rb = swap_rb ? 1 : 0; a.normalize = mean3 ? 1 : 0;
+  for (int c = 0; c < 3; ++c) { a.mean[c] = mean3 ? mean3[c] : 0.f; a.stdv[c] = std3 ? std3[c] : 1.f; }
+  a.pad_val = pad_val; a.out = out; a.Hp = Hp; a.Wp = Wp; a.label = label; a.label_out = label_out; a.seg_pad_val = seg_pad_val;
+  const unsigned grid = (unsigned)ceil_div64((int64_t)Hp * Wp, 256);
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool l64 = label && label_dtype == LEDB200_I64;
+  if (img_dtype == LEDB200_U8) {
+    if (l64) stack_pad_kernel<uint8_t, int64_t><<<grid, 256, 0, st>>>(a);
+    else stack_pad_kernel<uint8_t, uint8_t><<<grid, 256, 0, st>>>(a);
+  } else {
+    if (l64) stack_pad_kernel<float, int64_t><<<grid, 256, 0, st>>>(a);
+    else stack_pad_kernel<float, uint8_t><<<grid, 256, 0, st>>>(a);
+  }
+  LEDB_LAUNCH_OK("stack_pad_kernel");
   return LEDB200_OK;
 }
 

@@ -14,7 +14,9 @@
 //   BatchNorm (training) .......... batch statistics (double accumulation), normalise (+residual)(+ReLU),
 //                                   running-stat update; backward = one reduction (dgamma, dbeta) + one
 //                                   elementwise pass (dX, dResidual) with the ReLU mask recomputed from the output.
-//   bilinear resize ............... gather forward, scatter (red.add) backward, align_corners=False (wrappers.py:8-27)
+//   bilinear resize ............... gather forward AND gather backward (each source pixel sums the outputs that read it, in a
+//                                   fixed order), align_corners=False (wrappers.py:8-27)
+//   Every reduction is order-fixed (no floating-point atomics): a step is bit-reproducible run to run.
 //   add(+ReLU), avg-pool, channel copy (concat/slice), SGD+momentum over one flat parameter arena.
 // All tensors NHWC fp32, dense (pixel stride = C) unless an `ld` says otherwise.
 #include "kernels.h"
@@ -58,7 +60,7 @@ constexpr int WG_TH = 4, WG_TW = 16;      // output pixels per staged tile
 
 template <int KS>
 __global__ void __launch_bounds__(128, 2)
-wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ dw, int N, int H, int W,
+wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int N, int H, int W,
              int Cin, int Ho, int Wo, int Cout, int S, int pad, int tiles_x, int tiles_per_img, int64_t total_tiles) {
   extern __shared__ __align__(16) float sm[];
   const int IH = (WG_TH - 1) * S + KS, IW = (WG_TW - 1) * S + KS;
@@ -140,7 +142,9 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
         }
     }
   }
-  // merge into dW (OIHW) - partial sums from every CTA of the pixel dimension and both lanes
+  // partial sums (OIHW) of this CTA's pixel share and lane -> slot (2 * blockIdx.x + lane); wgrad_sum_kernel adds the
+  // slots in index order, so dW does not depend on which CTA finishes first (no floating-point atomics)
+  float* mine = part + (int64_t)(2 * blockIdx.x + lane) * ((int64_t)Cout * Cin * (KS * KS));
 #pragma unroll
   for (int a = 0; a < KS * KS; ++a)
 #pragma unroll
@@ -148,31 +152,43 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int ci = ci0 + 4 * cig + i, co = co0 + 4 * cog + j;
-        if (ci < Cin && co < Cout) atomicAdd(dw + ((int64_t)co * Cin + ci) * (KS * KS) + a, acc[a][i][j]);
+        if (ci < Cin && co < Cout) mine[((int64_t)co * Cin + ci) * (KS * KS) + a] = acc[a][i][j];
       }
+}
+
+__global__ void __launch_bounds__(kT) wgrad_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int64_t n,
+                                                       int slots) {
+  const int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
+  if (i >= n) return;
+  float s = 0.f;
+  for (int k = 0; k < slots; ++k) s += part[(int64_t)k * n + i];
+  dw[i] = s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // per-channel reductions over [npix][C] (C innermost).  Threads g < R*C own channel g % C and rows
-// g / C, g / C + R, ...; block partials go through shared-memory double atomics, then global ones.
+// g / C, g / C + R, ...; the threads of a block that share a channel are summed by ONE of them in thread order, every
+// block writes its [2][C] partial to `part[blockIdx.x]`, and chan_sum_kernel adds the blocks in index order: the
+// result is bit-reproducible (no atomics).
 // kind 0: (sum x, sum x^2)            -> BN batch statistics
 // kind 1: (sum dz, sum dz * xhat)     -> BN backward, dz = dout * (out > 0 if relu)
 // kind 2: (sum x, -)                  -> bias gradient
+constexpr int kMaxRedBlocks = 148 * 4;
 template <int KIND>
 __global__ void __launch_bounds__(kT)
 chan_reduce_kernel(const float* __restrict__ a, const float* __restrict__ y, const float* __restrict__ out,
                    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, int64_t npix, int C,
-                   double* __restrict__ acc /* [2][C] */) {
+                   double* __restrict__ part /* [gridDim.x][2][C] */) {
   extern __shared__ double sacc[];   // [2][C]
+  __shared__ double sd0[kT], sd1[kT];
   for (int i = threadIdx.x; i < 2 * C; i += kT) sacc[i] = 0.0;
-  __syncthreads();
   const int64_t T = (int64_t)gridDim.x * kT;
   const int64_t R = T / C;
   const int64_t g = blockIdx.x * (int64_t)kT + threadIdx.x;
+  double d0 = 0.0, d1 = 0.0;
   if (R > 0 && g < R * C) {
     const int c = (int)(g % C);
     float s0 = 0.f, s1 = 0.f;
-    double d0 = 0.0, d1 = 0.0;
     float m = 0.f, is = 0.f;
     if (KIND == 1) { m = mean[c]; is = invstd[c]; }
     int cnt = 0;
@@ -191,12 +207,28 @@ chan_reduce_kernel(const float* __restrict__ a, const float* __restrict__ y, con
       if (++cnt == 256) { d0 += s0; d1 += s1; s0 = s1 = 0.f; cnt = 0; }   // bound the fp32 run length
     }
     d0 += s0; d1 += s1;
-    atomicAdd(&sacc[c], d0);
-    if (KIND != 2) atomicAdd(&sacc[C + c], d1);
+  }
+  sd0[threadIdx.x] = d0; sd1[threadIdx.x] = d1;
+  __syncthreads();
+  // thread t < min(C, kT) is the first thread of its channel in this block: it adds the block's threads t, t + C, ...
+  if (threadIdx.x < C) {
+    double t0 = 0.0, t1 = 0.0;
+    for (int j = threadIdx.x; j < kT; j += C) { t0 += sd0[j]; t1 += sd1[j]; }
+    const int c = (int)(g % C);
+    sacc[c] = t0; sacc[C + c] = t1;
   }
   __syncthreads();
-  for (int i = threadIdx.x; i < (KIND == 2 ? C : 2 * C); i += kT)
-    if (sacc[i] != 0.0) atomicAdd(&acc[i], sacc[i]);
+  double* mine = part + (int64_t)blockIdx.x * 2 * C;
+  for (int i = threadIdx.x; i < 2 * C; i += kT) mine[i] = sacc[i];
+}
+
+__global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__ part, int nblocks, int n2c,
+                                                      double* __restrict__ acc) {
+  const int i = blockIdx.x * kT + threadIdx.x;
+  if (i >= n2c) return;
+  double s = 0.0;
+  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * n2c + i];
+  acc[i] = s;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double npix, float eps, float momentum,
@@ -254,6 +286,21 @@ __global__ void acc_to_float_kernel(const double* __restrict__ acc, float* __res
   if (c < C) out[c] = (float)acc[c];
 }
 
+// workspace layout of the per-channel reductions (doubles): [0, 4C + 8) accumulators (2C of a reduction; SyncBN keeps a second
+// copy and the sample count there), then kMaxRedBlocks block partials of 2C each
+inline int64_t bn_ws_doubles(int C) { return 4 * (int64_t)C + 8 + (int64_t)kMaxRedBlocks * 2 * C; }
+
+template <int KIND>
+int chan_reduce(const float* a, const float* y, const float* out, const float* mean, const float* invstd, int relu,
+                int64_t npix, int C, double* ws, cudaStream_t st) {
+  double* part = ws + 4 * (int64_t)C + 8;
+  const int grid = grid1d(npix * C, 4);                     // <= kMaxRedBlocks
+  chan_reduce_kernel<KIND><<<grid, kT, sizeof(double) * 2 * C, st>>>(a, y, out, mean, invstd, relu, npix, C, part);
+  chan_sum_kernel<<<ceil_div(2 * C, kT), kT, 0, st>>>(part, grid, 2 * C, ws);
+  LEDB_LAUNCH_OK("chan_reduce_kernel");
+  return LEDB200_OK;
+}
+
 // ---------------------------------------------------------------------------------------------
 // bilinear resize (align_corners=False), generic channel count
 __global__ void __launch_bounds__(kT)
@@ -275,24 +322,53 @@ resize_fwd_kernel(const float* __restrict__ src, float* __restrict__ out, int N,
   }
 }
 
+// candidate outputs that may read source index `s`: the source coordinate of output d is scale * (d + 0.5) - 0.5 and
+// it reads floor(.) and floor(.) + 1, so d lies in ((s - 0.5) / scale - 0.5, (s + 1.5) / scale - 0.5); one pixel of slack
+// either side, the exact membership is re-tested per candidate
+__device__ __forceinline__ void gather_range(int s, float scale, int out_size, int& lo, int& hi) {
+  lo = (int)floorf(((float)s - 0.5f) / scale - 0.5f) - 1;
+  hi = (int)ceilf(((float)s + 1.5f) / scale - 0.5f) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+// dsrc[n, ys, xs, c] = sum over the outputs (y, x) whose bilinear footprint holds (ys, xs) of dout * weight, rows then
+// columns in ascending order: the transpose of resize_fwd_kernel as a GATHER (no atomics, fixed summation order)
 __global__ void __launch_bounds__(kT)
 resize_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int N, int h, int w, int H, int W, int C,
                   float sh, float sw) {
-  const int64_t total = (int64_t)N * H * W * C;
+  const int64_t total = (int64_t)N * h * w * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
     int64_t p = i / C;
-    const int x = (int)(p % W), y = (int)((p / W) % H), n = (int)(p / ((int64_t)W * H));
-    int y0, y1, x0, x1;
-    float ly0, ly1, lx0, lx1;
-    bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
-    bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
-    const float g = dout[i];
-    float* d = dsrc + (int64_t)n * h * w * C + c;
-    atomicAdd(d + ((int64_t)y0 * w + x0) * C, g * ly0 * lx0);
-    atomicAdd(d + ((int64_t)y0 * w + x1) * C, g * ly0 * lx1);
-    atomicAdd(d + ((int64_t)y1 * w + x0) * C, g * ly1 * lx0);
-    atomicAdd(d + ((int64_t)y1 * w + x1) * C, g * ly1 * lx1);
+    const int xs = (int)(p % w), ys = (int)((p / w) % h), n = (int)(p / ((int64_t)w * h));
+    int ylo, yhi, xlo, xhi;
+    gather_range(ys, sh, H, ylo, yhi);
+    gather_range(xs, sw, W, xlo, xhi);
+    const float* g = dout + (int64_t)n * H * W * C + c;
+    float acc = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      float wy = 0.f;
+      if (y0 == ys) wy += ly0;
+      if (y1 == ys) wy += ly1;                     // y0 == y1 at the clamped border: both weights land on the same pixel
+      if (y0 != ys && y1 != ys) continue;
+      float row = 0.f;
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+        if (x0 != xs && x1 != xs) continue;
+        float wx = 0.f;
+        if (x0 == xs) wx += lx0;
+        if (x1 == xs) wx += lx1;
+        row = fmaf(g[((int64_t)y * W + x) * C], wx, row);
+      }
+      acc = fmaf(row, wy, acc);
+    }
+    dsrc[i] = acc;
   }
 }
 
@@ -453,6 +529,16 @@ int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float
 }
 
 // dw_oihw [Cout,Cin,k,k] (overwritten), dbias_opt [Cout] (overwritten); workspace >= 2*Cout doubles when dbias_opt
+int64_t ledb200_train_bn_workspace_bytes(int32_t C) { return C < 1 ? 0 : 8 * bn_ws_doubles(C); }
+
+int64_t ledb200_train_wgrad_workspace_bytes(int32_t Cin, int32_t Cout, int32_t k) {
+  if (Cin < 1 || Cout < 1 || (k != 1 && k != 3)) return 0;
+  const int gy = ceil_div(Cin, WG_CI), gz = ceil_div(Cout, WG_CO);
+  int64_t gx = (148 * 4) / (gy * gz);
+  if (gx < 1) gx = 1;
+  return 8 * bn_ws_doubles(Cout) + 4 * 2 * gx * (int64_t)Cout * Cin * k * k;
+}
+
 int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, float* dbias_opt, int32_t N, int32_t H,
                              int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace,
                              void* stream) {
@@ -461,7 +547,7 @@ int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, fl
   cudaStream_t st = (cudaStream_t)stream;
   const int pad = k / 2;
   const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
-  LEDB_CUDA_OK(cudaMemsetAsync(dw_oihw, 0, sizeof(float) * (size_t)Cout * Cin * k * k, st));
+  if (!workspace) return fail(LEDB200_EINVAL, "train_conv_wgrad: workspace of ledb200_train_wgrad_workspace_bytes() needed");
   const int tiles_x = ceil_div(Wo, WG_TW), tiles_y = ceil_div(Ho, WG_TH);
   const int64_t total_tiles = (int64_t)N * tiles_x * tiles_y;
   const int gy = ceil_div(Cin, WG_CI), gz = ceil_div(Cout, WG_CO);
@@ -471,22 +557,24 @@ int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, fl
   const int IH = (WG_TH - 1) * stride + k, IW = (WG_TW - 1) * stride + k;
   const size_t smem = sizeof(float) * ((size_t)IH * IW * WG_CI + WG_TH * WG_TW * WG_CO);
   dim3 grid((unsigned)gx, gy, gz);
+  // workspace: [bias-gradient accumulators and partials: bn_ws_doubles(Cout) doubles][2 * gx weight-gradient slots]
+  float* part = reinterpret_cast<float*>(reinterpret_cast<double*>(workspace) + bn_ws_doubles(Cout));
+  const int64_t nw = (int64_t)Cout * Cin * k * k;
   if (k == 3) {
     LEDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    wgrad_kernel<3><<<grid, 128, smem, st>>>(x, dy, dw_oihw, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
+    wgrad_kernel<3><<<grid, 128, smem, st>>>(x, dy, part, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
                                              tiles_x * tiles_y, total_tiles);
   } else {
-    wgrad_kernel<1><<<grid, 128, smem, st>>>(x, dy, dw_oihw, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
+    wgrad_kernel<1><<<grid, 128, smem, st>>>(x, dy, part, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
                                              tiles_x * tiles_y, total_tiles);
   }
+  wgrad_sum_kernel<<<(unsigned)ceil_div64(nw, kT), kT, 0, st>>>(part, dw_oihw, nw, 2 * (int)gx);
   LEDB_LAUNCH_OK("wgrad_kernel");
   if (dbias_opt) {
-    if (!workspace) return fail(LEDB200_EINVAL, "train_conv_wgrad: bias gradient needs a workspace");
     double* acc = (double*)workspace;
     const int64_t npix = (int64_t)N * Ho * Wo;
-    LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * Cout, st));
-    chan_reduce_kernel<2><<<grid1d(npix * Cout, 4), kT, sizeof(double) * 2 * Cout, st>>>(
-        dy, nullptr, nullptr, nullptr, nullptr, 0, npix, Cout, acc);
+    int rc = chan_reduce<2>(dy, nullptr, nullptr, nullptr, nullptr, 0, npix, Cout, acc, st);
+    if (rc) return rc;
     acc_to_float_kernel<<<ceil_div(Cout, 128), 128, 0, st>>>(acc, dbias_opt, Cout);
     LEDB_LAUNCH_OK("bias_grad");
   }
@@ -506,13 +594,9 @@ int ledb200_train_bn_reduce(const float* a, const float* y_opt, const float* out
     return fail(LEDB200_EINVAL, "train_bn_reduce: backward statistics need y, mean, invstd (and out for the ReLU mask)");
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = (double*)workspace;
-  LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
-  if (mode == 0)
-    chan_reduce_kernel<0><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(a, nullptr, nullptr, nullptr, nullptr,
-                                                                                 0, npix, C, acc);
-  else
-    chan_reduce_kernel<1><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(a, y_opt, out_opt, mean_opt,
-                                                                                 invstd_opt, relu, npix, C, acc);
+  int rc = mode == 0 ? chan_reduce<0>(a, nullptr, nullptr, nullptr, nullptr, 0, npix, C, acc, st)
+                     : chan_reduce<1>(a, y_opt, out_opt, mean_opt, invstd_opt, relu, npix, C, acc, st);
+  if (rc) return rc;
   LEDB_LAUNCH_OK("train_bn_reduce");
   return LEDB200_OK;
 }
@@ -554,7 +638,7 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
 
 // BatchNorm2d in training mode (+ residual add, + ReLU): out = [relu](bn(y) [+ res]).
 // save_mean/save_invstd [C] are outputs (needed by backward); running stats updated in place when given.
-// workspace: >= 2*C doubles.
+// workspace: ledb200_train_bn_workspace_bytes(C).
 int ledb200_train_bn_fwd(const float* y, const float* gamma, const float* beta, const float* res_opt, float* out,
                          float* save_mean, float* save_invstd, float* running_mean_opt, float* running_var_opt,
                          float momentum, float eps, int32_t relu, int64_t npix, int32_t C, void* workspace,
@@ -575,9 +659,8 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
   if (relu && !out) return fail(LEDB200_EINVAL, "train_bn_bwd: the ReLU mask needs the forward output");
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = (double*)workspace;
-  LEDB_CUDA_OK(cudaMemsetAsync(acc, 0, sizeof(double) * 2 * C, st));
-  chan_reduce_kernel<1><<<grid1d(npix * C, 4), kT, sizeof(double) * 2 * C, st>>>(dout, y, out, save_mean, save_invstd,
-                                                                               relu, npix, C, acc);
+  int rc = chan_reduce<1>(dout, y, out, save_mean, save_invstd, relu, npix, C, acc, st);
+  if (rc) return rc;
   bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy, dres_opt,
                                                        dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix);
   LEDB_LAUNCH_OK("train_bn_bwd");
@@ -597,8 +680,7 @@ int ledb200_train_resize_bwd(const float* dout, float* dsrc, int32_t N, int32_t 
                              int32_t C, void* stream) {
   if (!dout || !dsrc) return fail(LEDB200_EINVAL, "train_resize_bwd: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  LEDB_CUDA_OK(cudaMemsetAsync(dsrc, 0, sizeof(float) * (size_t)N * h * w * C, st));
-  resize_bwd_kernel<<<grid1d((int64_t)N * H * W * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, (float)h / (float)H,
+  resize_bwd_kernel<<<grid1d((int64_t)N * h * w * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, (float)h / (float)H,
                                                                   (float)w / (float)W);
   LEDB_LAUNCH_OK("resize_bwd_kernel");
   return LEDB200_OK;

@@ -23,13 +23,14 @@ SYMBOLS = [
     'ledb200_train_packed_weight_floats', 'ledb200_train_pack_weight', 'ledb200_train_conv_fwd',
     'ledb200_train_conv_dgrad', 'ledb200_train_conv_wgrad', 'ledb200_train_bn_fwd', 'ledb200_train_bn_bwd',
     'ledb200_train_bn_reduce', 'ledb200_train_bn_fwd_apply', 'ledb200_train_bn_bwd_apply',
+    'ledb200_train_bn_workspace_bytes', 'ledb200_train_wgrad_workspace_bytes',
     'ledb200_train_resize_fwd', 'ledb200_train_resize_bwd', 'ledb200_train_add_relu', 'ledb200_train_relu_bwd',
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
     'ledb200_getb_param_floats', 'ledb200_getb_create', 'ledb200_getb_destroy', 'ledb200_getb_forward',
-    'ledb200_postprocess', 'ledb200_slide_accumulate', 'ledb200_slide_finalize',
+    'ledb200_postprocess', 'ledb200_slide_accumulate', 'ledb200_slide_finalize', 'ledb200_slide_merge', 'ledb200_stack_pad',
     'ledb200_seam_param_floats', 'ledb200_seam_workspace_bytes', 'ledb200_seam_forward',
 ]
 
@@ -92,6 +93,10 @@ def get():
     lib.ledb200_train_conv_wgrad.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp]
     lib.ledb200_train_bn_fwd.argtypes = [vp] * 9 + [f32, f32, i32, i64, i32, vp, vp]
     lib.ledb200_train_bn_bwd.argtypes = [vp] * 10 + [i32, i64, i32, vp, vp]
+    lib.ledb200_train_bn_workspace_bytes.argtypes = [i32]
+    lib.ledb200_train_bn_workspace_bytes.restype = i64
+    lib.ledb200_train_wgrad_workspace_bytes.argtypes = [i32, i32, i32]
+    lib.ledb200_train_wgrad_workspace_bytes.restype = i64
     lib.ledb200_train_bn_reduce.argtypes = [vp] * 5 + [i32, i32, i64, i32, vp, vp]
     lib.ledb200_train_bn_fwd_apply.argtypes = [vp] * 9 + [f32, f32, i32, i64, C.c_double, i32, vp, vp]
     lib.ledb200_train_bn_bwd_apply.argtypes = [vp] * 10 + [i32, i64, C.c_double, i32, vp, vp]
@@ -120,6 +125,8 @@ def get():
     lib.ledb200_postprocess.argtypes = [vp, i32, i32, i32, vp, i32, i32, i32, i32, f32, vp, i32, vp, vp]
     lib.ledb200_slide_accumulate.argtypes = [vp, vp, vp] + [i32] * 8 + [vp]
     lib.ledb200_slide_finalize.argtypes = [vp, vp] + [i32] * 4 + [vp, i32, vp]
+    lib.ledb200_slide_merge.argtypes = [vp, i32, vp, vp] + [i32] * 6 + [vp, vp, i32, vp]
+    lib.ledb200_stack_pad.argtypes = [vp, i32, i32, i32, i32, vp, vp, f32, vp, i32, i32, vp, i32, vp, i32, vp]
     lib.ledb200_seam_param_floats.argtypes = [i32]
     lib.ledb200_seam_param_floats.restype = i64
     lib.ledb200_seam_workspace_bytes.argtypes = [i32, i32, i32]

@@ -169,9 +169,13 @@ class _EngineOwner(nn.Module):
     def _engine_kwargs(self):
         raise NotImplementedError
 
+    def engine_state(self):
+        """This module's tensors under the names the engine expects."""
+        return {self._prefix + k: v for k, v in self.state_dict().items()}
+
     def engine(self):
         if self._engine is None:
-            state = {self._prefix + k: v for k, v in self.state_dict().items()}
+            state = self.engine_state()
             self._engine = Engine(state, dtype=self.compute_dtype, allow_partial=True,
                                   **self._engine_kwargs())
         return self._engine
@@ -303,8 +307,9 @@ class LEDHead(_EngineOwner):
             raise ValueError('out_channels should be equal to num_classes, except binary segmentation '
                              f'set out_channels == 1 and num_classes == 2, but got out_channels='
                              f'{out_channels} and num_classes={num_classes}')
-        if out_channels == 1:
-            raise NotImplementedError('sigmoid/threshold heads (out_channels=1) are outside the LED-Net path')
+        if out_channels == 1 and threshold is None:                # decode_head.py:135-138
+            threshold = 0.3
+            warnings.warn('threshold is not defined for binary, and defaults to 0.3')
         if dropout_ratio and dropout_ratio > 0:
             raise NotImplementedError('the LED-Net config sets dropout_ratio=0 '
                                       '(configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:35)')
@@ -352,6 +357,25 @@ class LEDHead(_EngineOwner):
         return dict(num_classes=self.num_classes, channels=self.tap_channels,
                     head_channels=self.channels)
 
+    def _cls_params(self, conv):
+        """`out_channels=1` (decode_head.py:119-133): the one-channel classifier map is ADDED to the num_classes-channel
+        tap heads in predict_by_feat / loss_by_feat (decode_head.py:362-379, led_head.py:101-146), i.e. broadcast over
+        the classes - the same as a classifier whose single filter is repeated num_classes times (the final map has
+        num_classes channels, so base.py:187-192 takes the argmax branch, never the threshold one)."""
+        if self.out_channels == self.num_classes:
+            return conv.weight, conv.bias
+        return (conv.weight.expand(self.num_classes, -1, -1, -1).contiguous(),
+                conv.bias.expand(self.num_classes).contiguous() if conv.bias is not None else None)
+
+    def engine_state(self):
+        state = super().engine_state()
+        if self.out_channels != self.num_classes:
+            for name in ('conv_seg', 'aux_cls_seg'):
+                w, b = self._cls_params(getattr(self, name))
+                state[self._prefix + name + '.weight'] = w.detach().contiguous()
+                state[self._prefix + name + '.bias'] = b.detach().contiguous()
+        return state
+
     def forward(self, inputs):
         if self.training:
             return self._forward_train(inputs)
@@ -368,9 +392,9 @@ class LEDHead(_EngineOwner):
         self.reset_engine()
         c3, c5, x1, x2 = (_as_nhwc(t) for t in inputs)
         ctx = self._base_head_train(c5, self.head)
-        ctx = T.conv2d(ctx, self.conv_seg.weight, self.conv_seg.bias)           # cls_seg, decode_head.py:241-246
+        ctx = T.conv2d(ctx, *self._cls_params(self.conv_seg))                   # cls_seg, decode_head.py:241-246
         spa = self._base_head_train(c3, self.aux_head)
-        spa = T.conv2d(spa, self.aux_cls_seg.weight, self.aux_cls_seg.bias)
+        spa = T.conv2d(spa, *self._cls_params(self.aux_cls_seg))
         h1 = self._base_head_train(x1, self.head_x1)
         h2 = self._base_head_train(x2, self.head_x2)
         return tuple(_as_nchw_view(t) for t in (ctx, spa, h1, h2))

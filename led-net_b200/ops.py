@@ -143,3 +143,44 @@ def slide_finalize(preds, count, want_pred=False, pred_dtype=torch.int64):
                                            L.torch_dtype_code(pred) if want_pred else L.I64,
                                            L.stream_ptr(preds.device)), 'ledb200_slide_finalize')
     return preds, pred
+
+
+def slide_merge(crop_logits, origins, n_images, image_hw, want_logits=True, want_pred=False, pred_dtype=torch.int64):
+    """All crop windows of slide_inference at once: crop_logits fp32 [G*N,K,hc,wc] (window g of image n at g*N+n),
+    origins = [(y1, x1)] * G in the reference's grid order -> (logits [N,K,H,W] or None, pred [N,H,W] or None)."""
+    _need_cuda(crop_logits)
+    crop = crop_logits.contiguous().float()
+    G, N = len(origins), int(n_images)
+    GN, K, hc, wc = crop.shape
+    assert GN == G * N, 'crop batch must hold every window of every image'
+    H, W = (int(v) for v in image_hw)
+    out = torch.empty((N, K, H, W), dtype=torch.float32, device=crop.device) if want_logits else None
+    pred = torch.empty((N, H, W), dtype=pred_dtype, device=crop.device) if want_pred else None
+    y1 = (C.c_int32 * G)(*[int(o[0]) for o in origins])
+    x1 = (C.c_int32 * G)(*[int(o[1]) for o in origins])
+    L.check(L.get().ledb200_slide_merge(_p(crop), G, y1, x1, N, K, H, W, hc, wc, _p(out), _p(pred),
+                                        L.torch_dtype_code(pred) if want_pred else L.I64,
+                                        L.stream_ptr(crop.device)), 'ledb200_slide_merge')
+    return out, pred
+
+
+def stack_pad(img, out, swap_rb=False, mean=None, std=None, pad_val=0.0, label=None, label_out=None, seg_pad_val=255):
+    """SegDataPreProcessor + stack_batch for one sample: img [3,h,w] uint8 / fp32 -> out [3,Hp,Wp] fp32 (a slice of the
+    batch tensor), label [h,w] or [1,h,w] uint8 / int64 -> label_out [Hp,Wp] int64."""
+    _need_cuda(img, out, label, label_out)
+    img = img.contiguous()
+    assert img.dim() == 3 and img.shape[0] == 3 and out.is_contiguous() and out.dtype == torch.float32
+    if img.dtype not in (torch.uint8, torch.float32):
+        img = img.float()
+    if label is not None:
+        label = label.reshape(label.shape[-2:]).contiguous()
+        if label.dtype not in (torch.uint8, torch.int64):
+            label = label.to(torch.int64)
+        assert label_out.is_contiguous() and label_out.dtype == torch.int64
+    m3 = (C.c_float * 3)(*[float(v) for v in mean]) if mean is not None else None
+    s3 = (C.c_float * 3)(*[float(v) for v in std]) if std is not None else None
+    L.check(L.get().ledb200_stack_pad(_p(img), L.torch_dtype_code(img), img.shape[1], img.shape[2], int(bool(swap_rb)),
+                                      m3, s3, float(pad_val), _p(out), out.shape[-2], out.shape[-1], _p(label),
+                                      L.torch_dtype_code(label) if label is not None else L.U8, _p(label_out),
+                                      int(seg_pad_val), L.stream_ptr(img.device)), 'ledb200_stack_pad')
+    return out

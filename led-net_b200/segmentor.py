@@ -15,33 +15,97 @@ from .registry import MODELS
 from . import ops
 
 
+def _meta(sample):
+    """Where a dict-style data sample keeps its metainfo (SegDataSample.metainfo)."""
+    return sample.setdefault('metainfo', {}) if 'metainfo' in sample or 'gt_sem_seg' in sample else sample
+
+
 @MODELS.register_module()
 class SegDataPreProcessor(nn.Module):
-    """Holds mean/std/bgr_to_rgb.  On the fused path these are folded into the stem convolution's
-    prologue (raw uint8 in); `forward` is the stand-alone torch version for callers that want the
-    normalised float batch (plumbing, data_preprocessor.py:112-149, test-time branch)."""
+    """mmseg/models/data_preprocessor.py:98-151 on the device: per sample ONE kernel (ops.stack_pad) does the BGR<->RGB
+    swap, the float conversion, (x - mean) / std, the right / bottom padding of `stack_batch` (mmseg/utils/misc.py:30-128:
+    to `size`, or to the batch maximum rounded up to `size_divisor`; `pad_val` after the normalisation) and pads the label
+    map with `seg_pad_val`.  mean / std default to None = no normalisation, as in the reference.  On the fused inference
+    path (raw uint8 into `predict_labels`) the same mean / std / swap are the stem convolution's prologue instead."""
 
-    def __init__(self, mean=MEAN, std=STD, size=None, size_divisor=None, pad_val=0, seg_pad_val=255,
+    def __init__(self, mean=None, std=None, size=None, size_divisor=None, pad_val=0, seg_pad_val=255,
                  bgr_to_rgb=False, rgb_to_bgr=False, batch_augments=None, test_cfg=None):
         super().__init__()
-        assert not (bgr_to_rgb and rgb_to_bgr)
+        assert not (bgr_to_rgb and rgb_to_bgr), '`bgr2rgb` and `rgb2bgr` cannot be set to True at the same time'
+        assert (mean is None) == (std is None), 'mean and std should be both None or tuple'
+        if batch_augments is not None:
+            raise NotImplementedError('batch_augments are outside the LED-Net path (the config has none)')
         self.channel_conversion = bgr_to_rgb or rgb_to_bgr
         self.size, self.size_divisor, self.pad_val, self.seg_pad_val = size, size_divisor, pad_val, seg_pad_val
         self.test_cfg = test_cfg
-        self.register_buffer('mean', torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), False)
-        self.register_buffer('std', torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), False)
+        self._enable_normalize = mean is not None
+        if self._enable_normalize:
+            self.register_buffer('mean', torch.tensor(mean, dtype=torch.float32).view(-1, 1, 1), False)
+            self.register_buffer('std', torch.tensor(std, dtype=torch.float32).view(-1, 1, 1), False)
+        else:
+            self.mean = self.std = None
+
+    def mean_std(self):
+        """(mean, std) tuples for the engine's fused prologue (identity when normalisation is off)."""
+        if not self._enable_normalize:
+            return (0., 0., 0.), (1., 1., 1.)
+        return tuple(self.mean.flatten().tolist()), tuple(self.std.flatten().tolist())
+
+    @staticmethod
+    def _padded_hw(shapes, size, size_divisor):
+        """stack_batch's target shape; exactly one of size / size_divisor (misc.py:64-66)."""
+        assert (size is not None) ^ (size_divisor is not None), 'only one of size and size_divisor should be valid'
+        if size is not None:
+            hw = {(h + max(size[-2] - h, 0), w + max(size[-1] - w, 0)) for h, w in shapes}
+            assert len(hw) == 1, f'samples padded to `size` still differ in shape: {sorted(hw)}'   # torch.stack would fail
+            return hw.pop()
+        mh, mw = max(h for h, _ in shapes), max(w for _, w in shapes)
+        if size_divisor > 1:
+            mh, mw = -(-mh // size_divisor) * size_divisor, -(-mw // size_divisor) * size_divisor
+        return mh, mw
 
     def forward(self, data, training=False):
         inputs = data['inputs']
-        if isinstance(inputs, (list, tuple)):
-            inputs = torch.stack(list(inputs), 0)
-        if self.channel_conversion and inputs.shape[1] == 3:
-            inputs = inputs[:, [2, 1, 0]]
-        inputs = (inputs.float() - self.mean) / self.std
-        if training and self.size is not None:
-            ph, pw = max(self.size[0] - inputs.shape[-2], 0), max(self.size[1] - inputs.shape[-1], 0)
-            inputs = F.pad(inputs, (0, pw, 0, ph), value=self.pad_val)
-        return dict(inputs=inputs, data_samples=data.get('data_samples'))
+        samples = data.get('data_samples', None)
+        inputs = list(inputs) if isinstance(inputs, (list, tuple)) else list(inputs.unbind(0))
+        dev = next((t.device for t in inputs if t.is_cuda), None) or torch.device('cuda', torch.cuda.current_device())
+        inputs = [t.to(dev, non_blocking=True) for t in inputs]                     # BaseDataPreprocessor.cast_data
+        assert all(t.dim() == 3 and t.shape[0] == inputs[0].shape[0] for t in inputs)
+        if inputs[0].shape[0] != 3:
+            raise NotImplementedError('the device preprocessor handles 3-channel images (the LED-Net pipeline)')
+        shapes = [tuple(t.shape[-2:]) for t in inputs]
+        pad_labels = False
+        if training:
+            assert samples is not None, 'During training, `data_samples` must be define.'
+            Hp, Wp = self._padded_hw(shapes, self.size, self.size_divisor)
+            pad_labels = True
+        else:
+            assert all(sh == shapes[0] for sh in shapes), 'The image size in a batch should be the same.'
+            if self.test_cfg:
+                Hp, Wp = self._padded_hw(shapes, self.test_cfg.get('size', None), self.test_cfg.get('size_divisor', None))
+            else:
+                Hp, Wp = shapes[0]
+        out = torch.empty((len(inputs), 3, Hp, Wp), dtype=torch.float32, device=dev)
+        mean, std = self.mean_std() if self._enable_normalize else (None, None)
+        for i, t in enumerate(inputs):
+            h, w = shapes[i]
+            padding = (0, Wp - w, 0, Hp - h)                                        # (left, right, top, bottom)
+            s = samples[i] if samples is not None else None
+            lab = lab_out = None
+            if pad_labels and isinstance(s, dict) and 'gt_sem_seg' in s:
+                lab = s['gt_sem_seg']['data'].to(dev)
+                lab_out = torch.empty((1, Hp, Wp), dtype=torch.int64, device=dev)
+            ops.stack_pad(t, out[i], swap_rb=self.channel_conversion, mean=mean, std=std, pad_val=self.pad_val,
+                          label=lab, label_out=lab_out[0] if lab_out is not None else None, seg_pad_val=self.seg_pad_val)
+            if isinstance(s, dict):
+                if lab_out is not None:
+                    s['gt_sem_seg']['data'] = lab_out
+                if training:
+                    _meta(s).update(img_shape=(h, w), pad_shape=(Hp, Wp) if lab_out is not None else None,
+                                    padding_size=padding)
+                elif self.test_cfg:
+                    _meta(s).update(img_padding_size=padding, pad_shape=(Hp, Wp))
+        return dict(inputs=out, data_samples=samples)
 
 
 @MODELS.register_module()
@@ -82,12 +146,13 @@ class EncoderDecoder(nn.Module):
     def engine(self):
         if self._engine is None:
             state = {'backbone.' + k: v for k, v in self.backbone.state_dict().items()}
-            state.update({'decode_head.' + k: v for k, v in self.decode_head.state_dict().items()})
+            state.update(self.decode_head.engine_state() if hasattr(self.decode_head, 'engine_state') else
+                         {'decode_head.' + k: v for k, v in self.decode_head.state_dict().items()})
             pp = self.data_preprocessor
             kw = {}
             if pp is not None:
-                kw = dict(mean=tuple(pp.mean.flatten().tolist()), std=tuple(pp.std.flatten().tolist()),
-                          bgr_to_rgb=pp.channel_conversion)
+                mean, std = pp.mean_std()
+                kw = dict(mean=mean, std=std, bgr_to_rgb=pp.channel_conversion)
             self._engine = Engine(state, self.num_classes, self.backbone.channels,
                                   self.backbone.ppm_channels, self.decode_head.channels,
                                   dtype=self.compute_dtype, **kw)
@@ -137,25 +202,47 @@ class EncoderDecoder(nn.Module):
     def whole_inference(self, inputs, batch_img_metas=None):
         return self.encode_decode(inputs, batch_img_metas)
 
-    def slide_inference(self, inputs, batch_img_metas=None):
-        """encoder_decoder.py:241-292.  Every crop runs the fused engine; `preds += F.pad(...)`, the count matrix and
-        the final division are the slide_accumulate / slide_finalize kernels (no padded full-size copy per crop)."""
+    def _slide_windows(self, h_img, w_img):
+        """Window origins in the reference's grid order (encoder_decoder.py:262-278)."""
         h_stride, w_stride = self.test_cfg['stride']
         h_crop, w_crop = self.test_cfg['crop_size']
-        n, _, h_img, w_img = inputs.shape
         h_grids = max(h_img - h_crop + h_stride - 1, 0) // h_stride + 1
         w_grids = max(w_img - w_crop + w_stride - 1, 0) // w_stride + 1
-        preds = torch.zeros((n, self.out_channels, h_img, w_img), dtype=torch.float32, device=inputs.device)
-        count = torch.zeros((n, 1, h_img, w_img), dtype=torch.float32, device=inputs.device)
+        wins = []
         for hi in range(h_grids):
             for wi in range(w_grids):
                 y1, x1 = hi * h_stride, wi * w_stride
                 y2, x2 = min(y1 + h_crop, h_img), min(x1 + w_crop, w_img)
-                y1, x1 = max(y2 - h_crop, 0), max(x2 - w_crop, 0)
-                logit = self.encode_decode(inputs[:, :, y1:y2, x1:x2].contiguous())
-                ops.slide_accumulate(preds, count, logit, y1, x1)
+                wins.append((max(y2 - h_crop, 0), max(x2 - w_crop, 0), y2, x2))
+        return wins
+
+    MAX_SLIDE_BATCH = 64          # crop images per engine call on the batched path
+
+    def slide_inference(self, inputs, batch_img_metas=None, want_pred=False):
+        """encoder_decoder.py:241-292.  The crop windows are independent, so they run as ONE batch of the fused engine
+        (window g of image n at batch index g*n_img + n) and ops.slide_merge sums, divides (and optionally arg-maxes)
+        per output pixel in the reference's accumulation order - no full-size `preds` read-modify-write per crop.
+        More than MAX_SLIDE_BATCH crop images, or crops whose logits are not crop-sized (odd crop sizes round up),
+        take the sequential slide_accumulate / slide_finalize kernels instead."""
+        n, _, h_img, w_img = inputs.shape
+        wins = self._slide_windows(h_img, w_img)
+        hc, wc = wins[0][2] - wins[0][0], wins[0][3] - wins[0][1]
+        even = hc % 2 == 0 and wc % 2 == 0
+        if even and len(wins) * n <= self.MAX_SLIDE_BATCH:
+            crops = torch.cat([inputs[:, :, y1:y2, x1:x2] for (y1, x1, y2, x2) in wins], 0).contiguous()
+            logit = self.encode_decode(crops)
+            out, pred = ops.slide_merge(logit, [(y1, x1) for (y1, x1, _, _) in wins], n, (h_img, w_img),
+                                        want_logits=True, want_pred=want_pred)
+            return (out, pred) if want_pred else out
+        k = self.num_classes                       # channels of the fused logits (decode_head.py:362-379 broadcasts to K)
+        preds = torch.zeros((n, k, h_img, w_img), dtype=torch.float32, device=inputs.device)
+        count = torch.zeros((n, 1, h_img, w_img), dtype=torch.float32, device=inputs.device)
+        for (y1, x1, y2, x2) in wins:
+            logit = self.encode_decode(inputs[:, :, y1:y2, x1:x2].contiguous())
+            ops.slide_accumulate(preds, count, logit, y1, x1)
         assert (count == 0).sum() == 0
-        return ops.slide_finalize(preds, count)[0]
+        out, pred = ops.slide_finalize(preds, count, want_pred=want_pred)
+        return (out, pred) if want_pred else out
 
     def inference(self, inputs, batch_img_metas=None):
         mode = self.test_cfg.get('mode', 'whole')

@@ -33,7 +33,8 @@ def _st(t):
 
 
 def _ws(dev, c):
-    return torch.empty(2 * c, dtype=torch.float64, device=dev)
+    """Workspace of the per-channel reductions: accumulators + per-block partials (summed in a fixed order)."""
+    return torch.empty(L.get().ledb200_train_bn_workspace_bytes(c) // 8, dtype=torch.float64, device=dev)
 
 
 def _out_hw(h, w, k, s):
@@ -107,10 +108,10 @@ class _Conv(torch.autograd.Function):
                     'train_conv_dgrad')
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(weight)
-            ws = None
             if ctx.has_bias:
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)
-                ws = _ws(x.device, cout)
+            ws = torch.empty(lib.ledb200_train_wgrad_workspace_bytes(cin, cout, k) // 8, dtype=torch.float64,
+                             device=x.device)       # per-CTA partial sums, added in a fixed order (no atomics)
             L.check(lib.ledb200_train_conv_wgrad(_p(x), _p(dy), _p(dw), _p(db), n, h, w, cin, cout, k, ctx.stride,
                                                  _p(ws), _st(x)), 'train_conv_wgrad')
         return dx, dw, db, None
@@ -153,11 +154,11 @@ class _BNAct(torch.autograd.Function):
                                              int(relu), npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_fwd')
         else:
             import torch.distributed as dist
-            ws = torch.empty(2 * c + 1, dtype=torch.float64, device=y.device)
+            ws = _ws(y.device, c)
             L.check(lib.ledb200_train_bn_reduce(_p(y), None, None, None, None, 0, 0, npix, c, _p(ws), _st(y)),
                     'train_bn_reduce')
             ws[2 * c] = npix
-            dist.all_reduce(ws, group=group)             # one packed message per layer: (sum, sumsq, count)
+            dist.all_reduce(ws[:2 * c + 1], group=group)  # one packed message per layer: (sum, sumsq, count)
             total = float(ws[2 * c].item())
             L.check(lib.ledb200_train_bn_fwd_apply(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
                                                    _p(running_mean), _p(running_var), float(momentum), float(eps),
@@ -185,11 +186,11 @@ class _BNAct(torch.autograd.Function):
                                              npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_bwd')
         else:
             import torch.distributed as dist
-            ws = torch.empty(4 * c, dtype=torch.float64, device=y.device)
+            ws = _ws(y.device, c)
             L.check(lib.ledb200_train_bn_reduce(_p(dout), _p(y), _p(out), _p(mean), _p(invstd), 1, int(ctx.relu), npix,
                                                 c, _p(ws), _st(y)), 'train_bn_reduce')
-            ws[2 * c:].copy_(ws[:2 * c])
-            dist.all_reduce(ws[2 * c:], group=ctx.group)
+            ws[2 * c:4 * c].copy_(ws[:2 * c])
+            dist.all_reduce(ws[2 * c:4 * c], group=ctx.group)
             L.check(lib.ledb200_train_bn_bwd_apply(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
                                                    _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta),
                                                    int(ctx.relu), npix, ctx.total, c, _p(ws), _st(y)),

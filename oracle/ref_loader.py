@@ -272,3 +272,26 @@ def load_seam():
 
     _cache['seam'] = RefSEAM
     return RefSEAM
+
+
+# ---- stack_batch (mmseg/utils/misc.py:30-128), executed where it lies: the module's only package-relative import is a
+#      typing alias, stubbed here.
+def load_stack_batch():
+    if 'stack_batch' in _cache:
+        return _cache['stack_batch']
+    if not os.path.isfile(os.path.join(REF_ROOT, 'mmseg/utils/misc.py')):
+        raise FileNotFoundError(f'reference tree not found at {REF_ROOT}')
+    pkg = _PREFIX + '_utils'
+    saved = {k: sys.modules.get(k) for k in (pkg, pkg + '.typing_utils', pkg + '.misc')}
+    try:
+        _pkg(pkg)
+        _mod(pkg + '.typing_utils', SampleList=list)
+        m = _load(pkg + '.misc', 'mmseg/utils/misc.py')
+    finally:
+        for k, v in saved.items():
+            if v is None:
+                sys.modules.pop(k, None)
+            else:
+                sys.modules[k] = v
+    _cache['stack_batch'] = m.stack_batch
+    return m.stack_batch

@@ -59,3 +59,24 @@ def block_input(case_index, channels, shape, seed0, n_inputs=1):
     g = torch.Generator().manual_seed(seed0 + case_index)
     xs = [torch.randn(shape[0], channels, shape[1], shape[2], generator=g) for _ in range(n_inputs)]
     return xs[0] if n_inputs == 1 else xs
+
+
+# ---- SegDataPreProcessor / stack_batch cases: (tag, [(h, w)] per sample, size, size_divisor, pad_val, seg_pad_val)
+STACK_CASES = [
+    ('size', [(37, 52), (40, 64), (33, 64)], (40, 64), None, 0, 255),
+    ('divisor', [(37, 52), (45, 50)], None, 32, 0, 255),
+    ('divisor1', [(20, 31), (20, 31)], None, 1, 1.5, 7),
+    ('size_exact', [(16, 24)], (16, 24), None, 0, 255),
+]
+
+
+def stack_inputs(case_index, shapes, num_classes=19):
+    """uint8 BGR images [3,h,w] and int64 label maps [1,h,w] (with some 255 = ignore) per sample."""
+    g = torch.Generator().manual_seed(900 + case_index)
+    imgs = [torch.randint(0, 256, (3, h, w), generator=g, dtype=torch.uint8) for h, w in shapes]
+    labs = []
+    for h, w in shapes:
+        lab = torch.randint(0, num_classes, (1, h, w), generator=g, dtype=torch.int64)
+        lab[torch.rand(1, h, w, generator=g) < 0.05] = 255
+        labs.append(lab)
+    return imgs, labs

@@ -24,6 +24,9 @@ Fixtures
                     statistics made non-trivial (sesp_state_dict below).
 * mfaf.npz        : Muti_AFF (classification/model_utils.py) eval outputs on tests/block_cases.MFAF_CASES.
 * getb.npz        : GETBBlock (backbones/UNetFormer_GETB.py) eval outputs on tests/block_cases.GETB_CASES.
+* stack.npz       : stack_batch (mmseg/utils/misc.py:30-128) behind SegDataPreProcessor's normalisation statements
+                    (data_preprocessor.py:118-123) on tests/block_cases.STACK_CASES: padded batch, padded labels,
+                    padding_size metainfo.
 * seam.npz        : the SEAM edge gate of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338,388-389),
                     its own statements executed through oracle.ref_loader.load_seam (AST slice): the 0/1 edge mask
                     (bit-packed), the normalised edge response and the gated output on tests/block_cases.SEAM_CASES.
@@ -136,9 +139,64 @@ def make_seam():
     np.savez_compressed(os.path.join(OUT, 'seam.npz'), **out)
 
 
+class _StackSample:
+    """The part of SegDataSample that stack_batch touches (misc.py:98-121)."""
+
+    def __init__(self, label):
+        self.gt_sem_seg = _PixelData(label)
+        self.meta = {}
+
+    def __contains__(self, key):
+        return key == 'gt_sem_seg'
+
+    def set_metainfo(self, d):
+        self.meta.update(d)
+
+
+class _LabelData:
+    """PixelData stand-in whose `.data` can be deleted and re-assigned, `.shape` following it."""
+
+    def __init__(self, data):
+        self.data = data
+
+    @property
+    def shape(self):
+        return tuple(self.data.shape[-2:])
+
+
+def make_stack():
+    """stack.npz: the reference's stack_batch on normalised float images + label maps (tests/block_cases.STACK_CASES);
+    the normalisation in front of it is data_preprocessor.py:118-123's three statements, applied here verbatim."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import block_cases as bc
+    stack_batch = ref_loader.load_stack_batch()
+    mean = torch.tensor([123.675, 116.28, 103.53]).view(-1, 1, 1)
+    std = torch.tensor([58.395, 57.12, 57.375]).view(-1, 1, 1)
+    out = {}
+    for ci, (tag, shapes, size, div, pad_val, seg_pad_val) in enumerate(bc.STACK_CASES):
+        imgs, labs = bc.stack_inputs(ci, shapes)
+        inputs = [_input[[2, 1, 0], ...] for _input in imgs]
+        inputs = [_input.float() for _input in inputs]
+        inputs = [(_input - mean) / std for _input in inputs]
+        samples = []
+        for lab in labs:
+            smp = _StackSample(lab)
+            smp.gt_sem_seg = _LabelData(lab.clone())
+            samples.append(smp)
+        batch, samples = stack_batch(inputs=inputs, data_samples=samples, size=size, size_divisor=div,
+                                     pad_val=pad_val, seg_pad_val=seg_pad_val)
+        out[tag + '_inputs'] = batch.numpy()
+        out[tag + '_labels'] = torch.stack([smp.gt_sem_seg.data for smp in samples]).numpy().astype(np.int16)
+        out[tag + '_padding'] = np.array([smp.meta['padding_size'] for smp in samples], dtype=np.int32)
+    np.savez_compressed(os.path.join(OUT, 'stack.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
+    if 'stack' in sys.argv[1:]:           # regenerate only the stack_batch fixture
+        make_stack()
+        return
     if 'seam' in sys.argv[1:]:            # regenerate only the SEAM fixture
         make_seam()
         return
@@ -152,6 +210,7 @@ def main():
     make_sesp(ref)
     make_blocks(ref)
     make_seam()
+    make_stack()
 
     # ---------------- r0_head_k2 -------------------------------------------------
     ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,

@@ -268,17 +268,11 @@ def test_train_step_vs_oracle(K, hw, N):
     torch.cuda.synchronize()
     # train_step = zero_grad, backward, step: the step-2 gradients are still in .grad
     grads2 = {k: p.grad.detach().cpu().clone() for k, p in m.named_parameters()}
-    # after one lr = 0.01 step from random init the problem is worse conditioned: the fp32 oracle's own whole-vector
-    # error against float64 was measured between 3.4e-3 and 1.6e-2 from run to run (it is evaluated at the product's
-    # parameters, which carry the atomics' summation-order noise of step 1), ours between 2.5e-3 and 1.7e-2
-    # single tensors (max-norm) scatter more: 0.045-0.11 observed for ours, up to 0.11 for the fp32 oracle itself.
-    # Eleven more runs (profiles/r1g_train_step2_scatter.txt): step 1 repeats to three digits (2.04e-3 every run) while
-    # step 2 - evaluated at parameters that differ from run to run only by step 1's atomic summation order - scatters
-    # over two decades for BOTH implementations, independently of each other: whole-vector ours 3.8e-4 ... 3.1e-2, fp32
-    # oracle 5.0e-4 ... 6.0e-3 (1.6e-2 earlier); worst tensor ours 5.7e-4 ... 1.8e-1, fp32 oracle 7.3e-4 ... 1.1e-1.
-    # Step 2 is therefore a PLUMBING gate (stale weights, a missing zero_grad, wrong momentum or BN statistics are O(1)
-    # errors), set one decade above the observed scatter; the precision gate is step 1 (1e-2) and the per-op tests.
-    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2', cond_floor=cond, vec_tol=1e-1, tensor_tol=0.5)
+    # Round 1 had to gate step 2 at 1e-1 / 0.5: the weight-gradient and resize-backward kernels summed with fp32 atomics, so
+    # step 1's parameters (and with them step 2's conditioning) changed from run to run (profiles/r1g_train_step2_scatter.txt).
+    # Every reduction is order-fixed now (test_training_steps_are_bit_reproducible), step 2 repeats to the bit - measured
+    # whole-vector 2.2e-3 / 3.9e-3 for the two cases - and is gated exactly like step 1: 1e-2.
+    _check_grads(grads2, ref2_grads, ref2_grads64, 'step 2', cond_floor=cond)
     for k in shadow:
         shadow[k].grad = grads2[k].clone()
     opt_s.step()                                                    # second step exercises the momentum buffer
@@ -321,3 +315,27 @@ def test_syncbn_two_ranks_matches_full_batch():
                        capture_output=True, text=True, timeout=600)
     print(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+
+
+def test_training_steps_are_bit_reproducible():
+    """No floating-point atomics anywhere in the training kernels (weight gradients, BatchNorm statistics and the resize
+    backward sum per-CTA partials / gathers in a fixed order): three optimiser steps from the same weights on the same
+    batch land on the SAME bits, run after run."""
+    K, N, hw = 5, 2, (96, 160)
+    x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0)).to(DEV)
+    lab = synth.make_labels(N, *hw, K, seed=1)
+    samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(N)]
+    finals = []
+    for _ in range(2):
+        _, m = _train_pair(K)
+        opt = L.FlatSGD(m.parameters(), lr=0.01, momentum=0.9, weight_decay=5e-4)
+        for _ in range(3):
+            log = m.train_step(dict(inputs=x, data_samples=samples), opt)
+        torch.cuda.synchronize()
+        finals.append((opt.flat.detach().clone(), opt.flat_grad.detach().clone(), float(log['loss'].detach()),
+                       {k: b.detach().clone() for k, b in m.named_buffers()}))
+    assert torch.equal(finals[0][0], finals[1][0]), 'parameters differ between two identical runs'
+    assert torch.equal(finals[0][1], finals[1][1]), 'gradients differ between two identical runs'
+    assert finals[0][2] == finals[1][2]
+    for k, b in finals[0][3].items():
+        assert torch.equal(b, finals[1][3][k]), k

@@ -191,3 +191,19 @@ def test_seam_gate(golden_dir):
         ref = torch.from_numpy(g[tag])
         err = ((out[:, bc.SEAM_GOLDEN_CHANNELS] - ref).abs() * ~unstable3).max() / ref.abs().max()
         assert err < 2e-6, (tag, float(err))
+
+
+def test_oracle_stack_batch_matches_reference_golden(golden_dir):
+    """oracle.stack_batch + oracle.preprocess == the reference's stack_batch behind its normalisation statements
+    (tests/golden/stack.npz, generated by make_golden.py from mmseg/utils/misc.py executed where it lies)."""
+    import oracle
+    from block_cases import STACK_CASES, stack_inputs
+    gold = _load(golden_dir, 'stack.npz')
+    for ci, (tag, shapes, size, div, pad_val, seg_pad_val) in enumerate(STACK_CASES):
+        imgs, labs = stack_inputs(ci, shapes)
+        xs = [oracle.preprocess(im[None])[0] for im in imgs]
+        batch, lab, pads = oracle.stack_batch(xs, labs, size=size, size_divisor=div, pad_val=pad_val,
+                                              seg_pad_val=seg_pad_val)
+        np.testing.assert_array_equal(batch.numpy(), gold[tag + '_inputs'])
+        np.testing.assert_array_equal(lab.numpy(), gold[tag + '_labels'].astype(np.int64))
+        np.testing.assert_array_equal(np.array(pads), gold[tag + '_padding'])

@@ -20,7 +20,7 @@ def build_pair(num_classes, seed=2, dtype='fp32', channels=32, ppm=128, head_ch=
             dict(type='LEDNet', channels=channels, ppm_channels=ppm),
             dict(type='LEDHead', in_channels=4 * channels, channels=head_ch, num_classes=num_classes,
                  dropout_ratio=0., tap_channels=channels),
-            data_preprocessor=dict(type='SegDataPreProcessor', bgr_to_rgb=True),
+            data_preprocessor=dict(type='SegDataPreProcessor', mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True),
             compute_dtype=dtype).eval()
     m.load_state_dict(sd, strict=True)
     return o, m

@@ -91,7 +91,7 @@ def main():
                 n_sync += 1; bad_sync += (not same)
             else:
                 n_plain += 1; differing_plain += (not same)
-    good = bad_sync == 0 and n_sync > 40 and n_plain > 10
+    good = bad_sync == 0 and n_sync >= 30 and n_plain > 10
     ok = ok and good and bool(torch.isfinite(total))
     if rank == 0:
         print(f'syncbn model: loss {float(total):.4f}; {n_sync} SyncBN layers, {bad_sync} with rank-dependent running stats; '

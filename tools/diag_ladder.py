@@ -13,13 +13,14 @@ from lednet_b200 import synth
 from util import build_pair
 
 K = int(os.environ.get('K', 19))
+BASE = int(os.environ.get('LADDER_BASE_DBG', 0))      # e.g. 64: final rung without the uniform-corner shortcut
 o, m = build_pair(K, dtype='bf16')
 eng = m.engine()
 n, h, w = 16, 1024, 2048
 x = oracle.preprocess(synth.make_images_u8(n, h, w, seed=3)).cuda()
 pl, lg = eng.forward_infer(x, want_logits=True)
 r1_ref = eng.debug_fetch('hx1')                       # rung-mode r1 (fp16 -> fp32 NCHW, host)
-os.environ['LEDB200_LADDER_DBG'] = '8'
+os.environ['LEDB200_LADDER_DBG'] = str(8 | BASE)
 for run in range(6):
     p = eng.forward_infer(x)
     torch.cuda.synchronize()
@@ -38,7 +39,7 @@ os.environ['LEDB200_LADDER_DBG'] = '0'
 # ---- probe timings of head_x1 (final mode): which role bounds the kernel
 for dbg, what in [(0, 'everything on'), (1, 'no output phase'), (2, 'no up gather'), (3, 'no output phase, no up gather'),
                   (4, 'no MMAs'), (7, 'all off')]:
-    os.environ['LEDB200_LADDER_DBG'] = str(dbg)
+    os.environ['LEDB200_LADDER_DBG'] = str(dbg | BASE)
     eng.forward_infer(x)
     prof = dict(eng.profile_ops(iters=5))
     print(f'dbg {dbg:2d} {what:32s} head_x1 {prof["decode_head.head_x1"] * 1e3:7.1f} us   head_x2 {prof["decode_head.head_x2"] * 1e3:7.1f} us')

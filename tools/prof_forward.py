@@ -27,7 +27,7 @@ with warnings.catch_warnings():
     warnings.simplefilter('ignore')
     m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
                                                    dropout_ratio=0.),
-                         data_preprocessor=dict(type='SegDataPreProcessor', bgr_to_rgb=True)).eval()
+                         data_preprocessor=dict(type='SegDataPreProcessor', mean=[123.675, 116.28, 103.53], std=[58.395, 57.12, 57.375], bgr_to_rgb=True)).eval()
 m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
 img = synth.make_images_u8(args.batch, args.height, args.width, seed=0).cuda()
 x = img if args.u8 else ((img[:, [2, 1, 0]].float() - torch.tensor(L.engine.MEAN, device='cuda').view(1, 3, 1, 1))
