@@ -596,13 +596,69 @@ void build_trunk(Builder& B, bool raw_c5, bool head_inputs) {
   const int P = e.cfg.ppm_channels;
   const int hh = p.bufs[xc5].h, ww = p.bufs[xc5].w, cc = p.bufs[xc5].c;
   const std::string s = b + "spp.";
+  const int ks[3] = {5, 9, 17}, ss[3] = {2, 4, 8}, ps[3] = {2, 4, 8};
+  {
+    // Fused DAPPM (dappm.cu): pooled branches in one launch, everything at full DAPPM resolution in one clustered
+    // tcgen05 kernel - 2 launches for the module instead of 22.  bf16 engine, <= 8 tiles of 16 x 8 pixels per image.
+    const bool no_fused = getenv("LEDB200_NO_FUSED_DAPPM") != nullptr;   // read per plan build: tests compare both paths
+    DappmArgs probe;
+    probe.N = n; probe.H = hh; probe.W = ww; probe.C = cc; probe.P = P; probe.Cout = 4 * C; probe.out_ld = 4 * C;
+    if (!no_fused && B.dt == LEDB200_BF16 && e.cfg.conv_backend != 1 && dappm_eligible(probe)) {
+      int sdim[4][2], sbuf[4];
+      for (int i = 0; i < 4; ++i) {
+        sdim[i][0] = i < 3 ? (hh + 2 * ps[i] - ks[i]) / ss[i] + 1 : 1;
+        sdim[i][1] = i < 3 ? (ww + 2 * ps[i] - ks[i]) / ss[i] + 1 : 1;
+        sbuf[i] = B.buf("spp.s" + std::to_string(i + 1), n, sdim[i][0], sdim[i][1], P);
+      }
+      const int t0 = B.buf("spp.t_even", n, hh, ww, P), t1 = B.buf("spp.t_odd", n, hh, ww, P);
+      const int spp = B.buf("spp.out", n, hh, ww, 4 * C);
+      auto cv = [&e, s](const std::string& name) { return e.conv_by_name.at(s + name); };
+      auto af = [&e, s](const std::string& name) { return e.aff_by_name.at(s + name + ".bn"); };
+      int c_scale[4], c_proc[4], a_scale[4], a_proc[4];
+      for (int i = 0; i < 4; ++i) {
+        c_scale[i] = cv("scales." + std::to_string(i + 1) + ".1"); a_scale[i] = af("scales." + std::to_string(i + 1) + ".1");
+        c_proc[i] = cv("processes." + std::to_string(i)); a_proc[i] = af("processes." + std::to_string(i));
+      }
+      const int c_s0 = cv("scales.0"), c_sc = cv("shortcut"), c_comp = cv("compression");
+      const int a_s0 = af("scales.0"), a_sc = af("shortcut"), a_comp = af("compression");
+      const double npx = (double)n * hh * ww;
+      double flops = 2.0 * npx * (2.0 * cc * P + 4.0 * 9 * P * P + 5.0 * P * 4 * C);
+      double wbytes = 2.0 * (2.0 * cc * P + 4.0 * 9 * P * P + 5.0 * P * 4 * C + 4.0 * cc * P);
+      for (int i = 0; i < 4; ++i) flops += 2.0 * n * sdim[i][0] * sdim[i][1] * cc * P;
+      p.ops.push_back({"backbone.spp (pooled branches + fused chain)", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
+        DappmArgs a;
+        a.x = Builder::ptr(e, p, xc5); a.N = n; a.H = hh; a.W = ww; a.C = cc; a.P = P; a.Cout = 4 * C;
+        for (int i = 0; i < 4; ++i) {
+          a.pool_k[i] = i < 3 ? ks[i] : 0; a.pool_s[i] = i < 3 ? ss[i] : 1; a.pool_p[i] = i < 3 ? ps[i] : 0;
+          a.sh[i] = sdim[i][0]; a.sw[i] = sdim[i][1];
+          a.a_scale[i] = e.affs[a_scale[i]].scale; a.b_scale[i] = e.affs[a_scale[i]].shift;
+          a.w_scale[i] = e.convs[c_scale[i]].w_tc; a.bias_scale[i] = e.convs[c_scale[i]].bias;
+          a.s[i] = Builder::ptr(e, p, sbuf[i]);
+          a.a_proc[i] = e.affs[a_proc[i]].scale; a.b_proc[i] = e.affs[a_proc[i]].shift;
+          a.w_proc[i] = e.convs[c_proc[i]].w_tc; a.bias_proc[i] = e.convs[c_proc[i]].bias;
+        }
+        a.a_s0 = e.affs[a_s0].scale; a.b_s0 = e.affs[a_s0].shift; a.w_s0 = e.convs[c_s0].w_tc; a.bias_s0 = e.convs[c_s0].bias;
+        a.a_sc = e.affs[a_sc].scale; a.b_sc = e.affs[a_sc].shift; a.w_sc = e.convs[c_sc].w_tc; a.bias_sc = e.convs[c_sc].bias;
+        a.a_comp = e.affs[a_comp].scale; a.b_comp = e.affs[a_comp].shift; a.w_comp = e.convs[c_comp].w_tc;
+        a.bias_comp = e.convs[c_comp].bias;
+        a.t0 = Builder::ptr(e, p, t0); a.t1 = Builder::ptr(e, p, t1);
+        a.out = Builder::ptr(e, p, spp); a.out_ld = p.bufs[spp].ld;
+        return launch_dappm(a, st);
+      }, K_CONV_TC, flops, 2.0 * npx * (cc + 4 * C) + wbytes});
+      B.tag();
+      const int c5 = raw_c5 ? B.buf("c5", n, p.bufs[xs5].h, p.bufs[xs5].w, 4 * C) : -1;
+      const int c5h = head_inputs ? B.buf("c5h", n, p.bufs[xs5].h, p.bufs[xs5].w, 4 * C) : -1;
+      B.lane(0, true);
+      B.upadd("final.up_add", xs5, spp, c5, false, c5h, head_inputs ? aff(e, "decode_head.head.0.bn") : -1);
+      return;
+    }
+  }
   const int a0 = B.buf("spp.a0", n, hh, ww, cc), asc = B.buf("spp.asc", n, hh, ww, cc);
   B.affine2("spp.bnrelu(scales.0,shortcut)", xc5, a0, aff(e, s + "scales.0.bn"), asc, aff(e, s + "shortcut.bn"));
   const int cat = B.buf("spp.cat", n, hh, ww, 5 * P);
   const int acomp = aff(e, s + "compression.bn");
   int fprev = B.buf("spp.f0", n, hh, ww, P);
   B.conv(s + "scales.0", a0, fprev, -1, false, cat, acomp, 0, 0);
-  const int ks[3] = {5, 9, 17}, ss[3] = {2, 4, 8}, ps[3] = {2, 4, 8};
   for (int i = 1; i <= 4; ++i) {
     const std::string si = std::to_string(i);
     int ph, pw;

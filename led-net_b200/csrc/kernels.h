@@ -97,6 +97,32 @@ struct PoolArgs {
 };
 int launch_avgpool_bnrelu(const PoolArgs& a, cudaStream_t st);
 
+// The whole DAPPM (ppm.py:57-130) as two launches (dappm.cu): pooled branches, then one clustered tcgen05 kernel for the
+// 1x1 / 3x3 chain, the concat-free compression and the shortcut.  All tensors NHWC bf16, dense; BN as y = relu(a x + b).
+struct DappmArgs {
+  const void* x = nullptr;                         // [N,H,W,C] raw context features
+  int N = 0, H = 0, W = 0, C = 0, P = 0, Cout = 0; // P = ppm channels (128), Cout = 4 * channels (128)
+  // pooled branches i = 1..4: window / stride / pad (k == 0: global), pooled size, BN, 1x1 conv [P][C], output [N,sh,sw,P]
+  int pool_k[4] = {0, 0, 0, 0}, pool_s[4] = {1, 1, 1, 1}, pool_p[4] = {0, 0, 0, 0}, sh[4] = {0, 0, 0, 0}, sw[4] = {0, 0, 0, 0};
+  const float* a_scale[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* b_scale[4] = {nullptr, nullptr, nullptr, nullptr};
+  const __nv_bfloat16* w_scale[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* bias_scale[4] = {nullptr, nullptr, nullptr, nullptr};
+  void* s[4] = {nullptr, nullptr, nullptr, nullptr};
+  // scales[0] and shortcut (1x1, [P][C] / [Cout][C]), processes[0..3] (3x3, [P][9*P]), compression (1x1, [Cout][5*P])
+  const float *a_s0 = nullptr, *b_s0 = nullptr, *a_sc = nullptr, *b_sc = nullptr, *a_comp = nullptr, *b_comp = nullptr;
+  const float* a_proc[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float* b_proc[4] = {nullptr, nullptr, nullptr, nullptr};
+  const __nv_bfloat16 *w_s0 = nullptr, *w_sc = nullptr, *w_comp = nullptr;
+  const __nv_bfloat16* w_proc[4] = {nullptr, nullptr, nullptr, nullptr};
+  const float *bias_s0 = nullptr, *bias_sc = nullptr, *bias_comp = nullptr;
+  const float* bias_proc[4] = {nullptr, nullptr, nullptr, nullptr};
+  void *t0 = nullptr, *t1 = nullptr;               // ping-pong scratch [N,H,W,P]
+  void* out = nullptr; int out_ld = 0;             // [N,H,W,Cout]
+};
+bool dappm_eligible(const DappmArgs& a);
+int launch_dappm(const DappmArgs& a, cudaStream_t st);
+
 // out = relu(scale*x + shift) per channel; up to two outputs from one read.
 struct AffineArgs {
   const void* in = nullptr;
