@@ -224,6 +224,66 @@ def extra_train(args, rank, world, local, dev, dist, barrier):
     return out
 
 
+def extra_led(args, rank, world, local, dev, dist, barrier, batch=16, H=1024, W=2048, K=19):
+    """`LEDNet(variant='led')` (the LED wiring over STDC / GETB / MFAF / SEAM, led_variant.py) + LEDHead on the headline
+    workload: same step (labels + confusion matrix), the trunk running layer by layer through the C ABI."""
+    import warnings
+    import torch
+    import lednet_b200 as L
+    from lednet_b200 import synth, ops
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        m = L.EncoderDecoder(dict(type='LEDNet', variant='led'),
+                             dict(type='LEDHead', in_channels=128, channels=64, num_classes=K, dropout_ratio=0.),
+                             data_preprocessor=dict(type='SegDataPreProcessor', mean=list(L.engine.MEAN),
+                                                    std=list(L.engine.STD), bgr_to_rgb=True),
+                             compute_dtype=args.dtype).eval()
+    sd = synth.make_state_dict(m.state_dict(), seed=2)
+    sd['backbone.fusion_kernel'] = m.state_dict()['backbone.fusion_kernel'].clone()
+    m.load_state_dict(sd)
+    m.to(dev)
+    img = synth.make_images_u8(batch, H, W, seed=700 + rank).to(dev)
+    mean = torch.tensor(L.engine.MEAN, device=dev).view(1, 3, 1, 1)
+    std = torch.tensor(L.engine.STD, device=dev).view(1, 3, 1, 1)
+    x = ((img[:, [2, 1, 0]].float() - mean) / std).contiguous()
+    lab = synth.make_labels(batch, H, W, K, seed=800 + rank).to(torch.uint8).to(dev)
+    cm = torch.zeros((K + 1, K), dtype=torch.int64, device=dev)
+
+    def step():
+        pred = m.predict_labels(x)
+        ops.confusion_accumulate(pred, lab, K, 255, cm)
+        if dist is not None:
+            dist.all_reduce(cm.clone())
+
+    steps, warm = max(5, min(args.steps, 10)), 3
+    for _ in range(warm):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item() / steps
+    out = dict(metric=f"LED-Net(variant='led') img/s @{H}x{W} {args.dtype}", value=world * batch / (ms * 1e-3), unit=UNIT,
+               ms_per_step=ms, steps=steps, warmup=warm, n_gpus=world, dtype=args.dtype, data='synthetic',
+               params_M=sum(p.numel() for p in m.backbone.parameters()) / 1e6,
+               config=dict(workload="LEDNet(variant='led') + LEDHead whole inference, argmax + confusion matrix; trunk = "
+                                    'one C-ABI call per layer (no fused plan yet)', batch_per_gpu=batch, height=H, width=W,
+                           num_classes=K, l2='inputs larger than L2'),
+               clocks=sampler.stop() if rank == 0 else None)
+    del m, x, img
+    torch.cuda.empty_cache()
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -239,6 +299,8 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--profile-ops', action='store_true', help='print the per-op table to stderr')
     ap.add_argument('--conv-backend', type=int, default=0)
+    ap.add_argument('--variant', default='r0', choices=['r0', 'led'],
+                    help="led: time LEDNet(variant='led') on the headline workload and print ITS line instead")
     ap.add_argument('--no-extras', action='store_true', help='skip the sustained loop and the config-4 / config-5 blocks')
     ap.add_argument('--sustain-seconds', type=float, default=2.5)
     args = ap.parse_args()
@@ -281,6 +343,22 @@ def main():
         dist.init_process_group('nccl', device_id=dev)
 
     K, N, H, W = args.classes, args.batch, args.height, args.width
+    if args.variant == 'led':
+        def _barrier():
+            if dist is not None:
+                dist.barrier()
+            torch.cuda.synchronize()
+        line = extra_led(args, rank, world, local, dev, dist, _barrier, batch=N, H=H, W=W, K=K)
+        if rank == 0:
+            line.update(higher_is_better=True, scaling='weak', vs_baseline=None, variant='led')
+            sys.stdout.flush()
+            ctypes.CDLL(None).fflush(None)
+            os.dup2(real_stdout, 1)
+            print(json.dumps(line), flush=True)
+            os.dup2(2, 1)
+        if dist is not None:
+            dist.destroy_process_group()
+        return
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
         m = L.EncoderDecoder(dict(type='LEDNet'), dict(type='LEDHead', in_channels=128, channels=64, num_classes=K,
@@ -412,7 +490,8 @@ def main():
                          seconds=t3.item() * 1e-3, clocks=s2.stop() if rank == 0 else None)
         # the main workload's buffers are no longer needed by the extras
         extra = dict(config5=extra_config5(args, rank, world, local, dev, dist, barrier),
-                     train=extra_train(args, rank, world, local, dev, dist, barrier))
+                     train=extra_train(args, rank, world, local, dev, dist, barrier),
+                     led_variant=extra_led(args, rank, world, local, dev, dist, barrier))
 
     if rank != 0:
         if dist is not None:

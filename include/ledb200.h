@@ -359,6 +359,33 @@ int ledb200_stack_pad(const void* img, int32_t img_dtype, int32_t h, int32_t w, 
                       const float* std3, float pad_val, float* out, int32_t Hp, int32_t Wp, const void* label,
                       int32_t label_dtype, int64_t* label_out, int32_t seg_pad_val, void* stream);
 
+/* ---- layer-level operators for module compositions outside the R0 plan (the LED wiring, led_variant.py) ---------------
+ * A conv layer handle is ONE mmcv ConvModule (mmcv/cnn/bricks/conv_module.py; conv k = 1 | 3, stride 1 | 2, padding k/2)
+ * whose BatchNorm the caller folded into `weight` (OIHW, HOST fp32) / `bias` (nullable); `pre_scale` / `pre_shift`
+ * (nullable, HOST [Cin]) are the folded BN of a pre-activation module (order norm, act, conv: ppm.py:57-117), applied
+ * as relu(a x + b) in the conv prologue.  groups == Cin == Cout selects the depthwise 3x3 (stdc.py:52-61).  The weights
+ * stay on the device in both conv layouts; forward is one launch: the tcgen05 kernel for bf16 tensors of eligible
+ * shape (backend 0 / 2), else the CUDA-core kernel (backend 1 forces it).  out = [relu](conv(in) + bias [+ residual]).
+ * in / out / residual: NHWC of `dtype` (F32 | BF16) with pixel strides in elements (0 = dense), so a layer can read /
+ * write a channel slice of a wider buffer (concat without a copy). */
+typedef struct ledb200_conv_layer ledb200_conv_layer;
+int ledb200_conv_layer_create(const float* weight, const float* bias, const float* pre_scale, const float* pre_shift,
+                              int32_t Cin, int32_t Cout, int32_t ksize, int32_t stride, int32_t groups,
+                              ledb200_conv_layer** out);
+int ledb200_conv_layer_forward(ledb200_conv_layer* layer, const void* in, void* out, const void* residual, int32_t dtype,
+                               int32_t N, int32_t H, int32_t W, int32_t in_ld, int32_t out_ld, int32_t res_ld, int32_t relu,
+                               int32_t backend, void* stream);
+int ledb200_conv_layer_destroy(ledb200_conv_layer* layer);
+/* nn.AvgPool2d(k, s, p) with count_include_pad=True (stdc.py:80, ppm.py:68-90), or the global average when k == 0;
+ * F.interpolate(mode='bilinear', align_corners=False) (mmseg/models/utils/wrappers.py:8-27); out = [relu](a [+ b]).
+ * NHWC F32 | BF16, C a multiple of 8, pixel strides in elements (0 = dense). */
+int ledb200_avgpool2d(const void* in, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
+                      int32_t p, int32_t in_ld, int32_t out_ld, void* stream);
+int ledb200_resize_bilinear(const void* in, void* out, int32_t dtype, int32_t N, int32_t h, int32_t w, int32_t H, int32_t W,
+                            int32_t C, int32_t in_ld, int32_t out_ld, void* stream);
+int ledb200_add_relu(const void* a, const void* b, void* out, int32_t dtype, int64_t npix, int32_t C, int32_t a_ld, int32_t b_ld,
+                     int32_t out_ld, int32_t relu, void* stream);
+
 /* ---- SEAM edge gate -----------------------------------------------------
  * The inline edge path of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338, 388-389), eval mode:
  *   e = minmax_normalise(BN(conv3x3 C->1 (x))) over the whole tensor; b_s = [clamp(laplacian_stride_s(e), 0) > t] for

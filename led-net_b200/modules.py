@@ -192,12 +192,20 @@ class _EngineOwner(nn.Module):
 class LEDNet(_EngineOwner):
     _prefix = 'backbone.'
 
+    def __new__(cls, *args, variant='r0', **kwargs):
+        """variant='led' builds the LED wiring (led_variant.LEDTrunk: STDC stages + GETB + MFAF + SEAM after the
+        authors' speed prototype, tools/speed/ddrnet_speed.py:39-406) instead of the R0 trunk."""
+        if variant == 'led' and cls is LEDNet:
+            from .led_variant import LEDTrunk
+            return LEDTrunk(*args, **kwargs)
+        return super().__new__(cls)
+
     def __init__(self, in_channels=3, channels=32, ppm_channels=128, align_corners=False,
                  norm_cfg=_BN, act_cfg=_RELU, init_cfg=None, variant='r0'):
         super().__init__()
         if variant != 'r0':
-            raise ValueError("only variant='r0' exists: the LED wiring is withheld upstream "
-                             '(mmseg/models/backbones/lednet.py:1-8)')
+            raise ValueError(f"variant must be 'r0' (the DDRNet-23-slim body + stem taps) or 'led' (the LED wiring of the "
+                             f"authors' speed prototype), got {variant!r}")
         if align_corners:
             raise ValueError('align_corners=True is not supported by the B200 path')
         C = channels

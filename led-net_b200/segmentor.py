@@ -143,7 +143,21 @@ class EncoderDecoder(nn.Module):
                 part.set_compute_dtype(dtype)
         return self
 
+    @property
+    def _composed(self):
+        """layer-by-layer backbone (LEDNet(variant='led')) instead of the fused R0 engine plan"""
+        return getattr(self.backbone, 'composed', False)
+
+    def _float_inputs(self, inputs):
+        """raw uint8 batches go through the device preprocessor when the backbone is not the fused engine"""
+        if inputs.dtype != torch.uint8:
+            return inputs
+        pp = self.data_preprocessor or SegDataPreProcessor()
+        return pp(dict(inputs=inputs if inputs.shape[1] == 3 else inputs.permute(0, 3, 1, 2)))['inputs']
+
     def engine(self):
+        if self._composed:
+            raise RuntimeError("LEDNet(variant='led') runs layer by layer; there is no fused engine plan for it")
         if self._engine is None:
             state = {'backbone.' + k: v for k, v in self.backbone.state_dict().items()}
             state.update(self.decode_head.engine_state() if hasattr(self.decode_head, 'engine_state') else
@@ -162,6 +176,8 @@ class EncoderDecoder(nn.Module):
     def extract_feat(self, inputs):
         if self.training:
             return self.backbone(inputs)            # train-mode tape over csrc/train.cu
+        if self._composed:
+            return self.backbone(self._float_inputs(inputs))
         return self.engine().backbone_forward(inputs)
 
     def train(self, mode=True):
@@ -197,6 +213,8 @@ class EncoderDecoder(nn.Module):
 
     def encode_decode(self, inputs, batch_img_metas=None):
         """encoder_decoder.py:124-132: full-resolution logits [N,K,H,W] (fused, one call)."""
+        if self._composed:
+            return self.decode_head.predict(self.extract_feat(inputs))
         return self.engine().forward_infer(inputs, want_logits=True)[1]
 
     def whole_inference(self, inputs, batch_img_metas=None):
@@ -277,7 +295,8 @@ class EncoderDecoder(nn.Module):
             m = s.get('metainfo', s) if isinstance(s, dict) else {}
             return not (m.get('flip') or m.get('ori_shape') is not None and tuple(m['ori_shape']) != tuple(inputs.shape[-2:])
                         or any(m.get('img_padding_size', m.get('padding_size', [0] * 4))))
-        if self.test_cfg.get('mode', 'whole') == 'whole' and (data_samples is None or all(_plain(s) for s in data_samples)):
+        if (not self._composed and self.test_cfg.get('mode', 'whole') == 'whole'
+                and (data_samples is None or all(_plain(s) for s in data_samples))):
             pred, logits = self.engine().forward_infer(inputs, pred_dtype=torch.int64, want_logits=True)
             res = [{'seg_logits': {'data': logits[i]}, 'pred_sem_seg': {'data': pred[i:i + 1]}}
                    for i in range(pred.shape[0])]
@@ -292,6 +311,13 @@ class EncoderDecoder(nn.Module):
     @torch.no_grad()
     def predict_labels(self, inputs, pred=None, pred_dtype=torch.uint8):
         """Fused fast path: [N,3,H,W] float (normalised) or uint8 (raw BGR) -> labels [N,H,W]."""
+        if self._composed:
+            xc, h1, h2 = self.decode_head.forward(self.extract_feat(inputs))
+            out = ops.head_fuse_argmax(xc, h2, h1, pred_dtype=pred_dtype)[0]
+            if pred is not None:
+                pred.copy_(out)
+                return pred
+            return out
         return self.engine().forward_infer(inputs, pred=pred, pred_dtype=pred_dtype)
 
     def forward(self, inputs, data_samples=None, mode='tensor'):

@@ -295,3 +295,96 @@ def load_stack_batch():
                 sys.modules[k] = v
     _cache['stack_batch'] = m.stack_batch
     return m.stack_batch
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The LED wiring: class DDRNet1 of the authors' speed prototype (tools/speed/ddrnet_speed.py:39-406), the closest public
+# statement of figure 3 (the registered backbones/lednet.py is withheld).  The file cannot be imported (model_utils_speed,
+# thop, mmcv, `.cuda()` in __init__), so the CLASS DEFINITION is taken from the file's AST and executed where it lies
+# (nothing is copied) in a namespace that supplies its names:
+#   ConvModule / build_norm_layer ... oracle/mmcv_shim (third-party, restated)
+#   DAPPM, BasicBlock, Bottleneck, resize, GETB `Block`, Muti_AFF ... the reference's own files via load()
+#   STDCModule ... mmseg/models/backbones/stdc.py executed where it lies
+# Muti_AFF: the prototype imports the BN-less copy in tools/speed/model_utils_speed.py; the registered package's
+# classification/model_utils.py version (with BatchNorm) is used here, as the package's own LED-Net would.
+def load_ddrnet1():
+    import ast
+    import math
+
+    import torch
+    import torch.nn.functional as F
+
+    from . import mmcv_shim
+
+    if 'ddrnet1' in _cache:
+        return _cache['ddrnet1']
+    ref = load()
+    path = os.path.join(REF_ROOT, 'tools/speed/ddrnet_speed.py')
+    tree = ast.parse(open(path).read(), filename=path)
+    norm_fn = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == 'normalize_tensor')
+    cls = next(n for n in tree.body if isinstance(n, ast.ClassDef) and n.name == 'DDRNet1')
+    cls.decorator_list = []                                   # @MODELS.register_module(): no registry here
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+            self.init_cfg = init_cfg
+
+    # stdc.py where it lies, behind stubs for its imports
+    saved = {k: sys.modules.get(k) for k in list(sys.modules)
+             if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg')}
+    try:
+        _pkg('mmcv')
+        _mod('mmcv.cnn', ConvModule=mmcv_shim.ConvModule, build_norm_layer=mmcv_shim.build_norm_layer)
+        _pkg('mmengine')
+        _mod('mmengine.model', BaseModule=BaseModule, ModuleList=nn.ModuleList, Sequential=nn.Sequential)
+        _pkg('mmseg')
+        _mod('mmseg.registry', MODELS=_Registry())
+        _pkg('mmseg.models')
+        _mod('mmseg.models.utils', resize=ref.resize)
+        _pkg('mmseg.models.backbones')
+        _mod('mmseg.models.backbones.bisenetv1', AttentionRefinementModule=nn.Identity)
+        stdc = _load(_PREFIX + '_stdc', 'mmseg/models/backbones/stdc.py')
+    finally:
+        for k in [k for k in sys.modules if k.split('.')[0] in ('mmcv', 'mmengine', 'mmseg')]:
+            del sys.modules[k]
+        for k, v in saved.items():
+            if v is not None:
+                sys.modules[k] = v
+        sys.modules.pop(_PREFIX + '_stdc', None)
+
+    mod = ast.Module(body=[norm_fn, cls], type_ignores=[])
+    ast.fix_missing_locations(mod)
+    g = {'torch': torch, 'nn': nn, 'F': F, 'math': math, 'np': __import__('numpy'),
+         'ConvModule': mmcv_shim.ConvModule, 'build_norm_layer': mmcv_shim.build_norm_layer,
+         'BaseModule': BaseModule, 'Sequential': nn.Sequential, 'OptConfigType': object,
+         'DAPPM': ref.DAPPM, 'BasicBlock': ref.BasicBlock, 'Bottleneck': ref.Bottleneck, 'resize': ref.resize,
+         'STDCModule': stdc.STDCModule, 'Block': ref.GETBBlock, 'GlobalLocalAttention': None,
+         'Muti_AFF': ref.Muti_AFF}
+    exec(compile(mod, path, 'exec'), g)
+    proto = g['DDRNet1']
+
+    class RefLEDTrunk(proto):
+        """DDRNet1 built on the CPU (its __init__ moves the Laplacian to the GPU: `.cuda()` is a no-op while it runs) plus
+        the two stem taps LEDHead consumes (stem[0], stem[1] outputs: the R0 contract)."""
+
+        def __init__(self, **kw):
+            cuda = torch.Tensor.cuda
+            torch.Tensor.cuda = lambda t, *a, **k: t
+            try:
+                super().__init__(**kw)
+            finally:
+                torch.Tensor.cuda = cuda
+
+        def forward_with_taps(self, x):
+            taps = {}
+            h0 = self.stem[0].register_forward_hook(lambda m, i, o: taps.__setitem__('x1', o.clone()))
+            h1 = self.stem[1].register_forward_hook(lambda m, i, o: taps.__setitem__('x2', o.clone()))
+            try:
+                c5 = self.forward(x)
+            finally:
+                h0.remove(); h1.remove()
+            return c5, taps['x1'], taps['x2']
+
+    _cache['ddrnet1'] = RefLEDTrunk
+    return RefLEDTrunk

@@ -80,3 +80,20 @@ def stack_inputs(case_index, shapes, num_classes=19):
         lab[torch.rand(1, h, w, generator=g) < 0.05] = 255
         labs.append(lab)
     return imgs, labs
+
+
+# ---- LED wiring (LEDNet(variant='led') vs the prototype's DDRNet1): (tag, input [n, h, w]); the GETB blocks reflect-pad
+#      their input to a multiple of 8 and PyTorch wants that padding smaller than the map, so 1/64 of the input is >= 8
+LED_CASES = [('sq512', (1, 512, 512)), ('r512x768', (2, 512, 768))]
+LED_GOLDEN_CHANNELS = list(range(0, 128, 16))          # eight of the 128 output channels keep the fixture small
+
+
+def led_state_dict(template, seed=7):
+    sd = synth.make_state_dict(template, seed=seed)
+    sd['fusion_kernel'] = template['fusion_kernel'].detach().clone()       # fixed (0.6, 0.3, 0.1) mixing weights, not a weight
+    return sd
+
+
+def led_input(case_index, shape):
+    g = torch.Generator().manual_seed(300 + case_index)
+    return torch.randn(shape[0], 3, shape[1], shape[2], generator=g)

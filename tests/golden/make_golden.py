@@ -27,6 +27,8 @@ Fixtures
 * stack.npz       : stack_batch (mmseg/utils/misc.py:30-128) behind SegDataPreProcessor's normalisation statements
                     (data_preprocessor.py:118-123) on tests/block_cases.STACK_CASES: padded batch, padded labels,
                     padding_size metainfo.
+* led_trunk.npz   : the LED wiring = class DDRNet1 of the speed prototype, executed from its own file (AST) with the
+                    reference's own blocks, eval mode, + stem taps: eight output channels, per-channel means of c5/x1/x2.
 * seam.npz        : the SEAM edge gate of the authors' speed prototype (tools/speed/ddrnet_speed.py:282-338,388-389),
                     its own statements executed through oracle.ref_loader.load_seam (AST slice): the 0/1 edge mask
                     (bit-packed), the normalised edge response and the gated output on tests/block_cases.SEAM_CASES.
@@ -191,9 +193,32 @@ def make_stack():
     np.savez_compressed(os.path.join(OUT, 'stack.npz'), **out)
 
 
+def make_led():
+    """led_trunk.npz: the prototype's DDRNet1 (tools/speed/ddrnet_speed.py:39-406, executed through
+    oracle.ref_loader.load_ddrnet1) in eval mode + the two stem taps, on tests/block_cases.LED_CASES."""
+    sys.path.insert(0, os.path.join(ROOT, 'tests'))
+    import block_cases as bc
+    m = ref_loader.load_ddrnet1()().eval()
+    m.load_state_dict(bc.led_state_dict(m.state_dict()))
+    out = {}
+    for ci, (tag, shape) in enumerate(bc.LED_CASES):
+        x = bc.led_input(ci, shape)
+        with torch.no_grad():
+            c5, x1, x2 = m.forward_with_taps(x)
+        out[tag + '_c5'] = c5[:, bc.LED_GOLDEN_CHANNELS].numpy()
+        out[tag + '_c5_absmax'] = np.array(float(c5.abs().max()))
+        out[tag + '_c5_chan_mean'] = c5.mean(dim=(0, 2, 3)).numpy()          # every channel takes part in the check
+        out[tag + '_x1_chan_mean'] = x1.mean(dim=(0, 2, 3)).numpy()
+        out[tag + '_x2_chan_mean'] = x2.mean(dim=(0, 2, 3)).numpy()
+    np.savez_compressed(os.path.join(OUT, 'led_trunk.npz'), **out)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
+    if 'led' in sys.argv[1:]:             # regenerate only the LED-wiring fixture
+        make_led()
+        return
     if 'stack' in sys.argv[1:]:           # regenerate only the stack_batch fixture
         make_stack()
         return
@@ -211,6 +236,7 @@ def main():
     make_blocks(ref)
     make_seam()
     make_stack()
+    make_led()
 
     # ---------------- r0_head_k2 -------------------------------------------------
     ddr = ref.DDRNet(in_channels=3, channels=32, ppm_channels=128,
