@@ -126,6 +126,14 @@ int ledb200_backbone_forward(ledb200_handle* h, const void* img, int32_t img_lay
 int ledb200_head_forward(ledb200_handle* h, const float* c5, const float* x1, const float* x2,
                          int32_t N, int32_t h8, int32_t w8, int32_t h2, int32_t w2, int32_t h4,
                          int32_t w4, float* xc, float* hx1, float* hx2, void* stream);
+/* Head + fused tail on caller-owned features: c5 [N,h8,w8,4*channels], x1 [N,h2,w2,channels], x2 [N,h4,w4,channels], NHWC,
+ * dense, in the handle's dtype (F32 or BF16) - for a trunk that is not the R0 plan (LEDNet(variant='led')).  The
+ * pre-activation BN + ReLU of the three base heads (led_head.py:84-99), the head convs, predict_by_feat's ladder
+ * (decode_head.py:362-379) and the argmax (base.py:187-188) run as in ledb200_forward_infer: pred [N,2*h2,2*w2] (U8 or
+ * I64); logits_opt (nullable) fp32 [N,K,2*h2,2*w2]. */
+int ledb200_head_infer(ledb200_handle* h, const void* c5, const void* x1, const void* x2, int32_t N, int32_t h8, int32_t w8,
+                       int32_t h2, int32_t w2, int32_t h4, int32_t w4, void* pred, int32_t pred_dtype, float* logits_opt,
+                       void* stream);
 
 /* Copy a named internal activation of the last forward to HOST as fp32 NCHW (tests /
  * layer-wise parity).  `capacity` in floats; writes the shape to shape4 = {N,C,H,W}.

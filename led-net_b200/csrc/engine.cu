@@ -527,7 +527,7 @@ void add_stem0(Builder& B, int out_x1, int out_x1h) {
   }
 }
 
-enum { PLAN_INFER = 0, PLAN_BACKBONE = 1, PLAN_HEAD = 2 };
+enum { PLAN_INFER = 0, PLAN_BACKBONE = 1, PLAN_HEAD = 2, PLAN_HEAD_NHWC = 3 };
 
 // Trunk: returns buffer ids through the plan's by_name map: "x1","x2","c5" (raw, optional), "c5h","x1h","x2h".
 void build_trunk(Builder& B, bool raw_c5, bool head_inputs) {
@@ -826,6 +826,31 @@ void build_head_standalone(Builder& B, int h8, int w8, int h2, int w2, int h4, i
   add_export(B, "hx2", &ledb200_handle::ext_hx2);
 }
 
+// Head + fused tail on caller-owned NHWC features in the engine's dtype (a trunk that is not the R0 plan, e.g.
+// LEDNet(variant='led')): the three pre-activation BN + ReLU become one affine pass each, then the same fused head as
+// the whole-inference plan (tensor-core ladder, labels without full-resolution logits).
+void build_head_nhwc(Builder& B, int h8, int w8, int h2, int w2, int h4, int w4) {
+  ledb200_handle& e = B.e;
+  Plan& p = B.p;
+  const int n = p.n, C = e.cfg.channels;
+  const int dtype = B.dt;
+  auto pre = [&](const std::string& name, const std::string& bn, const float* ledb200_handle::*src, int c, int H, int W) {
+    const int out = B.buf(name, n, H, W, c);
+    const int ai = aff(e, bn);
+    p.ops.push_back({name + " (pre-activation)", [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
+      AffineArgs a;
+      a.in = e.*src; a.out_a = Builder::ptr(e, p, out); a.sa = e.affs[ai].scale; a.ba = e.affs[ai].shift;
+      a.dtype = dtype; a.npix = (int64_t)n * H * W; a.C = c;
+      return launch_affine_relu(a, st);
+    }, K_AFFINE, 0.0, 2.0 * esize(e) * (double)n * H * W * c});
+    B.tag();
+  };
+  pre("c5h", "decode_head.head.0.bn", &ledb200_handle::in_c5, 4 * C, h8, w8);
+  pre("x1h", "decode_head.head_x1.0.bn", &ledb200_handle::in_x1, C, h2, w2);
+  pre("x2h", "decode_head.head_x2.0.bn", &ledb200_handle::in_x2, C, h4, w4);
+  build_head_fused(B);
+}
+
 void drop_graphs(ledb200_handle& e);
 
 int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Plan** out) {
@@ -843,6 +868,8 @@ int get_plan(ledb200_handle& e, int kind, int n, int h, int w, int extra[6], Pla
         add_export(B, "c5", &ledb200_handle::ext_c5);
         add_export(B, "x1", &ledb200_handle::ext_x1);
         add_export(B, "x2", &ledb200_handle::ext_x2);
+      } else if (kind == PLAN_HEAD_NHWC) {
+        build_head_nhwc(B, extra[0], extra[1], extra[2], extra[3], extra[4], extra[5]);
       } else {
         build_head_standalone(B, extra[0], extra[1], extra[2], extra[3], extra[4], extra[5]);
       }
@@ -1069,6 +1096,23 @@ int ledb200_head_forward(ledb200_handle* h, const float* c5, const float* x1, co
   Plan* p = nullptr;
   if ((rc = get_plan(*h, PLAN_HEAD, N, 0, 0, extra, &p))) return rc;
   h->in_c5 = c5; h->in_x1 = x1; h->in_x2 = x2; h->ext_xc = xc; h->ext_hx1 = hx1; h->ext_hx2 = hx2;
+  return run_plan(*h, *p, (cudaStream_t)stream);
+}
+
+int ledb200_head_infer(ledb200_handle* h, const void* c5, const void* x1, const void* x2, int32_t N, int32_t h8, int32_t w8,
+                       int32_t h2, int32_t w2, int32_t h4, int32_t w4, void* pred, int32_t pred_dtype, float* logits_opt,
+                       void* stream) {
+  int rc = check_ready(h);
+  if (rc) return rc;
+  if (!c5 || !x1 || !x2 || !pred) return fail(LEDB200_EINVAL, "null buffer");
+  if (pred_dtype != LEDB200_U8 && pred_dtype != LEDB200_I64) return fail(LEDB200_EINVAL, "pred dtype must be U8 or I64");
+  int extra[6] = {h8, w8, h2, w2, h4, w4};
+  for (int v : extra) if (v < 1) return fail(LEDB200_EINVAL, "empty feature map");
+  if (N < 1) return fail(LEDB200_EINVAL, "need N >= 1");
+  Plan* p = nullptr;
+  if ((rc = get_plan(*h, PLAN_HEAD_NHWC, N, 0, 0, extra, &p))) return rc;
+  h->in_c5 = (const float*)c5; h->in_x1 = (const float*)x1; h->in_x2 = (const float*)x2;
+  h->ext_pred = pred; h->ext_pred_dtype = pred_dtype; h->ext_logits = logits_opt;
   return run_plan(*h, *p, (cudaStream_t)stream);
 }
 

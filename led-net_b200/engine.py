@@ -130,6 +130,29 @@ class Engine:
             L.stream_ptr(c5.device)), 'ledb200_head_forward')
         return xc, h1, h2
 
+    def head_infer(self, c5, x1, x2, pred=None, pred_dtype=torch.uint8, want_logits=False):
+        """Head + fused tail on NHWC features in the engine's dtype (NCHW-shaped channels_last views are taken as they
+        are): -> labels [N,2*h2,2*w2] (and fp32 logits [N,K,..] when asked)."""
+        want = torch.bfloat16 if self.dtype == L.BF16 else torch.float32
+        feats = []
+        for t in (c5, x1, x2):
+            v = t.permute(0, 2, 3, 1)                      # NCHW-shaped view over NHWC memory -> NHWC
+            if v.dtype != want:
+                v = v.to(want)
+            feats.append(v if v.is_contiguous() else v.contiguous())
+        c5n, x1n, x2n = feats
+        N = c5n.shape[0]
+        Ho, Wo = 2 * x1n.shape[1], 2 * x1n.shape[2]
+        if pred is None:
+            pred = torch.empty((N, Ho, Wo), dtype=pred_dtype, device=c5n.device)
+        logits = torch.empty((N, self.num_classes, Ho, Wo), dtype=torch.float32, device=c5n.device) if want_logits else None
+        L.check(self.lib.ledb200_head_infer(
+            self.h, C.c_void_p(c5n.data_ptr()), C.c_void_p(x1n.data_ptr()), C.c_void_p(x2n.data_ptr()), N,
+            c5n.shape[1], c5n.shape[2], x1n.shape[1], x1n.shape[2], x2n.shape[1], x2n.shape[2],
+            C.c_void_p(pred.data_ptr()), L.torch_dtype_code(pred),
+            C.c_void_p(logits.data_ptr()) if logits is not None else None, L.stream_ptr(c5n.device)), 'ledb200_head_infer')
+        return (pred, logits) if want_logits else pred
+
     # ------------------------------------------------------------------ introspection
     def debug_fetch(self, name):
         shp = (C.c_int32 * 4)()

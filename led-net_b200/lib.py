@@ -16,7 +16,7 @@ IMG_NCHW_F32, IMG_NCHW_U8, IMG_NHWC_U8 = 0, 1, 2
 SYMBOLS = [
     'ledb200_version', 'ledb200_last_error', 'ledb200_create', 'ledb200_destroy',
     'ledb200_set_param', 'ledb200_num_params', 'ledb200_param_name', 'ledb200_finalize',
-    'ledb200_forward_infer', 'ledb200_backbone_forward', 'ledb200_head_forward',
+    'ledb200_forward_infer', 'ledb200_backbone_forward', 'ledb200_head_forward', 'ledb200_head_infer',
     'ledb200_debug_fetch', 'ledb200_profile_ops', 'ledb200_op_info', 'ledb200_op_name', 'ledb200_plan_launches',
     'ledb200_head_fuse_argmax', 'ledb200_confusion_accumulate', 'ledb200_ohem_workspace_bytes',
     'ledb200_ohem_ce', 'ledb200_conv2d',
@@ -75,6 +75,7 @@ def get():
     lib.ledb200_forward_infer.argtypes = [vp, vp, i32, i32, i32, i32, vp, i32, vp, vp]
     lib.ledb200_backbone_forward.argtypes = [vp, vp, i32, i32, i32, i32, vp, vp, vp, vp]
     lib.ledb200_head_forward.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp, vp, vp]
+    lib.ledb200_head_infer.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, i32, vp, vp]
     lib.ledb200_debug_fetch.argtypes = [vp, C.c_char_p, vp, i64, C.POINTER(i32), vp]
     lib.ledb200_profile_ops.argtypes = [vp, i32, vp, i32, vp]
     lib.ledb200_op_name.argtypes = [vp, i32]

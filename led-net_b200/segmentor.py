@@ -214,7 +214,7 @@ class EncoderDecoder(nn.Module):
     def encode_decode(self, inputs, batch_img_metas=None):
         """encoder_decoder.py:124-132: full-resolution logits [N,K,H,W] (fused, one call)."""
         if self._composed:
-            return self.decode_head.predict(self.extract_feat(inputs))
+            return self.decode_head.engine().head_infer(*self.extract_feat(inputs), want_logits=True)[1]
         return self.engine().forward_infer(inputs, want_logits=True)[1]
 
     def whole_inference(self, inputs, batch_img_metas=None):
@@ -311,13 +311,8 @@ class EncoderDecoder(nn.Module):
     @torch.no_grad()
     def predict_labels(self, inputs, pred=None, pred_dtype=torch.uint8):
         """Fused fast path: [N,3,H,W] float (normalised) or uint8 (raw BGR) -> labels [N,H,W]."""
-        if self._composed:
-            xc, h1, h2 = self.decode_head.forward(self.extract_feat(inputs))
-            out = ops.head_fuse_argmax(xc, h2, h1, pred_dtype=pred_dtype)[0]
-            if pred is not None:
-                pred.copy_(out)
-                return pred
-            return out
+        if self._composed:       # composed trunk -> head engine on its NHWC features (fused ladder + argmax)
+            return self.decode_head.engine().head_infer(*self.extract_feat(inputs), pred=pred, pred_dtype=pred_dtype)
         return self.engine().forward_infer(inputs, pred=pred, pred_dtype=pred_dtype)
 
     def forward(self, inputs, data_samples=None, mode='tensor'):
