@@ -384,6 +384,24 @@ int ledb200_conv_layer_forward(ledb200_conv_layer* layer, const void* in, void* 
                                int32_t N, int32_t H, int32_t W, int32_t in_ld, int32_t out_ld, int32_t res_ld, int32_t relu,
                                int32_t backend, void* stream);
 int ledb200_conv_layer_destroy(ledb200_conv_layer* layer);
+/* The same layer fed by the caller's image (NCHW fp32, 3 channels): the stem convolution of a composed trunk.  bf16 output
+ * with stride 2 and Cout 16 / 32 runs the tensor-core stem kernel (csrc/stem_tc.cu), anything else the CUDA-core one. */
+int ledb200_conv_layer_forward_image(ledb200_conv_layer* layer, const void* img, int32_t img_layout, void* out, int32_t dtype,
+                                     int32_t N, int32_t H, int32_t W, int32_t out_ld, int32_t relu, void* stream);
+/* The whole DAPPM (mmseg/models/utils/ppm.py:57-130) as a handle: two launches per forward (csrc/dappm.cu: pooled branches,
+ * then ONE clustered tcgen05 kernel for scales[0], the four 3x3 processes, the concat-free compression and the shortcut).
+ * Every ConvModule of the module is pre-activation (norm, act, conv): `weight` OIHW HOST fp32, `bias` nullable, bn_scale /
+ * bn_shift = the folded BatchNorm on the INPUT channels (y = relu(a x + b)).  scales5[0] is scales[0], scales5[i] the conv of
+ * the pooled branch i.  x [N,H,W,C], out [N,H,W,Cout], NHWC dense BF16; ledb200_dappm_eligible() says whether a shape fits
+ * (C % 64 == 0, ppm = out channels = 128, at most 8 tiles of 16 x 8 pixels per image). */
+typedef struct { const float* weight; const float* bias; const float* bn_scale; const float* bn_shift; } ledb200_preact_conv;
+typedef struct ledb200_dappm ledb200_dappm;
+int ledb200_dappm_create(int32_t C, int32_t P, int32_t Cout, const ledb200_preact_conv* scales5,
+                         const ledb200_preact_conv* processes4, const ledb200_preact_conv* compression,
+                         const ledb200_preact_conv* shortcut, ledb200_dappm** out);
+int ledb200_dappm_eligible(int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t P, int32_t Cout);
+int ledb200_dappm_forward(ledb200_dappm* d, const void* x, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W, void* stream);
+int ledb200_dappm_destroy(ledb200_dappm* d);
 /* nn.AvgPool2d(k, s, p) with count_include_pad=True (stdc.py:80, ppm.py:68-90), or the global average when k == 0;
  * F.interpolate(mode='bilinear', align_corners=False) (mmseg/models/utils/wrappers.py:8-27); out = [relu](a [+ b]).
  * NHWC F32 | BF16, C a multiple of 8, pixel strides in elements (0 = dense). */

@@ -264,6 +264,26 @@ int ledb200_conv_layer_forward(ledb200_conv_layer* L, const void* in, void* out,
   return launch_conv_direct(a, st);
 }
 
+int ledb200_conv_layer_forward_image(ledb200_conv_layer* L, const void* img, int32_t img_layout, void* out, int32_t dtype, int32_t N,
+                                     int32_t H, int32_t W, int32_t out_ld, int32_t relu, void* stream) {
+  if (!L || !img || !out) return fail(LEDB200_EINVAL, "conv_layer_forward_image: null pointer");
+  if (L->depthwise || L->cin != 3 || L->k != 3) return fail(LEDB200_EINVAL, "conv_layer_forward_image: a dense 3x3 layer on 3 input channels");
+  if (!dt_ok(dtype)) return fail(LEDB200_EINVAL, "conv_layer_forward_image: output dtype must be F32 or BF16");
+  if (img_layout != LEDB200_IMG_NCHW_F32) return fail(LEDB200_EINVAL, "conv_layer_forward_image: image layout must be NCHW fp32");
+  if (out_ld == 0) out_ld = L->cout;
+  const int Ho = (H + 2 - 3) / L->stride + 1, Wo = (W + 2 - 3) / L->stride + 1;
+  ConvArgs a;
+  const int64_t HW = (int64_t)H * W;
+  a.in = img; a.in_dtype = LEDB200_F32; a.in_sn = 3 * HW; a.in_sc = HW; a.in_sh = W; a.in_sw = 1;
+  a.out = out; a.out_dtype = dtype; a.out_ld = out_ld;
+  a.bias = L->bias; a.w_direct = L->w_direct; a.w_tc = L->w_tc; a.cout_pad16 = L->cout_pad16; a.cout_pad_tc = L->cout_pad_tc;
+  a.N = N; a.H = H; a.W = W; a.Cin = 3; a.Ho = Ho; a.Wo = Wo; a.Cout = L->cout; a.ksize = 3; a.stride = L->stride; a.pad = 1;
+  a.dil = 1; a.relu = relu;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (stem_tc_eligible(a)) return launch_stem_tc(a, st);       // bf16 output, stride 2, Cout 16 / 32: tensor cores
+  return launch_conv_direct(a, st);
+}
+
 int ledb200_avgpool2d(const void* in, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t k, int32_t s,
                       int32_t p, int32_t in_ld, int32_t out_ld, void* stream) {
   if (!in || !out) return fail(LEDB200_EINVAL, "avgpool2d: null buffer");
@@ -322,6 +342,111 @@ int ledb200_add_relu(const void* a, const void* b, void* out, int32_t dtype, int
     add_relu_kernel<float><<<grid_for(total), kT, 0, st>>>((const float*)a, (const float*)b, (float*)out, npix, C, a_ld, b_ld, out_ld, relu);
   LEDB_LAUNCH_OK("add_relu_kernel");
   return LEDB200_OK;
+}
+
+// ---- the whole DAPPM as a handle: parameters folded and resident, scratch grown on demand; forward = the two launches
+//      of dappm.cu (bf16, <= 8 tiles of 16 x 8 pixels per image)
+struct ledb200_dappm {
+  int C = 0, P = 0, Cout = 0;
+  std::vector<void*> allocs;
+  const float *a_scale[5] = {}, *b_scale[5] = {}, *a_proc[4] = {}, *b_proc[4] = {}, *a_comp = nullptr, *b_comp = nullptr,
+              *a_sc = nullptr, *b_sc = nullptr;
+  const __nv_bfloat16 *w_scale[5] = {}, *w_proc[4] = {}, *w_comp = nullptr, *w_sc = nullptr;
+  const float *bias_scale[5] = {}, *bias_proc[4] = {}, *bias_comp = nullptr, *bias_sc = nullptr;
+  void* scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+namespace {
+int dappm_upload_conv(ledb200_dappm* D, const ledb200_preact_conv& pc, int cin, int cout, int k, const float** a, const float** b,
+                      const __nv_bfloat16** w, const float** bias) {
+  if (!pc.weight || !pc.bn_scale || !pc.bn_shift) return fail(LEDB200_EINVAL, "dappm_create: null parameter");
+  const int taps = k * k;
+  std::vector<float> av(pc.bn_scale, pc.bn_scale + cin), bv(pc.bn_shift, pc.bn_shift + cin);
+  std::vector<__nv_bfloat16> wt((size_t)cout * taps * cin);
+  for (int o = 0; o < cout; ++o)
+    for (int c = 0; c < cin; ++c)
+      for (int t = 0; t < taps; ++t) wt[((size_t)o * taps + t) * cin + c] = __float2bfloat16(pc.weight[((size_t)o * cin + c) * taps + t]);
+  float *da = nullptr, *db = nullptr, *dbias = nullptr;
+  __nv_bfloat16* dw = nullptr;
+  int rc = upload_vec(av, &da);
+  if (!rc) { D->allocs.push_back(da); rc = upload_vec(bv, &db); }
+  if (!rc) { D->allocs.push_back(db); rc = upload_vec(wt, &dw); }
+  if (!rc) D->allocs.push_back(dw);
+  if (!rc && pc.bias) {
+    std::vector<float> bz(pc.bias, pc.bias + cout);
+    rc = upload_vec(bz, &dbias);
+    if (!rc) D->allocs.push_back(dbias);
+  }
+  *a = da; *b = db; *w = dw; *bias = dbias;
+  return rc;
+}
+}  // namespace
+
+int ledb200_dappm_destroy(ledb200_dappm* D) {
+  if (!D) return LEDB200_OK;
+  for (void* p : D->allocs) cudaFree(p);
+  cudaFree(D->scratch);
+  delete D;
+  return LEDB200_OK;
+}
+
+int ledb200_dappm_create(int32_t C, int32_t P, int32_t Cout, const ledb200_preact_conv* scales5, const ledb200_preact_conv* processes4,
+                         const ledb200_preact_conv* compression, const ledb200_preact_conv* shortcut, ledb200_dappm** out) {
+  if (!scales5 || !processes4 || !compression || !shortcut || !out) return fail(LEDB200_EINVAL, "dappm_create: null pointer");
+  DappmArgs probe;
+  probe.N = 1; probe.H = 8; probe.W = 8; probe.C = C; probe.P = P; probe.Cout = Cout; probe.out_ld = Cout;
+  if (!dappm_eligible(probe)) return fail(LEDB200_EINVAL, "dappm_create: the fused DAPPM needs C % 64 == 0, ppm channels = out channels = 128");
+  ledb200_dappm* D = new ledb200_dappm();
+  D->C = C; D->P = P; D->Cout = Cout;
+  int rc = LEDB200_OK;
+  for (int i = 0; i < 5 && !rc; ++i) rc = dappm_upload_conv(D, scales5[i], C, P, 1, &D->a_scale[i], &D->b_scale[i], &D->w_scale[i], &D->bias_scale[i]);
+  for (int i = 0; i < 4 && !rc; ++i) rc = dappm_upload_conv(D, processes4[i], P, P, 3, &D->a_proc[i], &D->b_proc[i], &D->w_proc[i], &D->bias_proc[i]);
+  if (!rc) rc = dappm_upload_conv(D, *compression, 5 * P, Cout, 1, &D->a_comp, &D->b_comp, &D->w_comp, &D->bias_comp);
+  if (!rc) rc = dappm_upload_conv(D, *shortcut, C, Cout, 1, &D->a_sc, &D->b_sc, &D->w_sc, &D->bias_sc);
+  if (rc) { ledb200_dappm_destroy(D); return rc; }
+  *out = D;
+  return LEDB200_OK;
+}
+
+int ledb200_dappm_eligible(int32_t dtype, int32_t N, int32_t H, int32_t W, int32_t C, int32_t P, int32_t Cout) {
+  DappmArgs a;
+  a.N = N; a.H = H; a.W = W; a.C = C; a.P = P; a.Cout = Cout; a.out_ld = Cout;
+  return (dtype == LEDB200_BF16 && dappm_eligible(a)) ? 1 : 0;
+}
+
+int ledb200_dappm_forward(ledb200_dappm* D, const void* x, void* out, int32_t dtype, int32_t N, int32_t H, int32_t W, void* stream) {
+  if (!D || !x || !out) return fail(LEDB200_EINVAL, "dappm_forward: null pointer");
+  if (dtype != LEDB200_BF16) return fail(LEDB200_EINVAL, "dappm_forward: the fused DAPPM runs bf16 tensors");
+  DappmArgs a;
+  a.x = x; a.N = N; a.H = H; a.W = W; a.C = D->C; a.P = D->P; a.Cout = D->Cout; a.out = out; a.out_ld = D->Cout;
+  if (!dappm_eligible(a)) return fail(LEDB200_EINVAL, "dappm_forward: shape not eligible (more than 8 tiles of 16 x 8 pixels per image)");
+  static const int ks[3] = {5, 9, 17}, ss[3] = {2, 4, 8}, ps[3] = {2, 4, 8};
+  size_t need = 0, off[6];
+  for (int i = 0; i < 4; ++i) {
+    a.pool_k[i] = i < 3 ? ks[i] : 0; a.pool_s[i] = i < 3 ? ss[i] : 1; a.pool_p[i] = i < 3 ? ps[i] : 0;
+    a.sh[i] = i < 3 ? (H + 2 * ps[i] - ks[i]) / ss[i] + 1 : 1;
+    a.sw[i] = i < 3 ? (W + 2 * ps[i] - ks[i]) / ss[i] + 1 : 1;
+    if (a.sh[i] < 1 || a.sw[i] < 1) return fail(LEDB200_EINVAL, "dappm_forward: feature map smaller than a pooling window allows");
+    off[i] = need; need += ((size_t)N * a.sh[i] * a.sw[i] * D->P * 2 + 255) / 256 * 256;
+  }
+  for (int i = 4; i < 6; ++i) { off[i] = need; need += ((size_t)N * H * W * D->P * 2 + 255) / 256 * 256; }
+  if (need > D->scratch_bytes) {
+    LEDB_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    cudaFree(D->scratch); D->scratch = nullptr; D->scratch_bytes = 0;
+    LEDB_CUDA_OK(cudaMalloc(&D->scratch, need));
+    D->scratch_bytes = need;
+  }
+  char* base = (char*)D->scratch;
+  for (int i = 0; i < 4; ++i) {
+    a.s[i] = base + off[i];
+    a.a_scale[i] = D->a_scale[i + 1]; a.b_scale[i] = D->b_scale[i + 1]; a.w_scale[i] = D->w_scale[i + 1]; a.bias_scale[i] = D->bias_scale[i + 1];
+    a.a_proc[i] = D->a_proc[i]; a.b_proc[i] = D->b_proc[i]; a.w_proc[i] = D->w_proc[i]; a.bias_proc[i] = D->bias_proc[i];
+  }
+  a.t0 = base + off[4]; a.t1 = base + off[5];
+  a.a_s0 = D->a_scale[0]; a.b_s0 = D->b_scale[0]; a.w_s0 = D->w_scale[0]; a.bias_s0 = D->bias_scale[0];
+  a.a_sc = D->a_sc; a.b_sc = D->b_sc; a.w_sc = D->w_sc; a.bias_sc = D->bias_sc;
+  a.a_comp = D->a_comp; a.b_comp = D->b_comp; a.w_comp = D->w_comp; a.bias_comp = D->bias_comp;
+  return launch_dappm(a, (cudaStream_t)stream);
 }
 
 }  // extern "C"

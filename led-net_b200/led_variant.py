@@ -77,6 +77,11 @@ def _vp(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
 
+class _PreactConv(C.Structure):
+    """ledb200_preact_conv (include/ledb200.h): host pointers of one pre-activation ConvModule"""
+    _fields_ = [('weight', C.c_void_p), ('bias', C.c_void_p), ('bn_scale', C.c_void_p), ('bn_shift', C.c_void_p)]
+
+
 def _geom(t):
     """(pixel stride in elements) of an NHWC tensor or channel-slice view; the layout must be pixel-major."""
     n, h, w, c = t.shape
@@ -123,6 +128,7 @@ class LEDTrunk(nn.Module):
             [nn.Sequential(STDCModule(spa[i], spa[i + 1], 1, num_convs=num_convs)) for i in range(3)])
         self.spp = DAPPM(16 * Cc, ppm_channels, 4 * Cc)
         self._layers = {}
+        self._dappm_handle = None
         self.register_load_state_dict_post_hook(lambda m, keys: m.reset_engine())
 
     # ------------------------------------------------------------------ engine-like surface
@@ -131,6 +137,9 @@ class LEDTrunk(nn.Module):
         for h in self._layers.values():
             lib.ledb200_conv_layer_destroy(h)
         self._layers = {}
+        if self._dappm_handle is not None:
+            lib.ledb200_dappm_destroy(self._dappm_handle)
+            self._dappm_handle = None
         self._seam.reset_engine()
 
     def __del__(self):
@@ -257,11 +266,40 @@ class LEDTrunk(nn.Module):
             cur = self._cm(f'{name}.layers.{i}', m.layers[i], cur, relu=True, out=buf[..., offs[i]:offs[i + 1]])
         return buf
 
+    def _dappm_fused(self, spp, x):
+        """the two-launch DAPPM of csrc/dappm.cu behind a handle (bf16, <= 8 tiles of 16 x 8 pixels per image)"""
+        n, h, w, c = x.shape
+        lib = L.get()
+        if self._dappm_handle is None:
+            keep = []
+
+            def pc(m):
+                a, b = _fold_pre(m.bn)
+                wt = m.conv.weight.detach().float().cpu().contiguous()
+                bias = m.conv.bias.detach().float().cpu().contiguous() if m.conv.bias is not None else None
+                keep.extend([a, b, wt, bias])
+                return _PreactConv(_vp(wt).value, _vp(bias).value if bias is not None else None, _vp(a).value, _vp(b).value)
+            scales = (_PreactConv * 5)(pc(spp.scales[0]), *[pc(spp.scales[i][1]) for i in range(1, 5)])
+            procs = (_PreactConv * 4)(*[pc(m) for m in spp.processes])
+            comp, short = pc(spp.compression), pc(spp.shortcut)
+            hnd = C.c_void_p()
+            L.check(lib.ledb200_dappm_create(c, spp.scales[0].conv.out_channels, spp.shortcut.conv.out_channels,
+                                             C.cast(scales, C.c_void_p), C.cast(procs, C.c_void_p), C.byref(comp),
+                                             C.byref(short), C.byref(hnd)), 'ledb200_dappm_create')
+            self._dappm_handle = hnd
+        out = torch.empty((n, h, w, spp.shortcut.conv.out_channels), dtype=x.dtype, device=x.device)
+        L.check(lib.ledb200_dappm_forward(self._dappm_handle, _vp(x), _vp(out), L.torch_dtype_code(x), n, h, w,
+                                          L.stream_ptr(x.device)), 'ledb200_dappm_forward')
+        return out
+
     def _dappm(self, name, spp, x):
         """DAPPM.forward (ppm.py:119-130); every ConvModule is pre-activation (norm, act, conv)."""
         n, h, w, _ = x.shape
         P = spp.scales[0].conv.out_channels
         nsc = len(spp.scales)
+        if (x.is_contiguous() and nsc == 5 and
+                L.get().ledb200_dappm_eligible(L.torch_dtype_code(x), n, h, w, x.shape[3], P, spp.shortcut.conv.out_channels)):
+            return self._dappm_fused(spp, x)
         cat = torch.empty((n, h, w, nsc * P), dtype=x.dtype, device=x.device)
         prev = self._conv(name + '.scales.0', spp.scales[0].conv, spp.scales[0].bn, x, out=cat[..., :P], pre=True)
         for i, (k, s, p) in enumerate(_DAPPM_POOLS, start=1):
@@ -282,10 +320,13 @@ class LEDTrunk(nn.Module):
             raise L.LedB200Error("LEDNet(variant='led') needs a CUDA tensor (no CPU fallback)")
         dt = torch.bfloat16 if self.compute_dtype == 'bf16' else torch.float32
         out_size = (math.ceil(x.shape[-2] / 8), math.ceil(x.shape[-1] / 8))
-        xin = x.float().permute(0, 2, 3, 1).contiguous()                            # NHWC fp32 image (layout pass, plumbing)
-        x1 = self._cm('stem.0', self.stem[0], xin, relu=True)                        # 3-channel pixels: fp32 CUDA-core conv
-        if dt != torch.float32:
-            x1 = x1.to(dt)                                                          # storage cast to the compute dtype
+        # stem conv 0 straight from the NCHW fp32 image (bf16: the tensor-core stem kernel of the R0 engine)
+        xin = x.float().contiguous()
+        n, _, hi, wi = xin.shape
+        x1 = torch.empty((n, (hi - 1) // 2 + 1, (wi - 1) // 2 + 1, self.channels), dtype=dt, device=x.device)
+        L.check(L.get().ledb200_conv_layer_forward_image(
+            self._handle('stem.0', self.stem[0].conv, self.stem[0].bn), _vp(xin), L.IMG_NCHW_F32, _vp(x1),
+            L.torch_dtype_code(x1), n, hi, wi, self.channels, 1, L.stream_ptr(x.device)), 'stem.0')
         x2 = self._cm('stem.1', self.stem[1], x1, relu=True)
         t = self._basic_layer('stem.2', self.stem[2], x2, True)
         xs8 = self._basic_layer('stem.4', self.stem[4], t, True)                    # 1/8, 64 channels

@@ -33,7 +33,8 @@ SYMBOLS = [
     'ledb200_postprocess', 'ledb200_slide_accumulate', 'ledb200_slide_finalize', 'ledb200_slide_merge', 'ledb200_stack_pad',
     'ledb200_seam_param_floats', 'ledb200_seam_workspace_bytes', 'ledb200_seam_forward',
     'ledb200_conv_layer_create', 'ledb200_conv_layer_forward', 'ledb200_conv_layer_destroy',
-    'ledb200_avgpool2d', 'ledb200_resize_bilinear', 'ledb200_add_relu',
+    'ledb200_avgpool2d', 'ledb200_resize_bilinear', 'ledb200_add_relu', 'ledb200_conv_layer_forward_image',
+    'ledb200_dappm_create', 'ledb200_dappm_eligible', 'ledb200_dappm_forward', 'ledb200_dappm_destroy',
 ]
 
 
@@ -133,6 +134,11 @@ def get():
     lib.ledb200_conv_layer_create.argtypes = [vp, vp, vp, vp] + [i32] * 5 + [C.POINTER(vp)]
     lib.ledb200_conv_layer_forward.argtypes = [vp, vp, vp, vp] + [i32] * 9 + [vp]
     lib.ledb200_conv_layer_destroy.argtypes = [vp]
+    lib.ledb200_conv_layer_forward_image.argtypes = [vp, vp, i32, vp] + [i32] * 6 + [vp]
+    lib.ledb200_dappm_create.argtypes = [i32, i32, i32, vp, vp, vp, vp, C.POINTER(vp)]
+    lib.ledb200_dappm_eligible.argtypes = [i32] * 7
+    lib.ledb200_dappm_forward.argtypes = [vp, vp, vp] + [i32] * 4 + [vp]
+    lib.ledb200_dappm_destroy.argtypes = [vp]
     lib.ledb200_avgpool2d.argtypes = [vp, vp] + [i32] * 10 + [vp]
     lib.ledb200_resize_bilinear.argtypes = [vp, vp] + [i32] * 9 + [vp]
     lib.ledb200_add_relu.argtypes = [vp, vp, vp, i32, i64] + [i32] * 5 + [vp]
