@@ -356,7 +356,9 @@ struct Builder {
     const bool use_tc = conv_uses_tc(cname, in, out, res, out2, up);
     const double es_ = (double)esize(e), npo = (double)bi.n * Ho * Wo;
     const double flops = 2.0 * npo * d.cout * d.cin * d.k * d.k;
-    const double bytes = es_ * ((double)bi.n * bi.h * bi.w * d.cin + npo * d.cout * ((out >= 0) + (out2 >= 0) + (res >= 0))) +
+    // every tensor read once and written once.  A second, pre-activated copy of the output (x2h, DAPPM
+    // inputs ...) is an implementation choice, not an algorithmic byte: the output is counted ONCE.
+    const double bytes = es_ * ((double)bi.n * bi.h * bi.w * d.cin + npo * d.cout * ((out >= 0 || out2 >= 0) + (res >= 0))) +
                          es_ * (double)d.cout * d.cin * d.k * d.k +
                          (up >= 0 ? es_ * (double)p.bufs[up].n * p.bufs[up].h * p.bufs[up].w * d.cout : 0.0);
     p.ops.push_back({cname, [=](ledb200_handle& e, Plan& p, cudaStream_t st) -> int {
@@ -447,7 +449,7 @@ struct Builder {
       const Buf& bs = p.bufs[src];
       const Buf& bo = p.bufs[out >= 0 ? out : out2];
       const double big = (double)bo.n * bo.h * bo.w * bs.c;
-      p.ops.back().bytes = esize(e) * (big * ((base >= 0) + (out >= 0) + (out2 >= 0)) + (double)bs.n * bs.h * bs.w * bs.c);
+      p.ops.back().bytes = esize(e) * (big * ((base >= 0) + (out >= 0 || out2 >= 0)) + (double)bs.n * bs.h * bs.w * bs.c);
       p.ops.back().flops = 8.0 * big;
     }
   }
@@ -476,7 +478,7 @@ struct Builder {
       return launch_affine_relu(a, st);
     }, K_AFFINE, 0.0, 0.0});
     tag();
-    p.ops.back().bytes = esize(e) * (double)p.bufs[in].n * p.bufs[in].h * p.bufs[in].w * p.bufs[in].c * (1 + (oa >= 0) + (ob >= 0));
+    p.ops.back().bytes = esize(e) * (double)p.bufs[in].n * p.bufs[in].h * p.bufs[in].w * p.bufs[in].c * (1 + (oa >= 0 || ob >= 0));
   }
 };
 
@@ -523,7 +525,7 @@ void add_stem0(Builder& B, int out_x1, int out_x1h) {
     const double npo = (double)bo.n * bo.h * bo.w;
     B.p.ops.back().flops = 2.0 * npo * bo.c * 27;
     // image counted at the engine's activation width (SURVEY section 8d counts bf16 activations)
-    B.p.ops.back().bytes = esize(B.e) * ((double)n * H * W * 3 + npo * bo.c * (1 + (out_x1h >= 0)));
+    B.p.ops.back().bytes = esize(B.e) * ((double)n * H * W * 3 + npo * bo.c);     // x1 once; the x1h copy is not credited
   }
 }
 
