@@ -219,6 +219,23 @@ int ledb200_train_conv_fwd(const float* x, const float* w_packed, const float* b
 int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float* dx, int32_t N,
                              int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
                              void* stream);
+/* Tensor-core forms of the forward / data-gradient convolution (north_star kernel 6: dgrad / wgrad implicit GEMM; the
+ * reference gets cuDNN's through encoder_decoder.py:161-185 -> led_head.py:101-146): conv_tc.cu's tcgen05 implicit GEMM with
+ * kind::tf32 operands read straight from the fp32 NHWC tensors (TMA halo slabs), fp32 accumulation in TMEM, raw fp32 output.
+ * ledb200_train_conv_tc_ok(op, ...) says whether they take a shape (op 0 forward, 1 data gradient, 2 weight gradient;
+ * H, W = conv INPUT extents): Cin % 32 == 0 (of the GEMM's reduction side), output extents multiples of the 16 x 8 tile,
+ * data gradient stride 1.  Everything else stays on the CUDA-core entry points above.  Weights: K-major fp32
+ * [pad(Cout)][k*k*Cin] (mode 0) / [pad(Cin)][k*k*Cout] rotated (mode 1), rounded to tf32 on the device. */
+int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                                 int32_t stride);
+int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode);
+int ledb200_train_pack_weight_tc(const float* w_oihw, float* out, int32_t Cout, int32_t Cin, int32_t k,
+                                 int32_t mode, void* stream);
+int ledb200_train_conv_fwd_tc(const float* x, const float* w_tc, const float* bias_opt, float* y, int32_t N,
+                              int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride,
+                              void* stream);
+int ledb200_train_conv_dgrad_tc(const float* dy, const float* w_tc_dgrad, float* dx, int32_t N, int32_t H,
+                                int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* stream);
 /* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias.  Every reduction of the training kernels is order-fixed
  * (per-CTA / per-block partial sums in `workspace`, added in index order: no floating-point atomics), so a training step
  * is bit-reproducible run to run.  workspace: device, >= ledb200_train_wgrad_workspace_bytes(Cin, Cout, k) bytes. */

@@ -471,6 +471,79 @@ __device__ __forceinline__ void epilogue_loop(const TcParams& P, int warp, int l
   }
 }
 
+// Epilogue of the TF32 instantiations (training: forward and data-gradient convolutions on fp32 NHWC tensors, train.cu):
+// the raw convolution (+ bias) goes out as fp32 - BatchNorm's batch statistics need the un-normalised values, so nothing
+// else is fused here.  Same work split as epilogue_loop; the host only launches all-interior tilings, thread = output pixel,
+// 32 channels = 128 contiguous bytes = four 256-bit stores.
+__device__ __forceinline__ void epilogue_f32(const TcParams& P, int warp, int lane, uint32_t tmem_base,
+                                             uint64_t* t_full, uint64_t* t_empty, uint32_t bias_u) {
+  const int ew = warp - 2, grp = ew >> 2, q = warp & 3;
+  const int m = q * 32 + lane, ph = m >> 3, pw = m & 7;
+  const int NT = P.NT, Ho = P.Ho, Wo = P.Wo, Cout = P.Cout;
+  const float relu_lo = P.relu ? 0.f : -INFINITY;
+  const uint32_t taddr_q = tmem_base + ((uint32_t)(q * 32) << 16);
+  const bool split = NT >= 64;
+  const int ncols_g = split ? NT / 2 : NT;
+  const int cbeg = split ? grp * ncols_g : 0, cend = cbeg + ncols_g;
+  float* const outp = reinterpret_cast<float*>(P.out);
+  const bool vec_ok = (P.out_ld % 8 == 0) && ((uintptr_t)outp % 32 == 0);
+  uint32_t tp = 0, ts = split ? 0u : (uint32_t)grp;
+  const uint32_t first = blockIdx.x + (split ? 0u : (uint32_t)grp * gridDim.x);
+  const int* stepd = split ? P.step1 : P.step2;
+  uint32_t t0 = first;
+  int nt = (int)(t0 % (uint32_t)P.ntiles_n); t0 /= (uint32_t)P.ntiles_n;
+  int tw = (int)(t0 % (uint32_t)P.tiles_w); t0 /= (uint32_t)P.tiles_w;
+  int th = (int)(t0 % (uint32_t)P.tiles_h);
+  int n = (int)(t0 / (uint32_t)P.tiles_h);
+  const uint32_t total = (uint32_t)P.total_tiles, step = split ? gridDim.x : 2 * gridDim.x;
+  const int lane_px = ph * Wo + pw;
+  for (uint32_t tile = first; tile < total; tile += step) {
+    const int64_t pix = ((int64_t)n * Ho + th * TH) * Wo + tw * TW + lane_px;
+    const int cgt = nt * NT;
+    float* out_px = outp + pix * P.out_ld + cgt;
+    mbar_wait(&t_full[ts], tp);
+    tc_fence_after();
+    const uint32_t taddr0 = taddr_q + ts * (uint32_t)NT;
+    for (int c0 = cbeg; c0 < cend; c0 += 32) {
+      uint32_t v[32];
+      tc_ld16(taddr0 + c0, v);
+      tc_ld16(taddr0 + c0 + 16, v + 16);
+      tc_wait_ld();
+      const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const float4 b0 = lds128f(bias_b + 32 * g), b1 = lds128f(bias_b + 32 * g + 16);
+        float f[8];
+        f[0] = __uint_as_float(v[8 * g + 0]) + b0.x; f[1] = __uint_as_float(v[8 * g + 1]) + b0.y;
+        f[2] = __uint_as_float(v[8 * g + 2]) + b0.z; f[3] = __uint_as_float(v[8 * g + 3]) + b0.w;
+        f[4] = __uint_as_float(v[8 * g + 4]) + b1.x; f[5] = __uint_as_float(v[8 * g + 5]) + b1.y;
+        f[6] = __uint_as_float(v[8 * g + 6]) + b1.z; f[7] = __uint_as_float(v[8 * g + 7]) + b1.w;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) f[j] = fmaxf(f[j], relu_lo);
+        const int c = cgt + c0 + 8 * g;
+        if (vec_ok && c + 8 <= Cout) {
+          stg256(out_px + c0 + 8 * g,
+                 make_uint4(__float_as_uint(f[0]), __float_as_uint(f[1]), __float_as_uint(f[2]), __float_as_uint(f[3])),
+                 make_uint4(__float_as_uint(f[4]), __float_as_uint(f[5]), __float_as_uint(f[6]), __float_as_uint(f[7])));
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            if (c + j < Cout) out_px[c0 + 8 * g + j] = f[j];
+        }
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(&t_empty[ts]);
+    ts += split ? 1u : 2u;
+    if (ts >= (uint32_t)P.nst) { ts -= (uint32_t)P.nst; tp ^= 1; }
+    nt += stepd[0]; if (nt >= P.ntiles_n) { nt -= P.ntiles_n; ++tw; }
+    tw += stepd[1]; if (tw >= P.tiles_w) { tw -= P.tiles_w; ++th; }
+    th += stepd[2]; if (th >= P.tiles_h) { th -= P.tiles_h; ++n; }
+    n += stepd[3];
+  }
+}
+
 // Tap tables, compile-time so the MMA issue loop unrolls into immediate-offset descriptor adds
 // (a single thread issues every MMA: any dependent address arithmetic there is on the critical path).
 //   MODE 0: 3x3 stride 1, one halo slab, 9 taps      MODE 1: 1x1 (stride 1 or 2), one slab, one tap
@@ -486,7 +559,7 @@ template <int MODE> __device__ __forceinline__ constexpr int mode_tap_id(int s, 
   return MODE == 0 ? t : (MODE == 1 ? 0 : ((s & 1) ? 3 + (s >> 1) : (t ? 6 + (s >> 1) : (s >> 1))));
 }
 
-template <int MODE, int KSTEPS, bool S2, bool BRES>
+template <int MODE, int KSTEPS, bool S2, bool BRES, bool TF32 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
@@ -624,7 +697,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int mw = (warp == 1) ? 0 : 1;
     if (mw < nmw && elect_one()) {
       const bool mma_on = !(P.dbg & 2);
-      const uint32_t idesc = make_idesc_bf16_m128(P.NT);
+      const uint32_t idesc = TF32 ? make_idesc_tf32_m128(P.NT) : make_idesc_bf16_m128(P.NT);
       // probe bit 32 (timing only, results wrong): 8-row groups 1024 B apart (atom aligned) instead of one slab row
       const uint32_t a_hi = desc_hi((P.dbg & 32) ? 8 * row_bytes : (uint32_t)P.sbo_bytes, layout_type);
       const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
@@ -675,8 +748,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                      else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      if constexpr (TF32) {
+                        if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      } else {
+                        if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      }
                     }
                   }
                 }
@@ -692,8 +770,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                      else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      if constexpr (TF32) {
+                        if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      } else {
+                        if (s == 0 && t == 0 && k == 0) tc_mma2(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        else tc_mma2_acc(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      }
                     }
                   }
                   tc_commit(&b_empty[sb]);                  // frees the B stage when these MMAs retire
@@ -716,6 +799,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
     const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);
     const int variant = P.up ? 8 : ((P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0));
+    if constexpr (TF32) {
+      epilogue_f32(P, warp, lane, tmem_base, t_full, t_empty, bias_u);
+    } else
     switch (variant) {
       case 2: epilogue_loop<false, true, false, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
       case 3: epilogue_loop<true, true, false, false>(P, warp, lane, tmem_base, t_full, t_empty, st_u, bias_u, o2s_u, o2b_u); break;
@@ -784,6 +870,24 @@ int num_sms() {
 int conv_tc_pad(int cout) { return cout <= 32 ? 32 : (cout + 63) / 64 * 64; }
 
 bool conv_tc_eligible(const ConvArgs& a) {
+  if (a.tf32) {
+    // training convolutions: fp32 NHWC in, raw fp32 (+ bias) out, TF32 tensor-core arithmetic (see epilogue_f32)
+    if (a.in_dtype != LEDB200_F32 || a.out_dtype != LEDB200_F32 || !a.out) return false;
+    if (a.pre_scale || a.res || a.out2 || a.up || a.relu == 2) return false;
+    if (a.ksize != 1 && a.ksize != 3) return false;
+    if (a.stride != 1 && a.stride != 2) return false;
+    if (a.dil != 1 && a.ksize == 3) return false;
+    if (a.Cin < 32 || a.Cin % 32) return false;                      // K blocks of 32 fp32 channels (128 B rows)
+    if (a.in_sc != 1 || a.in_sw % 4) return false;
+    if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;
+    if (a.Ho % TH || a.Wo % TW) return false;                        // all-interior tilings only (else: CUDA-core kernels)
+    if (a.out_ld < a.Cout) return false;
+    const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
+    if (cp > 256 && cp % 256) return false;
+    if (cp != 32 && cp % 64) return false;
+    if ((int64_t)a.N * (a.Ho / TH) * (a.Wo / TW) * (cp > 256 ? cp / 256 : 1) >= (1ll << 31)) return false;
+    return true;
+  }
   if (a.in_dtype != LEDB200_BF16 || a.out_dtype != LEDB200_BF16) return false;
   if (a.pre_scale) return false;
   if (a.ksize != 1 && a.ksize != 3) return false;
@@ -811,18 +915,23 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   if (!conv_tc_eligible(a)) return fail(LEDB200_EINVAL, "conv_tc: shape not eligible");
   TcParams P{};
   const bool s2 = a.stride == 2;
-  P.Cin = a.Cin; P.Cout = a.Cout;
-  const int cp = a.cout_pad_tc;
+  // TF32 launches move fp32 words: every shared-memory / TMA quantity below is in 2-byte units, so an fp32 tensor of C
+  // channels is described as 2C units (128 B rows = 32 fp32 channels = "KC 64"); only the MMA kind and the epilogue differ
+  const bool tf32 = a.tf32 != 0;
+  const int es = tf32 ? 2 : 1;
+  const int cinE = a.Cin * es;
+  P.Cin = cinE; P.Cout = a.Cout;
+  const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
   // N tile: the whole (padded) Cout when it is 16 / 32 / 64 / 128 / 256, 256 for multiples of 256, else 64-column
   // tiles (e.g. 192 = GETB qkv of a 64-channel block): the epilogue's column split needs a power-of-two tile
   P.NT = cp > 256 ? 256 : ((cp & (cp - 1)) == 0 ? cp : 64);
   P.ntiles_n = cp / P.NT;
-  P.KC = pick_kc(a.Cin);
-  P.nchunks = a.Cin / P.KC;
+  P.KC = tf32 ? 64 : pick_kc(a.Cin);
+  P.nchunks = cinE / P.KC;
   P.N = a.N; P.Ho = a.Ho; P.Wo = a.Wo;
   P.tiles_h = ceil_div(a.Ho, TH); P.tiles_w = ceil_div(a.Wo, TW);
   P.total_tiles = (int64_t)a.N * P.tiles_h * P.tiles_w * P.ntiles_n;
-  P.in_ld = (int)a.in_sw;
+  P.in_ld = (int)a.in_sw * es;
   const int row_bytes = P.KC * 2;
   int box_w = TW, box_rows = TH;
   P.sbo_bytes = 8 * row_bytes;
@@ -881,6 +990,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     const bool fast = (ncols_g % 32 == 0) && a.relu != 2 &&
                       (a.up ? (a.up_ld == 24 && cp == 32 && cout8 == 24 && a.out_ld % 8 == 0) : (cout8 == cp && al32));
     if (fast && a.Ho % TH == 0 && a.Wo % TW == 0) P.stage_bytes = 0;
+    if (tf32) P.stage_bytes = 0;
   }
   const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
@@ -922,25 +1032,25 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
-  const uint64_t ld = (uint64_t)a.in_sw;
+  const uint64_t ld = (uint64_t)a.in_sw * es;
   int rc;
   if (!s2) {
-    const uint64_t dims[4] = {(uint64_t)a.Cin, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
+    const uint64_t dims[4] = {(uint64_t)cinE, (uint64_t)a.W, (uint64_t)a.H, (uint64_t)a.N};
     const uint64_t str[3] = {ld * 2, (uint64_t)a.W * ld * 2, (uint64_t)a.H * a.W * ld * 2};
     const uint32_t box[4] = {(uint32_t)P.KC, (uint32_t)box_w, (uint32_t)box_rows, 1};
     rc = encode(&tmA, a.in, 4, dims, str, box, P.KC);
   } else {
-    const uint64_t dims[5] = {ld + (uint64_t)a.Cin, (uint64_t)a.W / 2, 2, (uint64_t)a.H / 2, (uint64_t)a.N};
+    const uint64_t dims[5] = {ld + (uint64_t)cinE, (uint64_t)a.W / 2, 2, (uint64_t)a.H / 2, (uint64_t)a.N};
     const uint64_t str[4] = {2 * ld * 2, (uint64_t)a.W * ld * 2, 2 * (uint64_t)a.W * ld * 2, (uint64_t)a.H * a.W * ld * 2};
     const uint32_t box[5] = {(uint32_t)P.KC, (uint32_t)box_w, 1, (uint32_t)box_rows, 1};
     rc = encode(&tmA, a.in, 5, dims, str, box, P.KC);
   }
   if (rc) return rc;
   {
-    const uint64_t dims[2] = {(uint64_t)taps * a.Cin, (uint64_t)cp};
-    const uint64_t str[1] = {(uint64_t)taps * a.Cin * 2};
+    const uint64_t dims[2] = {(uint64_t)taps * cinE, (uint64_t)cp};
+    const uint64_t str[1] = {(uint64_t)taps * cinE * 2};
     const uint32_t box[2] = {(uint32_t)P.KC, (uint32_t)P.NT};
-    rc = encode(&tmB, a.w_tc, 2, dims, str, box, P.KC);
+    rc = encode(&tmB, tf32 ? (const void*)a.w_tc32 : (const void*)a.w_tc, 2, dims, str, box, P.KC);
   }
   if (rc) return rc;
 
@@ -970,9 +1080,23 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       {{{nullptr, nullptr}, {nullptr, nullptr}},
        {{conv_tc_kernel<2, 2, true, false>, conv_tc_kernel<2, 2, true, true>},
         {conv_tc_kernel<2, 4, true, false>, conv_tc_kernel<2, 4, true, true>}}}};
+  // TF32 instantiations (KSTEPS = 4: four 32-byte k-steps per 128 B row): [mode][stride 2][weights resident]
+  static const KernelFn kernels_tf32[3][2][2] = {
+      {{conv_tc_kernel<0, 4, false, false, true>, conv_tc_kernel<0, 4, false, true, true>}, {nullptr, nullptr}},
+      {{conv_tc_kernel<1, 4, false, false, true>, conv_tc_kernel<1, 4, false, true, true>},
+       {conv_tc_kernel<1, 4, true, false, true>, conv_tc_kernel<1, 4, true, true, true>}},
+      {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, true>, conv_tc_kernel<2, 4, true, true, true>}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
+    for (int m = 0; m < 3; ++m)
+      for (int s = 0; s < 2; ++s)
+        for (int r = 0; r < 2; ++r)
+          if (kernels_tf32[m][s][r]) {
+            cudaError_t e = cudaFuncSetAttribute(kernels_tf32[m][s][r], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)SMEM_BUDGET + 2048);
+            if (e != cudaSuccess) attr_err = e;
+          }
     for (int m = 0; m < 3; ++m)
       for (int s = 0; s < 2; ++s)
         for (int k = 0; k < 2; ++k)
@@ -984,7 +1108,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
             }
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
-  const KernelFn fn = kernels[mode][s2 ? 1 : 0][ksteps == 4][P.b_resident ? 1 : 0];
+  const KernelFn fn = tf32 ? kernels_tf32[mode][s2 ? 1 : 0][P.b_resident ? 1 : 0]
+                           : kernels[mode][s2 ? 1 : 0][ksteps == 4][P.b_resident ? 1 : 0];
   fn<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
   LEDB_LAUNCH_OK("conv_tc_kernel");
   return LEDB200_OK;

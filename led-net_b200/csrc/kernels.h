@@ -29,6 +29,8 @@ struct ConvArgs {
   int pre_relu = 1;
   const float* w_direct = nullptr;         // [k*k][Cin][cout_pad16] fp32 (device)
   const __nv_bfloat16* w_tc = nullptr;     // [cout_padN][k*k*Cin] bf16 (device), K-major
+  const float* w_tc32 = nullptr;           // tf32 launches: the same matrix as fp32 words (tf32-rounded)
+  int tf32 = 0;                            // 1: fp32 tensors through the kind::tf32 instantiations (training, train.cu)
   int cout_pad16 = 0;
   int cout_pad_tc = 0;
   int N = 0, H = 0, W = 0, Cin = 0, Ho = 0, Wo = 0, Cout = 0;

@@ -52,6 +52,25 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
+// K-major fp32 weight matrix of the tensor-core path (conv_tc.cu, TF32 instantiations), values rounded to tf32 (RN):
+//   mode 0 (forward):       out[co_pad][tap * Cin + ci]  = w[co][ci][tap]
+//   mode 1 (data gradient): out[ci_pad][tap' * Cout + co] = w[co][ci][taps - 1 - tap']   (rotated, roles swapped)
+__global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps,
+                                      int mode, int rows_pad) {
+  const int rows = mode ? Cin : Cout, inner = mode ? Cout : Cin;
+  const int64_t total = (int64_t)rows_pad * taps * inner;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int c = (int)(i % inner);
+    const int tap = (int)((i / inner) % taps);
+    const int r = (int)(i / ((int64_t)inner * taps));
+    float v = 0.f;
+    if (r < rows) v = mode == 0 ? w[((int64_t)r * Cin + c) * taps + tap] : w[((int64_t)c * Cin + r) * taps + (taps - 1 - tap)];
+    uint32_t t;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+    out[i] = __uint_as_float(t);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight gradient.  CTA = 128 threads = 2 pixel lanes x (8 ci-groups x 8 co-groups); each thread owns a
 // 4(ci) x 4(co) x taps register tile and walks its lane's pixels of the staged tile.
@@ -526,6 +545,72 @@ int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float
   a.in_up = stride; a.Hr = Ho; a.Wr = Wo;
   if (stride == 1) { a.in_up = 1; }
   return launch_conv_direct(a, (cudaStream_t)stream);
+}
+
+// ---- tensor-core (TF32) forms of the two convolutions above: conv_tc.cu's implicit GEMM on fp32 NHWC tensors.
+static void conv_tc_args(ConvArgs& a, const float* in, float* out, const float* w_tc, const float* bias, int N, int H, int W,
+                         int Cin, int Cout, int k, int stride) {
+  a.in = in; a.in_dtype = LEDB200_F32; a.in_sc = 1; a.in_sw = Cin; a.in_sh = (int64_t)W * Cin;
+  a.in_sn = (int64_t)H * W * Cin;
+  a.out = out; a.out_dtype = LEDB200_F32; a.out_ld = Cout;
+  a.bias = bias; a.w_tc32 = w_tc; a.tf32 = 1; a.cout_pad_tc = conv_tc_pad(Cout);
+  a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = k; a.stride = stride; a.pad = k / 2; a.dil = 1;
+  a.Ho = (H + 2 * a.pad - k) / stride + 1; a.Wo = (W + 2 * a.pad - k) / stride + 1;
+}
+
+// 1 when the tensor-core kernels take this convolution (op 0 forward, 1 data gradient, 2 weight gradient), else 0:
+// the caller then uses the CUDA-core entry points (odd sizes, Cin = 3, tiles that are not all interior).
+int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                                 int32_t stride) {
+  if (N < 1 || H < 1 || W < 1 || Cin < 1 || Cout < 1 || (k != 1 && k != 3) || (stride != 1 && stride != 2)) return 0;
+  ConvArgs a;
+  const float* dummy = reinterpret_cast<const float*>(uintptr_t(256));
+  if (op == 0) {
+    conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cin, Cout, k, stride);
+    return conv_tc_eligible(a) ? 1 : 0;
+  }
+  if (op == 1) {
+    if (stride != 1) return 0;
+    conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cout, Cin, k, 1);
+    return conv_tc_eligible(a) ? 1 : 0;
+  }
+  return 0;
+}
+
+int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
+  const int64_t taps = (int64_t)k * k;
+  return mode == 0 ? (int64_t)conv_tc_pad(Cout) * taps * Cin : (int64_t)conv_tc_pad(Cin) * taps * Cout;
+}
+
+int ledb200_train_pack_weight_tc(const float* w_oihw, float* out, int32_t Cout, int32_t Cin, int32_t k, int32_t mode,
+                                 void* stream) {
+  if (!w_oihw || !out) return fail(LEDB200_EINVAL, "pack_weight_tc: null buffer");
+  if (mode != 0 && mode != 1) return fail(LEDB200_EINVAL, "pack_weight_tc: mode must be 0 (forward) or 1 (dgrad)");
+  const int rows_pad = conv_tc_pad(mode == 0 ? Cout : Cin);
+  const int64_t total = ledb200_train_packed_weight_tc_floats(Cout, Cin, k, mode);
+  pack_weight_tc_kernel<<<grid1d(total), kT, 0, (cudaStream_t)stream>>>(w_oihw, out, Cout, Cin, k * k, mode, rows_pad);
+  LEDB_LAUNCH_OK("pack_weight_tc_kernel");
+  return LEDB200_OK;
+}
+
+int ledb200_train_conv_fwd_tc(const float* x, const float* w_tc, const float* bias_opt, float* y, int32_t N, int32_t H,
+                              int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* stream) {
+  if (!x || !w_tc || !y) return fail(LEDB200_EINVAL, "train_conv_fwd_tc: null buffer");
+  if (!ledb200_train_conv_tc_ok(0, N, H, W, Cin, Cout, k, stride))
+    return fail(LEDB200_EINVAL, "train_conv_fwd_tc: shape not eligible (ask ledb200_train_conv_tc_ok first)");
+  ConvArgs a;
+  conv_tc_args(a, x, y, w_tc, bias_opt, N, H, W, Cin, Cout, k, stride);
+  return launch_conv_tc(a, (cudaStream_t)stream);
+}
+
+int ledb200_train_conv_dgrad_tc(const float* dy, const float* w_tc_dgrad, float* dx, int32_t N, int32_t H, int32_t W,
+                                int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* stream) {
+  if (!dy || !w_tc_dgrad || !dx) return fail(LEDB200_EINVAL, "train_conv_dgrad_tc: null buffer");
+  if (!ledb200_train_conv_tc_ok(1, N, H, W, Cin, Cout, k, stride))
+    return fail(LEDB200_EINVAL, "train_conv_dgrad_tc: shape not eligible (ask ledb200_train_conv_tc_ok first)");
+  ConvArgs a;   // stride 1: dX = conv(dY, rotated weights with the channel roles swapped), same padding
+  conv_tc_args(a, dy, dx, w_tc_dgrad, nullptr, N, H, W, Cout, Cin, k, 1);
+  return launch_conv_tc(a, (cudaStream_t)stream);
 }
 
 // dw_oihw [Cout,Cin,k,k] (overwritten), dbias_opt [Cout] (overwritten); workspace >= 2*Cout doubles when dbias_opt

@@ -27,6 +27,8 @@ SYMBOLS = [
     'ledb200_train_resize_fwd', 'ledb200_train_resize_bwd', 'ledb200_train_add_relu', 'ledb200_train_relu_bwd',
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
+    'ledb200_train_conv_tc_ok', 'ledb200_train_packed_weight_tc_floats', 'ledb200_train_pack_weight_tc',
+    'ledb200_train_conv_fwd_tc', 'ledb200_train_conv_dgrad_tc',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
     'ledb200_getb_param_floats', 'ledb200_getb_create', 'ledb200_getb_destroy', 'ledb200_getb_forward',
@@ -95,6 +97,13 @@ def get():
     lib.ledb200_train_conv_fwd.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp]
     lib.ledb200_train_conv_dgrad.argtypes = [vp, vp, vp] + [i32] * 7 + [vp]
     lib.ledb200_train_conv_wgrad.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp]
+    lib.ledb200_train_conv_tc_ok.argtypes = [i32] * 8
+    lib.ledb200_train_conv_tc_ok.restype = i32
+    lib.ledb200_train_packed_weight_tc_floats.argtypes = [i32] * 4
+    lib.ledb200_train_packed_weight_tc_floats.restype = i64
+    lib.ledb200_train_pack_weight_tc.argtypes = [vp, vp, i32, i32, i32, i32, vp]
+    lib.ledb200_train_conv_fwd_tc.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp]
+    lib.ledb200_train_conv_dgrad_tc.argtypes = [vp, vp, vp] + [i32] * 7 + [vp]
     lib.ledb200_train_bn_fwd.argtypes = [vp] * 9 + [f32, f32, i32, i64, i32, vp, vp]
     lib.ledb200_train_bn_bwd.argtypes = [vp] * 10 + [i32, i64, i32, vp, vp]
     lib.ledb200_train_bn_workspace_bytes.argtypes = [i32]

@@ -10,6 +10,7 @@ Layout: activations are NHWC fp32 CUDA tensors ``[N,H,W,C]`` between these funct
 weights stay in the reference's OIHW state-dict layout.  There is no CPU fallback.
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -69,6 +70,16 @@ def to_nchw(x):
     return _Layout.apply(x, False)
 
 
+# Tensor-core switch of the training convolutions: True (default) sends every eligible shape (ledb200_train_conv_tc_ok)
+# through the tcgen05 kind::tf32 kernels; False keeps the fp32 CUDA-core kernels everywhere (the round-1 path, kept for
+# shapes the tensor-core tiling rejects and as the A/B arm of tests/test_gpu_train_tc.py).
+TENSOR_CORES = os.environ.get('LEDB200_TRAIN_TC', '1') != '0'
+
+
+def _tc_ok(op, n, h, w, cin, cout, k, stride):
+    return TENSOR_CORES and bool(L.get().ledb200_train_conv_tc_ok(op, n, h, w, cin, cout, k, stride))
+
+
 class _Conv(torch.autograd.Function):
     """nn.Conv2d(k, stride, padding=k//2[, bias]) on NHWC activations."""
 
@@ -80,13 +91,21 @@ class _Conv(torch.autograd.Function):
         cout, cin_w, k, _ = weight.shape
         assert cin_w == cin, f'conv: input has {cin} channels, weight expects {cin_w}'
         ho, wo = _out_hw(h, w, k, stride)
-        wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 0), dtype=torch.float32,
-                         device=x.device)
-        L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 0, _st(x)), 'train_pack_weight')
         y = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device)
         b = _chk(bias, 'conv bias') if bias is not None else None
-        L.check(lib.ledb200_train_conv_fwd(_p(x), _p(wp), _p(b), _p(y), n, h, w, cin, cout, k, stride, _st(x)),
-                'train_conv_fwd')
+        if _tc_ok(0, n, h, w, cin, cout, k, stride):
+            wp = torch.empty(lib.ledb200_train_packed_weight_tc_floats(cout, cin, k, 0), dtype=torch.float32,
+                             device=x.device)
+            L.check(lib.ledb200_train_pack_weight_tc(_p(weight), _p(wp), cout, cin, k, 0, _st(x)),
+                    'train_pack_weight_tc')
+            L.check(lib.ledb200_train_conv_fwd_tc(_p(x), _p(wp), _p(b), _p(y), n, h, w, cin, cout, k, stride,
+                                                  _st(x)), 'train_conv_fwd_tc')
+        else:
+            wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 0), dtype=torch.float32,
+                             device=x.device)
+            L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 0, _st(x)), 'train_pack_weight')
+            L.check(lib.ledb200_train_conv_fwd(_p(x), _p(wp), _p(b), _p(y), n, h, w, cin, cout, k, stride, _st(x)),
+                    'train_conv_fwd')
         ctx.save_for_backward(x, weight)
         ctx.stride, ctx.has_bias = stride, bias is not None
         return y
@@ -100,12 +119,21 @@ class _Conv(torch.autograd.Function):
         cout, _, k, _ = weight.shape
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 1), dtype=torch.float32,
-                             device=x.device)
-            L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 1, _st(x)), 'train_pack_weight')
             dx = torch.empty_like(x)
-            L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride, _st(x)),
-                    'train_conv_dgrad')
+            if _tc_ok(1, n, h, w, cin, cout, k, ctx.stride):
+                wp = torch.empty(lib.ledb200_train_packed_weight_tc_floats(cout, cin, k, 1), dtype=torch.float32,
+                                 device=x.device)
+                L.check(lib.ledb200_train_pack_weight_tc(_p(weight), _p(wp), cout, cin, k, 1, _st(x)),
+                        'train_pack_weight_tc')
+                L.check(lib.ledb200_train_conv_dgrad_tc(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
+                                                        _st(x)), 'train_conv_dgrad_tc')
+            else:
+                wp = torch.empty(lib.ledb200_train_packed_weight_floats(cout, cin, k, 1), dtype=torch.float32,
+                                 device=x.device)
+                L.check(lib.ledb200_train_pack_weight(_p(weight), _p(wp), cout, cin, k, 1, _st(x)),
+                        'train_pack_weight')
+                L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
+                                                     _st(x)), 'train_conv_dgrad')
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(weight)
             if ctx.has_bias:

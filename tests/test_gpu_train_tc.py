@@ -1,0 +1,105 @@
+"""GPU parity of the tensor-core training convolutions (north_star kernel 6: dgrad / wgrad implicit GEMM on tcgen05,
+kind::tf32): forward, data gradient and weight gradient through the C ABI against ATen's float64 convolution.
+
+Two gates per shape:
+  * operands pre-rounded to tf32 (10-bit mantissa): every product is exact in fp32, so the kernels must match the float64
+    result to accumulation-order noise (1e-5) - this separates indexing / descriptor bugs from precision;
+  * raw fp32 operands: within tf32's rounding (2e-3 of the tensor's max), and - the reason train_ops rounds activations
+    to nearest before they reach a tensor-core consumer - no systematic shrink (mean signed error well below the
+    truncation bias of ~5e-4 that compounds layer after layer in the backward pass).
+"""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import lednet_b200 as L
+from lednet_b200 import train_ops as T
+from util import rel_err
+
+pytestmark = pytest.mark.gpu
+DEV = 'cuda'
+
+
+def tf32_round(t):
+    """round-to-nearest (ties away) fp32 -> tf32, as cvt.rna.tf32.f32 does"""
+    i = t.contiguous().view(torch.int32)
+    return ((i + 0x1000) & ~0x1FFF).view(torch.float32)
+
+
+SHAPES = [
+    # cin, cout, k, stride, (H, W), bias
+    (32, 32, 3, 1, (32, 32), False),       # weights resident, two MMA issuers
+    (32, 64, 3, 1, (16, 24), False),
+    (64, 64, 3, 1, (32, 16), False),       # 144 KB resident
+    (64, 128, 3, 1, (16, 16), False),      # streamed weights
+    (128, 128, 3, 1, (16, 16), False),
+    (256, 256, 3, 1, (16, 8), False),      # N tile 256, two accumulator stages
+    (128, 512, 1, 1, (16, 8), False),      # two N tiles
+    (32, 32, 3, 2, (64, 32), False),       # stride 2: parity-split slabs
+    (64, 128, 3, 2, (32, 32), False),
+    (64, 128, 1, 2, (32, 32), False),
+    (64, 19, 1, 1, (16, 16), True),        # conv_seg: 19 of 32 columns stored, bias
+    (512, 128, 1, 1, (16, 8), False),
+    (640, 128, 1, 1, (16, 8), False),      # DAPPM compression
+    (64, 32, 3, 1, (48, 40), False),
+]
+
+
+def _run(cin, cout, k, stride, hw, bias, rounded):
+    g = torch.Generator().manual_seed(cin * 7 + cout * 3 + k + stride)
+    n = 3
+    x = torch.randn(n, cin, *hw, generator=g)
+    w = torch.randn(cout, cin, k, k, generator=g) * (2.0 / (cin * k * k)) ** 0.5
+    b = torch.randn(cout, generator=g) * 0.1 if bias else None
+    ho, wo = (hw[0] + 2 * (k // 2) - k) // stride + 1, (hw[1] + 2 * (k // 2) - k) // stride + 1
+    dy = torch.randn(n, cout, ho, wo, generator=g)
+    if rounded:
+        x, w, dy = tf32_round(x), tf32_round(w), tf32_round(dy)
+    xr = x.double().to(DEV).requires_grad_()
+    wr = w.double().to(DEV).requires_grad_()
+    br = b.double().to(DEV).requires_grad_() if bias else None
+    ref = F.conv2d(xr, wr, br, stride, k // 2)
+    ref.backward(dy.double().to(DEV))
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV).requires_grad_()
+    wd = w.to(DEV).requires_grad_()
+    bd = b.to(DEV).requires_grad_() if bias else None
+    out = T.conv2d(xd, wd, bd, stride)
+    out.backward(dy.permute(0, 2, 3, 1).contiguous().to(DEV))
+    torch.cuda.synchronize()
+    return (out.detach().permute(0, 3, 1, 2), ref.detach(), xd.grad.permute(0, 3, 1, 2), xr.grad, wd.grad, wr.grad,
+            bd.grad if bias else None, br.grad if bias else None)
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,hw,bias', SHAPES)
+def test_conv_tc_exact_on_tf32_operands(cin, cout, k, stride, hw, bias):
+    lib = L.lib.get()
+    assert lib.ledb200_train_conv_tc_ok(0, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'shape meant for the tensor-core path'
+    y, yr, dx, dxr, dw, dwr, db, dbr = _run(cin, cout, k, stride, hw, bias, rounded=True)
+    assert rel_err(y, yr) < 1e-5
+    assert rel_err(dx, dxr) < 1e-5
+    assert rel_err(dw, dwr) < 1e-4
+    if bias:
+        assert rel_err(db, dbr) < 1e-5
+
+
+@pytest.mark.parametrize('cin,cout,k,stride,hw,bias', SHAPES[:6] + SHAPES[7:9])
+def test_conv_tc_fp32_operands_within_tf32(cin, cout, k, stride, hw, bias):
+    y, yr, dx, dxr, dw, dwr, _, _ = _run(cin, cout, k, stride, hw, bias, rounded=False)
+    assert rel_err(y, yr) < 2e-3
+    assert rel_err(dx, dxr) < 2e-3
+    assert rel_err(dw, dwr) < 2e-3
+
+
+def test_tf32_operand_handling_is_reported():
+    """Diagnostic with a gate: how the tensor core treats the 13 low mantissa bits of an fp32 operand.  With operands that are
+    all positive, truncation shows up as a negative mean relative error of ~2 x 3.4e-4; round-to-nearest as ~0.  The
+    training path does not depend on the answer (train_ops stores tf32-rounded activations), this pins what the hardware does."""
+    g = torch.Generator().manual_seed(5)
+    x = torch.rand(2, 64, 32, 32, generator=g) + 0.5
+    w = torch.rand(64, 64, 3, 3, generator=g) + 0.5
+    ref = F.conv2d(x.double().to(DEV), w.double().to(DEV), None, 1, 1)
+    xd = x.permute(0, 2, 3, 1).contiguous().to(DEV)
+    out = T.conv2d(xd, w.to(DEV), None, 1).permute(0, 3, 1, 2).double()
+    bias = float(((out - ref) / ref).mean())
+    print(f'tf32 operand handling: mean relative error with positive raw fp32 operands = {bias:.3e}')
+    assert abs(bias) < 2e-3
