@@ -226,6 +226,10 @@ int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float
  * H, W = conv INPUT extents): Cin % 32 == 0 (of the GEMM's reduction side), output extents multiples of the 16 x 8 tile,
  * data gradient stride 1.  Everything else stays on the CUDA-core entry points above.  Weights: K-major fp32
  * [pad(Cout)][k*k*Cin] (mode 0) / [pad(Cin)][k*k*Cout] rotated (mode 1), rounded to tf32 on the device. */
+/* tf32 storage mode of the training element-wise kernels (BatchNorm apply / backward, resize, add, pool, concat): on = every
+ * tensor they write is rounded to tf32 (nearest), because the tensor core truncates raw fp32 operands.  Process-wide;
+ * returns the previous setting.  train_ops.set_tensor_cores() keeps it in step with the convolution path. */
+int ledb200_train_set_tf32_rounding(int32_t on);
 int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                                  int32_t stride);
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode);
@@ -236,6 +240,14 @@ int ledb200_train_conv_fwd_tc(const float* x, const float* w_tc, const float* bi
                               void* stream);
 int ledb200_train_conv_dgrad_tc(const float* dy, const float* w_tc_dgrad, float* dx, int32_t N, int32_t H,
                                 int32_t W, int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* stream);
+/* Weight gradient on the tensor cores (wgrad_tc.cu): 3x3, stride 1 or 2, Cin and Cout multiples of 32, no bias gradient.
+ * The pixel is the GEMM's reduction dimension: both operands are read MN-major straight from the TMA-staged NHWC slabs, the
+ * accumulators stay in TMEM for the CTA's whole life, per-CTA partials are added in a fixed order (bit-reproducible).
+ * workspace: device, >= ledb200_train_wgrad_tc_workspace_bytes(...) bytes. */
+int64_t ledb200_train_wgrad_tc_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                                               int32_t stride);
+int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
+                                int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace, void* stream);
 /* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias.  Every reduction of the training kernels is order-fixed
  * (per-CTA / per-block partial sums in `workspace`, added in index order: no floating-point atomics), so a training step
  * is bit-reproducible run to run.  workspace: device, >= ledb200_train_wgrad_workspace_bytes(Cin, Cout, k) bytes. */

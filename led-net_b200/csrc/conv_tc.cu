@@ -851,7 +851,9 @@ int encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, con
   cuuint32_t b[5], es[5];
   for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) s[i] = strides_bytes[i];
-  const CUtensorMapSwizzle sw = kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+  // kc = 1064: 128 B rows swizzled in 32-byte chunks (the only layout tcgen05 reads MN-major tf32 operands from, wgrad_tc.cu)
+  const CUtensorMapSwizzle sw = kc == 1064 ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B
+                                : kc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kc == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), d, s, b, es,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(LEDB200_ECUDA, "cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
@@ -865,6 +867,12 @@ int num_sms() {
   return n;
 }
 }  // namespace
+
+// tensor-map encoder for the other tcgen05 kernels of the library (wgrad_tc.cu): tiled, 2-byte units, swizzle by box width
+int tc_encode_tiled(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                    const uint32_t* box, int kc) {
+  return encode(m, base, rank, dims, strides_bytes, box, kc);
+}
 
 // 32 is the smallest N tile: the epilogue fast path works on 32-column blocks, and an N = 16 MMA costs the same A fetch
 int conv_tc_pad(int cout) { return cout <= 32 ? 32 : (cout + 63) / 64 * 64; }

@@ -19,12 +19,23 @@
 //   Every reduction is order-fixed (no floating-point atomics): a step is bit-reproducible run to run.
 //   add(+ReLU), avg-pool, channel copy (concat/slice), SGD+momentum over one flat parameter arena.
 // All tensors NHWC fp32, dense (pixel stride = C) unless an `ld` says otherwise.
-#include "kernels.h"
+#include "tc_common.cuh"
 
 namespace ledb {
 namespace {
 
 constexpr int kT = 256;
+// tf32 storage mode (ledb200_train_set_tf32_rounding): every activation / gradient tensor these kernels write is rounded to
+// tf32 (round to nearest, cvt.rna) so that a tensor-core consumer, which TRUNCATES raw fp32 operands to tf32 (measured:
+// tests/test_gpu_train_tc.py, -3.7e-4 mean), sees exactly representable values - truncation would shrink every data
+// gradient by ~3e-4 per layer, compounding to percents at the stem.  Off: plain fp32 stores (the CUDA-core path).
+int g_round = 0;
+__device__ __forceinline__ float rt(float v, int rnd) {
+  if (!rnd) return v;
+  uint32_t t;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
+  return __uint_as_float(t);
+}
 inline int grid1d(int64_t work, int per_sm = 8) {
   int64_t b = ceil_div64(work, kT);
   const int64_t cap = 148 * per_sm;
@@ -271,12 +282,12 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double
 __global__ void __launch_bounds__(kT)
 bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                float* __restrict__ out, int relu, int64_t total, int C) {
+                float* __restrict__ out, int relu, int64_t total, int C, int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
     float v = fmaf((y[i] - mean[c]) * invstd[c], gamma[c], beta[c]);
     if (res) v += res[i];
-    out[i] = relu ? fmaxf(v, 0.f) : v;
+    out[i] = rt(relu ? fmaxf(v, 0.f) : v, rnd);
   }
 }
 
@@ -286,7 +297,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const double* __restrict__ acc, const double* __restrict__ acc_local, float* __restrict__ dy,
                     float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total,
-                    int C, float invM) {
+                    int C, float invM, int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
     float dz = dout[i];
@@ -294,7 +305,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
     const float db = (float)acc[c], dg = (float)acc[C + c];
     const float is = invstd[c];
     const float xhat = (y[i] - mean[c]) * is;
-    dy[i] = gamma[c] * is * (dz - db * invM - xhat * dg * invM);
+    dy[i] = rt(gamma[c] * is * (dz - db * invM - xhat * dg * invM), rnd);
     if (dres) dres[i] = dz;
     if (i < C) { dbeta[c] = (float)acc_local[c]; dgamma[c] = (float)acc_local[C + c]; }   // parameter gradients stay rank-local (DDP averages them)
   }
@@ -324,7 +335,7 @@ int chan_reduce(const float* a, const float* y, const float* out, const float* m
 // bilinear resize (align_corners=False), generic channel count
 __global__ void __launch_bounds__(kT)
 resize_fwd_kernel(const float* __restrict__ src, float* __restrict__ out, int N, int h, int w, int H, int W, int C,
-                  float sh, float sw) {
+                  float sh, float sw, int rnd) {
   const int64_t total = (int64_t)N * H * W * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
@@ -337,7 +348,7 @@ resize_fwd_kernel(const float* __restrict__ src, float* __restrict__ out, int N,
     const float* s = src + (int64_t)n * h * w * C + c;
     const float r0 = fmaf(s[((int64_t)y0 * w + x1) * C], lx1, s[((int64_t)y0 * w + x0) * C] * lx0);
     const float r1 = fmaf(s[((int64_t)y1 * w + x1) * C], lx1, s[((int64_t)y1 * w + x0) * C] * lx0);
-    out[i] = fmaf(r1, ly1, r0 * ly0);
+    out[i] = rt(fmaf(r1, ly1, r0 * ly0), rnd);
   }
 }
 
@@ -355,7 +366,7 @@ __device__ __forceinline__ void gather_range(int s, float scale, int out_size, i
 // columns in ascending order: the transpose of resize_fwd_kernel as a GATHER (no atomics, fixed summation order)
 __global__ void __launch_bounds__(kT)
 resize_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int N, int h, int w, int H, int W, int C,
-                  float sh, float sw) {
+                  float sh, float sw, int rnd) {
   const int64_t total = (int64_t)N * h * w * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
@@ -387,24 +398,25 @@ resize_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int 
       }
       acc = fmaf(row, wy, acc);
     }
-    dsrc[i] = acc;
+    dsrc[i] = rt(acc, rnd);
   }
 }
 
 // out = [relu](a [+ b]);  backward: dx = dout * (out > 0)
 __global__ void __launch_bounds__(kT)
 add_relu_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, int relu,
-                int64_t n) {
+                int64_t n, int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT) {
     float v = a[i];
     if (b) v += b[i];
-    out[i] = relu ? fmaxf(v, 0.f) : v;
+    out[i] = rt(relu ? fmaxf(v, 0.f) : v, rnd);
   }
 }
 __global__ void __launch_bounds__(kT)
-relu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dx, int64_t n) {
+relu_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dx, int64_t n,
+                int rnd) {
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < n; i += (int64_t)gridDim.x * kT)
-    dx[i] = out[i] > 0.f ? dout[i] : 0.f;
+    dx[i] = out[i] > 0.f ? rt(dout[i], rnd) : 0.f;
 }
 
 // AvgPool2d(k,s,p,count_include_pad=True) (k > 0) or global average (k == 0)
@@ -415,7 +427,7 @@ __device__ __forceinline__ float pool_inv(int o, int k, int s, int p, int extent
 }
 __global__ void __launch_bounds__(kT)
 avgpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int N, int H, int W, int C, int Ho, int Wo,
-                   int k, int s, int p) {
+                   int k, int s, int p, int rnd) {
   const int64_t total = (int64_t)N * Ho * Wo * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
@@ -431,12 +443,12 @@ avgpool_fwd_kernel(const float* __restrict__ in, float* __restrict__ out, int N,
     float acc = 0.f;
     for (int y = y0; y < y1; ++y)
       for (int x = x0; x < x1; ++x) acc += in[(((int64_t)n * H + y) * W + x) * C + c];
-    out[i] = acc * inv;
+    out[i] = rt(acc * inv, rnd);
   }
 }
 __global__ void __launch_bounds__(kT)
 avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int N, int H, int W, int C, int Ho, int Wo,
-                   int k, int s, int p) {
+                   int k, int s, int p, int rnd) {
   const int64_t total = (int64_t)N * H * W * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
@@ -455,19 +467,19 @@ avgpool_bwd_kernel(const float* __restrict__ dout, float* __restrict__ din, int 
           acc += dout[(((int64_t)n * Ho + oy) * Wo + ox) * C + c] /
                  (pool_inv(oy, k, s, p, H) * pool_inv(ox, k, s, p, W));
     }
-    din[i] = acc;
+    din[i] = rt(acc, rnd);
   }
 }
 
 // dst[p*dst_ld + dst_off + c] = src[p*src_ld + src_off + c]  (concat / slice along channels)
 __global__ void __launch_bounds__(kT)
 copy_channels_kernel(const float* __restrict__ src, int src_ld, int src_off, float* __restrict__ dst, int dst_ld,
-                     int dst_off, int64_t npix, int C) {
+                     int dst_off, int64_t npix, int C, int rnd) {
   const int64_t total = npix * C;
   for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
     const int c = (int)(i % C);
     const int64_t p = i / C;
-    dst[p * dst_ld + dst_off + c] = src[p * src_ld + src_off + c];
+    dst[p * dst_ld + dst_off + c] = rt(src[p * src_ld + src_off + c], rnd);
   }
 }
 
@@ -501,6 +513,12 @@ int conv_common(ConvArgs& a, const float* in, float* out, const float* w_packed,
 using namespace ledb;
 
 extern "C" {
+
+int ledb200_train_set_tf32_rounding(int32_t on) {
+  const int prev = g_round;
+  g_round = on ? 1 : 0;
+  return prev;
+}
 
 int64_t ledb200_train_packed_weight_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
   const int64_t taps = (int64_t)k * k;
@@ -574,7 +592,19 @@ int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, in
     conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cout, Cin, k, 1);
     return conv_tc_eligible(a) ? 1 : 0;
   }
+  if (op == 2) return wgrad_tc_eligible(N, H, W, Cin, Cout, k, stride) ? 1 : 0;
   return 0;
+}
+
+int64_t ledb200_train_wgrad_tc_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
+                                               int32_t stride) {
+  return wgrad_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride);
+}
+
+int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
+                                int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace, void* stream) {
+  if (!x || !dy || !dw_oihw || !workspace) return fail(LEDB200_EINVAL, "train_conv_wgrad_tc: null buffer");
+  return launch_wgrad_tc(x, dy, dw_oihw, N, H, W, Cin, Cout, k, stride, workspace, (cudaStream_t)stream);
 }
 
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
@@ -698,7 +728,7 @@ int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* 
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, C, total_count, eps, momentum, save_mean,
                                                        save_invstd, running_mean_opt, running_var_opt);
   bn_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
-                                                   npix * C, C);
+                                                   npix * C, C, g_round);
   LEDB_LAUNCH_OK("train_bn_fwd_apply");
   return LEDB200_OK;
 }
@@ -716,7 +746,7 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
   const double* acc = (const double*)workspace;
   bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(dout, y, out, gamma, save_mean, save_invstd,
                                                                          acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta,
-                                                                         relu, npix * C, C, (float)(1.0 / total_count));
+                                                                         relu, npix * C, C, (float)(1.0 / total_count), g_round);
   LEDB_LAUNCH_OK("train_bn_bwd_apply");
   return LEDB200_OK;
 }
@@ -747,7 +777,7 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
   int rc = chan_reduce<1>(dout, y, out, save_mean, save_invstd, relu, npix, C, acc, st);
   if (rc) return rc;
   bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy, dres_opt,
-                                                       dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix);
+                                                       dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix, g_round);
   LEDB_LAUNCH_OK("train_bn_bwd");
   return LEDB200_OK;
 }
@@ -756,7 +786,7 @@ int ledb200_train_resize_fwd(const float* src, float* out, int32_t N, int32_t h,
                              int32_t C, void* stream) {
   if (!src || !out) return fail(LEDB200_EINVAL, "train_resize_fwd: null buffer");
   resize_fwd_kernel<<<grid1d((int64_t)N * H * W * C), kT, 0, (cudaStream_t)stream>>>(
-      src, out, N, h, w, H, W, C, (float)h / (float)H, (float)w / (float)W);
+      src, out, N, h, w, H, W, C, (float)h / (float)H, (float)w / (float)W, g_round);
   LEDB_LAUNCH_OK("resize_fwd_kernel");
   return LEDB200_OK;
 }
@@ -766,21 +796,21 @@ int ledb200_train_resize_bwd(const float* dout, float* dsrc, int32_t N, int32_t 
   if (!dout || !dsrc) return fail(LEDB200_EINVAL, "train_resize_bwd: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
   resize_bwd_kernel<<<grid1d((int64_t)N * h * w * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, (float)h / (float)H,
-                                                                  (float)w / (float)W);
+                                                                  (float)w / (float)W, g_round);
   LEDB_LAUNCH_OK("resize_bwd_kernel");
   return LEDB200_OK;
 }
 
 int ledb200_train_add_relu(const float* a, const float* b_opt, float* out, int32_t relu, int64_t n, void* stream) {
   if (!a || !out) return fail(LEDB200_EINVAL, "train_add_relu: null buffer");
-  add_relu_kernel<<<grid1d(n), kT, 0, (cudaStream_t)stream>>>(a, b_opt, out, relu, n);
+  add_relu_kernel<<<grid1d(n), kT, 0, (cudaStream_t)stream>>>(a, b_opt, out, relu, n, g_round);
   LEDB_LAUNCH_OK("add_relu_kernel");
   return LEDB200_OK;
 }
 
 int ledb200_train_relu_bwd(const float* dout, const float* out, float* dx, int64_t n, void* stream) {
   if (!dout || !out || !dx) return fail(LEDB200_EINVAL, "train_relu_bwd: null buffer");
-  relu_bwd_kernel<<<grid1d(n), kT, 0, (cudaStream_t)stream>>>(dout, out, dx, n);
+  relu_bwd_kernel<<<grid1d(n), kT, 0, (cudaStream_t)stream>>>(dout, out, dx, n, g_round);
   LEDB_LAUNCH_OK("relu_bwd_kernel");
   return LEDB200_OK;
 }
@@ -789,7 +819,7 @@ int ledb200_train_avgpool_fwd(const float* in, float* out, int32_t N, int32_t H,
                               int32_t Wo, int32_t k, int32_t s, int32_t p, void* stream) {
   if (!in || !out) return fail(LEDB200_EINVAL, "train_avgpool_fwd: null buffer");
   avgpool_fwd_kernel<<<grid1d((int64_t)N * Ho * Wo * C), kT, 0, (cudaStream_t)stream>>>(in, out, N, H, W, C, Ho, Wo, k,
-                                                                                      s, p);
+                                                                                      s, p, g_round);
   LEDB_LAUNCH_OK("avgpool_fwd_kernel");
   return LEDB200_OK;
 }
@@ -798,7 +828,7 @@ int ledb200_train_avgpool_bwd(const float* dout, float* din, int32_t N, int32_t 
                               int32_t Wo, int32_t k, int32_t s, int32_t p, void* stream) {
   if (!dout || !din) return fail(LEDB200_EINVAL, "train_avgpool_bwd: null buffer");
   avgpool_bwd_kernel<<<grid1d((int64_t)N * H * W * C), kT, 0, (cudaStream_t)stream>>>(dout, din, N, H, W, C, Ho, Wo, k,
-                                                                                    s, p);
+                                                                                    s, p, g_round);
   LEDB_LAUNCH_OK("avgpool_bwd_kernel");
   return LEDB200_OK;
 }
@@ -808,7 +838,7 @@ int ledb200_train_copy_channels(const float* src, int32_t src_ld, int32_t src_of
   if (!src || !dst) return fail(LEDB200_EINVAL, "train_copy_channels: null buffer");
   if (src_off + C > src_ld || dst_off + C > dst_ld) return fail(LEDB200_EINVAL, "train_copy_channels: slice out of range");
   copy_channels_kernel<<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(src, src_ld, src_off, dst, dst_ld, dst_off,
-                                                                        npix, C);
+                                                                        npix, C, g_round);
   LEDB_LAUNCH_OK("copy_channels_kernel");
   return LEDB200_OK;
 }

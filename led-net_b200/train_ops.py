@@ -74,9 +74,27 @@ def to_nchw(x):
 # through the tcgen05 kind::tf32 kernels; False keeps the fp32 CUDA-core kernels everywhere (the round-1 path, kept for
 # shapes the tensor-core tiling rejects and as the A/B arm of tests/test_gpu_train_tc.py).
 TENSOR_CORES = os.environ.get('LEDB200_TRAIN_TC', '1') != '0'
+_rounding_synced = None
+
+
+def set_tensor_cores(on):
+    """Switch the training convolutions between the tcgen05 tf32 kernels and the fp32 CUDA-core kernels; the element-wise
+    kernels' tf32 storage mode (ledb200_train_set_tf32_rounding) follows.  Returns the previous setting."""
+    global TENSOR_CORES, _rounding_synced
+    prev = TENSOR_CORES
+    TENSOR_CORES = bool(on)
+    L.get().ledb200_train_set_tf32_rounding(int(TENSOR_CORES))
+    _rounding_synced = TENSOR_CORES
+    return prev
+
+
+def _sync_mode():
+    if _rounding_synced is not TENSOR_CORES:
+        set_tensor_cores(TENSOR_CORES)
 
 
 def _tc_ok(op, n, h, w, cin, cout, k, stride):
+    _sync_mode()
     return TENSOR_CORES and bool(L.get().ledb200_train_conv_tc_ok(op, n, h, w, cin, cout, k, stride))
 
 
@@ -134,7 +152,13 @@ class _Conv(torch.autograd.Function):
                         'train_pack_weight')
                 L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
                                                      _st(x)), 'train_conv_dgrad')
-        if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        if ctx.needs_input_grad[1] and not ctx.has_bias and _tc_ok(2, n, h, w, cin, cout, k, ctx.stride):
+            dw = torch.empty_like(weight)
+            ws = torch.empty(lib.ledb200_train_wgrad_tc_workspace_bytes(n, h, w, cin, cout, k, ctx.stride) // 4,
+                             dtype=torch.float32, device=x.device)   # per-CTA partial sums, added in a fixed order
+            L.check(lib.ledb200_train_conv_wgrad_tc(_p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, ctx.stride, _p(ws),
+                                                    _st(x)), 'train_conv_wgrad_tc')
+        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(weight)
             if ctx.has_bias:
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)
@@ -230,6 +254,7 @@ def bn_act(y, bn, res=None, relu=False):
     """`bn`: an nn.BatchNorm2d in training mode (its running stats are updated like PyTorch does).  When the
     module carries `sync = True` (built from norm_cfg type 'SyncBN') and a process group of more than one rank is
     initialised, the batch statistics are those of the GLOBAL batch (torch.nn.SyncBatchNorm)."""
+    _sync_mode()
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return _BNAct.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu,

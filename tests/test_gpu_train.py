@@ -17,6 +17,15 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(autouse=True)
+def _fp32_kernels_by_default():
+    """The per-kernel tests hold the fp32 CUDA-core kernels to 1e-5: run them in that mode.  The whole-step tests switch
+    to the tensor-core (tf32) path themselves through the `tc` parameter."""
+    prev = T.set_tensor_cores(False)
+    yield
+    T.set_tensor_cores(prev)
+
+
 def nhwc(t):
     return t.permute(0, 2, 3, 1).contiguous().to(DEV)
 
@@ -200,8 +209,9 @@ def _check_grads(mine_grads, ref_grads, ref_grads64, tag, cond_floor=0.0, vec_to
     return cond
 
 
+@pytest.mark.parametrize('tc', [False, True], ids=['fp32', 'tf32'])
 @pytest.mark.parametrize('K,hw,N', [(19, (128, 256), 2), (2, (192, 320), 3)])
-def test_train_step_vs_oracle(K, hw, N):
+def test_train_step_vs_oracle(K, hw, N, tc):
     """Loss and every parameter gradient against the oracle in train mode.
 
     Conditioning: train-mode BatchNorm backward subtracts per-channel means of the incoming gradient
@@ -211,6 +221,10 @@ def test_train_step_vs_oracle(K, hw, N):
     error against float64 on that tensor, 1.5 x the fp32 oracle's worst tensor) with at most 4 tensors
     needing the last term, plus an absolute floor for gradients that are analytically zero (a BN bias
     directly in front of another train-mode BN)."""
+    T.set_tensor_cores(tc)
+    # loss gate: the fp32 kernels reproduce the float64 loss to 1e-4; tf32 operands (10-bit mantissa, the convolutions of
+    # every eligible layer) to 2e-3 - both far inside north_star's 1e-2.  The GRADIENT gates are the same in both modes.
+    loss_tol = 2e-3 if tc else 1e-4
     o, m = _train_pair(K)
     x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0))
     lab = synth.make_labels(N, *hw, K, seed=1)
@@ -227,7 +241,7 @@ def test_train_step_vs_oracle(K, hw, N):
     total.backward()
     torch.cuda.synchronize()
     for k in ('loss_context', 'loss_spatial'):
-        assert abs(float(losses['decode.' + k].detach()) - float(ref64[k])) < 1e-4 * abs(float(ref64[k])), k
+        assert abs(float(losses['decode.' + k].detach()) - float(ref64[k])) < loss_tol * abs(float(ref64[k])), k
     assert abs(float(losses['decode.acc_seg']) - float(ref['acc_seg'])) < 1e-2
     got = dict(m.named_parameters())
     assert set(got) == set(ref_grads)
@@ -237,7 +251,7 @@ def test_train_step_vs_oracle(K, hw, N):
     bufs_o = dict(o.named_buffers())
     for k, b in m.named_buffers():
         if k.endswith('running_mean') or k.endswith('running_var'):
-            assert rel_err(b.cpu(), bufs_o[k]) < 1e-4, k
+            assert rel_err(b.cpu(), bufs_o[k]) < (2e-3 if tc else 1e-4), k
     # ---- SGD update over two steps (the second exercises the momentum buffer).
     # The optimiser ARITHMETIC is checked exactly: torch.optim.SGD on a CPU shadow of the parameters fed
     # with the product's own gradients must land on the same values as FlatSGD's one-launch kernel.
@@ -279,7 +293,7 @@ def test_train_step_vs_oracle(K, hw, N):
     for k, p in m.named_parameters():
         assert rel_err(p.detach().cpu(), shadow[k].detach()) < 1e-6, k
     tot2, tot2_64 = (float(r['loss_context'] + r['loss_spatial']) for r in (ref2, ref2_64))
-    assert abs(float(log['loss'].detach()) - tot2_64) < max(1e-4 * abs(tot2_64), 3 * abs(tot2 - tot2_64))
+    assert abs(float(log['loss'].detach()) - tot2_64) < max(loss_tol * abs(tot2_64), 3 * abs(tot2 - tot2_64))
 
 
 def test_eval_after_train_uses_updated_weights():
@@ -317,11 +331,13 @@ def test_syncbn_two_ranks_matches_full_batch():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
 
 
-def test_training_steps_are_bit_reproducible():
+@pytest.mark.parametrize('tc', [False, True], ids=['fp32', 'tf32'])
+def test_training_steps_are_bit_reproducible(tc):
     """No floating-point atomics anywhere in the training kernels (weight gradients, BatchNorm statistics and the resize
     backward sum per-CTA partials / gathers in a fixed order): three optimiser steps from the same weights on the same
     batch land on the SAME bits, run after run."""
-    K, N, hw = 5, 2, (96, 160)
+    T.set_tensor_cores(tc)
+    K, N, hw = (5, 2, (128, 256)) if tc else (5, 2, (96, 160))
     x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0)).to(DEV)
     lab = synth.make_labels(N, *hw, K, seed=1)
     samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(N)]

@@ -20,6 +20,13 @@ pytestmark = pytest.mark.gpu
 DEV = 'cuda'
 
 
+@pytest.fixture(autouse=True)
+def _tensor_cores_on():
+    prev = T.set_tensor_cores(True)
+    yield
+    T.set_tensor_cores(prev)
+
+
 def tf32_round(t):
     """round-to-nearest (ties away) fp32 -> tf32, as cvt.rna.tf32.f32 does"""
     i = t.contiguous().view(torch.int32)
@@ -74,6 +81,8 @@ def _run(cin, cout, k, stride, hw, bias, rounded):
 def test_conv_tc_exact_on_tf32_operands(cin, cout, k, stride, hw, bias):
     lib = L.lib.get()
     assert lib.ledb200_train_conv_tc_ok(0, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'shape meant for the tensor-core path'
+    if k == 3 and cout % 32 == 0:
+        assert lib.ledb200_train_conv_tc_ok(2, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'weight gradient on tensor cores'
     y, yr, dx, dxr, dw, dwr, db, dbr = _run(cin, cout, k, stride, hw, bias, rounded=True)
     assert rel_err(y, yr) < 1e-5
     assert rel_err(dx, dxr) < 1e-5
