@@ -225,11 +225,17 @@ int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float
  * ledb200_train_conv_tc_ok(op, ...) says whether they take a shape (op 0 forward, 1 data gradient, 2 weight gradient;
  * H, W = conv INPUT extents): Cin % 32 == 0 (of the GEMM's reduction side), output extents multiples of the 16 x 8 tile,
  * data gradient stride 1.  Everything else stays on the CUDA-core entry points above.  Weights: K-major fp32
- * [pad(Cout)][k*k*Cin] (mode 0) / [pad(Cin)][k*k*Cout] rotated (mode 1), rounded to tf32 on the device. */
+ * [pad(Cout)][k*k*Cin] (mode 0) / [pad(Cin)][k*k*Cout] rotated (mode 1) rounded to tf32 on the device, followed by a second
+ * matrix of the same shape holding the remainders w - tf32(w) (the three-pass mode's w_lo). */
 /* tf32 storage mode of the training element-wise kernels (BatchNorm apply / backward, resize, add, pool, concat): on = every
  * tensor they write is rounded to tf32 (nearest), because the tensor core truncates raw fp32 operands.  Process-wide;
  * returns the previous setting.  train_ops.set_tensor_cores() keeps it in step with the convolution path. */
 int ledb200_train_set_tf32_rounding(int32_t on);
+/* Tensor-core passes per product of the *_tc entry points below.  3 (default): error-compensated "3 x TF32" -
+ * x = x_hi + x_lo, w = w_hi + w_lo, x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi with exact products and fp32 accumulation:
+ * fp32-grade results from the tensor pipe (the low parts are formed in shared memory next to every TMA-staged slab).
+ * 1: a single tf32 pass (10-bit mantissa operands, cuDNN's allow_tf32 numerics).  Process-wide; returns the previous value. */
+int ledb200_train_set_tf32_passes(int32_t passes);
 int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                                  int32_t stride);
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode);

@@ -559,10 +559,21 @@ template <int MODE> __device__ __forceinline__ constexpr int mode_tap_id(int s, 
   return MODE == 0 ? t : (MODE == 1 ? 0 : ((s & 1) ? 3 + (s >> 1) : (t ? 6 + (s >> 1) : (s >> 1))));
 }
 
-template <int MODE, int KSTEPS, bool S2, bool BRES, bool TF32 = false>
-__global__ void __launch_bounds__(kThreads, 1)
+// TF32: 0 = bf16 operands (inference); 1 = one kind::tf32 pass over the raw fp32 operands (the tensor core keeps 10 mantissa
+// bits and TRUNCATES the rest); 3 = error-compensated "3 x TF32": x = x_hi + x_lo, w = w_hi + w_lo and
+//   x*w ~= x_hi*w_hi + x_hi*w_lo + x_lo*w_hi        (dropped: x_lo*w_lo ~ 2^-22; products exact, fp32 accumulation)
+// - fp32-grade results from the tensor pipe, which the training step needs: train-mode BatchNorm makes LED-Net's gradient
+// so ill-conditioned that tf32-level operand rounding alone moves it by tens of percent (tools/diag_tf32_grads.py).
+// x_hi is what the hardware truncation of the raw slab yields; x_lo = x - trunc(x) is written next to every TMA-staged
+// slab by four converter warps (11..14); w_hi / w_lo come pre-split from the host side (rows [0, cp) and [cp, 2 cp)).
+template <int TF32> __device__ __forceinline__ constexpr int conv_tc_threads() { return TF32 == 3 ? kThreads + 128 : kThreads; }
+
+template <int MODE, int KSTEPS, bool S2, bool BRES, int TF32 = 0>
+__global__ void __launch_bounds__(conv_tc_threads<TF32>(), 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ TcParams P) {
+  constexpr int NTHR = conv_tc_threads<TF32>();
+  constexpr bool X3 = TF32 == 3;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A ring][B ring or resident B][epilogue staging][bias / out2 affine][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -580,7 +591,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint64_t* b_empty = b_full + 8;          // [8]
   uint64_t* t_full = b_empty + 8;          // [4]
   uint64_t* t_empty = t_full + 4;          // [4]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 4);
+  uint64_t* a_lo_full = t_empty + 4;       // [8] X3: the low-part slab next to A stage i is written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_lo_full + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   TL(0, threadIdx.x == 0); TLG(12, threadIdx.x == 0);
@@ -591,6 +603,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     prefetch_tensormap(&tmB);
     for (int i = 0; i < 8; ++i) {
       mbar_init(&a_full[i], 1); mbar_init(&a_empty[i], 1); mbar_init(&b_full[i], 1); mbar_init(&b_empty[i], 1);
+      mbar_init(&a_lo_full[i], 4);
     }
     for (int i = 0; i < 4; ++i) { mbar_init(&t_full[i], 1); mbar_init(&t_empty[i], P.NT >= 64 ? 8 : 4); }
     mbar_fence_init();
@@ -598,11 +611,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       // whole folded weight matrix once per persistent CTA: one barrier, one expect_tx for all boxes.  Issued by
       // the thread that initialised the barriers, BEFORE the CTA-wide sync: the weight fetch (up to 150 KB, the
       // longest latency of the ramp) overlaps the TMEM allocation and the bias loads instead of following them
-      mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes);
+      mbar_expect_tx(&b_full[0], (uint32_t)(P.nchunks * P.ntaps_total) * P.b_box_bytes * (X3 ? 2u : 1u));
       for (int ch = 0; ch < P.nchunks; ++ch)
-        for (int t = 0; t < P.ntaps_total; ++t)
+        for (int t = 0; t < P.ntaps_total; ++t) {
           tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes), &tmB, smem_u32(&b_full[0]),
                       t * P.Cin + ch * P.KC, 0);
+          if (X3) tma_load_2d(smem_u32(sB + (size_t)(ch * 9 + t) * P.b_tile_bytes + P.b_tile_bytes / 2), &tmB,
+                              smem_u32(&b_full[0]), t * P.Cin + ch * P.KC, P.cp);
+        }
     }
     TL(1, true);
   }
@@ -616,17 +632,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   uint32_t tmem_base = 0;
   if (warp == 0) {
     __syncwarp();
-    asm volatile("bar.arrive 1, %0;" ::"n"(kThreads) : "memory");
+    asm volatile("bar.arrive 1, %0;" ::"n"(NTHR) : "memory");
   } else {
     // per-channel epilogue constants, zero padded to cp so no channel guard is needed later
-    for (int c = threadIdx.x - 32; c < P.cp; c += kThreads - 32) {
+    for (int c = threadIdx.x - 32; c < P.cp; c += NTHR - 32) {
       const bool in = c < P.Cout;
       s_bias[c] = (P.bias && in) ? P.bias[c] : 0.f;
       s_o2s[c] = in ? (P.o2_scale ? P.o2_scale[c] : 1.f) : 0.f;
       s_o2b[c] = (P.o2_shift && in) ? P.o2_shift[c] : 0.f;
     }
     tc_fence_before();
-    asm volatile("bar.sync 1, %0;" ::"n"(kThreads) : "memory");
+    asm volatile("bar.sync 1, %0;" ::"n"(NTHR) : "memory");
     tc_fence_after();
     TL(2, threadIdx.x == 32);
     tmem_base = *tmem_slot;
@@ -666,9 +682,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (!BRES) {
               for (int t = 0; t < sl.ntaps; ++t) {
                 mbar_wait(&b_empty[sb], pb ^ 1);
-                mbar_expect_tx(&b_full[sb], P.b_box_bytes);
+                mbar_expect_tx(&b_full[sb], P.b_box_bytes * (X3 ? 2u : 1u));
                 tma_load_2d(smem_u32(sB + (size_t)sb * P.b_tile_bytes), &tmB, smem_u32(&b_full[sb]),
                             sl.tap_id[t] * P.Cin + ch * P.KC, nt * P.NT);
+                if (X3) tma_load_2d(smem_u32(sB + (size_t)sb * P.b_tile_bytes + P.b_tile_bytes / 2), &tmB,
+                                    smem_u32(&b_full[sb]), sl.tap_id[t] * P.Cin + ch * P.KC, P.cp + nt * P.NT);
                 if (++sb == P.SB) { sb = 0; pb ^= 1; }
               }
             }
@@ -697,7 +715,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int mw = (warp == 1) ? 0 : 1;
     if (mw < nmw && elect_one()) {
       const bool mma_on = !(P.dbg & 2);
-      const uint32_t idesc = TF32 ? make_idesc_tf32_m128(P.NT) : make_idesc_bf16_m128(P.NT);
+      const uint32_t idesc = TF32 != 0 ? make_idesc_tf32_m128(P.NT) : make_idesc_bf16_m128(P.NT);
       // probe bit 32 (timing only, results wrong): 8-row groups 1024 B apart (atom aligned) instead of one slab row
       const uint32_t a_hi = desc_hi((P.dbg & 32) ? 8 * row_bytes : (uint32_t)P.sbo_bytes, layout_type);
       const uint32_t b_hi = desc_hi(8 * row_bytes, layout_type);
@@ -736,6 +754,63 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             TL(5, tile == blockIdx.x && ch == 0 && s == 0);
             const uint32_t a_lo = a_lo0 + (uint32_t)sa * a_stage16;
+            if constexpr (X3) {
+              // three passes per (tap, k-step); the low-part slab is only needed for the third, so its barrier is waited
+              // for after the raw-slab MMAs of the slab (resident weights) or of the first tap (streamed weights) are queued
+              const uint32_t a_half16 = a_stage16 >> 1, b_half16 = b_tile16 >> 1;
+              if (BRES) {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  if (t < mode_taps<MODE>(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                    }
+                  }
+                }
+                mbar_wait(&a_lo_full[sa], pa);
+                tc_fence_after();
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  if (t < mode_taps<MODE>(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + a_half16 + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                    }
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int t = 0; t < 9; ++t) {
+                  if (t < mode_taps<MODE>(s)) {
+                    mbar_wait(&b_full[sb], pb);
+                    tc_fence_after();
+                    const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_tile16;
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                    }
+                    if (t == 0) { mbar_wait(&a_lo_full[sa], pa); tc_fence_after(); }
+#pragma unroll
+                    for (int k = 0; k < KSTEPS; ++k) {
+                      const uint32_t al = a_lo + a_half16 + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                    }
+                    tc_commit(&b_empty[sb]);
+                    if (++sb == P.SB) { sb = 0; pb ^= 1; }
+                  }
+                }
+              }
+            } else
             if (BRES) {
               // resident weights: no per-tap waits, so the slab's MMAs are ONE straight-line block - every
               // descriptor word is the per-slab base plus an immediate and the uniform registers the in-flight
@@ -748,7 +823,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if constexpr (TF32) {
+                      if constexpr (TF32 != 0) {
                         if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
                         else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
                       } else {
@@ -770,7 +845,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if constexpr (TF32) {
+                      if constexpr (TF32 != 0) {
                         if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
                         else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
                       } else {
@@ -795,11 +870,39 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
     }
     __syncwarp();
+  } else if (warp >= 11) {
+    // =========================== X3 only: low-part converter, warps 11..14 ========================
+    // walks the A ring exactly like the producer; for every landed slab writes x - trunc_tf32(x) (exact in fp32) into the
+    // second half of the stage.  The swizzle is a permutation of 16-byte chunks, so an element-wise pass over the raw
+    // bytes keeps the layout.  generic-proxy writes -> fence.proxy.async -> the MMAs (async proxy) may read them.
+    if constexpr (X3) {
+      const uint32_t ctid = threadIdx.x - 11 * 32;
+      int sa = 0, pa = 0;
+      const uint32_t total = (uint32_t)P.total_tiles;
+      const int slabs_per_tile = P.nchunks * P.nslabs;
+      for (uint32_t tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        for (int i = 0; i < slabs_per_tile; ++i) {
+          mbar_wait(&a_full[sa], pa);
+          const uint32_t src = smem_u32(sA + (size_t)sa * P.a_stage_bytes), dst = src + P.a_stage_bytes / 2;
+          for (uint32_t o = ctid * 16; o < P.a_box_bytes; o += 128 * 16) {
+            const uint4 v = lds128(src + o);
+            sts128(dst + o, __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u)),
+                   __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u)),
+                   __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u)),
+                   __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u)));
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&a_lo_full[sa]);
+          if (++sa == P.SA) { sa = 0; pa ^= 1; }
+        }
+      }
+    }
   } else if (warp < 10) {
     // =========================== epilogue: two groups of 4 warps (see epilogue_loop) ==============
     const uint32_t st_u = smem_u32(sStage), bias_u = smem_u32(s_bias), o2s_u = smem_u32(s_o2s), o2b_u = smem_u32(s_o2b);
     const int variant = P.up ? 8 : ((P.res ? 1 : 0) | (P.out ? 2 : 0) | (P.out2 ? 4 : 0));
-    if constexpr (TF32) {
+    if constexpr (TF32 != 0) {
       epilogue_f32(P, warp, lane, tmem_base, t_full, t_empty, bias_u);
     } else
     switch (variant) {
@@ -926,6 +1029,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   // TF32 launches move fp32 words: every shared-memory / TMA quantity below is in 2-byte units, so an fp32 tensor of C
   // channels is described as 2C units (128 B rows = 32 fp32 channels = "KC 64"); only the MMA kind and the epilogue differ
   const bool tf32 = a.tf32 != 0;
+  const bool x3 = a.tf32 == 3;          // error-compensated three-pass mode: low-part slab / weight rows next to every tile
   const int es = tf32 ? 2 : 1;
   const int cinE = a.Cin * es;
   P.Cin = cinE; P.Cout = a.Cout;
@@ -933,6 +1037,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   // N tile: the whole (padded) Cout when it is 16 / 32 / 64 / 128 / 256, 256 for multiples of 256, else 64-column
   // tiles (e.g. 192 = GETB qkv of a 64-channel block): the epilogue's column split needs a power-of-two tile
   P.NT = cp > 256 ? 256 : ((cp & (cp - 1)) == 0 ? cp : 64);
+  if (x3 && P.NT > 128) P.NT = 128;     // two weight halves per tile: keep the B ring inside shared memory
   P.ntiles_n = cp / P.NT;
   P.KC = tf32 ? 64 : pick_kc(a.Cin);
   P.nchunks = cinE / P.KC;
@@ -979,8 +1084,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     Slab& s = P.slabs[0];
     s.c_mul = 0; s.dw = 0; s.dh = 0; s.ph = 0; s.ntaps = 1; s.tap_pix[0] = 0; s.tap_id[0] = 0;
   }
-  P.a_stage_bytes = (uint32_t)((box_rows * box_w * row_bytes + 1023) / 1024 * 1024);
-  P.b_tile_bytes = (uint32_t)((P.NT * row_bytes + 1023) / 1024 * 1024);
+  P.a_stage_bytes = (uint32_t)((box_rows * box_w * row_bytes + 1023) / 1024 * 1024) * (x3 ? 2u : 1u);
+  P.b_tile_bytes = (uint32_t)((P.NT * row_bytes + 1023) / 1024 * 1024) * (x3 ? 2u : 1u);
   P.a_box_bytes = (uint32_t)(box_rows * box_w * row_bytes);
   P.b_box_bytes = (uint32_t)(P.NT * row_bytes);
   const int taps = a.ksize * a.ksize;
@@ -1000,12 +1105,26 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     if (fast && a.Ho % TH == 0 && a.Wo % TW == 0) P.stage_bytes = 0;
     if (tf32) P.stage_bytes = 0;
   }
-  const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 40 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
+  const uint32_t bar_bytes = (uint32_t)((3 * cp * 4 + 48 * 8 + 16 + 1023) / 1024 * 1024) + P.stage_bytes;
   const uint32_t b_res_bytes = (uint32_t)(P.nchunks * 9) * P.b_tile_bytes;
   P.b_resident = (P.ntiles_n == 1 && b_res_bytes <= (P.stage_bytes ? 100u : 150u) * 1024) ? 1 : 0;
   static const bool no_resident = getenv("LEDB200_TC_NO_RESIDENT") != nullptr;
   if (no_resident) P.b_resident = 0;
   uint32_t left = SMEM_BUDGET - bar_bytes - 1024;
+  if (x3) {
+    // three-pass mode: an A stage is two slabs (raw + low part, ~47 KB for a 3x3 halo slab), so the A ring is sized first
+    if (P.b_resident && b_res_bytes + 2 * P.a_stage_bytes > left) P.b_resident = 0;
+    if (P.b_resident) {
+      left -= b_res_bytes;
+      P.SB = 1;
+      P.SA = (int)std::min<uint32_t>(8, left / P.a_stage_bytes);
+    } else {
+      if (left < 2 * P.a_stage_bytes + 2 * P.b_tile_bytes) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
+      P.SB = (int)std::min<uint32_t>(8, (left - 2 * P.a_stage_bytes) / P.b_tile_bytes);
+      left -= P.SB * P.b_tile_bytes;
+      P.SA = (int)std::min<uint32_t>(8, left / P.a_stage_bytes);
+    }
+  } else {
   if (P.b_resident) {
     left -= b_res_bytes;
     P.SB = 1;
@@ -1014,6 +1133,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
     left -= P.SB * P.b_tile_bytes;
   }
   P.SA = (int)std::min<uint32_t>(8, left / P.a_stage_bytes);
+  }
   if (P.SA < 2) return fail(LEDB200_EINVAL, "conv_tc: shared memory plan does not fit");
   {
     // Two MMA issuers alternate tiles (see the kernel).  An mbarrier parity wait is only sound when the waiter is at
@@ -1055,7 +1175,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   }
   if (rc) return rc;
   {
-    const uint64_t dims[2] = {(uint64_t)taps * cinE, (uint64_t)cp};
+    const uint64_t dims[2] = {(uint64_t)taps * cinE, (uint64_t)cp * (tf32 ? 2 : 1)};   // tf32: rows [cp, 2 cp) = low parts
     const uint64_t str[1] = {(uint64_t)taps * cinE * 2};
     const uint32_t box[2] = {(uint32_t)P.KC, (uint32_t)P.NT};
     rc = encode(&tmB, tf32 ? (const void*)a.w_tc32 : (const void*)a.w_tc, 2, dims, str, box, P.KC);
@@ -1088,23 +1208,28 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       {{{nullptr, nullptr}, {nullptr, nullptr}},
        {{conv_tc_kernel<2, 2, true, false>, conv_tc_kernel<2, 2, true, true>},
         {conv_tc_kernel<2, 4, true, false>, conv_tc_kernel<2, 4, true, true>}}}};
-  // TF32 instantiations (KSTEPS = 4: four 32-byte k-steps per 128 B row): [mode][stride 2][weights resident]
-  static const KernelFn kernels_tf32[3][2][2] = {
-      {{conv_tc_kernel<0, 4, false, false, true>, conv_tc_kernel<0, 4, false, true, true>}, {nullptr, nullptr}},
-      {{conv_tc_kernel<1, 4, false, false, true>, conv_tc_kernel<1, 4, false, true, true>},
-       {conv_tc_kernel<1, 4, true, false, true>, conv_tc_kernel<1, 4, true, true, true>}},
-      {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, true>, conv_tc_kernel<2, 4, true, true, true>}}};
+  // TF32 instantiations (KSTEPS = 4: four 32-byte k-steps per 128 B row): [three-pass][mode][stride 2][weights resident]
+  static const KernelFn kernels_tf32[2][3][2][2] = {
+      {{{conv_tc_kernel<0, 4, false, false, 1>, conv_tc_kernel<0, 4, false, true, 1>}, {nullptr, nullptr}},
+       {{conv_tc_kernel<1, 4, false, false, 1>, conv_tc_kernel<1, 4, false, true, 1>},
+        {conv_tc_kernel<1, 4, true, false, 1>, conv_tc_kernel<1, 4, true, true, 1>}},
+       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 1>, conv_tc_kernel<2, 4, true, true, 1>}}},
+      {{{conv_tc_kernel<0, 4, false, false, 3>, conv_tc_kernel<0, 4, false, true, 3>}, {nullptr, nullptr}},
+       {{conv_tc_kernel<1, 4, false, false, 3>, conv_tc_kernel<1, 4, false, true, 3>},
+        {conv_tc_kernel<1, 4, true, false, 3>, conv_tc_kernel<1, 4, true, true, 3>}},
+       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 3>, conv_tc_kernel<2, 4, true, true, 3>}}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
-    for (int m = 0; m < 3; ++m)
-      for (int s = 0; s < 2; ++s)
-        for (int r = 0; r < 2; ++r)
-          if (kernels_tf32[m][s][r]) {
-            cudaError_t e = cudaFuncSetAttribute(kernels_tf32[m][s][r], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                 (int)SMEM_BUDGET + 2048);
-            if (e != cudaSuccess) attr_err = e;
-          }
+    for (int x = 0; x < 2; ++x)
+      for (int m = 0; m < 3; ++m)
+        for (int s = 0; s < 2; ++s)
+          for (int r = 0; r < 2; ++r)
+            if (kernels_tf32[x][m][s][r]) {
+              cudaError_t e = cudaFuncSetAttribute(kernels_tf32[x][m][s][r], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                   (int)SMEM_BUDGET + 2048);
+              if (e != cudaSuccess) attr_err = e;
+            }
     for (int m = 0; m < 3; ++m)
       for (int s = 0; s < 2; ++s)
         for (int k = 0; k < 2; ++k)
@@ -1116,9 +1241,9 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
             }
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("conv_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
-  const KernelFn fn = tf32 ? kernels_tf32[mode][s2 ? 1 : 0][P.b_resident ? 1 : 0]
+  const KernelFn fn = tf32 ? kernels_tf32[x3 ? 1 : 0][mode][s2 ? 1 : 0][P.b_resident ? 1 : 0]
                            : kernels[mode][s2 ? 1 : 0][ksteps == 4][P.b_resident ? 1 : 0];
-  fn<<<grid, kThreads, smem, st>>>(tmA, tmB, P);
+  fn<<<grid, x3 ? kThreads + 128 : kThreads, smem, st>>>(tmA, tmB, P);
   LEDB_LAUNCH_OK("conv_tc_kernel");
   return LEDB200_OK;
 }

@@ -11,10 +11,10 @@ namespace ledb {
 int tc_encode_tiled(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                     const uint32_t* box, int kc);
 // weight gradient on the tensor cores (wgrad_tc.cu)
-bool wgrad_tc_eligible(int N, int H, int W, int Cin, int Cout, int k, int stride);
-int64_t wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride);
+bool wgrad_tc_eligible(int N, int H, int W, int Cin, int Cout, int k, int stride, int passes);
+int64_t wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride, int passes);
 int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    void* workspace, cudaStream_t st);
+                    int passes, void* workspace, cudaStream_t st);
 namespace tc {
 
 __device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }

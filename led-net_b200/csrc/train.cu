@@ -19,6 +19,8 @@
 //   Every reduction is order-fixed (no floating-point atomics): a step is bit-reproducible run to run.
 //   add(+ReLU), avg-pool, channel copy (concat/slice), SGD+momentum over one flat parameter arena.
 // All tensors NHWC fp32, dense (pixel stride = C) unless an `ld` says otherwise.
+#include <algorithm>
+
 #include "tc_common.cuh"
 
 namespace ledb {
@@ -30,6 +32,9 @@ constexpr int kT = 256;
 // tests/test_gpu_train_tc.py, -3.7e-4 mean), sees exactly representable values - truncation would shrink every data
 // gradient by ~3e-4 per layer, compounding to percents at the stem.  Off: plain fp32 stores (the CUDA-core path).
 int g_round = 0;
+// tensor-core passes per product (ledb200_train_set_tf32_passes): 3 = error-compensated 3 x TF32 (fp32-grade, default),
+// 1 = single tf32 pass (cuDNN's allow_tf32 numerics; callers then also switch the tf32 storage mode on)
+int g_passes = 3;
 __device__ __forceinline__ float rt(float v, int rnd) {
   if (!rnd) return v;
   uint32_t t;
@@ -63,7 +68,8 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, float* __restric
   }
 }
 
-// K-major fp32 weight matrix of the tensor-core path (conv_tc.cu, TF32 instantiations), values rounded to tf32 (RN):
+// K-major fp32 weight matrices of the tensor-core path (conv_tc.cu, TF32 instantiations): w_hi = w rounded to tf32 (RN)
+// followed by w_lo = w - w_hi, each
 //   mode 0 (forward):       out[co_pad][tap * Cin + ci]  = w[co][ci][tap]
 //   mode 1 (data gradient): out[ci_pad][tap' * Cout + co] = w[co][ci][taps - 1 - tap']   (rotated, roles swapped)
 __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int taps,
@@ -78,7 +84,9 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
     if (r < rows) v = mode == 0 ? w[((int64_t)r * Cin + c) * taps + tap] : w[((int64_t)c * Cin + r) * taps + (taps - 1 - tap)];
     uint32_t t;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(t) : "f"(v));
-    out[i] = __uint_as_float(t);
+    const float hi = __uint_as_float(t);
+    out[i] = hi;                 // rows [0, rows_pad): w rounded to tf32
+    out[total + i] = v - hi;     // rows [rows_pad, 2 rows_pad): the remainder (exact), second operand of the three-pass mode
   }
 }
 
@@ -252,13 +260,88 @@ chan_reduce_kernel(const float* __restrict__ a, const float* __restrict__ y, con
   for (int i = threadIdx.x; i < 2 * C; i += kT) mine[i] = sacc[i];
 }
 
+// The same reductions with thread = FOUR consecutive channels (C % 4 == 0, 16-byte aligned rows, < 2^31 elements): 128-bit
+// loads and 32-bit index arithmetic (the scalar kernels above spend most of their issue slots on 64-bit div / mod).
+template <int KIND>
+__global__ void __launch_bounds__(kT)
+chan_reduce4_kernel(const float4* __restrict__ a, const float4* __restrict__ y, const float4* __restrict__ out,
+                    const float* __restrict__ mean, const float* __restrict__ invstd, int relu, uint32_t npix, uint32_t C4,
+                    double* __restrict__ part /* [gridDim.x][2][C] */) {
+  extern __shared__ double sacc[];   // [2][C]
+  __shared__ double sd[2][4][kT];
+  const uint32_t C = C4 * 4;
+  const uint32_t T = gridDim.x * kT;
+  const uint32_t R = T / C4;
+  const uint32_t g = blockIdx.x * kT + threadIdx.x;
+  double d0[4] = {0.0, 0.0, 0.0, 0.0}, d1[4] = {0.0, 0.0, 0.0, 0.0};
+  if (R > 0 && g < R * C4) {
+    const uint32_t c4 = g % C4;
+    float s0[4] = {0.f, 0.f, 0.f, 0.f}, s1[4] = {0.f, 0.f, 0.f, 0.f};
+    float4 m = make_float4(0.f, 0.f, 0.f, 0.f), is = m;
+    if (KIND == 1) { m = *reinterpret_cast<const float4*>(mean + 4 * c4); is = *reinterpret_cast<const float4*>(invstd + 4 * c4); }
+    int cnt = 0;
+    for (uint32_t r = g / C4; r < npix; r += R) {
+      const uint32_t i = r * C4 + c4;
+      const float4 v = __ldg(a + i);
+      if (KIND == 0) {
+        s0[0] += v.x; s0[1] += v.y; s0[2] += v.z; s0[3] += v.w;
+        s1[0] = fmaf(v.x, v.x, s1[0]); s1[1] = fmaf(v.y, v.y, s1[1]); s1[2] = fmaf(v.z, v.z, s1[2]); s1[3] = fmaf(v.w, v.w, s1[3]);
+      } else if (KIND == 1) {
+        float4 dz = v;
+        if (relu) {
+          const float4 o = __ldg(out + i);
+          if (!(o.x > 0.f)) dz.x = 0.f;
+          if (!(o.y > 0.f)) dz.y = 0.f;
+          if (!(o.z > 0.f)) dz.z = 0.f;
+          if (!(o.w > 0.f)) dz.w = 0.f;
+        }
+        const float4 yy = __ldg(y + i);
+        s0[0] += dz.x; s0[1] += dz.y; s0[2] += dz.z; s0[3] += dz.w;
+        s1[0] = fmaf(dz.x, (yy.x - m.x) * is.x, s1[0]); s1[1] = fmaf(dz.y, (yy.y - m.y) * is.y, s1[1]);
+        s1[2] = fmaf(dz.z, (yy.z - m.z) * is.z, s1[2]); s1[3] = fmaf(dz.w, (yy.w - m.w) * is.w, s1[3]);
+      } else {
+        s0[0] += v.x; s0[1] += v.y; s0[2] += v.z; s0[3] += v.w;
+      }
+      if (++cnt == 256) {                       // bound the fp32 run length
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
+        cnt = 0;
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; }
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) { sd[0][j][threadIdx.x] = d0[j]; sd[1][j][threadIdx.x] = d1[j]; }
+  for (uint32_t i = threadIdx.x; i < 2 * C; i += kT) sacc[i] = 0.0;
+  __syncthreads();
+  // thread t < min(C4, kT) is the first thread of its channel group in this block: it adds threads t, t + C4, ... in order
+  if (threadIdx.x < C4) {
+    const uint32_t c4 = g % C4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      double t0 = 0.0, t1 = 0.0;
+      for (uint32_t k = threadIdx.x; k < kT; k += C4) { t0 += sd[0][j][k]; t1 += sd[1][j][k]; }
+      sacc[4 * c4 + j] = t0; sacc[C + 4 * c4 + j] = t1;
+    }
+  }
+  __syncthreads();
+  double* mine = part + (int64_t)blockIdx.x * 2 * C;
+  for (uint32_t i = threadIdx.x; i < 2 * C; i += kT) mine[i] = sacc[i];
+}
+
+// acc[i] = sum over the blocks' partials, one WARP per output: lane l adds blocks l, l + 32, ... in index order and the 32
+// lane sums are combined by a fixed shuffle tree - the order depends only on (nblocks), never on scheduling.
+// (round 2 measured the one-thread-per-output version at 57 us per launch, 7 ms per training step: 592 dependent loads)
 __global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__ part, int nblocks, int n2c,
                                                       double* __restrict__ acc) {
-  const int i = blockIdx.x * kT + threadIdx.x;
+  const int i = (blockIdx.x * kT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n2c) return;
   double s = 0.0;
-  for (int b = 0; b < nblocks; ++b) s += part[(int64_t)b * n2c + i];
-  acc[i] = s;
+  for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * n2c + i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+  if (lane == 0) acc[i] = s;
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double npix, float eps, float momentum,
@@ -311,6 +394,64 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
   }
 }
 
+// vectorised forms of the two kernels above (C % 4 == 0, aligned, < 2^31 elements)
+__global__ void __launch_bounds__(kT)
+bn_apply4_kernel(const float4* __restrict__ y, const float4* __restrict__ res, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                 float4* __restrict__ out, int relu, uint32_t total4, uint32_t C4, int rnd) {
+  const float lo = relu ? 0.f : -INFINITY;
+  for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < total4; i += gridDim.x * kT) {
+    const uint32_t c = (i % C4) * 4;
+    const float4 v = __ldg(y + i);
+    const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c), b = *reinterpret_cast<const float4*>(beta + c);
+    float4 o;
+    o.x = fmaf((v.x - m.x) * is.x, g.x, b.x); o.y = fmaf((v.y - m.y) * is.y, g.y, b.y);
+    o.z = fmaf((v.z - m.z) * is.z, g.z, b.z); o.w = fmaf((v.w - m.w) * is.w, g.w, b.w);
+    if (res) { const float4 r = __ldg(res + i); o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w; }
+    o.x = rt(fmaxf(o.x, lo), rnd); o.y = rt(fmaxf(o.y, lo), rnd); o.z = rt(fmaxf(o.z, lo), rnd); o.w = rt(fmaxf(o.w, lo), rnd);
+    out[i] = o;
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply4_kernel(const float4* __restrict__ dout, const float4* __restrict__ y, const float4* __restrict__ out,
+                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                     const double* __restrict__ acc, const double* __restrict__ acc_local, float4* __restrict__ dy,
+                     float4* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu,
+                     uint32_t total4, uint32_t C4, float invM, int rnd) {
+  const uint32_t C = C4 * 4;
+  for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < total4; i += gridDim.x * kT) {
+    const uint32_t c = (i % C4) * 4;
+    float4 dz = __ldg(dout + i);
+    if (relu) {
+      const float4 o = __ldg(out + i);
+      if (!(o.x > 0.f)) dz.x = 0.f;
+      if (!(o.y > 0.f)) dz.y = 0.f;
+      if (!(o.z > 0.f)) dz.z = 0.f;
+      if (!(o.w > 0.f)) dz.w = 0.f;
+    }
+    const float4 yy = __ldg(y + i);
+    const float4 m = *reinterpret_cast<const float4*>(mean + c), is = *reinterpret_cast<const float4*>(invstd + c);
+    const float4 g = *reinterpret_cast<const float4*>(gamma + c);
+    const float dzv[4] = {dz.x, dz.y, dz.z, dz.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+    const float mv[4] = {m.x, m.y, m.z, m.w}, isv[4] = {is.x, is.y, is.z, is.w}, gv[4] = {g.x, g.y, g.z, g.w};
+    float o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float db = (float)acc[c + j], dg = (float)acc[C + c + j];
+      const float xhat = (yv[j] - mv[j]) * isv[j];
+      o[j] = rt(gv[j] * isv[j] * (dzv[j] - db * invM - xhat * dg * invM), rnd);
+    }
+    dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dres) dres[i] = dz;
+    if (i < C4) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { dbeta[c + j] = (float)acc_local[c + j]; dgamma[c + j] = (float)acc_local[C + c + j]; }
+    }
+  }
+}
+
 __global__ void acc_to_float_kernel(const double* __restrict__ acc, float* __restrict__ out, int C) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c < C) out[c] = (float)acc[c];
@@ -318,6 +459,12 @@ __global__ void acc_to_float_kernel(const double* __restrict__ acc, float* __res
 
 // workspace layout of the per-channel reductions (doubles): [0, 4C + 8) accumulators (2C of a reduction; SyncBN keeps a second
 // copy and the sample count there), then kMaxRedBlocks block partials of 2C each
+inline bool vec4_ok(int C, int64_t total, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr,
+                    const void* p3 = nullptr, const void* p4 = nullptr) {
+  return C % 4 == 0 && total < (1ll << 31) &&
+         ((uintptr_t)p0 | (uintptr_t)p1 | (uintptr_t)p2 | (uintptr_t)p3 | (uintptr_t)p4) % 16 == 0;
+}
+
 inline int64_t bn_ws_doubles(int C) { return 4 * (int64_t)C + 8 + (int64_t)kMaxRedBlocks * 2 * C; }
 
 template <int KIND>
@@ -325,8 +472,13 @@ int chan_reduce(const float* a, const float* y, const float* out, const float* m
                 int64_t npix, int C, double* ws, cudaStream_t st) {
   double* part = ws + 4 * (int64_t)C + 8;
   const int grid = grid1d(npix * C, 4);                     // <= kMaxRedBlocks
+  if (vec4_ok(C, npix * C, a, y, out) && ((uintptr_t)mean | (uintptr_t)invstd) % 16 == 0)
+    chan_reduce4_kernel<KIND><<<grid, kT, sizeof(double) * 2 * C, st>>>(
+        reinterpret_cast<const float4*>(a), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), mean, invstd,
+        relu, (uint32_t)npix, (uint32_t)(C / 4), part);
+  else
   chan_reduce_kernel<KIND><<<grid, kT, sizeof(double) * 2 * C, st>>>(a, y, out, mean, invstd, relu, npix, C, part);
-  chan_sum_kernel<<<ceil_div(2 * C, kT), kT, 0, st>>>(part, grid, 2 * C, ws);
+  chan_sum_kernel<<<ceil_div(2 * C * 32, kT), kT, 0, st>>>(part, grid, 2 * C, ws);
   LEDB_LAUNCH_OK("chan_reduce_kernel");
   return LEDB200_OK;
 }
@@ -399,6 +551,130 @@ resize_bwd_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int 
       acc = fmaf(row, wy, acc);
     }
     dsrc[i] = rt(acc, rnd);
+  }
+}
+
+// Row-decomposed forms of the two resize kernels (same arithmetic, same summation order, bit-identical results): one block
+// row per (image, output row), so the vertical coordinates are block-uniform and the per-element index arithmetic is one
+// 32-bit div / mod by C; V = 4 channels per thread through 128-bit accesses when C % 4 == 0.
+// (round 2 measured the flat kernels at 10x the HBM time on the head's logit ladder: 64-bit div / mod per element and, in
+// the backward gather, a bilinear_coord per (row, column) candidate pair instead of per row and per column)
+template <int V> struct VecT { using type = float; };
+template <> struct VecT<4> { using type = float4; };
+__device__ __forceinline__ float vget(const float& v, int) { return v; }
+__device__ __forceinline__ float vget(const float4& v, int j) { return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w)); }
+__device__ __forceinline__ void vset(float& v, int, float x) { v = x; }
+__device__ __forceinline__ void vset(float4& v, int j, float x) { if (j == 0) v.x = x; else if (j == 1) v.y = x; else if (j == 2) v.z = x; else v.w = x; }
+
+template <int V>
+__global__ void __launch_bounds__(kT)
+resize_fwd_row_kernel(const float* __restrict__ src, float* __restrict__ out, int h, int w, int H, int W, int C, float sh,
+                      float sw, int rnd) {
+  using T = typename VecT<V>::type;
+  const uint32_t row = blockIdx.x, n = row / (uint32_t)H, y = row % (uint32_t)H;
+  int y0, y1;
+  float ly0, ly1;
+  bilinear_coord((int)y, sh, h, y0, y1, ly0, ly1);
+  const float* s0 = src + ((int64_t)n * h + y0) * w * C;
+  const float* s1 = src + ((int64_t)n * h + y1) * w * C;
+  float* o = out + (int64_t)row * W * C;
+  const uint32_t len = (uint32_t)W * C;
+  for (uint32_t j = (blockIdx.y * kT + threadIdx.x) * V; j < len; j += gridDim.y * kT * V) {
+    const uint32_t x = j / (uint32_t)C, c = j % (uint32_t)C;
+    int x0, x1;
+    float lx0, lx1;
+    bilinear_coord((int)x, sw, w, x0, x1, lx0, lx1);
+    const T a = __ldg(reinterpret_cast<const T*>(s0 + x0 * C + c)), b = __ldg(reinterpret_cast<const T*>(s0 + x1 * C + c));
+    const T cc = __ldg(reinterpret_cast<const T*>(s1 + x0 * C + c)), d = __ldg(reinterpret_cast<const T*>(s1 + x1 * C + c));
+    T r;
+#pragma unroll
+    for (int k = 0; k < V; ++k) {
+      const float r0 = fmaf(vget(b, k), lx1, vget(a, k) * lx0);
+      const float r1 = fmaf(vget(d, k), lx1, vget(cc, k) * lx0);
+      vset(r, k, rt(fmaf(r1, ly1, r0 * ly0), rnd));
+    }
+    *reinterpret_cast<T*>(o + j) = r;
+  }
+}
+
+template <int V>
+__global__ void __launch_bounds__(kT)
+resize_bwd_row_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int h, int w, int H, int W, int C, float sh,
+                      float sw, int rnd) {
+  using T = typename VecT<V>::type;
+  const uint32_t row = blockIdx.x, n = row / (uint32_t)h, ys = row % (uint32_t)h;
+  int ylo, yhi;
+  gather_range((int)ys, sh, H, ylo, yhi);
+  const float* g = dout + (int64_t)n * H * W * C;
+  float* o = dsrc + (int64_t)row * w * C;
+  const uint32_t len = (uint32_t)w * C;
+  constexpr int XMAX = 8;
+  for (uint32_t j = (blockIdx.y * kT + threadIdx.x) * V; j < len; j += gridDim.y * kT * V) {
+    const uint32_t xs = j / (uint32_t)C, c = j % (uint32_t)C;
+    int xlo, xhi;
+    gather_range((int)xs, sw, W, xlo, xhi);
+    const int nx = xhi - xlo + 1;
+    float wxs[XMAX];
+    if (nx <= XMAX) {
+#pragma unroll
+      for (int k = 0; k < XMAX; ++k) {
+        float wx = 0.f;
+        if (k < nx) {
+          int x0, x1;
+          float lx0, lx1;
+          bilinear_coord(xlo + k, sw, w, x0, x1, lx0, lx1);
+          if (x0 == (int)xs) wx += lx0;
+          if (x1 == (int)xs) wx += lx1;
+          if (x0 != (int)xs && x1 != (int)xs) wx = -1.f;       // not a member (a member's weight may be exactly 0)
+        }
+        wxs[k] = wx;
+      }
+    }
+    float acc[V];
+#pragma unroll
+    for (int k = 0; k < V; ++k) acc[k] = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      float wy = 0.f;
+      if (y0 == (int)ys) wy += ly0;
+      if (y1 == (int)ys) wy += ly1;
+      if (y0 != (int)ys && y1 != (int)ys) continue;
+      float rowv[V];
+#pragma unroll
+      for (int k = 0; k < V; ++k) rowv[k] = 0.f;
+      const float* gr = g + ((int64_t)y * W) * C + c;
+      if (nx <= XMAX) {
+#pragma unroll
+        for (int k = 0; k < XMAX; ++k) {
+          if (k < nx && wxs[k] >= 0.f) {
+            const T v = __ldg(reinterpret_cast<const T*>(gr + (xlo + k) * C));
+#pragma unroll
+            for (int q = 0; q < V; ++q) rowv[q] = fmaf(vget(v, q), wxs[k], rowv[q]);
+          }
+        }
+      } else {
+        for (int x = xlo; x <= xhi; ++x) {
+          int x0, x1;
+          float lx0, lx1;
+          bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+          if (x0 != (int)xs && x1 != (int)xs) continue;
+          float wx = 0.f;
+          if (x0 == (int)xs) wx += lx0;
+          if (x1 == (int)xs) wx += lx1;
+          const T v = __ldg(reinterpret_cast<const T*>(gr + x * C));
+#pragma unroll
+          for (int q = 0; q < V; ++q) rowv[q] = fmaf(vget(v, q), wx, rowv[q]);
+        }
+      }
+#pragma unroll
+      for (int q = 0; q < V; ++q) acc[q] = fmaf(rowv[q], wy, acc[q]);
+    }
+    T r;
+#pragma unroll
+    for (int q = 0; q < V; ++q) vset(r, q, rt(acc[q], rnd));
+    *reinterpret_cast<T*>(o + j) = r;
   }
 }
 
@@ -520,6 +796,13 @@ int ledb200_train_set_tf32_rounding(int32_t on) {
   return prev;
 }
 
+int ledb200_train_set_tf32_passes(int32_t passes) {
+  if (passes != 1 && passes != 3) return fail(LEDB200_EINVAL, "train_set_tf32_passes: 1 or 3");
+  const int prev = g_passes;
+  g_passes = passes;
+  return prev;
+}
+
 int64_t ledb200_train_packed_weight_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
   const int64_t taps = (int64_t)k * k;
   return mode == 0 ? taps * Cin * ((Cout + 15) / 16 * 16) : taps * Cout * ((Cin + 15) / 16 * 16);
@@ -571,7 +854,7 @@ static void conv_tc_args(ConvArgs& a, const float* in, float* out, const float* 
   a.in = in; a.in_dtype = LEDB200_F32; a.in_sc = 1; a.in_sw = Cin; a.in_sh = (int64_t)W * Cin;
   a.in_sn = (int64_t)H * W * Cin;
   a.out = out; a.out_dtype = LEDB200_F32; a.out_ld = Cout;
-  a.bias = bias; a.w_tc32 = w_tc; a.tf32 = 1; a.cout_pad_tc = conv_tc_pad(Cout);
+  a.bias = bias; a.w_tc32 = w_tc; a.tf32 = g_passes; a.cout_pad_tc = conv_tc_pad(Cout);
   a.N = N; a.H = H; a.W = W; a.Cin = Cin; a.Cout = Cout; a.ksize = k; a.stride = stride; a.pad = k / 2; a.dil = 1;
   a.Ho = (H + 2 * a.pad - k) / stride + 1; a.Wo = (W + 2 * a.pad - k) / stride + 1;
 }
@@ -592,24 +875,24 @@ int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, in
     conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cout, Cin, k, 1);
     return conv_tc_eligible(a) ? 1 : 0;
   }
-  if (op == 2) return wgrad_tc_eligible(N, H, W, Cin, Cout, k, stride) ? 1 : 0;
+  if (op == 2) return wgrad_tc_eligible(N, H, W, Cin, Cout, k, stride, g_passes) ? 1 : 0;
   return 0;
 }
 
 int64_t ledb200_train_wgrad_tc_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                                                int32_t stride) {
-  return wgrad_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride);
+  return wgrad_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride, g_passes);
 }
 
 int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
                                 int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace, void* stream) {
   if (!x || !dy || !dw_oihw || !workspace) return fail(LEDB200_EINVAL, "train_conv_wgrad_tc: null buffer");
-  return launch_wgrad_tc(x, dy, dw_oihw, N, H, W, Cin, Cout, k, stride, workspace, (cudaStream_t)stream);
+  return launch_wgrad_tc(x, dy, dw_oihw, N, H, W, Cin, Cout, k, stride, g_passes, workspace, (cudaStream_t)stream);
 }
 
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
   const int64_t taps = (int64_t)k * k;
-  return mode == 0 ? (int64_t)conv_tc_pad(Cout) * taps * Cin : (int64_t)conv_tc_pad(Cin) * taps * Cout;
+  return 2 * (mode == 0 ? (int64_t)conv_tc_pad(Cout) * taps * Cin : (int64_t)conv_tc_pad(Cin) * taps * Cout);
 }
 
 int ledb200_train_pack_weight_tc(const float* w_oihw, float* out, int32_t Cout, int32_t Cin, int32_t k, int32_t mode,
@@ -617,7 +900,7 @@ int ledb200_train_pack_weight_tc(const float* w_oihw, float* out, int32_t Cout, 
   if (!w_oihw || !out) return fail(LEDB200_EINVAL, "pack_weight_tc: null buffer");
   if (mode != 0 && mode != 1) return fail(LEDB200_EINVAL, "pack_weight_tc: mode must be 0 (forward) or 1 (dgrad)");
   const int rows_pad = conv_tc_pad(mode == 0 ? Cout : Cin);
-  const int64_t total = ledb200_train_packed_weight_tc_floats(Cout, Cin, k, mode);
+  const int64_t total = ledb200_train_packed_weight_tc_floats(Cout, Cin, k, mode) / 2;
   pack_weight_tc_kernel<<<grid1d(total), kT, 0, (cudaStream_t)stream>>>(w_oihw, out, Cout, Cin, k * k, mode, rows_pad);
   LEDB_LAUNCH_OK("pack_weight_tc_kernel");
   return LEDB200_OK;
@@ -727,6 +1010,11 @@ int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* 
   cudaStream_t st = (cudaStream_t)stream;
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, C, total_count, eps, momentum, save_mean,
                                                        save_invstd, running_mean_opt, running_var_opt);
+  if (vec4_ok(C, npix * C, y, res_opt, out, gamma, beta) && ((uintptr_t)save_mean | (uintptr_t)save_invstd) % 16 == 0)
+    bn_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(res_opt), gamma, beta, save_mean, save_invstd,
+        reinterpret_cast<float4*>(out), relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), g_round);
+  else
   bn_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
                                                    npix * C, C, g_round);
   LEDB_LAUNCH_OK("train_bn_fwd_apply");
@@ -744,6 +1032,12 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
   if (relu && !out) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: the ReLU mask needs the forward output");
   if (total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: bad sample count");
   const double* acc = (const double*)workspace;
+  if (vec4_ok(C, npix * C, dout, y, out, dy, dres_opt) && ((uintptr_t)gamma | (uintptr_t)save_mean | (uintptr_t)save_invstd) % 16 == 0)
+    bn_bwd_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
+        save_mean, save_invstd, acc + 2 * C, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta,
+        relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), (float)(1.0 / total_count), g_round);
+  else
   bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(dout, y, out, gamma, save_mean, save_invstd,
                                                                          acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta,
                                                                          relu, npix * C, C, (float)(1.0 / total_count), g_round);
@@ -776,6 +1070,12 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
   double* acc = (double*)workspace;
   int rc = chan_reduce<1>(dout, y, out, save_mean, save_invstd, relu, npix, C, acc, st);
   if (rc) return rc;
+  if (vec4_ok(C, npix * C, dout, y, out, dy, dres_opt) && ((uintptr_t)gamma | (uintptr_t)save_mean | (uintptr_t)save_invstd) % 16 == 0)
+    bn_bwd_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
+        save_mean, save_invstd, acc, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta, relu,
+        (uint32_t)(npix * C / 4), (uint32_t)(C / 4), 1.f / (float)npix, g_round);
+  else
   bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy, dres_opt,
                                                        dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix, g_round);
   LEDB_LAUNCH_OK("train_bn_bwd");
@@ -785,8 +1085,15 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
 int ledb200_train_resize_fwd(const float* src, float* out, int32_t N, int32_t h, int32_t w, int32_t H, int32_t W,
                              int32_t C, void* stream) {
   if (!src || !out) return fail(LEDB200_EINVAL, "train_resize_fwd: null buffer");
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  if ((int64_t)N * H < (1ll << 31) && (int64_t)std::max(W, w) * C < (1ll << 30)) {
+    const int V = (C % 4 == 0 && ((uintptr_t)src | (uintptr_t)out) % 16 == 0) ? 4 : 1;
+    dim3 grid((unsigned)(N * H), (unsigned)std::min(8, ceil_div(W * C, kT * V * 4)));
+    if (V == 4) resize_fwd_row_kernel<4><<<grid, kT, 0, (cudaStream_t)stream>>>(src, out, h, w, H, W, C, sh, sw, g_round);
+    else resize_fwd_row_kernel<1><<<grid, kT, 0, (cudaStream_t)stream>>>(src, out, h, w, H, W, C, sh, sw, g_round);
+  } else
   resize_fwd_kernel<<<grid1d((int64_t)N * H * W * C), kT, 0, (cudaStream_t)stream>>>(
-      src, out, N, h, w, H, W, C, (float)h / (float)H, (float)w / (float)W, g_round);
+      src, out, N, h, w, H, W, C, sh, sw, g_round);
   LEDB_LAUNCH_OK("resize_fwd_kernel");
   return LEDB200_OK;
 }
@@ -795,8 +1102,14 @@ int ledb200_train_resize_bwd(const float* dout, float* dsrc, int32_t N, int32_t 
                              int32_t C, void* stream) {
   if (!dout || !dsrc) return fail(LEDB200_EINVAL, "train_resize_bwd: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
-  resize_bwd_kernel<<<grid1d((int64_t)N * h * w * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, (float)h / (float)H,
-                                                                  (float)w / (float)W, g_round);
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  if ((int64_t)N * h < (1ll << 31) && (int64_t)std::max(W, w) * C < (1ll << 30)) {
+    const int V = (C % 4 == 0 && ((uintptr_t)dout | (uintptr_t)dsrc) % 16 == 0) ? 4 : 1;
+    dim3 grid((unsigned)(N * h), (unsigned)std::min(8, ceil_div(w * C, kT * V * 2)));
+    if (V == 4) resize_bwd_row_kernel<4><<<grid, kT, 0, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
+    else resize_bwd_row_kernel<1><<<grid, kT, 0, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
+  } else
+  resize_bwd_kernel<<<grid1d((int64_t)N * h * w * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, sh, sw, g_round);
   LEDB_LAUNCH_OK("resize_bwd_kernel");
   return LEDB200_OK;
 }

@@ -59,8 +59,11 @@ struct WgParams {
   float* part;             // [units * G][nacc][96][ncols]
 };
 
-template <bool S2>
-__global__ void __launch_bounds__(kThreads, 1)
+// X3: error-compensated three-pass mode (see conv_tc.cu): both operands are activations here, so warps 6..9 write the low
+// parts x - trunc_tf32(x) of EVERY slab of a stage (X and dY) into the stage's second half, and each product becomes
+//   X_raw * dY_raw + X_lo * dY_raw + X_raw * dY_lo      (the tensor core truncates the raw operands itself)
+template <bool S2, bool X3>
+__global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ WgParams P) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -70,7 +73,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   uint64_t* full = bars;          // [8]
   uint64_t* empty = bars + 8;     // [8]
   uint64_t* done = bars + 16;     // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
+  uint64_t* lo_full = bars + 17;  // [8] X3: low parts of stage i written
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 25);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x / P.G, g = blockIdx.x % P.G;
@@ -80,7 +84,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmX);
     prefetch_tensormap(&tmY);
-    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); }
+    for (int i = 0; i < 8; ++i) { mbar_init(&full[i], 1); mbar_init(&empty[i], 1); mbar_init(&lo_full[i], 4); }
     mbar_init(done, 1);
     mbar_fence_init();
   }
@@ -132,33 +136,41 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       const uint32_t a_lbo = (128u >> 4) << 16, b_lbo = (P.yslab_bytes >> 4) << 16;
       int s = 0, ph = 0;
       uint32_t first = 0;                                          // 0 until the accumulators hold a first product
+      const uint32_t half = X3 ? P.stage_bytes / 2 : 0u;           // offset of the low-part copy of a stage
       for (int64_t t = g; t < P.tiles; t += P.G) {
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(stages + (size_t)s * P.stage_bytes);
         const uint32_t sy = st + (uint32_t)(P.ncc * nx) * P.xslab_bytes;
-        for (int r = 0; r < TH; ++r) {
-          const uint32_t b_lo = (((sy + (uint32_t)(r * TW) * 128u) >> 4) & 0x3FFFu) | b_lbo;
-          for (int c = 0; c < P.ncc; ++c) {
+        // pass 0: raw x raw; X3 passes 1, 2 (after the converter warps have arrived): X_lo x dY_raw, X_raw x dY_lo
+#pragma unroll 1
+        for (int pass = 0; pass < (X3 ? 3 : 1); ++pass) {
+          if (X3 && pass == 1) { mbar_wait(&lo_full[s], ph); tc_fence_after(); }
+          const uint32_t xo = (pass == 1) ? half : 0u, yo = (pass == 2) ? half : 0u;
+          for (int r = 0; r < TH; ++r) {
+            const uint32_t b_lo = (((sy + yo + (uint32_t)(r * TW) * 128u) >> 4) & 0x3FFFu) | b_lbo;
+            const uint32_t acc = first | (uint32_t)r | (uint32_t)pass;
+            for (int c = 0; c < P.ncc; ++c) {
 #pragma unroll
-            for (int kh = 0; kh < 3; ++kh) {
-              if (S2) {
-                // input row 2*oh + kh - 1: kh = 0 -> odd rows, slab row r (slab starts at half-row oh0 - 1);
-                // kh = 1 -> even rows, slab row r; kh = 2 -> odd rows, slab row r + 1
-                const int pr = (kh == 1) ? 0 : 1, srow = (kh == 2) ? r + 1 : r;
+              for (int kh = 0; kh < 3; ++kh) {
+                if (S2) {
+                  // input row 2*oh + kh - 1: kh = 0 -> odd rows, slab row r (slab starts at half-row oh0 - 1);
+                  // kh = 1 -> even rows, slab row r; kh = 2 -> odd rows, slab row r + 1
+                  const int pr = (kh == 1) ? 0 : 1, srow = (kh == 2) ? r + 1 : r;
 #pragma unroll
-                for (int pc = 0; pc < 2; ++pc) {
-                  // pc = 1: atoms 0, 1 = filter columns 0, 2 (odd columns ow - 1, ow); pc = 0: atom 0 = filter column 1
-                  const uint32_t xs = st + (uint32_t)(c * 4 + pr * 2 + pc) * P.xslab_bytes;
-                  const uint32_t a_lo = (((xs + (uint32_t)(srow * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
-                  const uint32_t d = tmem_base + (uint32_t)(((c * 3 + kh) * 2 + pc) * P.ncols);
-                  tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, first | (uint32_t)r);
+                  for (int pc = 0; pc < 2; ++pc) {
+                    // pc = 1: atoms 0, 1 = filter columns 0, 2 (odd columns ow - 1, ow); pc = 0: atom 0 = filter column 1
+                    const uint32_t xs = st + xo + (uint32_t)(c * 4 + pr * 2 + pc) * P.xslab_bytes;
+                    const uint32_t a_lo = (((xs + (uint32_t)(srow * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
+                    const uint32_t d = tmem_base + (uint32_t)(((c * 3 + kh) * 2 + pc) * P.ncols);
+                    tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+                  }
+                } else {
+                  const uint32_t xs = st + xo + (uint32_t)c * P.xslab_bytes;
+                  const uint32_t a_lo = (((xs + (uint32_t)((r + kh) * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
+                  const uint32_t d = tmem_base + (uint32_t)((c * 3 + kh) * P.ncols);
+                  tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                 }
-              } else {
-                const uint32_t xs = st + (uint32_t)c * P.xslab_bytes;
-                const uint32_t a_lo = (((xs + (uint32_t)((r + kh) * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
-                const uint32_t d = tmem_base + (uint32_t)((c * 3 + kh) * P.ncols);
-                tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, first | (uint32_t)r);
               }
             }
           }
@@ -170,6 +182,29 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
       tc_commit(done);
     }
     __syncwarp();
+  } else if (warp >= 6) {
+    if constexpr (X3) {
+      // low-part converter: element-wise over the raw bytes of the stage's first half (the swizzle only permutes 16-byte chunks)
+      const uint32_t ctid = threadIdx.x - 6 * 32, half = P.stage_bytes / 2;
+      int s = 0, ph = 0;
+      for (int64_t t = g; t < P.tiles; t += P.G) {
+        mbar_wait(&full[s], ph);
+        const uint32_t src = smem_u32(stages + (size_t)s * P.stage_bytes), dst = src + half;
+        for (uint32_t o = ctid * 16; o < half; o += 128 * 16) {
+          uint4 v;
+          asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(src + o) : "memory");
+          const uint32_t a = __float_as_uint(__uint_as_float(v.x) - __uint_as_float(v.x & 0xFFFFE000u));
+          const uint32_t b = __float_as_uint(__uint_as_float(v.y) - __uint_as_float(v.y & 0xFFFFE000u));
+          const uint32_t c = __float_as_uint(__uint_as_float(v.z) - __uint_as_float(v.z & 0xFFFFE000u));
+          const uint32_t d = __float_as_uint(__uint_as_float(v.w) - __uint_as_float(v.w & 0xFFFFE000u));
+          asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst + o), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+        }
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&lo_full[s]);
+        if (++s == P.nstages) { s = 0; ph ^= 1; }
+      }
+    }
   } else {
     // ---- drain: warp q owns TMEM lanes [32q, 32q + 32) = accumulator rows of filter column q (stride 1); the fourth
     // quadrant holds the unused shift.  part[cta][acc][row 0..95][ncols]
@@ -235,7 +270,7 @@ struct WgPlan {
   int grid;
   size_t smem;
   int64_t part_floats;
-  bool ok;
+  bool ok, x3;
 };
 
 int num_sms() {
@@ -244,7 +279,8 @@ int num_sms() {
   return n;
 }
 
-WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride) {
+WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int passes) {
+  const bool x3 = passes == 3;
   WgPlan pl{};
   pl.ok = false;
   if (k != 3 || (stride != 1 && stride != 2)) return pl;
@@ -257,11 +293,11 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride) {
   const int bi = Cin / 32, bo = Cout / 32;
   const int acc_per_c = P.s2 ? 6 : 3;
   // output-channel blocks per CTA: up to 4 (N = 128); stride 2 keeps 2 so that two stages of four X slabs fit
-  P.nco = std::min(bo, P.s2 ? 2 : 4);
+  P.nco = std::min(bo, (P.s2 || x3) ? 2 : 4);   // three-pass mode: every slab exists twice (raw + low part)
   while (bo % P.nco) --P.nco;
   P.ncols = P.nco * 32;
   P.ncc = std::max(1, std::min(bi, 512 / (acc_per_c * P.ncols)));
-  P.ncc = std::min(P.ncc, P.s2 ? 1 : 2);
+  P.ncc = std::min(P.ncc, (P.s2 || x3) ? 1 : 2);
   while (bi % P.ncc) --P.ncc;
   P.nacc = P.ncc * acc_per_c;
   P.units_ci = bi / P.ncc; P.units_co = bo / P.nco;
@@ -276,11 +312,11 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride) {
   P.xslab_bytes = (xbox + 512 + 1023) / 1024 * 1024;      // + the fourth (unused) atom's over-read of up to three pixel rows
   P.yslab_bytes = TH * TW * 128;
   const int nx = P.s2 ? 4 : 1;
-  P.stage_bytes = (uint32_t)(P.ncc * nx) * P.xslab_bytes + (uint32_t)P.nco * P.yslab_bytes;
+  P.stage_bytes = ((uint32_t)(P.ncc * nx) * P.xslab_bytes + (uint32_t)P.nco * P.yslab_bytes) * (x3 ? 2u : 1u);
   P.tx_bytes = (uint32_t)(P.ncc * nx) * xbox + (uint32_t)P.nco * P.yslab_bytes;
   const uint32_t avail = SMEM_MAX - 1024 - 256;
   P.nstages = (int)std::min<uint32_t>(6, avail / P.stage_bytes);
-  if (P.nstages < 2) return pl;
+  if (P.nstages < (x3 ? 1 : 2)) return pl;       // stride 2 in three-pass mode runs a single stage (load, convert, multiply in turn)
   uint32_t cols = 32;
   while (cols < (uint32_t)(P.nacc * P.ncols)) cols <<= 1;
   if (cols > 512) return pl;
@@ -288,6 +324,7 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride) {
   P.in_ld2 = Cin * 2;
   pl.grid = units * P.G;
   pl.smem = 1024 + (size_t)P.nstages * P.stage_bytes + 256;
+  pl.x3 = x3;
   pl.part_floats = (int64_t)pl.grid * P.nacc * 96 * P.ncols;
   pl.ok = true;
   return pl;
@@ -295,18 +332,18 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride) {
 
 }  // namespace
 
-bool wgrad_tc_eligible(int N, int H, int W, int Cin, int Cout, int k, int stride) {
-  return plan(N, H, W, Cin, Cout, k, stride).ok;
+bool wgrad_tc_eligible(int N, int H, int W, int Cin, int Cout, int k, int stride, int passes) {
+  return plan(N, H, W, Cin, Cout, k, stride, passes).ok;
 }
 
-int64_t wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride) {
-  const WgPlan pl = plan(N, H, W, Cin, Cout, k, stride);
+int64_t wgrad_tc_workspace_bytes(int N, int H, int W, int Cin, int Cout, int k, int stride, int passes) {
+  const WgPlan pl = plan(N, H, W, Cin, Cout, k, stride, passes);
   return pl.ok ? pl.part_floats * 4 : 0;
 }
 
 int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, int W, int Cin, int Cout, int k, int stride,
-                    void* workspace, cudaStream_t st) {
-  WgPlan pl = plan(N, H, W, Cin, Cout, k, stride);
+                    int passes, void* workspace, cudaStream_t st) {
+  WgPlan pl = plan(N, H, W, Cin, Cout, k, stride, passes);
   if (!pl.ok) return fail(LEDB200_EINVAL, "wgrad_tc: shape not eligible");
   WgParams& P = pl.P;
   P.part = reinterpret_cast<float*>(workspace);
@@ -337,14 +374,22 @@ int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, in
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    cudaError_t e = cudaFuncSetAttribute(wgrad_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-    if (e != cudaSuccess) attr_err = e;
-    e = cudaFuncSetAttribute(wgrad_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
-    if (e != cudaSuccess) attr_err = e;
+    const void* fns[4] = {(const void*)wgrad_tc_kernel<false, false>, (const void*)wgrad_tc_kernel<true, false>,
+                          (const void*)wgrad_tc_kernel<false, true>, (const void*)wgrad_tc_kernel<true, true>};
+    for (const void* f : fns) {
+      cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
+      if (e != cudaSuccess) attr_err = e;
+    }
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("wgrad_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
-  if (P.s2) wgrad_tc_kernel<true><<<pl.grid, kThreads, pl.smem, st>>>(tmX, tmY, P);
-  else wgrad_tc_kernel<false><<<pl.grid, kThreads, pl.smem, st>>>(tmX, tmY, P);
+  const int nthr = pl.x3 ? kThreads + 128 : kThreads;
+  if (pl.x3) {
+    if (P.s2) wgrad_tc_kernel<true, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+    else wgrad_tc_kernel<false, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+  } else {
+    if (P.s2) wgrad_tc_kernel<true, false><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+    else wgrad_tc_kernel<false, false><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+  }
   LEDB_LAUNCH_OK("wgrad_tc_kernel");
   const int64_t total = (int64_t)Cout * Cin * 9;
   wgrad_tc_sum_kernel<<<(int)std::min<int64_t>(ceil_div64(total, 256), 148 * 8), 256, 0, st>>>(P.part, dw, Cin, Cout, P.ncc, P.nco,

@@ -70,32 +70,58 @@ def to_nchw(x):
     return _Layout.apply(x, False)
 
 
-# Tensor-core switch of the training convolutions: True (default) sends every eligible shape (ledb200_train_conv_tc_ok)
-# through the tcgen05 kind::tf32 kernels; False keeps the fp32 CUDA-core kernels everywhere (the round-1 path, kept for
-# shapes the tensor-core tiling rejects and as the A/B arm of tests/test_gpu_train_tc.py).
-TENSOR_CORES = os.environ.get('LEDB200_TRAIN_TC', '1') != '0'
+# Tensor-core switch of the training convolutions.
+#   TENSOR_CORES  True (default): every eligible shape (ledb200_train_conv_tc_ok) runs on the tcgen05 kind::tf32 kernels;
+#                 False: the fp32 CUDA-core kernels everywhere (the round-1 path, still used for shapes the tiling rejects).
+#   TC_FAST       False (default): error-compensated three-pass products (3 x TF32) - fp32-grade results, which the 1e-2
+#                 gradient gate needs (train-mode BatchNorm makes this network's gradient ill-conditioned: tf32 operand
+#                 rounding alone moves it by tens of percent, tools/diag_tf32_grads.py);
+#                 True: one tf32 pass (what cuDNN does under torch.backends.cudnn.allow_tf32) with tf32-rounded activation
+#                 storage, because the tensor core truncates raw fp32 operands.
+# Environment: LEDB200_TRAIN_TC = 0 | 1 | fast.
+_env = os.environ.get('LEDB200_TRAIN_TC', '1')
+TENSOR_CORES = _env != '0'
+TC_FAST = _env == 'fast'
 _rounding_synced = None
+_passes_synced = None
 
 
-def set_tensor_cores(on):
-    """Switch the training convolutions between the tcgen05 tf32 kernels and the fp32 CUDA-core kernels; the element-wise
-    kernels' tf32 storage mode (ledb200_train_set_tf32_rounding) follows.  Returns the previous setting."""
-    global TENSOR_CORES, _rounding_synced
-    prev = TENSOR_CORES
-    TENSOR_CORES = bool(on)
-    L.get().ledb200_train_set_tf32_rounding(int(TENSOR_CORES))
-    _rounding_synced = TENSOR_CORES
+def set_tensor_cores(on, fast=False):
+    """Select the convolution path of the training step (see above).  Returns the previous (on, fast) pair."""
+    global TENSOR_CORES, TC_FAST
+    prev = (TENSOR_CORES, TC_FAST)
+    if isinstance(on, tuple):
+        on, fast = on
+    TENSOR_CORES, TC_FAST = bool(on), bool(fast)
+    _sync_mode()
     return prev
 
 
 def _sync_mode():
-    if _rounding_synced is not TENSOR_CORES:
-        set_tensor_cores(TENSOR_CORES)
+    global _passes_synced
+    want = 1 if TC_FAST else 3
+    if _passes_synced != want:
+        L.check(L.get().ledb200_train_set_tf32_passes(want), 'train_set_tf32_passes')
+        _passes_synced = want
+
+
+def _round_for(shape):
+    """tf32 storage for the tensor an element-wise kernel is about to write ([N, H, W, C]): only in the single-pass mode,
+    and only for tensors a tensor-core convolution can consume (extents that tile into 16 x 8 pixel blocks)."""
+    global _rounding_synced
+    on = bool(TENSOR_CORES and TC_FAST and len(shape) == 4 and shape[1] % 16 == 0 and shape[2] % 8 == 0)
+    if _rounding_synced is not on:
+        L.get().ledb200_train_set_tf32_rounding(int(on))
+        _rounding_synced = on
+
+
+TC_OPS = 7   # diagnostic mask (tools/diag_tf32_grads.py): 1 forward, 2 data gradient, 4 weight gradient on tensor cores
 
 
 def _tc_ok(op, n, h, w, cin, cout, k, stride):
     _sync_mode()
-    return TENSOR_CORES and bool(L.get().ledb200_train_conv_tc_ok(op, n, h, w, cin, cout, k, stride))
+    return (TENSOR_CORES and bool(TC_OPS & (1 << op))
+            and bool(L.get().ledb200_train_conv_tc_ok(op, n, h, w, cin, cout, k, stride)))
 
 
 class _Conv(torch.autograd.Function):
@@ -136,6 +162,29 @@ class _Conv(torch.autograd.Function):
         n, h, w, cin = x.shape
         cout, _, k, _ = weight.shape
         dx = dw = db = None
+        # An output-channel count that is not a multiple of 32 (the K-class head convs, K = 19) keeps the gradient kernels off
+        # the tensor cores: dY's channels are their reduction (dgrad) / N (wgrad) side.  Zero-pad dY and the weight to the
+        # next multiple of 32 - one extra pass over dY - and slice the weight gradient afterwards.
+        ho, wo = _out_hw(h, w, k, ctx.stride)
+        cpad = (cout + 31) // 32 * 32
+        if (cpad != cout and TENSOR_CORES and not ctx.has_bias
+                and (_tc_ok(1, n, h, w, cin, cpad, k, ctx.stride) or _tc_ok(2, n, h, w, cin, cpad, k, ctx.stride))):
+            dyp = torch.zeros((n, ho, wo, cpad), dtype=torch.float32, device=dy.device)
+            L.check(lib.ledb200_train_copy_channels(_p(dy), cout, 0, _p(dyp), cpad, 0, n * ho * wo, cout, _st(dy)),
+                    'train_copy_channels')
+            wpad = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=weight.device)
+            wpad[:cout].copy_(weight)
+            dxp, dwp, _ = _Conv._backward_core(ctx, x, wpad, dyp, False)
+            return dxp, (dwp[:cout].contiguous() if dwp is not None else None), None, None
+        dx, dw, db = _Conv._backward_core(ctx, x, weight, dy, ctx.has_bias)
+        return dx, dw, db, None
+
+    @staticmethod
+    def _backward_core(ctx, x, weight, dy, has_bias):
+        lib = L.get()
+        n, h, w, cin = x.shape
+        cout, _, k, _ = weight.shape
+        dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty_like(x)
             if _tc_ok(1, n, h, w, cin, cout, k, ctx.stride):
@@ -152,21 +201,21 @@ class _Conv(torch.autograd.Function):
                         'train_pack_weight')
                 L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
                                                      _st(x)), 'train_conv_dgrad')
-        if ctx.needs_input_grad[1] and not ctx.has_bias and _tc_ok(2, n, h, w, cin, cout, k, ctx.stride):
+        if ctx.needs_input_grad[1] and not has_bias and _tc_ok(2, n, h, w, cin, cout, k, ctx.stride):
             dw = torch.empty_like(weight)
             ws = torch.empty(lib.ledb200_train_wgrad_tc_workspace_bytes(n, h, w, cin, cout, k, ctx.stride) // 4,
                              dtype=torch.float32, device=x.device)   # per-CTA partial sums, added in a fixed order
             L.check(lib.ledb200_train_conv_wgrad_tc(_p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, ctx.stride, _p(ws),
                                                     _st(x)), 'train_conv_wgrad_tc')
-        elif ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
+        elif ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(weight)
-            if ctx.has_bias:
+            if has_bias:
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)
             ws = torch.empty(lib.ledb200_train_wgrad_workspace_bytes(cin, cout, k) // 8, dtype=torch.float64,
                              device=x.device)       # per-CTA partial sums, added in a fixed order (no atomics)
             L.check(lib.ledb200_train_conv_wgrad(_p(x), _p(dy), _p(dw), _p(db), n, h, w, cin, cout, k, ctx.stride,
                                                  _p(ws), _st(x)), 'train_conv_wgrad')
-        return dx, dw, db, None
+        return dx, dw, db
 
 
 def conv2d(x, weight, bias=None, stride=1):
@@ -192,6 +241,7 @@ class _BNAct(torch.autograd.Function):
     @staticmethod
     def forward(ctx, y, gamma, beta, res, running_mean, running_var, momentum, eps, relu, group):
         y = _chk(y, 'bn input')
+        _round_for(y.shape)
         c = y.shape[-1]
         npix = y.numel() // c
         out = torch.empty_like(y)
@@ -223,6 +273,7 @@ class _BNAct(torch.autograd.Function):
     def backward(ctx, dout):
         y, out, gamma, mean, invstd = ctx.saved_tensors
         dout = _chk(dout, 'bn grad')
+        _round_for(y.shape)
         c = y.shape[-1]
         npix = y.numel() // c
         dy = torch.empty_like(y)
@@ -254,7 +305,6 @@ def bn_act(y, bn, res=None, relu=False):
     """`bn`: an nn.BatchNorm2d in training mode (its running stats are updated like PyTorch does).  When the
     module carries `sync = True` (built from norm_cfg type 'SyncBN') and a process group of more than one rank is
     initialised, the batch statistics are those of the GLOBAL batch (torch.nn.SyncBatchNorm)."""
-    _sync_mode()
     if bn.num_batches_tracked is not None:
         bn.num_batches_tracked.add_(1)
     return _BNAct.apply(y, bn.weight, bn.bias, res, bn.running_mean, bn.running_var, bn.momentum, bn.eps, relu,
@@ -268,6 +318,7 @@ class _Resize(torch.autograd.Function):
         n, h, w, c = x.shape
         H, W = int(size[0]), int(size[1])
         out = torch.empty((n, H, W, c), dtype=torch.float32, device=x.device)
+        _round_for(out.shape)
         L.check(L.get().ledb200_train_resize_fwd(_p(x), _p(out), n, h, w, H, W, c, _st(x)), 'train_resize_fwd')
         ctx.shape = (n, h, w, c, H, W)
         return out
@@ -277,6 +328,7 @@ class _Resize(torch.autograd.Function):
         n, h, w, c, H, W = ctx.shape
         dout = _chk(dout, 'resize grad')
         dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
+        _round_for(dx.shape)
         L.check(L.get().ledb200_train_resize_bwd(_p(dout), _p(dx), n, h, w, H, W, c, _st(dout)), 'train_resize_bwd')
         return dx, None
 
@@ -294,6 +346,7 @@ class _AddRelu(torch.autograd.Function):
         if bb is not None:
             assert a.shape == bb.shape, f'add: {tuple(a.shape)} vs {tuple(bb.shape)}'
         out = torch.empty_like(a)
+        _round_for(out.shape)
         L.check(L.get().ledb200_train_add_relu(_p(a), _p(bb), _p(out), int(relu), a.numel(), _st(a)),
                 'train_add_relu')
         ctx.relu, ctx.has_b = relu, b is not None
@@ -307,6 +360,7 @@ class _AddRelu(torch.autograd.Function):
         if ctx.relu:
             (out,) = ctx.saved_tensors
             dx = torch.empty_like(out)
+            _round_for(dx.shape)
             L.check(L.get().ledb200_train_relu_bwd(_p(dout), _p(out), _p(dx), out.numel(), _st(out)),
                     'train_relu_bwd')
         else:
@@ -329,6 +383,7 @@ class _AvgPool(torch.autograd.Function):
         n, h, w, c = x.shape
         ho, wo = (1, 1) if k == 0 else ((h + 2 * p - k) // s + 1, (w + 2 * p - k) // s + 1)
         out = torch.empty((n, ho, wo, c), dtype=torch.float32, device=x.device)
+        _round_for(out.shape)
         L.check(L.get().ledb200_train_avgpool_fwd(_p(x), _p(out), n, h, w, c, ho, wo, k, s, p, _st(x)),
                 'train_avgpool_fwd')
         ctx.cfg = (n, h, w, c, ho, wo, k, s, p)
@@ -339,6 +394,7 @@ class _AvgPool(torch.autograd.Function):
         n, h, w, c, ho, wo, k, s, p = ctx.cfg
         dout = _chk(dout, 'pool grad')
         dx = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
+        _round_for(dx.shape)
         L.check(L.get().ledb200_train_avgpool_bwd(_p(dout), _p(dx), n, h, w, c, ho, wo, k, s, p, _st(dout)),
                 'train_avgpool_bwd')
         return dx, None, None, None
@@ -356,6 +412,7 @@ class _Cat(torch.autograd.Function):
         n, h, w, _ = xs[0].shape
         cs = [x.shape[-1] for x in xs]
         out = torch.empty((n, h, w, sum(cs)), dtype=torch.float32, device=xs[0].device)
+        _round_for(out.shape)
         off = 0
         for x, c in zip(xs, cs):
             L.check(L.get().ledb200_train_copy_channels(_p(x), c, 0, _p(out), sum(cs), off, n * h * w, c, _st(x)),
@@ -368,6 +425,7 @@ class _Cat(torch.autograd.Function):
     def backward(ctx, dout):
         dout = _chk(dout, 'cat grad')
         n, h, w, ct = dout.shape
+        _round_for(dout.shape)
         outs, off = [], 0
         for c in ctx.cs:
             d = torch.empty((n, h, w, c), dtype=torch.float32, device=dout.device)
