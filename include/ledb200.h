@@ -185,6 +185,20 @@ int ledb200_ohem_ce(const float* logits, const int64_t* target, int32_t N, int32
                     float loss_weight, const float* class_weight_opt, float* out3,
                     float* dlogits_opt, void* workspace, void* stream);
 
+/* The same loss taken over logits = resize(r1, (H, W), mode='bilinear', align_corners=False) WITHOUT materialising them:
+ * r1 is the last rung of LEDHead's training ladder (led_head.py:101-146 / decode_head.py:362-379), device fp32 NHWC
+ * [N,h,w,K], K <= 32.  Every full-resolution pixel interpolates its K logits in registers (bit-identical to the resize
+ * kernel's values); the backward gathers, per r1 pixel, the outputs that read it and re-derives their softmax, in the
+ * resize backward's summation order.  fwd fills out3 and leaves the per-pixel probabilities and the selection threshold in
+ * `workspace` (>= ledb200_ohem_workspace_bytes(N*H*W)); bwd reads them and writes d(loss)/d(r1) [N,h,w,K], scaled by the
+ * device scalar grad_scale_opt (the upstream gradient of the loss; NULL = 1). */
+int ledb200_ohem_up_fwd(const float* r1_nhwc, const int64_t* target, int32_t N, int32_t K, int32_t h, int32_t w,
+                        int32_t H, int32_t W, int32_t ignore_label, float thres, int64_t min_kept, float loss_weight,
+                        const float* class_weight_opt, float* out3, void* workspace, void* stream);
+int ledb200_ohem_up_bwd(const float* r1_nhwc, const int64_t* target, int32_t N, int32_t K, int32_t h, int32_t w,
+                        int32_t H, int32_t W, int32_t ignore_label, float loss_weight, const float* class_weight_opt,
+                        const float* grad_scale_opt, const void* workspace, float* d_r1, void* stream);
+
 /* One convolution through the same launchers the engine uses (unit tests, SESP etc.).
  * NHWC in/out of `dtype`; weight host fp32 OIHW [Cout,Cin,kh,kw] folded by the caller;
  * bias host fp32 [Cout] or NULL; pre_scale/pre_shift host fp32 [Cin] or NULL
@@ -223,8 +237,9 @@ int ledb200_train_conv_dgrad(const float* dy, const float* w_packed_dgrad, float
  * reference gets cuDNN's through encoder_decoder.py:161-185 -> led_head.py:101-146): conv_tc.cu's tcgen05 implicit GEMM with
  * kind::tf32 operands read straight from the fp32 NHWC tensors (TMA halo slabs), fp32 accumulation in TMEM, raw fp32 output.
  * ledb200_train_conv_tc_ok(op, ...) says whether they take a shape (op 0 forward, 1 data gradient, 2 weight gradient;
- * H, W = conv INPUT extents): Cin % 32 == 0 (of the GEMM's reduction side), output extents multiples of the 16 x 8 tile,
- * data gradient stride 1.  Everything else stays on the CUDA-core entry points above.  Weights: K-major fp32
+ * H, W = conv INPUT extents): Cin % 32 == 0 (of the GEMM's reduction side), output extents multiples of the 16 x 8 tile.
+ * The data gradient of a stride-2 convolution runs as its four parity classes (3x3; weights from pack mode 2) or as the
+ * even-even class over a zeroed gradient (1x1; pack mode 1).  Everything else stays on the CUDA-core entry points above.  Weights: K-major fp32
  * [pad(Cout)][k*k*Cin] (mode 0) / [pad(Cin)][k*k*Cout] rotated (mode 1) rounded to tf32 on the device, followed by a second
  * matrix of the same shape holding the remainders w - tf32(w) (the three-pass mode's w_lo). */
 /* tf32 storage mode of the training element-wise kernels (BatchNorm apply / backward, resize, add, pool, concat): on = every

@@ -28,6 +28,23 @@ int ledb200_confusion_accumulate(const void* pred, const void* gt, int32_t pred_
 
 int64_t ledb200_ohem_workspace_bytes(int64_t npix) { return ohem_workspace_bytes(npix); }
 
+int ledb200_ohem_up_fwd(const float* r1_nhwc, const int64_t* target, int32_t N, int32_t K, int32_t h, int32_t w, int32_t H,
+                        int32_t W, int32_t ignore_label, float thres, int64_t min_kept, float loss_weight,
+                        const float* class_weight_opt, float* out3, void* workspace, void* stream) {
+  if (!out3) return fail(LEDB200_EINVAL, "ohem_up: null output");
+  if ((!r1_nhwc || !target) && (int64_t)N * H * W > 0) return fail(LEDB200_EINVAL, "ohem_up: null input");
+  return launch_ohem_up(r1_nhwc, target, N, K, h, w, H, W, ignore_label, thres, min_kept, loss_weight, class_weight_opt, out3,
+                        workspace, (cudaStream_t)stream);
+}
+
+int ledb200_ohem_up_bwd(const float* r1_nhwc, const int64_t* target, int32_t N, int32_t K, int32_t h, int32_t w, int32_t H,
+                        int32_t W, int32_t ignore_label, float loss_weight, const float* class_weight_opt,
+                        const float* grad_scale_opt, const void* workspace, float* d_r1, void* stream) {
+  if (!r1_nhwc || !target) return fail(LEDB200_EINVAL, "ohem_up_bwd: null input");
+  return launch_ohem_up_bwd(r1_nhwc, target, N, K, h, w, H, W, ignore_label, loss_weight, class_weight_opt, grad_scale_opt,
+                            workspace, d_r1, (cudaStream_t)stream);
+}
+
 int ledb200_ohem_ce(const float* logits, const int64_t* target, int32_t N, int32_t K, int32_t H, int32_t W,
                     int32_t ignore_label, float thres, int64_t min_kept, float loss_weight,
                     const float* class_weight_opt, float* out3, float* dlogits_opt, void* workspace, void* stream) {

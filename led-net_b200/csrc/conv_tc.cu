@@ -80,6 +80,13 @@ struct TcParams {
   // optional: out += bilinear x2 upsample (align_corners=False) of `up` [N, up_h, up_w, up_ld], added AFTER the ReLU
   const __nv_bfloat16* up; int up_ld, up_h, up_w;
   int up_f16, out_f16;               // ladder rungs are kept in fp16 (11-bit mantissa; logits are far inside its range)
+  // TF32 epilogue only: output pixel (oy, ox) of image n lands at ((n * o_H + oy * o_mul + o_a) * o_W + ox * o_mul + o_b):
+  // o_mul = 2 writes one parity class of a twice-as-large tensor (data gradient of a stride-2 convolution)
+  int o_mul, o_a, o_b, o_H, o_W;
+  // three-pass mode: the two correction passes (x_hi*w_lo, x_lo*w_hi) accumulate into their OWN TMEM columns, lo_off columns
+  // after the main accumulator of the same stage, and the epilogue adds the two.  The tensor core's accumulator truncates at
+  // the magnitude of the running sum; small addends kept apart lose nothing to it (measured: 2e-5 -> 7e-6 at K = 2304).
+  int lo_off;
   int tl_launch;                     // launch ordinal (timeline probe builds only: slot of g_tc_tl)
   int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 32 atom-aligned A row groups, 64 empty epilogue, 128 single MMA issuer
 };
@@ -496,9 +503,8 @@ __device__ __forceinline__ void epilogue_f32(const TcParams& P, int warp, int la
   int th = (int)(t0 % (uint32_t)P.tiles_h);
   int n = (int)(t0 / (uint32_t)P.tiles_h);
   const uint32_t total = (uint32_t)P.total_tiles, step = split ? gridDim.x : 2 * gridDim.x;
-  const int lane_px = ph * Wo + pw;
   for (uint32_t tile = first; tile < total; tile += step) {
-    const int64_t pix = ((int64_t)n * Ho + th * TH) * Wo + tw * TW + lane_px;
+    const int64_t pix = ((int64_t)n * P.o_H + (th * TH + ph) * P.o_mul + P.o_a) * P.o_W + (tw * TW + pw) * P.o_mul + P.o_b;
     const int cgt = nt * NT;
     float* out_px = outp + pix * P.out_ld + cgt;
     mbar_wait(&t_full[ts], tp);
@@ -509,6 +515,14 @@ __device__ __forceinline__ void epilogue_f32(const TcParams& P, int warp, int la
       tc_ld16(taddr0 + c0, v);
       tc_ld16(taddr0 + c0 + 16, v + 16);
       tc_wait_ld();
+      if (P.lo_off) {
+        uint32_t u[32];
+        tc_ld16(taddr0 + (uint32_t)P.lo_off + c0, u);
+        tc_ld16(taddr0 + (uint32_t)P.lo_off + c0 + 16, u + 16);
+        tc_wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+      }
       const uint32_t bias_b = bias_u + (uint32_t)(cgt + c0) * 4;
 #pragma unroll
       for (int g = 0; g < 4; ++g) {
@@ -548,6 +562,7 @@ __device__ __forceinline__ void epilogue_f32(const TcParams& P, int warp, int la
 // (a single thread issues every MMA: any dependent address arithmetic there is on the critical path).
 //   MODE 0: 3x3 stride 1, one halo slab, 9 taps      MODE 1: 1x1 (stride 1 or 2), one slab, one tap
 //   MODE 2: 3x3 stride 2, six parity slabs: slab 2*kw -> taps (kh=0, kh=2), slab 2*kw+1 -> tap kh=1
+//   MODE 3: one halo slab, taps from the launch's table (P.slabs[0]) - the four parity sub-convolutions of a stride-2 data gradient
 template <int MODE> __device__ __forceinline__ constexpr int mode_slabs() { return MODE == 2 ? 6 : 1; }
 template <int MODE> __device__ __forceinline__ constexpr int mode_taps(int s) {
   return MODE == 0 ? 9 : (MODE == 1 ? 1 : ((s & 1) ? 1 : 2));
@@ -574,6 +589,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                const __grid_constant__ TcParams P) {
   constexpr int NTHR = conv_tc_threads<TF32>();
   constexpr bool X3 = TF32 == 3;
+#define NTAPS(s) (MODE == 3 ? P.slabs[0].ntaps : mode_taps<MODE == 3 ? 0 : MODE>(s))
+#define TAPPIX(s, t) (MODE == 3 ? P.slabs[0].tap_pix[t] : mode_tap_pix<MODE == 3 ? 0 : MODE>(s, t))
+#define TAPID(s, t) (MODE == 3 ? P.slabs[0].tap_id[t] : mode_tap_id<MODE == 3 ? 0 : MODE>(s, t))
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve: [A ring][B ring or resident B][epilogue staging][bias / out2 affine][barriers]
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -758,17 +776,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               // three passes per (tap, k-step); the low-part slab is only needed for the third, so its barrier is waited
               // for after the raw-slab MMAs of the slab (resident weights) or of the first tap (streamed weights) are queued
               const uint32_t a_half16 = a_stage16 >> 1, b_half16 = b_tile16 >> 1;
+              const uint32_t d_lo = d_tmem + (uint32_t)P.lo_off;        // correction passes: their own accumulator
               if (BRES) {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                  if (t < mode_taps<MODE>(s)) {
-                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+                  if (t < NTAPS(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)TAPID(s, t) * b_tile16;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                      else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
-                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                      const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) {
+                        tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
+                      } else {
+                        tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                        tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                      }
                     }
                   }
                 }
@@ -776,34 +799,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 tc_fence_after();
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                  if (t < mode_taps<MODE>(s)) {
-                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+                  if (t < NTAPS(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)TAPID(s, t) * b_tile16;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + a_half16 + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      const uint32_t al = a_lo + a_half16 + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
+                      tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + 2 * k, b_hi, idesc);
                     }
                   }
                 }
               } else {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                  if (t < mode_taps<MODE>(s)) {
+                  if (t < NTAPS(s)) {
                     mbar_wait(&b_full[sb], pb);
                     tc_fence_after();
                     const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_tile16;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                      else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
-                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                      const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
+                      if (s == 0 && t == 0 && k == 0) {
+                        tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                        tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
+                      } else {
+                        tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                        tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
+                      }
                     }
                     if (t == 0) { mbar_wait(&a_lo_full[sa], pa); tc_fence_after(); }
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + a_half16 + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
-                      tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      const uint32_t al = a_lo + a_half16 + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
+                      tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + 2 * k, b_hi, idesc);
                     }
                     tc_commit(&b_empty[sb]);
                     if (++sb == P.SB) { sb = 0; pb ^= 1; }
@@ -818,11 +845,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
               if (mma_on) {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
-                  if (t < mode_taps<MODE>(s)) {
-                    const uint32_t b_lo = b_chunk + (uint32_t)mode_tap_id<MODE>(s, t) * b_tile16;
+                  if (t < NTAPS(s)) {
+                    const uint32_t b_lo = b_chunk + (uint32_t)TAPID(s, t) * b_tile16;
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
                       if constexpr (TF32 != 0) {
                         if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
                         else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
@@ -837,14 +864,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             } else {
 #pragma unroll
               for (int t = 0; t < 9; ++t) {
-                if (t < mode_taps<MODE>(s)) {
+                if (t < NTAPS(s)) {
                   mbar_wait(&b_full[sb], pb);
                   tc_fence_after();
                   const uint32_t b_lo = b_lo0 + (uint32_t)sb * b_tile16;
                   if (mma_on) {
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
-                      const uint32_t al = a_lo + (((uint32_t)mode_tap_pix<MODE>(s, t) * ROWB + k * 32) >> 4);
+                      const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
                       if constexpr (TF32 != 0) {
                         if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
                         else tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
@@ -928,6 +955,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   TL(11, threadIdx.x == 32); TLG(13, threadIdx.x == 32);
 }
 
+#undef NTAPS
+#undef TAPPIX
+#undef TAPID
+
 // ------------------------------------------------------------------ host side
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -992,6 +1023,7 @@ bool conv_tc_eligible(const ConvArgs& a) {
     if (a.in_sc != 1 || a.in_sw % 4) return false;
     if (a.stride == 2 && ((a.H & 1) || (a.W & 1))) return false;
     if (a.Ho % TH || a.Wo % TW) return false;                        // all-interior tilings only (else: CUDA-core kernels)
+    if (a.sub && a.stride != 1) return false;
     if (a.out_ld < a.Cout) return false;
     const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
     if (cp > 256 && cp % 256) return false;
@@ -1049,6 +1081,23 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   int box_w = TW, box_rows = TH;
   P.sbo_bytes = 8 * row_bytes;
   // ---- slab tables
+  int sub_taps = 0;
+  if (a.sub && a.ksize == 3) {
+    // parity class of a stride-2 data gradient: the halo slab of a 3x3 convolution, taps at offsets {0, +1} (odd parity)
+    // or {0} (even parity) per axis, in the order the class's weight matrix is packed (train.cu pack mode 2)
+    P.nslabs = 1; box_rows = TH + 2; box_w = TW + 2;
+    P.sbo_bytes = box_w * row_bytes;
+    Slab& s = P.slabs[0];
+    s.c_mul = 0; s.dw = -1; s.dh = -1; s.ph = 0;
+    for (int ir = 0; ir < (a.sub_a ? 2 : 1); ++ir)
+      for (int ic = 0; ic < (a.sub_b ? 2 : 1); ++ic) {
+        const int dr = a.sub_a ? 1 - ir : 0, dc = a.sub_b ? 1 - ic : 0;   // filter row 0 reads dY row i + 1, row 2 reads row i
+        s.tap_pix[sub_taps] = (1 + dr) * box_w + (1 + dc);
+        s.tap_id[sub_taps] = sub_taps;
+        ++sub_taps;
+      }
+    s.ntaps = sub_taps;
+  } else
   if (a.ksize == 3 && !s2) {
     // ONE halo slab (TH+2) x (TW+2) per Cin chunk; every tap is a row- AND column-shifted window of it:
     // the descriptor start address is not swizzle-atom aligned and SBO = (TW+2) rows.  The hardware
@@ -1088,7 +1137,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   P.b_tile_bytes = (uint32_t)((P.NT * row_bytes + 1023) / 1024 * 1024) * (x3 ? 2u : 1u);
   P.a_box_bytes = (uint32_t)(box_rows * box_w * row_bytes);
   P.b_box_bytes = (uint32_t)(P.NT * row_bytes);
-  const int taps = a.ksize * a.ksize;
+  const int taps = sub_taps ? sub_taps : a.ksize * a.ksize;
   P.ntaps_total = taps;
   // ---- shared-memory plan
   P.cp = cp;
@@ -1146,9 +1195,10 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   }
   const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
                       (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
-  P.nst = (4 * P.NT <= 512) ? 4 : 2;
+  P.nst = (4 * P.NT * (x3 ? 2 : 1) <= 512) ? 4 : 2;
+  P.lo_off = x3 ? P.nst * P.NT : 0;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(P.nst * P.NT)) cols <<= 1;
+  while (cols < (uint32_t)(P.nst * P.NT * (x3 ? 2 : 1))) cols <<= 1;
   P.tmem_cols = cols;
   P.out = (__nv_bfloat16*)a.out; P.out_ld = a.out_ld;
   P.out2 = (__nv_bfloat16*)a.out2; P.out2_ld = a.out2_ld; P.o2_scale = a.o2_scale; P.o2_shift = a.o2_shift;
@@ -1157,6 +1207,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   { static int tl_counter = 0; P.tl_launch = tl_counter++; }
   P.up = (const __nv_bfloat16*)a.up; P.up_ld = a.up_ld; P.up_h = a.up_h; P.up_w = a.up_w;
   P.up_f16 = a.up_f16; P.out_f16 = a.out_f16;
+  P.o_mul = a.sub ? 2 : 1; P.o_a = a.sub ? a.sub_a : 0; P.o_b = a.sub ? a.sub_b : 0;
+  P.o_H = a.Ho * P.o_mul; P.o_W = a.Wo * P.o_mul;
 
   // ---- tensor maps
   CUtensorMap tmA, tmB;
@@ -1193,7 +1245,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
       d[3] = (int)(stp / (uint32_t)P.tiles_h);
     }
   }
-  const int mode = (a.ksize == 1) ? 1 : (s2 ? 2 : 0);
+  const int mode = (a.ksize == 1) ? 1 : (sub_taps ? 3 : (s2 ? 2 : 0));
   const int ksteps = P.KC / 16;
   using KernelFn = void (*)(const CUtensorMap, const CUtensorMap, const TcParams);
   // [mode][stride 2][KC == 64][weights resident]
@@ -1209,20 +1261,22 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
        {{conv_tc_kernel<2, 2, true, false>, conv_tc_kernel<2, 2, true, true>},
         {conv_tc_kernel<2, 4, true, false>, conv_tc_kernel<2, 4, true, true>}}}};
   // TF32 instantiations (KSTEPS = 4: four 32-byte k-steps per 128 B row): [three-pass][mode][stride 2][weights resident]
-  static const KernelFn kernels_tf32[2][3][2][2] = {
+  static const KernelFn kernels_tf32[2][4][2][2] = {
       {{{conv_tc_kernel<0, 4, false, false, 1>, conv_tc_kernel<0, 4, false, true, 1>}, {nullptr, nullptr}},
        {{conv_tc_kernel<1, 4, false, false, 1>, conv_tc_kernel<1, 4, false, true, 1>},
         {conv_tc_kernel<1, 4, true, false, 1>, conv_tc_kernel<1, 4, true, true, 1>}},
-       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 1>, conv_tc_kernel<2, 4, true, true, 1>}}},
+       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 1>, conv_tc_kernel<2, 4, true, true, 1>}},
+       {{conv_tc_kernel<3, 4, false, false, 1>, conv_tc_kernel<3, 4, false, true, 1>}, {nullptr, nullptr}}},
       {{{conv_tc_kernel<0, 4, false, false, 3>, conv_tc_kernel<0, 4, false, true, 3>}, {nullptr, nullptr}},
        {{conv_tc_kernel<1, 4, false, false, 3>, conv_tc_kernel<1, 4, false, true, 3>},
         {conv_tc_kernel<1, 4, true, false, 3>, conv_tc_kernel<1, 4, true, true, 3>}},
-       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 3>, conv_tc_kernel<2, 4, true, true, 3>}}}};
+       {{nullptr, nullptr}, {conv_tc_kernel<2, 4, true, false, 3>, conv_tc_kernel<2, 4, true, true, 3>}},
+       {{conv_tc_kernel<3, 4, false, false, 3>, conv_tc_kernel<3, 4, false, true, 3>}, {nullptr, nullptr}}}};
   static std::once_flag attr_once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(attr_once, [] {
     for (int x = 0; x < 2; ++x)
-      for (int m = 0; m < 3; ++m)
+      for (int m = 0; m < 4; ++m)
         for (int s = 0; s < 2; ++s)
           for (int r = 0; r < 2; ++r)
             if (kernels_tf32[x][m][s][r]) {

@@ -30,7 +30,11 @@ struct ConvArgs {
   const float* w_direct = nullptr;         // [k*k][Cin][cout_pad16] fp32 (device)
   const __nv_bfloat16* w_tc = nullptr;     // [cout_padN][k*k*Cin] bf16 (device), K-major
   const float* w_tc32 = nullptr;           // tf32 launches: the same matrix as fp32 words (tf32-rounded)
-  int tf32 = 0;                            // 1: fp32 tensors through the kind::tf32 instantiations (training, train.cu)
+  int tf32 = 0;                            // 1 / 3: fp32 tensors through the kind::tf32 instantiations, passes per product (training, train.cu)
+  // tf32 only - one parity class (sub_a, sub_b) of the data gradient of a stride-2 convolution: a stride-1 convolution over
+  // dY whose taps are the filter rows / columns of that parity (offsets 0 / +1) and whose output pixel (i, j) is written to
+  // (2 i + sub_a, 2 j + sub_b) of the [N, 2 Ho, 2 Wo] gradient.  w_tc32 then holds that class's own K-major matrix.
+  int sub = 0, sub_a = 0, sub_b = 0;
   int cout_pad16 = 0;
   int cout_pad_tc = 0;
   int N = 0, H = 0, W = 0, Cin = 0, Ho = 0, Wo = 0, Cout = 0;
@@ -175,5 +179,14 @@ int64_t ohem_workspace_bytes(int64_t npix);
 int launch_ohem(const float* logits, const int64_t* target, int N, int K, int H, int W, int ignore_label,
                 float thres, int64_t min_kept, float loss_weight, const float* class_weight, float* out3,
                 float* dlogits, void* workspace, cudaStream_t st);
+
+// fused ladder top + OHEM CE: the loss (and its gradient) of the bilinear upsample of the NHWC rung r1 [N,h,w,K] to [N,H,W]
+// without the full-resolution logits (ohem.cu); same workspace as launch_ohem
+int launch_ohem_up(const float* r1, const int64_t* target, int N, int K, int h, int w, int H, int W, int ignore_label,
+                   float thres, int64_t min_kept, float loss_weight, const float* class_weight, float* out3,
+                   void* workspace, cudaStream_t st);
+int launch_ohem_up_bwd(const float* r1, const int64_t* target, int N, int K, int h, int w, int H, int W, int ignore_label,
+                       float loss_weight, const float* class_weight, const float* gscale, const void* workspace, float* dr1,
+                       cudaStream_t st);
 
 }  // namespace ledb

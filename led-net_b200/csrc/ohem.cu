@@ -198,6 +198,214 @@ ohem_backward_kernel(const float* __restrict__ logits, const int64_t* __restrict
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Fused top of the training ladder (led_head.py:101-146 -> decode_head.py:362-379 -> OhemCrossEntropy): the loss of
+//   logits = resize(r1, (H, W), bilinear, align_corners=False)          r1: NHWC [N, h, w, K], the half-resolution rung
+// WITHOUT the full-resolution logit tensor.  Round 2's launch list had the un-fused chain - resize forward (957 MB out at
+// 12 x 1024^2 x 19), NHWC->NCHW, the OHEM kernels over NCHW, the gradient's NCHW->NHWC and the resize backward gather - at
+// 17 ms of a 63 ms training step, all of it moving a tensor that only exists to be reduced.  Here every full-resolution
+// pixel interpolates its K logits in registers (same fmaf sequence as resize_fwd, so the values are bit-identical), and
+// the backward is a gather per r1 pixel over the outputs that read it, each re-deriving its softmax - the order of
+// resize_bwd's sums is kept, so d(r1) is bit-identical to the un-fused path as well.
+constexpr int kMaxK = 32;
+
+template <int KT>
+__device__ __forceinline__ void up_logits(const float* __restrict__ r1n, int y, int x, int h, int w, int K, float sh, float sw,
+                                          float* v) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+  bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+  const float* a = r1n + ((int64_t)y0 * w + x0) * K;
+  const float* b = r1n + ((int64_t)y0 * w + x1) * K;
+  const float* c = r1n + ((int64_t)y1 * w + x0) * K;
+  const float* d = r1n + ((int64_t)y1 * w + x1) * K;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    if (k < K) {
+      const float r0 = fmaf(__ldg(b + k), lx1, __ldg(a + k) * lx0);
+      const float r1v = fmaf(__ldg(d + k), lx1, __ldg(c + k) * lx0);
+      v[k] = fmaf(r1v, ly1, r0 * ly0);
+    }
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kT)
+ohem_up_pixel_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, int K, int h, int w, int H, int W,
+                     int64_t npix, int ignore, const float* __restrict__ cw, float sh, float sw, float* __restrict__ prob,
+                     float* __restrict__ loss, OhemState* s) {
+  __shared__ float shm[kT / 32];
+  float nvalid = 0.f, ncorrect = 0.f;
+  const int64_t HW = (int64_t)H * W;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < npix; i += (int64_t)gridDim.x * kT) {
+    const int64_t n = i / HW, hw = i % HW;
+    const int y = (int)(hw / W), x = (int)(hw % W);
+    float v[KT];
+    up_logits<KT>(r1 + n * (int64_t)h * w * K, y, x, h, w, K, sh, sw, v);
+    const int64_t yt = target[i];
+    float m = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K && v[k] > m) { m = v[k]; am = k; }
+    float p = 2.0f, l = 0.f;
+    if (yt != ignore) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) sum += expf(v[k] - m);
+      const int yy = (yt >= 0 && yt < K) ? (int)yt : 0;
+      float xy = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k == yy) xy = v[k] - m;
+      p = expf(xy) / sum;
+      l = -(xy - logf(sum)) * (cw ? cw[yy] : 1.f);
+      nvalid += 1.f;
+      ncorrect += (am == (int)yt) ? 1.f : 0.f;
+    }
+    prob[i] = p;
+    loss[i] = l;
+  }
+  const float a = block_sum(nvalid, shm);
+  const float b = block_sum(ncorrect, shm);
+  if (threadIdx.x == 0) {
+    atomicAdd(&s->nvalid, (unsigned long long)a);
+    atomicAdd(&s->ncorrect, (unsigned long long)b);
+  }
+}
+
+// candidate outputs that may read source index `sidx` (same bounds as train.cu's gather_range)
+__device__ __forceinline__ void up_gather_range(int sidx, float scale, int out_size, int& lo, int& hi) {
+  lo = (int)floorf(((float)sidx - 0.5f) / scale - 0.5f) - 1;
+  hi = (int)ceilf(((float)sidx + 1.5f) / scale - 0.5f) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+
+// d(r1)[n, ys, xs, :] = sum over the outputs (y, x) whose bilinear footprint holds (ys, xs) of wy * wx * d(logits)[n, :, y, x],
+// d(logits) = gscale * loss_weight / kept * (softmax - onehot) on kept pixels (ohem_backward_kernel), rows then columns ascending
+template <int KT>
+__global__ void __launch_bounds__(128)
+ohem_up_bwd_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, const float* __restrict__ prob, int K,
+                   int h, int w, int H, int W, int64_t nsrc, int ignore, const float* __restrict__ cw, float loss_weight,
+                   const float* __restrict__ gscale, float sh, float sw, const OhemState* __restrict__ s,
+                   float* __restrict__ dr1) {
+  const float thr = s->threshold;
+  const float scale = loss_weight / s->kept * (gscale ? gscale[0] : 1.f);
+  const int64_t hwsrc = (int64_t)h * w;
+  for (int64_t i = blockIdx.x * 128ll + threadIdx.x; i < nsrc; i += (int64_t)gridDim.x * 128) {
+    const int64_t n = i / hwsrc, r = i % hwsrc;
+    const int ys = (int)(r / w), xs = (int)(r % w);
+    const float* r1n = r1 + n * hwsrc * K;
+    int ylo, yhi, xlo, xhi;
+    up_gather_range(ys, sh, H, ylo, yhi);
+    up_gather_range(xs, sw, W, xlo, xhi);
+    float acc[KT];
+#pragma unroll
+    for (int k = 0; k < KT; ++k) acc[k] = 0.f;
+    for (int y = ylo; y <= yhi; ++y) {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      if (y0 != ys && y1 != ys) continue;
+      float wy = 0.f;
+      if (y0 == ys) wy += ly0;
+      if (y1 == ys) wy += ly1;
+      float rowv[KT];
+#pragma unroll
+      for (int k = 0; k < KT; ++k) rowv[k] = 0.f;
+      for (int x = xlo; x <= xhi; ++x) {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+        if (x0 != xs && x1 != xs) continue;
+        float wx = 0.f;
+        if (x0 == xs) wx += lx0;
+        if (x1 == xs) wx += lx1;
+        const int64_t pi = (n * H + y) * W + x;
+        const float p = prob[pi];
+        if (!((p < thr) && (p <= 1.5f))) continue;          // not kept: its gradient row is zero (fmaf(0, wx, row) == row)
+        float v[KT];
+        up_logits<KT>(r1n, y, x, h, w, K, sh, sw, v);
+        const int64_t yt = target[pi];
+        const int yy = (yt >= 0 && yt < K) ? (int)yt : 0;
+        float m = -INFINITY;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < K) m = fmaxf(m, v[k]);
+        float sum = 0.f;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < K) sum += expf(v[k] - m);
+        const float g = scale * (cw ? cw[yy] : 1.f);
+        const float inv = 1.f / sum;
+#pragma unroll
+        for (int k = 0; k < KT; ++k)
+          if (k < K) rowv[k] = fmaf(g * (expf(v[k] - m) * inv - (k == yy ? 1.f : 0.f)), wx, rowv[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < KT; ++k) acc[k] = fmaf(rowv[k], wy, acc[k]);
+    }
+    float* o = dr1 + i * K;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K) o[k] = acc[k];
+  }
+}
+
+}  // namespace
+
+int launch_ohem_up(const float* r1, const int64_t* target, int N, int K, int h, int w, int H, int W, int ignore_label,
+                   float thres, int64_t min_kept, float loss_weight, const float* class_weight, float* out3,
+                   void* workspace, cudaStream_t st) {
+  if (K < 1 || K > kMaxK || N < 0 || H < 1 || W < 1 || h < 1 || w < 1) return fail(LEDB200_EINVAL, "ohem_up: bad shape (K <= 32)");
+  if (!workspace) return fail(LEDB200_EINVAL, "ohem_up: workspace is null");
+  const int64_t npix = (int64_t)N * H * W;
+  auto* s = reinterpret_cast<OhemState*>(workspace);
+  float* prob = reinterpret_cast<float*>(reinterpret_cast<char*>(workspace) + ((sizeof(OhemState) + 255) / 256) * 256);
+  float* loss = prob + npix;
+  if (min_kept < 1) min_kept = 1;
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, ceil_div64(npix, kT)));
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  ohem_init_kernel<<<1, 256, 0, st>>>(s);
+  if (npix > 0) {
+    if (K <= 8) ohem_up_pixel_kernel<8><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
+    else if (K <= 20) ohem_up_pixel_kernel<20><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
+    else ohem_up_pixel_kernel<32><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
+  }
+  ohem_rank_kernel<<<1, 1, 0, st>>>(s, (long long)min_kept);
+  const int shifts[3] = {21, 10, 0}, nbins[3] = {2048, 2048, 1024};
+  for (int p = 0; p < 3; ++p) {
+    if (npix > 0) ohem_hist_kernel<<<grid, kT, 0, st>>>(prob, npix, s, p, shifts[p], nbins[p]);
+    ohem_find_kernel<<<1, 1, 0, st>>>(s, p, shifts[p], nbins[p], thres);
+  }
+  ohem_reduce_kernel<<<kPartials, kT, 0, st>>>(prob, loss, npix, s);
+  ohem_final_kernel<<<1, 1, 0, st>>>(s, loss_weight, out3);
+  LEDB_LAUNCH_OK("ohem_up kernels");
+  return LEDB200_OK;
+}
+
+int launch_ohem_up_bwd(const float* r1, const int64_t* target, int N, int K, int h, int w, int H, int W, int ignore_label,
+                       float loss_weight, const float* class_weight, const float* gscale, const void* workspace, float* dr1,
+                       cudaStream_t st) {
+  if (K < 1 || K > kMaxK) return fail(LEDB200_EINVAL, "ohem_up_bwd: bad shape (K <= 32)");
+  if (!workspace || !dr1) return fail(LEDB200_EINVAL, "ohem_up_bwd: null buffer");
+  const int64_t nsrc = (int64_t)N * h * w;
+  if (nsrc == 0) return LEDB200_OK;
+  auto* s = reinterpret_cast<const OhemState*>(workspace);
+  const float* prob = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + ((sizeof(OhemState) + 255) / 256) * 256);
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 16, ceil_div64(nsrc, 128)));
+  const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  if (K <= 8) ohem_up_bwd_kernel<8><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);
+  else if (K <= 20) ohem_up_bwd_kernel<20><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);
+  else ohem_up_bwd_kernel<32><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);
+  LEDB_LAUNCH_OK("ohem_up_bwd_kernel");
+  return LEDB200_OK;
+}
+
+namespace {
 }  // namespace
 
 int64_t ohem_workspace_bytes(int64_t npix) {

@@ -90,6 +90,32 @@ __global__ void pack_weight_tc_kernel(const float* __restrict__ w, float* __rest
   }
 }
 
+// mode 2: the four parity classes (a, b) of the data gradient of a 3x3 STRIDE-2 convolution (conv_tc.cu MODE 3), one pair of
+// hi / lo matrices [ci_pad][nt * Cout] per class, classes in the order (0,0), (0,1), (1,0), (1,1) with nt = 1, 2, 2, 4 taps:
+// tap (ir, ic) of class (a, b) is filter element (kh, kw) = (a ? 2 ir : 1, b ? 2 ic : 1).
+__global__ void pack_weight_tc_sub_kernel(const float* __restrict__ w, float* __restrict__ out, int Cout, int Cin, int rows_pad) {
+  const int64_t total = (int64_t)rows_pad * 9 * Cout;
+  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+    const int co = (int)(i % Cout);
+    const int q = (int)((i / Cout) % 9);           // tap slot over all classes
+    const int r = (int)(i / ((int64_t)Cout * 9));   // input channel (row of the matrix)
+    const int cls = q < 1 ? 0 : (q < 3 ? 1 : (q < 5 ? 2 : 3));
+    const int before = cls == 0 ? 0 : (cls == 1 ? 1 : (cls == 2 ? 3 : 5));
+    const int a = cls >> 1, b = cls & 1, t = q - before, nt = (a ? 2 : 1) * (b ? 2 : 1);
+    const int ir = b ? t >> 1 : t, ic = b ? t & 1 : 0;
+    const int kh = a ? 2 * ir : 1, kw = b ? 2 * ic : 1;
+    float v = 0.f;
+    if (r < Cin) v = w[(((int64_t)co * Cin + r) * 3 + kh) * 3 + kw];
+    uint32_t tt;
+    asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(tt) : "f"(v));
+    const float hi = __uint_as_float(tt);
+    float* base = out + 2 * (int64_t)rows_pad * Cout * before;       // this class's hi matrix; lo follows it
+    const int64_t e = ((int64_t)r * nt + t) * Cout + co;
+    base[e] = hi;
+    base[(int64_t)rows_pad * nt * Cout + e] = v - hi;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // weight gradient.  CTA = 128 threads = 2 pixel lanes x (8 ci-groups x 8 co-groups); each thread owns a
 // 4(ci) x 4(co) x taps register tile and walks its lane's pixels of the staged tile.
@@ -871,7 +897,12 @@ int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, in
     return conv_tc_eligible(a) ? 1 : 0;
   }
   if (op == 1) {
-    if (stride != 1) return 0;
+    if (stride == 2) {   // parity classes over dY's extents
+      if ((H & 1) || (W & 1)) return 0;
+      conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H / 2, W / 2, Cout, Cin, k, 1);
+      a.sub = 1;
+      return conv_tc_eligible(a) ? 1 : 0;
+    }
     conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cout, Cin, k, 1);
     return conv_tc_eligible(a) ? 1 : 0;
   }
@@ -892,14 +923,21 @@ int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw,
 
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
   const int64_t taps = (int64_t)k * k;
-  return 2 * (mode == 0 ? (int64_t)conv_tc_pad(Cout) * taps * Cin : (int64_t)conv_tc_pad(Cin) * taps * Cout);
+  return 2 * (mode == 0 ? (int64_t)conv_tc_pad(Cout) * taps * Cin : (int64_t)conv_tc_pad(Cin) * taps * Cout);   // modes 1, 2: same size
 }
 
 int ledb200_train_pack_weight_tc(const float* w_oihw, float* out, int32_t Cout, int32_t Cin, int32_t k, int32_t mode,
                                  void* stream) {
   if (!w_oihw || !out) return fail(LEDB200_EINVAL, "pack_weight_tc: null buffer");
-  if (mode != 0 && mode != 1) return fail(LEDB200_EINVAL, "pack_weight_tc: mode must be 0 (forward) or 1 (dgrad)");
+  if (mode != 0 && mode != 1 && mode != 2)
+    return fail(LEDB200_EINVAL, "pack_weight_tc: mode must be 0 (forward), 1 (dgrad) or 2 (dgrad of a 3x3 stride-2 convolution)");
   const int rows_pad = conv_tc_pad(mode == 0 ? Cout : Cin);
+  if (mode == 2) {
+    if (k != 3) return fail(LEDB200_EINVAL, "pack_weight_tc: mode 2 is for 3x3 filters");
+    pack_weight_tc_sub_kernel<<<grid1d((int64_t)rows_pad * 9 * Cout), kT, 0, (cudaStream_t)stream>>>(w_oihw, out, Cout, Cin, rows_pad);
+    LEDB_LAUNCH_OK("pack_weight_tc_sub_kernel");
+    return LEDB200_OK;
+  }
   const int64_t total = ledb200_train_packed_weight_tc_floats(Cout, Cin, k, mode) / 2;
   pack_weight_tc_kernel<<<grid1d(total), kT, 0, (cudaStream_t)stream>>>(w_oihw, out, Cout, Cin, k * k, mode, rows_pad);
   LEDB_LAUNCH_OK("pack_weight_tc_kernel");
@@ -921,7 +959,28 @@ int ledb200_train_conv_dgrad_tc(const float* dy, const float* w_tc_dgrad, float*
   if (!dy || !w_tc_dgrad || !dx) return fail(LEDB200_EINVAL, "train_conv_dgrad_tc: null buffer");
   if (!ledb200_train_conv_tc_ok(1, N, H, W, Cin, Cout, k, stride))
     return fail(LEDB200_EINVAL, "train_conv_dgrad_tc: shape not eligible (ask ledb200_train_conv_tc_ok first)");
-  ConvArgs a;   // stride 1: dX = conv(dY, rotated weights with the channel roles swapped), same padding
+  ConvArgs a;
+  if (stride == 2) {
+    // dX[2i + a, 2j + b] = sum over the filter rows / columns of that parity: four stride-1 convolutions over dY (3x3, weights
+    // from pack mode 2), or one over the even-even class after zeroing dX (1x1, weights from pack mode 1)
+    const int Ho = H / 2, Wo = W / 2;
+    if (k == 1) {
+      LEDB_CUDA_OK(cudaMemsetAsync(dx, 0, sizeof(float) * (size_t)N * H * W * Cin, (cudaStream_t)stream));
+      conv_tc_args(a, dy, dx, w_tc_dgrad, nullptr, N, Ho, Wo, Cout, Cin, 1, 1);
+      a.sub = 1;
+      return launch_conv_tc(a, (cudaStream_t)stream);
+    }
+    const int before[4] = {0, 1, 3, 5};
+    const int64_t rows_pad = conv_tc_pad(Cin);
+    for (int cls = 0; cls < 4; ++cls) {
+      conv_tc_args(a, dy, dx, w_tc_dgrad + 2 * rows_pad * Cout * before[cls], nullptr, N, Ho, Wo, Cout, Cin, 3, 1);
+      a.sub = 1; a.sub_a = cls >> 1; a.sub_b = cls & 1;
+      const int rc = launch_conv_tc(a, (cudaStream_t)stream);
+      if (rc) return rc;
+    }
+    return LEDB200_OK;
+  }
+  // stride 1: dX = conv(dY, rotated weights with the channel roles swapped), same padding
   conv_tc_args(a, dy, dx, w_tc_dgrad, nullptr, N, H, W, Cout, Cin, k, 1);
   return launch_conv_tc(a, (cudaStream_t)stream);
 }

@@ -149,7 +149,9 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           const uint32_t xo = (pass == 1) ? half : 0u, yo = (pass == 2) ? half : 0u;
           for (int r = 0; r < TH; ++r) {
             const uint32_t b_lo = (((sy + yo + (uint32_t)(r * TW) * 128u) >> 4) & 0x3FFFu) | b_lbo;
-            const uint32_t acc = first | (uint32_t)r | (uint32_t)pass;
+            // passes 1, 2 accumulate into their own columns (lo_cols after the main ones): pass 1 opens them on the first tile
+            const uint32_t acc = pass == 2 ? 1u : (first | (uint32_t)r);
+            const uint32_t dcol = pass ? (uint32_t)(P.nacc * P.ncols) : 0u;
             for (int c = 0; c < P.ncc; ++c) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
@@ -162,13 +164,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
                     // pc = 1: atoms 0, 1 = filter columns 0, 2 (odd columns ow - 1, ow); pc = 0: atom 0 = filter column 1
                     const uint32_t xs = st + xo + (uint32_t)(c * 4 + pr * 2 + pc) * P.xslab_bytes;
                     const uint32_t a_lo = (((xs + (uint32_t)(srow * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
-                    const uint32_t d = tmem_base + (uint32_t)(((c * 3 + kh) * 2 + pc) * P.ncols);
+                    const uint32_t d = tmem_base + dcol + (uint32_t)(((c * 3 + kh) * 2 + pc) * P.ncols);
                     tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                   }
                 } else {
                   const uint32_t xs = st + xo + (uint32_t)c * P.xslab_bytes;
                   const uint32_t a_lo = (((xs + (uint32_t)((r + kh) * P.slab_w) * 128u) >> 4) & 0x3FFFu) | a_lbo;
-                  const uint32_t d = tmem_base + (uint32_t)((c * 3 + kh) * P.ncols);
+                  const uint32_t d = tmem_base + dcol + (uint32_t)((c * 3 + kh) * P.ncols);
                   tc_mma2_tf32(d, a_lo, a_hi, b_lo, b_hi, idesc, acc);
                 }
               }
@@ -220,6 +222,13 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
           if (has_work) {
             tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * P.ncols + c0), v);
             tc_wait_ld();
+            if (X3) {   // main + correction accumulator
+              uint32_t u[16];
+              tc_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)((P.nacc + a) * P.ncols + c0), u);
+              tc_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+            }
           } else {
 #pragma unroll
             for (int j = 0; j < 16; ++j) v[j] = 0u;
@@ -293,7 +302,7 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int passe
   const int bi = Cin / 32, bo = Cout / 32;
   const int acc_per_c = P.s2 ? 6 : 3;
   // output-channel blocks per CTA: up to 4 (N = 128); stride 2 keeps 2 so that two stages of four X slabs fit
-  P.nco = std::min(bo, (P.s2 || x3) ? 2 : 4);   // three-pass mode: every slab exists twice (raw + low part)
+  P.nco = std::min(bo, (P.s2 && x3) ? 1 : ((P.s2 || x3) ? 2 : 4));   // three-pass mode: every slab and accumulator exists twice
   while (bo % P.nco) --P.nco;
   P.ncols = P.nco * 32;
   P.ncc = std::max(1, std::min(bi, 512 / (acc_per_c * P.ncols)));
@@ -318,7 +327,7 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int passe
   P.nstages = (int)std::min<uint32_t>(6, avail / P.stage_bytes);
   if (P.nstages < (x3 ? 1 : 2)) return pl;       // stride 2 in three-pass mode runs a single stage (load, convert, multiply in turn)
   uint32_t cols = 32;
-  while (cols < (uint32_t)(P.nacc * P.ncols)) cols <<= 1;
+  while (cols < (uint32_t)(P.nacc * P.ncols * (x3 ? 2 : 1))) cols <<= 1;
   if (cols > 512) return pl;
   P.tmem_cols = cols;
   P.in_ld2 = Cin * 2;

@@ -19,7 +19,7 @@ SYMBOLS = [
     'ledb200_forward_infer', 'ledb200_backbone_forward', 'ledb200_head_forward', 'ledb200_head_infer',
     'ledb200_debug_fetch', 'ledb200_profile_ops', 'ledb200_op_info', 'ledb200_op_name', 'ledb200_plan_launches',
     'ledb200_head_fuse_argmax', 'ledb200_confusion_accumulate', 'ledb200_ohem_workspace_bytes',
-    'ledb200_ohem_ce', 'ledb200_conv2d',
+    'ledb200_ohem_ce', 'ledb200_ohem_up_fwd', 'ledb200_ohem_up_bwd', 'ledb200_conv2d',
     'ledb200_train_packed_weight_floats', 'ledb200_train_pack_weight', 'ledb200_train_conv_fwd',
     'ledb200_train_conv_dgrad', 'ledb200_train_conv_wgrad', 'ledb200_train_bn_fwd', 'ledb200_train_bn_bwd',
     'ledb200_train_bn_reduce', 'ledb200_train_bn_fwd_apply', 'ledb200_train_bn_bwd_apply',
@@ -91,6 +91,8 @@ def get():
     lib.ledb200_ohem_workspace_bytes.argtypes = [i64]
     lib.ledb200_ohem_workspace_bytes.restype = i64
     lib.ledb200_ohem_ce.argtypes = [vp, vp, i32, i32, i32, i32, i32, f32, i64, f32, vp, vp, vp, vp, vp]
+    lib.ledb200_ohem_up_fwd.argtypes = [vp, vp] + [i32] * 7 + [f32, i64, f32, vp, vp, vp, vp]
+    lib.ledb200_ohem_up_bwd.argtypes = [vp, vp] + [i32] * 7 + [f32, vp, vp, vp, vp, vp]
     lib.ledb200_conv2d.argtypes = [vp, vp, vp, i32] + [i32] * 8 + [vp, vp, vp, vp, i32, i32, i32, i32, vp]
     lib.ledb200_train_packed_weight_floats.argtypes = [i32] * 4
     lib.ledb200_train_packed_weight_floats.restype = i64

@@ -27,6 +27,43 @@ class _OhemFn(torch.autograd.Function):
         return grad * g, None, None
 
 
+class _OhemUpFn(torch.autograd.Function):
+    """OhemCrossEntropy of resize(r1, size, bilinear) for an NHWC rung r1 [N,h,w,K], without the full-resolution logits
+    (csrc/ohem.cu: ohem_up_*): the top of LEDHead's training ladder (led_head.py:101-146)."""
+
+    @staticmethod
+    def forward(ctx, r1, target, mod, size):
+        from . import lib as L
+        lib = L.get()
+        r1 = r1.contiguous()
+        target = target.contiguous().to(torch.int64)
+        n, h, w, k = r1.shape
+        H, W = int(size[0]), int(size[1])
+        ws = torch.empty(lib.ledb200_ohem_workspace_bytes(n * H * W), dtype=torch.uint8, device=r1.device)
+        out3 = torch.empty(3, dtype=torch.float32, device=r1.device)
+        cw = None
+        if mod.class_weight is not None:
+            cw = torch.as_tensor(mod.class_weight, dtype=torch.float32, device=r1.device).contiguous()
+        L.check(lib.ledb200_ohem_up_fwd(ops._p(r1), ops._p(target), n, k, h, w, H, W, mod.ignore_label, float(mod.thresh),
+                                        int(mod.min_kept), float(mod.loss_weight), ops._p(cw), ops._p(out3), ops._p(ws),
+                                        L.stream_ptr(r1.device)), 'ledb200_ohem_up_fwd')
+        ctx.save_for_backward(r1, target, ws)
+        ctx.cfg = (n, k, h, w, H, W, mod.ignore_label, float(mod.loss_weight), cw)
+        mod.last_stats = out3
+        return out3[0].clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        from . import lib as L
+        r1, target, ws = ctx.saved_tensors
+        n, k, h, w, H, W, ign, lw, cw = ctx.cfg
+        d = torch.empty_like(r1)
+        g = g.reshape(1).float().contiguous()
+        L.check(L.get().ledb200_ohem_up_bwd(ops._p(r1), ops._p(target), n, k, h, w, H, W, ign, lw, ops._p(cw), ops._p(g),
+                                            ops._p(ws), ops._p(d), L.stream_ptr(r1.device)), 'ledb200_ohem_up_bwd')
+        return d, None, None, None
+
+
 @MODELS.register_module()
 class OhemCrossEntropy(nn.Module):
 
@@ -43,6 +80,10 @@ class OhemCrossEntropy(nn.Module):
 
     def forward(self, score, target):
         return _OhemFn.apply(score, target, self)
+
+    def forward_upsampled(self, r1_nhwc, target, size):
+        """loss of resize(r1, size) for an NHWC rung, fused (no full-resolution logits); K <= 32, CUDA fp32."""
+        return _OhemUpFn.apply(r1_nhwc, target, self, tuple(size))
 
     @property
     def loss_name(self):

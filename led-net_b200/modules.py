@@ -435,12 +435,21 @@ class LEDHead(_EngineOwner):
         hw = tuple(label.shape[2:])
         hw4, hw2 = tuple(s // 4 for s in hw), tuple(s // 2 for s in hw)
 
-        def ladder(t):
+        def rung(t):
             t = T.add(h2, T.resize(t, hw4))
-            t = T.add(h1, T.resize(t, hw2))
-            return T.to_nchw(T.resize(t, hw))
-        ctx, spa = ladder(ctx), ladder(spa)
+            return T.add(h1, T.resize(t, hw2))
         label = label.squeeze(1)
+        K = ctx.shape[-1]
+        fused = (K <= 32 and all(hasattr(l, 'forward_upsampled') for l in self.loss_decode[:2])
+                 and self.loss_decode[0].ignore_label == self.ignore_index)
+        if fused:
+            # the last x2 of the ladder, the softmax / OHEM selection and (for the context map) the accuracy in one kernel
+            # family: the full-resolution logits [N,K,H,W] never exist (csrc/ohem.cu, ohem_up_*)
+            loss_c = self.loss_decode[0].forward_upsampled(rung(ctx), label, hw)
+            acc = self.loss_decode[0].last_stats[2:3].clone()
+            loss_s = self.loss_decode[1].forward_upsampled(rung(spa), label, hw)
+            return dict(loss_context=loss_c, loss_spatial=loss_s, acc_seg=acc)
+        ctx, spa = (T.to_nchw(T.resize(rung(t), hw)) for t in (ctx, spa))
         return dict(loss_context=self.loss_decode[0](ctx, label),
                     loss_spatial=self.loss_decode[1](spa, label),
                     acc_seg=accuracy(ctx, label, ignore_index=self.ignore_index))

@@ -190,7 +190,8 @@ class _Conv(torch.autograd.Function):
             if _tc_ok(1, n, h, w, cin, cout, k, ctx.stride):
                 wp = torch.empty(lib.ledb200_train_packed_weight_tc_floats(cout, cin, k, 1), dtype=torch.float32,
                                  device=x.device)
-                L.check(lib.ledb200_train_pack_weight_tc(_p(weight), _p(wp), cout, cin, k, 1, _st(x)),
+                L.check(lib.ledb200_train_pack_weight_tc(_p(weight), _p(wp), cout, cin, k,
+                                                         2 if (ctx.stride == 2 and k == 3) else 1, _st(x)),
                         'train_pack_weight_tc')
                 L.check(lib.ledb200_train_conv_dgrad_tc(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
                                                         _st(x)), 'train_conv_dgrad_tc')

@@ -91,6 +91,7 @@ def test_conv_tc_three_pass_is_fp32_grade(cin, cout, k, stride, hw, bias):
     T.set_tensor_cores(True, fast=False)
     _assert_tc(cin, cout, k, stride, hw)
     y, yr, dx, dxr, dw, dwr, db, dbr = _run(cin, cout, k, stride, hw, bias, rounded=False)
+    print(f'three-pass {cin}->{cout} k{k} s{stride}: fwd {rel_err(y, yr):.1e} dgrad {rel_err(dx, dxr):.1e} wgrad {rel_err(dw, dwr):.1e}')
     assert rel_err(y, yr) < 5e-5
     assert rel_err(dx, dxr) < 5e-5
     assert rel_err(dw, dwr) < 1e-4

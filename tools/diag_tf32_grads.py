@@ -40,9 +40,10 @@ def report(tag, grads, top=8):
 
 report('fp32 oracle (CPU)', g32)
 samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].cuda())) for i in range(N)]
-for tag, tc, ops in (('product fp32 kernels', False, 7), ('product tf32 all', True, 7), ('tf32 fwd only', True, 1),
-                     ('tf32 dgrad only', True, 2), ('tf32 wgrad only', True, 4), ('tf32 storage only (no TC conv)', True, 0)):
-    T.set_tensor_cores(tc)
+for tag, tc, fast, ops in (('product fp32 CUDA cores', False, False, 7), ('product tensor cores, 3 passes', True, False, 7),
+                           ('  3 passes, forward only', True, False, 1), ('  3 passes, dgrad only', True, False, 2),
+                           ('  3 passes, wgrad only', True, False, 4), ('product tensor cores, 1 pass (fast)', True, True, 7)):
+    T.set_tensor_cores(tc, fast=fast)
     T.TC_OPS = ops
     _, m = _train_pair(K)
     total, _ = m.parse_losses(m.loss(x.cuda(), samples))
