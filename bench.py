@@ -196,29 +196,45 @@ def extra_train(args, rank, world, local, dev, dist, barrier):
         return log
 
     steps, warm = 5, 2
-    for _ in range(warm):
-        step()
+    T = L.train_ops
+
+    def timed():
+        for _ in range(warm):
+            step()
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            lg = step()
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item() / steps, lg
+
+    prev = T.set_tensor_cores(True, fast=False)
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
-        log = step()
-    e1.record()
-    barrier()
-    t = torch.tensor([e0.elapsed_time(e1)], device=dev)
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t.item() / steps
+    ms, log = timed()                        # headline: tensor cores, three error-compensated tf32 passes (fp32-grade, parity-gated)
+    clocks = sampler.stop() if rank == 0 else None
+    mode = T.compute_mode()
+    T.set_tensor_cores(True, fast=True)
+    ms_fast, _ = timed()                     # one tf32 pass (cuDNN allow_tf32 numerics): reported, not the headline
+    T.set_tensor_cores(False)
+    ms_cuda, _ = timed()                     # round-1 fp32 CUDA-core kernels
+    T.set_tensor_cores(prev)
     out = dict(metric='LED-Net train img/s @1024x1024', value=world * N / (ms * 1e-3), unit=UNIT, ms_per_step=ms, steps=steps,
-               warmup=warm, n_gpus=world, dtype=L.train_ops.COMPUTE if hasattr(L.train_ops, 'COMPUTE') else 'f32',
+               warmup=warm, n_gpus=world, dtype=mode,
                loss=float(log['loss'].detach()),
+               other_modes=dict(tf32_single_pass_ms=ms_fast, f32_cuda_cores_ms=ms_cuda),
                config=dict(workload='BASELINE config 4: fwd + OHEM CE x2 + bwd + gradient all-reduce + SGD', batch_per_gpu=N,
                            height=S, width=S, num_classes=K, norm=norm['type'],
+                           arithmetic='convolutions (forward, data and weight gradients) on tcgen05 kind::tf32 with three '
+                                      'error-compensated passes, fp32 storage and accumulation; BatchNorm / resize / OHEM fp32',
                            parallelism=f'dp{world} (flat fp32 gradient all-reduce over NCCL)'),
-               peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, clocks=sampler.stop() if rank == 0 else None)
+               peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30, clocks=clocks)
     del m, opt, x, lab, samples
     torch.cuda.empty_cache()
     return out

@@ -11,6 +11,9 @@
 // The masked mean uses a fixed grid and fixed-order block partials (deterministic).
 //
 // logits fp32 NCHW (what LEDHead.loss_by_feat hands the loss), target int64.
+#include <algorithm>
+#include <cmath>
+
 #include "kernels.h"
 
 namespace ledb {
@@ -355,6 +358,275 @@ ohem_up_bwd_kernel(const float* __restrict__ r1, const int64_t* __restrict__ tar
   }
 }
 
+// Tiled forms.  Flat one-thread-per-pixel kernels read the four neighbour rungs with 4 x K scalar loads whose addresses are
+// 76 bytes apart across a warp (K = 19): LSU-bound at ~10 x the HBM time.  A CTA instead stages the r1 patch its outputs read
+// into shared memory with coalesced row copies (odd pixel stride: conflict-free), and interpolates from there.
+//   forward : 32 x 32 outputs per CTA
+//   backward: 8 x 16 r1 pixels per CTA; d(logits) of every output that reads one of them ((2*8+2) x (2*16+2) for the x2
+//             ladder) is written to shared memory first - ONE softmax per output instead of one per (output, source) pair -
+//             then each thread gathers its source pixel's footprint from there, in the same order as the flat kernel.
+constexpr int kTileSY = 8, kTileSX = 16, kTileO = 32;
+
+template <int KT>
+__device__ __forceinline__ void up_logits_smem(const float* __restrict__ sp, int sc, int sy0, int sx0, int y, int x, int h, int w,
+                                               int K, int KS, float sh, float sw, float* v) {
+  int y0, y1, x0, x1;
+  float ly0, ly1, lx0, lx1;
+  bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+  bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+  const float* a = sp + ((y0 - sy0) * sc + (x0 - sx0)) * KS;
+  const float* b = sp + ((y0 - sy0) * sc + (x1 - sx0)) * KS;
+  const float* c = sp + ((y1 - sy0) * sc + (x0 - sx0)) * KS;
+  const float* d = sp + ((y1 - sy0) * sc + (x1 - sx0)) * KS;
+#pragma unroll
+  for (int k = 0; k < KT; ++k) {
+    if (k < K) {
+      const float r0 = fmaf(b[k], lx1, a[k] * lx0);
+      const float r1v = fmaf(d[k], lx1, c[k] * lx0);
+      v[k] = fmaf(r1v, ly1, r0 * ly0);
+    }
+  }
+}
+
+// stage r1[n, sy0..sy1, sx0..sx1, :] as [row][col][KS]; rows are contiguous in global memory
+__device__ __forceinline__ void stage_patch(const float* __restrict__ r1n, float* __restrict__ sp, int w, int K, int KS, int sy0,
+                                            int sy1, int sx0, int sx1, int nthr) {
+  const int sc = sx1 - sx0 + 1, rowlen = sc * K;
+  for (int r = sy0; r <= sy1; ++r) {
+    const float* src = r1n + ((int64_t)r * w + sx0) * K;
+    float* dst = sp + (r - sy0) * sc * KS;
+    for (int i = threadIdx.x; i < rowlen; i += nthr) dst[(i / K) * KS + (i % K)] = __ldg(src + i);
+  }
+}
+
+template <int KT>
+__global__ void __launch_bounds__(kT)
+ohem_up_pixel_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, int K, int h, int w, int H, int W,
+                           int tiles_x, int tiles_y, int cap, int ignore, const float* __restrict__ cw, float sh, float sw,
+                           float* __restrict__ prob, float* __restrict__ loss, OhemState* s) {
+  extern __shared__ float sp[];
+  __shared__ float shm[kT / 32];
+  const int KS = K | 1;
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
+  const int oy0 = ty * kTileO, ox0 = tx * kTileO, oy1 = min(oy0 + kTileO, H) - 1, ox1 = min(ox0 + kTileO, W) - 1;
+  int sy0, sy1, sx0, sx1, t0;
+  float f0, f1;
+  bilinear_coord(oy0, sh, h, sy0, t0, f0, f1);
+  bilinear_coord(oy1, sh, h, t0, sy1, f0, f1);
+  bilinear_coord(ox0, sw, w, sx0, t0, f0, f1);
+  bilinear_coord(ox1, sw, w, t0, sx1, f0, f1);
+  const int sc = sx1 - sx0 + 1;
+  if ((sy1 - sy0 + 1) * sc * KS > cap) __trap();
+  stage_patch(r1 + (int64_t)n * h * w * K, sp, w, K, KS, sy0, sy1, sx0, sx1, kT);
+  __syncthreads();
+  float nvalid = 0.f, ncorrect = 0.f;
+  const int tw = ox1 - ox0 + 1, th = oy1 - oy0 + 1;
+  for (int o = threadIdx.x; o < tw * th; o += kT) {
+    const int y = oy0 + o / tw, x = ox0 + o % tw;
+    const int64_t i = ((int64_t)n * H + y) * W + x;
+    float v[KT];
+    up_logits_smem<KT>(sp, sc, sy0, sx0, y, x, h, w, K, KS, sh, sw, v);
+    const int64_t yt = target[i];
+    float m = -INFINITY;
+    int am = 0;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (k < K && v[k] > m) { m = v[k]; am = k; }
+    float p = 2.0f, l = 0.f;
+    if (yt != ignore) {
+      const int yy = (yt >= 0 && yt < K) ? (int)yt : 0;
+      float sum = 0.f, xy = 0.f, ey = 0.f;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (k < K) {
+          const float e = expf(v[k] - m);          // expf costs ~20 instructions: evaluated once per class
+          sum += e;
+          if (k == yy) { xy = v[k] - m; ey = e; }
+        }
+      p = ey / sum;
+      l = -(xy - logf(sum)) * (cw ? cw[yy] : 1.f);
+      nvalid += 1.f;
+      ncorrect += (am == (int)yt) ? 1.f : 0.f;
+    }
+    prob[i] = p;
+    loss[i] = l;
+  }
+  const float a = block_sum(nvalid, shm);
+  const float b = block_sum(ncorrect, shm);
+  if (threadIdx.x == 0) {
+    atomicAdd(&s->nvalid, (unsigned long long)a);
+    atomicAdd(&s->ncorrect, (unsigned long long)b);
+  }
+}
+
+// EXACT: K == KT (the class loops carry no `k < K` guards - a quarter of the instructions of the guarded form).
+// 256 threads: all of them produce d(logits) of the region; in the gather two threads share a source pixel, one per half of
+// the classes, so no warp idles through it.
+template <int KT, bool EXACT>
+__global__ void __launch_bounds__(2 * kTileSY * kTileSX)
+ohem_up_bwd_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, const float* __restrict__ prob,
+                         int K_, int h, int w, int H, int W, int tiles_x, int tiles_y, int cap_g, int cap_p, int ignore,
+                         const float* __restrict__ cw, float loss_weight, const float* __restrict__ gscale, float sh, float sw,
+                         const OhemState* __restrict__ s, float* __restrict__ dr1) {
+  extern __shared__ float sg[];                 // [region outputs][KS] d(logits), then the staged r1 patch
+  constexpr int NT = 2 * kTileSY * kTileSX;
+  const int K = EXACT ? KT : K_;
+  const int KS = K | 1;                         // odd pixel stride: conflict-free when lanes walk neighbouring pixels
+  const float thr = s->threshold;
+  const float scale = loss_weight / s->kept * (gscale ? gscale[0] : 1.f);
+  const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
+  const int ys0 = ty * kTileSY, xs0 = tx * kTileSX;
+  const int ys1 = min(ys0 + kTileSY, h) - 1, xs1 = min(xs0 + kTileSX, w) - 1;
+  int ylo, yhi, xlo, xhi, t0;
+  up_gather_range(ys0, sh, H, ylo, t0);
+  up_gather_range(ys1, sh, H, t0, yhi);
+  up_gather_range(xs0, sw, W, xlo, t0);
+  up_gather_range(xs1, sw, W, t0, xhi);
+  const int rh = yhi - ylo + 1, rw = xhi - xlo + 1;
+  // r1 patch read by the region's outputs
+  int sy0, sy1, sx0, sx1;
+  float f0, f1;
+  bilinear_coord(ylo, sh, h, sy0, t0, f0, f1);
+  bilinear_coord(yhi, sh, h, t0, sy1, f0, f1);
+  bilinear_coord(xlo, sw, w, sx0, t0, f0, f1);
+  bilinear_coord(xhi, sw, w, t0, sx1, f0, f1);
+  const int sc = sx1 - sx0 + 1;
+  if (rh * rw * KS > cap_g || (sy1 - sy0 + 1) * sc * KS > cap_p) __trap();
+  float* sp = sg + cap_g;
+  stage_patch(r1 + (int64_t)n * h * w * K, sp, w, K, KS, sy0, sy1, sx0, sx1, NT);
+  __syncthreads();
+  for (int o = threadIdx.x; o < rh * rw; o += NT) {
+    const int y = ylo + o / rw, x = xlo + o % rw;
+    const int64_t pi = ((int64_t)n * H + y) * W + x;
+    const float p = prob[pi];
+    float* dst = sg + o * KS;
+    if (!((p < thr) && (p <= 1.5f))) {
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) dst[k] = 0.f;
+      continue;
+    }
+    float v[KT];
+    {
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+      const float* a = sp + ((y0 - sy0) * sc + (x0 - sx0)) * KS;
+      const float* b = sp + ((y0 - sy0) * sc + (x1 - sx0)) * KS;
+      const float* c = sp + ((y1 - sy0) * sc + (x0 - sx0)) * KS;
+      const float* d = sp + ((y1 - sy0) * sc + (x1 - sx0)) * KS;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) {
+          const float r0 = fmaf(b[k], lx1, a[k] * lx0);
+          const float r1v = fmaf(d[k], lx1, c[k] * lx0);
+          v[k] = fmaf(r1v, ly1, r0 * ly0);
+        }
+    }
+    const int64_t yt = target[pi];
+    const int yy = (yt >= 0 && yt < K) ? (int)yt : 0;
+    float m = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (EXACT || k < K) m = fmaxf(m, v[k]);
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (EXACT || k < K) { v[k] = expf(v[k] - m); sum += v[k]; }     // one expf per class (~10 instructions each)
+    const float g = scale * (cw ? cw[yy] : 1.f);
+    const float inv = 1.f / sum;
+#pragma unroll
+    for (int k = 0; k < KT; ++k)
+      if (EXACT || k < K) dst[k] = g * (v[k] * inv - (k == yy ? 1.f : 0.f));
+  }
+  __syncthreads();
+  // gather: thread pair (2 p, 2 p + 1) owns source pixel p; the first takes classes [0, KH), the second [KH, K)
+  constexpr int KH = (KT + 1) / 2;
+  const int pidx = threadIdx.x >> 1, half = threadIdx.x & 1;
+  const int ys = ys0 + pidx / kTileSX, xs = xs0 + pidx % kTileSX;
+  if (ys > ys1 || xs > xs1) return;
+  const int k0 = half * KH;
+  int cylo, cyhi, cxlo, cxhi;
+  up_gather_range(ys, sh, H, cylo, cyhi);
+  up_gather_range(xs, sw, W, cxlo, cxhi);
+  float acc[KH];
+#pragma unroll
+  for (int k = 0; k < KH; ++k) acc[k] = 0.f;
+  for (int y = cylo; y <= cyhi; ++y) {
+    int y0, y1;
+    float ly0, ly1;
+    bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+    if (y0 != ys && y1 != ys) continue;
+    float wy = 0.f;
+    if (y0 == ys) wy += ly0;
+    if (y1 == ys) wy += ly1;
+    float rowv[KH];
+#pragma unroll
+    for (int k = 0; k < KH; ++k) rowv[k] = 0.f;
+    for (int x = cxlo; x <= cxhi; ++x) {
+      int x0, x1;
+      float lx0, lx1;
+      bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+      if (x0 != xs && x1 != xs) continue;
+      float wx = 0.f;
+      if (x0 == xs) wx += lx0;
+      if (x1 == xs) wx += lx1;
+      const float* src = sg + ((y - ylo) * rw + (x - xlo)) * KS + k0;
+#pragma unroll
+      for (int k = 0; k < KH; ++k)
+        if (k0 + k < K) rowv[k] = fmaf(src[k], wx, rowv[k]);
+    }
+#pragma unroll
+    for (int k = 0; k < KH; ++k) acc[k] = fmaf(rowv[k], wy, acc[k]);
+  }
+  float* o = dr1 + (((int64_t)n * h + ys) * w + xs) * K + k0;
+#pragma unroll
+  for (int k = 0; k < KH; ++k)
+    if (k0 + k < K) o[k] = acc[k];
+}
+
+// host mirrors of the device index formulas, for sizing the shared-memory tiles (the kernels trap if a tile exceeds them)
+void host_bilinear(int dst, float scale, int in_size, int& i0, int& i1) {
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > in_size - 1) i0 = in_size - 1;
+  i1 = i0 + ((i0 < in_size - 1) ? 1 : 0);
+}
+void host_gather_range(int sidx, float scale, int out_size, int& lo, int& hi) {
+  lo = (int)floorf(((float)sidx - 0.5f) / scale - 0.5f) - 1;
+  hi = (int)ceilf(((float)sidx + 1.5f) / scale - 0.5f) + 1;
+  if (lo < 0) lo = 0;
+  if (hi > out_size - 1) hi = out_size - 1;
+}
+// backward: largest (output region, r1 patch) extents along one axis over all source tiles of `tile` pixels
+void bwd_extents(int src, int out, float scale, int tile, int& region, int& patch) {
+  region = patch = 0;
+  for (int s0 = 0; s0 < src; s0 += tile) {
+    const int s1 = std::min(s0 + tile, src) - 1;
+    int lo, hi, t, p0, p1;
+    host_gather_range(s0, scale, out, lo, t);
+    host_gather_range(s1, scale, out, t, hi);
+    host_bilinear(lo, scale, src, p0, t);
+    host_bilinear(hi, scale, src, t, p1);
+    region = std::max(region, hi - lo + 1);
+    patch = std::max(patch, p1 - p0 + 1);
+  }
+}
+// forward: largest r1 patch extent along one axis over all output tiles
+int fwd_extent(int src, int out, float scale) {
+  int best = 0;
+  for (int o0 = 0; o0 < out; o0 += kTileO) {
+    const int o1 = std::min(o0 + kTileO, out) - 1;
+    int p0, p1, t;
+    host_bilinear(o0, scale, src, p0, t);
+    host_bilinear(o1, scale, src, t, p1);
+    best = std::max(best, p1 - p0 + 1);
+  }
+  return best;
+}
+
 }  // namespace
 
 int launch_ohem_up(const float* r1, const int64_t* target, int N, int K, int h, int w, int H, int W, int ignore_label,
@@ -370,7 +642,25 @@ int launch_ohem_up(const float* r1, const int64_t* target, int N, int K, int h, 
   const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 8, ceil_div64(npix, kT)));
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
   ohem_init_kernel<<<1, 256, 0, st>>>(s);
+  bool tiled = false;
   if (npix > 0) {
+    const int cap = (fwd_extent(h, H, sh) + 1) * (fwd_extent(w, W, sw) + 1) * (K | 1);
+    const int tiles_x = ceil_div(W, kTileO), tiles_y = ceil_div(H, kTileO);
+    const int64_t tiles = (int64_t)N * tiles_x * tiles_y;
+    if ((size_t)cap * 4 <= 96 * 1024 && tiles < (1ll << 31)) {
+      tiled = true;
+      auto run = [&](auto kern) -> int {
+        LEDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+        kern<<<(unsigned)tiles, kT, (size_t)cap * 4, st>>>(r1, target, K, h, w, H, W, tiles_x, tiles_y, cap, ignore_label,
+                                                         class_weight, sh, sw, prob, loss, s);
+        LEDB_LAUNCH_OK("ohem_up_pixel_tiled_kernel");
+        return LEDB200_OK;
+      };
+      const int rc = K <= 8 ? run(ohem_up_pixel_tiled_kernel<8>) : (K <= 20 ? run(ohem_up_pixel_tiled_kernel<20>) : run(ohem_up_pixel_tiled_kernel<32>));
+      if (rc) return rc;
+    }
+  }
+  if (npix > 0 && !tiled) {
     if (K <= 8) ohem_up_pixel_kernel<8><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
     else if (K <= 20) ohem_up_pixel_kernel<20><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
     else ohem_up_pixel_kernel<32><<<grid, kT, 0, st>>>(r1, target, K, h, w, H, W, npix, ignore_label, class_weight, sh, sw, prob, loss, s);
@@ -396,8 +686,31 @@ int launch_ohem_up_bwd(const float* r1, const int64_t* target, int N, int K, int
   if (nsrc == 0) return LEDB200_OK;
   auto* s = reinterpret_cast<const OhemState*>(workspace);
   const float* prob = reinterpret_cast<const float*>(reinterpret_cast<const char*>(workspace) + ((sizeof(OhemState) + 255) / 256) * 256);
-  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 16, ceil_div64(nsrc, 128)));
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
+  {
+    int ry, py, rx, px;
+    bwd_extents(h, H, sh, kTileSY, ry, py);
+    bwd_extents(w, W, sw, kTileSX, rx, px);
+    const int cap_g = (ry + 1) * (rx + 1) * (K | 1), cap_p = (py + 1) * (px + 1) * (K | 1);
+    const size_t smem = (size_t)(cap_g + cap_p) * sizeof(float);
+    const int tiles_x = ceil_div(w, kTileSX), tiles_y = ceil_div(h, kTileSY);
+    const int64_t tiles = (int64_t)N * tiles_x * tiles_y;
+    if (smem <= 160 * 1024 && tiles < (1ll << 31)) {
+      auto run = [&](auto kern) -> int {
+        LEDB_CUDA_OK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        kern<<<(unsigned)tiles, 2 * kTileSY * kTileSX, smem, st>>>(r1, target, prob, K, h, w, H, W, tiles_x, tiles_y, cap_g, cap_p, ignore_label,
+                                                  class_weight, loss_weight, gscale, sh, sw, s, dr1);
+        LEDB_LAUNCH_OK("ohem_up_bwd_tiled_kernel");
+        return LEDB200_OK;
+      };
+      if (K == 19) return run(ohem_up_bwd_tiled_kernel<19, true>);     // Cityscapes
+      if (K == 2) return run(ohem_up_bwd_tiled_kernel<2, true>);       // the reference config's two-class set
+      if (K <= 8) return run(ohem_up_bwd_tiled_kernel<8, false>);
+      if (K <= 20) return run(ohem_up_bwd_tiled_kernel<20, false>);
+      return run(ohem_up_bwd_tiled_kernel<32, false>);
+    }
+  }
+  const int grid = (int)std::max<int64_t>(1, std::min<int64_t>(148 * 16, ceil_div64(nsrc, 128)));
   if (K <= 8) ohem_up_bwd_kernel<8><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);
   else if (K <= 20) ohem_up_bwd_kernel<20><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);
   else ohem_up_bwd_kernel<32><<<grid, 128, 0, st>>>(r1, target, prob, K, h, w, H, W, nsrc, ignore_label, class_weight, loss_weight, gscale, sh, sw, s, dr1);

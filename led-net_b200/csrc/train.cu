@@ -220,6 +220,81 @@ wgrad_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* _
       }
 }
 
+// Weight gradient of a 3x3 convolution with a handful of input channels (the stem's first layer, Cin = 3: too narrow for
+// TMA / the tensor-core tiling, and the register-tile kernel above spends its time staging 32-channel tiles that are 90 %
+// padding - 2.8 ms per step).  Lane = output channel, warp = a slab of output rows: a thread keeps all 9 x CI products of its
+// channel in registers, reads dY once (coalesced across the warp) and the 3 x 3 x CI input patch as warp-wide broadcasts.
+// Per-row fp32 sums are folded into double; every warp writes its partial to its own slot, slots are added in order afterwards.
+template <int CI>
+__global__ void __launch_bounds__(256)
+wgrad_small_cin_kernel(const float* __restrict__ x, const float* __restrict__ dy, float* __restrict__ part, int N, int H, int W,
+                       int Ho, int Wo, int Cout, int S, int nseg) {
+  __shared__ float red[8][9 * CI][32];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int co = blockIdx.y * 32 + lane;
+  const bool co_ok = co < Cout;
+  constexpr int SEG = 64;                                 // output columns per work item
+  const int64_t items = (int64_t)N * Ho * nseg;
+  double dacc[9 * CI];
+#pragma unroll
+  for (int i = 0; i < 9 * CI; ++i) dacc[i] = 0.0;
+  // work item = (output row, 64-column segment); items are dealt round-robin to the grid's warps - the order in which a
+  // warp meets its items and the slot order of the final sum are fixed, so the result is reproducible
+  for (int64_t it = (int64_t)blockIdx.x * 8 + warp; it < items; it += (int64_t)gridDim.x * 8) {
+    const int64_t r = it / nseg;
+    const int seg = (int)(it % nseg);
+    const int n = (int)(r / Ho), oy = (int)(r % Ho);
+    const float* dr = dy + r * Wo * Cout + co;
+    const float* xrow[3];
+    float rmask[3];
+#pragma unroll
+    for (int kh = 0; kh < 3; ++kh) {
+      const int iy = oy * S + kh - 1;
+      const bool ok = iy >= 0 && iy < H;
+      rmask[kh] = ok ? 1.f : 0.f;
+      xrow[kh] = x + ((int64_t)n * H + (ok ? iy : 0)) * W * CI;
+    }
+    float acc[9 * CI];
+#pragma unroll
+    for (int i = 0; i < 9 * CI; ++i) acc[i] = 0.f;
+    const int ox1 = min(Wo, (seg + 1) * SEG);
+#pragma unroll 2
+    for (int ox = seg * SEG; ox < ox1; ++ox) {
+      const float d = co_ok ? __ldg(dr + (int64_t)ox * Cout) : 0.f;
+#pragma unroll
+      for (int kw = 0; kw < 3; ++kw) {
+        const int ix = ox * S + kw - 1;
+        const bool ok = (unsigned)ix < (unsigned)W;
+        const int ixc = ok ? ix : 0;
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+          const float dm = ok ? d * rmask[kh] : 0.f;
+#pragma unroll
+          for (int c = 0; c < CI; ++c)
+            acc[(kh * 3 + kw) * CI + c] = fmaf(__ldg(xrow[kh] + ixc * CI + c), dm, acc[(kh * 3 + kw) * CI + c]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < 9 * CI; ++i) dacc[i] += acc[i];
+  }
+#pragma unroll
+  for (int i = 0; i < 9 * CI; ++i) red[warp][i][lane] = (float)dacc[i];
+  __syncthreads();
+  // block partial = the eight warps in warp order -> slot blockIdx.x
+  float* mine = part + (int64_t)blockIdx.x * ((int64_t)Cout * CI * 9);
+  for (int e = threadIdx.x; e < 9 * CI * 32; e += 256) {
+    const int i = e >> 5, l = e & 31;
+    const int c_o = blockIdx.y * 32 + l;
+    if (c_o >= Cout) continue;
+    float sum = 0.f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) sum += red[wv][i][l];
+    const int t = i / CI, c = i % CI;
+    mine[((int64_t)c_o * CI + c) * 9 + t] = sum;
+  }
+}
+
 __global__ void __launch_bounds__(kT) wgrad_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int64_t n,
                                                        int slots) {
   const int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x;
@@ -264,7 +339,7 @@ chan_reduce_kernel(const float* __restrict__ a, const float* __restrict__ y, con
       } else if (KIND == 1) {
         float dz = a[i];
         if (relu && !(out[i] > 0.f)) dz = 0.f;
-        s0 += dz; s1 = fmaf(dz, (y[i] - m) * is, s1);
+        s0 += dz; d1 += (double)dz * ((double)(y[i] - m) * (double)is);
       } else {
         s0 += a[i];
       }
@@ -323,12 +398,14 @@ chan_reduce4_kernel(const float4* __restrict__ a, const float4* __restrict__ y, 
         }
         const float4 yy = __ldg(y + i);
         s0[0] += dz.x; s0[1] += dz.y; s0[2] += dz.z; s0[3] += dz.w;
-        s1[0] = fmaf(dz.x, (yy.x - m.x) * is.x, s1[0]); s1[1] = fmaf(dz.y, (yy.y - m.y) * is.y, s1[1]);
-        s1[2] = fmaf(dz.z, (yy.z - m.z) * is.z, s1[2]); s1[3] = fmaf(dz.w, (yy.w - m.w) * is.w, s1[3]);
+        // sum dz * xhat straight into double: this sum and sum dz are what BatchNorm's backward subtracts from dz (a
+        // cancellation that amplifies their rounding by the network's conditioning); the kernel is memory-bound either way
+        d1[0] += (double)dz.x * ((double)(yy.x - m.x) * (double)is.x); d1[1] += (double)dz.y * ((double)(yy.y - m.y) * (double)is.y);
+        d1[2] += (double)dz.z * ((double)(yy.z - m.z) * (double)is.z); d1[3] += (double)dz.w * ((double)(yy.w - m.w) * (double)is.w);
       } else {
         s0[0] += v.x; s0[1] += v.y; s0[2] += v.z; s0[3] += v.w;
       }
-      if (++cnt == 256) {                       // bound the fp32 run length
+      if (++cnt == 64) {                        // bound the fp32 run length
 #pragma unroll
         for (int j = 0; j < 4; ++j) { d0[j] += s0[j]; d1[j] += s1[j]; s0[j] = s1[j] = 0.f; }
         cnt = 0;
@@ -388,11 +465,14 @@ __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double
 }
 
 // out = [relu]((y - mean) * invstd * gamma + beta [+ res])
+// IT: index type - uint32_t when the tensor has < 2^32 elements (a 64-bit modulo per element is most of this kernel's time)
+template <typename IT>
 __global__ void __launch_bounds__(kT)
 bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ res, const float* __restrict__ gamma,
                 const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
-                float* __restrict__ out, int relu, int64_t total, int C, int rnd) {
-  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+                float* __restrict__ out, int relu, int64_t total_, int C_, int rnd) {
+  const IT total = (IT)total_, C = (IT)C_;
+  for (IT i = blockIdx.x * (IT)kT + threadIdx.x; i < total; i += (IT)gridDim.x * kT) {
     const int c = (int)(i % C);
     float v = fmaf((y[i] - mean[c]) * invstd[c], gamma[c], beta[c]);
     if (res) v += res[i];
@@ -401,20 +481,22 @@ bn_apply_kernel(const float* __restrict__ y, const float* __restrict__ res, cons
 }
 
 // dy = gamma * invstd * (dz - dbeta/M - xhat * dgamma/M); dres = dz
+template <typename IT>
 __global__ void __launch_bounds__(kT)
 bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y, const float* __restrict__ out,
                     const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
                     const double* __restrict__ acc, const double* __restrict__ acc_local, float* __restrict__ dy,
-                    float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total,
-                    int C, float invM, int rnd) {
-  for (int64_t i = blockIdx.x * (int64_t)kT + threadIdx.x; i < total; i += (int64_t)gridDim.x * kT) {
+                    float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total_,
+                    int C_, float invM, int rnd) {
+  const IT total = (IT)total_, C = (IT)C_;
+  for (IT i = blockIdx.x * (IT)kT + threadIdx.x; i < total; i += (IT)gridDim.x * kT) {
     const int c = (int)(i % C);
     float dz = dout[i];
     if (relu && !(out[i] > 0.f)) dz = 0.f;
-    const float db = (float)acc[c], dg = (float)acc[C + c];
     const float is = invstd[c];
-    const float xhat = (y[i] - mean[c]) * is;
-    dy[i] = rt(gamma[c] * is * (dz - db * invM - xhat * dg * invM), rnd);
+    const double xhat = (double)(y[i] - mean[c]) * (double)is;
+    const double br = (double)dz - acc[c] * (double)invM - xhat * (acc[C + c] * (double)invM);
+    dy[i] = rt((float)((double)gamma[c] * (double)is * br), rnd);
     if (dres) dres[i] = dz;
     if (i < C) { dbeta[c] = (float)acc_local[c]; dgamma[c] = (float)acc_local[C + c]; }   // parameter gradients stay rank-local (DDP averages them)
   }
@@ -465,9 +547,10 @@ bn_bwd_apply4_kernel(const float4* __restrict__ dout, const float4* __restrict__
     float o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-      const float db = (float)acc[c + j], dg = (float)acc[C + c + j];
-      const float xhat = (yv[j] - mv[j]) * isv[j];
-      o[j] = rt(gv[j] * isv[j] * (dzv[j] - db * invM - xhat * dg * invM), rnd);
+      // dz - mean(dz) - xhat * mean(dz * xhat) in double: the subtraction cancels most of dz in the deep layers
+      const double xhat = (double)(yv[j] - mv[j]) * (double)isv[j];
+      const double br = (double)dzv[j] - acc[c + j] * (double)invM - xhat * (acc[C + c + j] * (double)invM);
+      o[j] = rt((float)((double)gv[j] * (double)isv[j] * br), rnd);
     }
     dy[i] = make_float4(o[0], o[1], o[2], o[3]);
     if (dres) dres[i] = dz;
@@ -1017,6 +1100,19 @@ int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, fl
   // workspace: [bias-gradient accumulators and partials: bn_ws_doubles(Cout) doubles][2 * gx weight-gradient slots]
   float* part = reinterpret_cast<float*>(reinterpret_cast<double*>(workspace) + bn_ws_doubles(Cout));
   const int64_t nw = (int64_t)Cout * Cin * k * k;
+  if (k == 3 && Cin <= 4 && (int64_t)N * Ho >= 64) {
+    // narrow-input form (stem): one slot per block; slots fit the workspace sized for 2 * gx slots above
+    const int nseg = ceil_div(Wo, 64);
+    const int64_t items = (int64_t)N * Ho * nseg;
+    const int nslots = (int)std::max<int64_t>(1, std::min<int64_t>(2 * gx, std::min<int64_t>(ceil_div64(items, 8), 148 * 8)));
+    dim3 g2((unsigned)nslots, (unsigned)ceil_div(Cout, 32));
+    if (Cin == 1) wgrad_small_cin_kernel<1><<<g2, 256, 0, st>>>(x, dy, part, N, H, W, Ho, Wo, Cout, stride, nseg);
+    else if (Cin == 2) wgrad_small_cin_kernel<2><<<g2, 256, 0, st>>>(x, dy, part, N, H, W, Ho, Wo, Cout, stride, nseg);
+    else if (Cin == 3) wgrad_small_cin_kernel<3><<<g2, 256, 0, st>>>(x, dy, part, N, H, W, Ho, Wo, Cout, stride, nseg);
+    else wgrad_small_cin_kernel<4><<<g2, 256, 0, st>>>(x, dy, part, N, H, W, Ho, Wo, Cout, stride, nseg);
+    wgrad_sum_kernel<<<(unsigned)ceil_div64(nw, kT), kT, 0, st>>>(part, dw_oihw, nw, nslots);
+    LEDB_LAUNCH_OK("wgrad_small_cin_kernel");
+  } else
   if (k == 3) {
     LEDB_CUDA_OK(cudaFuncSetAttribute(wgrad_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     wgrad_kernel<3><<<grid, 128, smem, st>>>(x, dy, part, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
@@ -1025,7 +1121,8 @@ int ledb200_train_conv_wgrad(const float* x, const float* dy, float* dw_oihw, fl
     wgrad_kernel<1><<<grid, 128, smem, st>>>(x, dy, part, N, H, W, Cin, Ho, Wo, Cout, stride, pad, tiles_x,
                                              tiles_x * tiles_y, total_tiles);
   }
-  wgrad_sum_kernel<<<(unsigned)ceil_div64(nw, kT), kT, 0, st>>>(part, dw_oihw, nw, 2 * (int)gx);
+  if (!(k == 3 && Cin <= 4 && (int64_t)N * Ho >= 64))
+    wgrad_sum_kernel<<<(unsigned)ceil_div64(nw, kT), kT, 0, st>>>(part, dw_oihw, nw, 2 * (int)gx);
   LEDB_LAUNCH_OK("wgrad_kernel");
   if (dbias_opt) {
     double* acc = (double*)workspace;
@@ -1073,9 +1170,12 @@ int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* 
     bn_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
         reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(res_opt), gamma, beta, save_mean, save_invstd,
         reinterpret_cast<float4*>(out), relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), g_round);
+  else if (npix * C < (1ll << 32))
+    bn_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
+                                                               npix * C, C, g_round);
   else
-  bn_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
-                                                   npix * C, C, g_round);
+    bn_apply_kernel<int64_t><<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
+                                                              npix * C, C, g_round);
   LEDB_LAUNCH_OK("train_bn_fwd_apply");
   return LEDB200_OK;
 }
@@ -1096,10 +1196,14 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
         reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
         save_mean, save_invstd, acc + 2 * C, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta,
         relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), (float)(1.0 / total_count), g_round);
+  else if (npix * C < (1ll << 32))
+    bn_bwd_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(
+        dout, y, out, gamma, save_mean, save_invstd, acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta, relu, npix * C, C,
+        (float)(1.0 / total_count), g_round);
   else
-  bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(dout, y, out, gamma, save_mean, save_invstd,
-                                                                         acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta,
-                                                                         relu, npix * C, C, (float)(1.0 / total_count), g_round);
+    bn_bwd_apply_kernel<int64_t><<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(
+        dout, y, out, gamma, save_mean, save_invstd, acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta, relu, npix * C, C,
+        (float)(1.0 / total_count), g_round);
   LEDB_LAUNCH_OK("train_bn_bwd_apply");
   return LEDB200_OK;
 }
@@ -1134,9 +1238,14 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
         reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
         save_mean, save_invstd, acc, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta, relu,
         (uint32_t)(npix * C / 4), (uint32_t)(C / 4), 1.f / (float)npix, g_round);
+  else if (npix * C < (1ll << 32))
+    bn_bwd_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy,
+                                                                   dres_opt, dgamma, dbeta, relu, npix * C, C,
+                                                                   1.f / (float)npix, g_round);
   else
-  bn_bwd_apply_kernel<<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy, dres_opt,
-                                                       dgamma, dbeta, relu, npix * C, C, 1.f / (float)npix, g_round);
+    bn_bwd_apply_kernel<int64_t><<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy,
+                                                                  dres_opt, dgamma, dbeta, relu, npix * C, C,
+                                                                  1.f / (float)npix, g_round);
   LEDB_LAUNCH_OK("train_bn_bwd");
   return LEDB200_OK;
 }

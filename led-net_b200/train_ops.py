@@ -97,6 +97,12 @@ def set_tensor_cores(on, fast=False):
     return prev
 
 
+def compute_mode():
+    """Arithmetic of the training convolutions right now: 'tf32x3' (tensor cores, three error-compensated passes, fp32-grade),
+    'tf32' (tensor cores, one pass) or 'f32' (CUDA cores)."""
+    return ('tf32' if TC_FAST else 'tf32x3') if TENSOR_CORES else 'f32'
+
+
 def _sync_mode():
     global _passes_synced
     want = 1 if TC_FAST else 3

@@ -83,9 +83,9 @@ def main():
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = ms.item() / args.steps
     if rank == 0:
-        print(json.dumps(dict(metric='LED-Net train img/s @1024x1024 fp32', value=world * N / (ms_step * 1e-3),
+        print(json.dumps(dict(metric='LED-Net train img/s @1024x1024', value=world * N / (ms_step * 1e-3),
                               unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
-                              dtype='f32', data='synthetic', loss=float(log['loss'].detach()),
+                              dtype=L.train_ops.compute_mode(), data='synthetic', loss=float(log['loss'].detach()),
                               phases_ms=dict(forward_loss=phases[0] / args.steps, backward=phases[1] / args.steps,
                                              allreduce_sgd=phases[2] / args.steps),
                               peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
