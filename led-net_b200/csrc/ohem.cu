@@ -494,6 +494,35 @@ ohem_up_bwd_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict
   if (rh * rw * KS > cap_g || (sy1 - sy0 + 1) * sc * KS > cap_p) __trap();
   float* sp = sg + cap_g;
   stage_patch(r1 + (int64_t)n * h * w * K, sp, w, K, KS, sy0, sy1, sx0, sx1, NT);
+  // candidate outputs and weights of the tile's 8 source rows / 16 source columns, once per CTA (the gather below would
+  // otherwise run a bilinear_coord per (row, column) candidate pair and thread: half of the kernel's instructions)
+  __shared__ int t_lo[kTileSY + kTileSX], t_n[kTileSY + kTileSX];
+  __shared__ float t_w[kTileSY + kTileSX][8];
+  if (threadIdx.x < kTileSY + kTileSX) {
+    const bool isrow = threadIdx.x < kTileSY;
+    const int sidx = isrow ? ys0 + (int)threadIdx.x : xs0 + (int)threadIdx.x - kTileSY;
+    const float sc_ = isrow ? sh : sw;
+    const int in_sz = isrow ? h : w, out_sz = isrow ? H : W;
+    int lo, hi;
+    up_gather_range(sidx, sc_, out_sz, lo, hi);
+    int cnt = hi - lo + 1;
+    if (cnt > 8 || sidx >= in_sz) cnt = -1;                  // -1: walk the candidates on the fly
+    t_lo[threadIdx.x] = lo; t_n[threadIdx.x] = cnt;
+    for (int k = 0; k < 8; ++k) {
+      float wv = -1.f;                                       // -1: not a member (a member's weight may be exactly 0)
+      if (k < cnt) {
+        int i0, i1;
+        float l0, l1;
+        bilinear_coord(lo + k, sc_, in_sz, i0, i1, l0, l1);
+        if (i0 == sidx || i1 == sidx) {
+          wv = 0.f;
+          if (i0 == sidx) wv += l0;
+          if (i1 == sidx) wv += l1;
+        }
+      }
+      t_w[threadIdx.x][k] = wv;
+    }
+  }
   __syncthreads();
   for (int o = threadIdx.x; o < rh * rw; o += NT) {
     const int y = ylo + o / rw, x = xlo + o % rw;
@@ -547,31 +576,49 @@ ohem_up_bwd_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict
   const int ys = ys0 + pidx / kTileSX, xs = xs0 + pidx % kTileSX;
   if (ys > ys1 || xs > xs1) return;
   const int k0 = half * KH;
+  const int ti = pidx / kTileSX, tj = kTileSY + pidx % kTileSX;
+  const bool tab = t_n[ti] >= 0 && t_n[tj] >= 0;
   int cylo, cyhi, cxlo, cxhi;
-  up_gather_range(ys, sh, H, cylo, cyhi);
-  up_gather_range(xs, sw, W, cxlo, cxhi);
+  if (tab) {
+    cylo = t_lo[ti]; cyhi = cylo + t_n[ti] - 1; cxlo = t_lo[tj]; cxhi = cxlo + t_n[tj] - 1;
+  } else {
+    up_gather_range(ys, sh, H, cylo, cyhi);
+    up_gather_range(xs, sw, W, cxlo, cxhi);
+  }
   float acc[KH];
 #pragma unroll
   for (int k = 0; k < KH; ++k) acc[k] = 0.f;
   for (int y = cylo; y <= cyhi; ++y) {
-    int y0, y1;
-    float ly0, ly1;
-    bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
-    if (y0 != ys && y1 != ys) continue;
-    float wy = 0.f;
-    if (y0 == ys) wy += ly0;
-    if (y1 == ys) wy += ly1;
+    float wy;
+    if (tab) {
+      wy = t_w[ti][y - cylo];
+      if (wy < 0.f) continue;
+    } else {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      if (y0 != ys && y1 != ys) continue;
+      wy = 0.f;
+      if (y0 == ys) wy += ly0;
+      if (y1 == ys) wy += ly1;
+    }
     float rowv[KH];
 #pragma unroll
     for (int k = 0; k < KH; ++k) rowv[k] = 0.f;
     for (int x = cxlo; x <= cxhi; ++x) {
-      int x0, x1;
-      float lx0, lx1;
-      bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
-      if (x0 != xs && x1 != xs) continue;
-      float wx = 0.f;
-      if (x0 == xs) wx += lx0;
-      if (x1 == xs) wx += lx1;
+      float wx;
+      if (tab) {
+        wx = t_w[tj][x - cxlo];
+        if (wx < 0.f) continue;
+      } else {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+        if (x0 != xs && x1 != xs) continue;
+        wx = 0.f;
+        if (x0 == xs) wx += lx0;
+        if (x1 == xs) wx += lx1;
+      }
       const float* src = sg + ((y - ylo) * rw + (x - xlo)) * KS + k0;
 #pragma unroll
       for (int k = 0; k < KH; ++k)

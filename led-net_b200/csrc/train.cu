@@ -706,65 +706,106 @@ resize_fwd_row_kernel(const float* __restrict__ src, float* __restrict__ out, in
   }
 }
 
+// The horizontal candidates and weights of a source column depend on the column only: a block (one source row) computes
+// them ONCE per column into shared memory - the flat form recomputed up to eight bilinear_coord per (column, channel)
+// element, 3/4 of its instructions at C = 19.  Columns with more than XMAX candidates (down-scaling) are walked on the fly.
+constexpr int kBwdXMax = 8;
+struct BwdCol { int xlo, nx; float wx[kBwdXMax]; };
+
 template <int V>
 __global__ void __launch_bounds__(kT)
 resize_bwd_row_kernel(const float* __restrict__ dout, float* __restrict__ dsrc, int h, int w, int H, int W, int C, float sh,
                       float sw, int rnd) {
   using T = typename VecT<V>::type;
+  extern __shared__ unsigned char bwd_smem[];
+  BwdCol* cols = reinterpret_cast<BwdCol*>(bwd_smem);
+  __shared__ int s_ylo, s_ny;
+  __shared__ float s_wy[16];
   const uint32_t row = blockIdx.x, n = row / (uint32_t)h, ys = row % (uint32_t)h;
-  int ylo, yhi;
-  gather_range((int)ys, sh, H, ylo, yhi);
+  for (int xs = threadIdx.x; xs < w; xs += kT) {
+    int xlo, xhi;
+    gather_range(xs, sw, W, xlo, xhi);
+    BwdCol c;
+    c.xlo = xlo; c.nx = xhi - xlo + 1;
+#pragma unroll
+    for (int k = 0; k < kBwdXMax; ++k) {
+      float wx = -1.f;                                       // -1: not a member (a member's weight may be exactly 0)
+      if (k < c.nx) {
+        int x0, x1;
+        float lx0, lx1;
+        bilinear_coord(xlo + k, sw, w, x0, x1, lx0, lx1);
+        if (x0 == xs || x1 == xs) {
+          wx = 0.f;
+          if (x0 == xs) wx += lx0;
+          if (x1 == xs) wx += lx1;
+        }
+      }
+      c.wx[k] = wx;
+    }
+    cols[xs] = c;
+  }
+  if (threadIdx.x == 0) {
+    int ylo, yhi;
+    gather_range((int)ys, sh, H, ylo, yhi);
+    int ny = yhi - ylo + 1;
+    if (ny > 16) ny = -1;                                    // too many vertical candidates for the table: computed per thread
+    s_ylo = ylo; s_ny = ny;
+    for (int k = 0; k < 16 && k < ny; ++k) {
+      int y0, y1;
+      float ly0, ly1;
+      bilinear_coord(ylo + k, sh, h, y0, y1, ly0, ly1);
+      float wy = -1.f;
+      if (y0 == (int)ys || y1 == (int)ys) {
+        wy = 0.f;
+        if (y0 == (int)ys) wy += ly0;
+        if (y1 == (int)ys) wy += ly1;
+      }
+      s_wy[k] = wy;
+    }
+  }
+  __syncthreads();
+  int ylo = s_ylo, yhi;
+  const int ny = s_ny;
+  if (ny < 0) gather_range((int)ys, sh, H, ylo, yhi); else yhi = ylo + ny - 1;
   const float* g = dout + (int64_t)n * H * W * C;
   float* o = dsrc + (int64_t)row * w * C;
   const uint32_t len = (uint32_t)w * C;
-  constexpr int XMAX = 8;
   for (uint32_t j = (blockIdx.y * kT + threadIdx.x) * V; j < len; j += gridDim.y * kT * V) {
     const uint32_t xs = j / (uint32_t)C, c = j % (uint32_t)C;
-    int xlo, xhi;
-    gather_range((int)xs, sw, W, xlo, xhi);
-    const int nx = xhi - xlo + 1;
-    float wxs[XMAX];
-    if (nx <= XMAX) {
-#pragma unroll
-      for (int k = 0; k < XMAX; ++k) {
-        float wx = 0.f;
-        if (k < nx) {
-          int x0, x1;
-          float lx0, lx1;
-          bilinear_coord(xlo + k, sw, w, x0, x1, lx0, lx1);
-          if (x0 == (int)xs) wx += lx0;
-          if (x1 == (int)xs) wx += lx1;
-          if (x0 != (int)xs && x1 != (int)xs) wx = -1.f;       // not a member (a member's weight may be exactly 0)
-        }
-        wxs[k] = wx;
-      }
-    }
+    const BwdCol& col = cols[xs];
+    const int xlo = col.xlo, nx = col.nx;
     float acc[V];
 #pragma unroll
     for (int k = 0; k < V; ++k) acc[k] = 0.f;
     for (int y = ylo; y <= yhi; ++y) {
-      int y0, y1;
-      float ly0, ly1;
-      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
-      float wy = 0.f;
-      if (y0 == (int)ys) wy += ly0;
-      if (y1 == (int)ys) wy += ly1;
-      if (y0 != (int)ys && y1 != (int)ys) continue;
+      float wy;
+      if (ny >= 0) {
+        wy = s_wy[y - ylo];
+        if (wy < 0.f) continue;
+      } else {
+        int y0, y1;
+        float ly0, ly1;
+        bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+        if (y0 != (int)ys && y1 != (int)ys) continue;
+        wy = 0.f;
+        if (y0 == (int)ys) wy += ly0;
+        if (y1 == (int)ys) wy += ly1;
+      }
       float rowv[V];
 #pragma unroll
       for (int k = 0; k < V; ++k) rowv[k] = 0.f;
       const float* gr = g + ((int64_t)y * W) * C + c;
-      if (nx <= XMAX) {
+      if (nx <= kBwdXMax) {
 #pragma unroll
-        for (int k = 0; k < XMAX; ++k) {
-          if (k < nx && wxs[k] >= 0.f) {
+        for (int k = 0; k < kBwdXMax; ++k) {
+          if (k < nx && col.wx[k] >= 0.f) {
             const T v = __ldg(reinterpret_cast<const T*>(gr + (xlo + k) * C));
 #pragma unroll
-            for (int q = 0; q < V; ++q) rowv[q] = fmaf(vget(v, q), wxs[k], rowv[q]);
+            for (int q = 0; q < V; ++q) rowv[q] = fmaf(vget(v, q), col.wx[k], rowv[q]);
           }
         }
       } else {
-        for (int x = xlo; x <= xhi; ++x) {
+        for (int x = xlo; x < xlo + nx; ++x) {
           int x0, x1;
           float lx0, lx1;
           bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
@@ -1271,11 +1312,13 @@ int ledb200_train_resize_bwd(const float* dout, float* dsrc, int32_t N, int32_t 
   if (!dout || !dsrc) return fail(LEDB200_EINVAL, "train_resize_bwd: null buffer");
   cudaStream_t st = (cudaStream_t)stream;
   const float sh = (float)h / (float)H, sw = (float)w / (float)W;
-  if ((int64_t)N * h < (1ll << 31) && (int64_t)std::max(W, w) * C < (1ll << 30)) {
+  if ((int64_t)N * h < (1ll << 31) && (int64_t)std::max(W, w) * C < (1ll << 30) && (size_t)w * sizeof(BwdCol) <= 40 * 1024) {
     const int V = (C % 4 == 0 && ((uintptr_t)dout | (uintptr_t)dsrc) % 16 == 0) ? 4 : 1;
-    dim3 grid((unsigned)(N * h), (unsigned)std::min(8, ceil_div(w * C, kT * V * 2)));
-    if (V == 4) resize_bwd_row_kernel<4><<<grid, kT, 0, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
-    else resize_bwd_row_kernel<1><<<grid, kT, 0, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
+    // one block per source row when the row is short (the column table is per block), up to 4 otherwise
+    dim3 grid((unsigned)(N * h), (unsigned)std::min(4, ceil_div(w * C, kT * V * 8)));
+    const size_t smem = (size_t)w * sizeof(BwdCol);
+    if (V == 4) resize_bwd_row_kernel<4><<<grid, kT, smem, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
+    else resize_bwd_row_kernel<1><<<grid, kT, smem, st>>>(dout, dsrc, h, w, H, W, C, sh, sw, g_round);
   } else
   resize_bwd_kernel<<<grid1d((int64_t)N * h * w * C), kT, 0, st>>>(dout, dsrc, N, h, w, H, W, C, sh, sw, g_round);
   LEDB_LAUNCH_OK("resize_bwd_kernel");
