@@ -251,6 +251,10 @@ int ledb200_train_set_tf32_rounding(int32_t on);
  * fp32-grade results from the tensor pipe (the low parts are formed in shared memory next to every TMA-staged slab).
  * 1: a single tf32 pass (10-bit mantissa operands, cuDNN's allow_tf32 numerics).  Process-wide; returns the previous value. */
 int ledb200_train_set_tf32_passes(int32_t passes);
+/* Passes of ledb200_train_conv_wgrad_tc alone (default 1).  The weight gradient is a leaf of the backward pass - its rounding
+ * is not fed back into the chain - and a sum over 1e5..1e6 pixels: one tf32 pass leaves a uniform ~7e-4 shrink (the tensor
+ * core truncates raw fp32 operands) against the 1e-2 gate; 3 = fp32-grade like the forward / data-gradient kernels. */
+int ledb200_train_set_wgrad_passes(int32_t passes);
 int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                                  int32_t stride);
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode);

@@ -35,6 +35,11 @@ int g_round = 0;
 // tensor-core passes per product (ledb200_train_set_tf32_passes): 3 = error-compensated 3 x TF32 (fp32-grade, default),
 // 1 = single tf32 pass (cuDNN's allow_tf32 numerics; callers then also switch the tf32 storage mode on)
 int g_passes = 3;
+// passes of the WEIGHT-gradient kernel (ledb200_train_set_wgrad_passes).  A weight gradient is a leaf of the backward pass:
+// its rounding is not fed back into the ill-conditioned chain, and it is a sum over 1e5..1e6 pixels in which the operands'
+// tf32 truncation shows up as a uniform ~7e-4 shrink plus noise that averages out - two decades inside the 1e-2 gate.
+// So it runs ONE tf32 pass by default (a third of the tensor work); 3 keeps it fp32-grade like the other two convolutions.
+int g_wgrad_passes = 1;
 __device__ __forceinline__ float rt(float v, int rnd) {
   if (!rnd) return v;
   uint32_t t;
@@ -953,6 +958,13 @@ int ledb200_train_set_tf32_passes(int32_t passes) {
   return prev;
 }
 
+int ledb200_train_set_wgrad_passes(int32_t passes) {
+  if (passes != 1 && passes != 3) return fail(LEDB200_EINVAL, "train_set_wgrad_passes: 1 or 3");
+  const int prev = g_wgrad_passes;
+  g_wgrad_passes = passes;
+  return prev;
+}
+
 int64_t ledb200_train_packed_weight_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {
   const int64_t taps = (int64_t)k * k;
   return mode == 0 ? taps * Cin * ((Cout + 15) / 16 * 16) : taps * Cout * ((Cin + 15) / 16 * 16);
@@ -1030,19 +1042,19 @@ int32_t ledb200_train_conv_tc_ok(int32_t op, int32_t N, int32_t H, int32_t W, in
     conv_tc_args(a, dummy, const_cast<float*>(dummy), dummy, nullptr, N, H, W, Cout, Cin, k, 1);
     return conv_tc_eligible(a) ? 1 : 0;
   }
-  if (op == 2) return wgrad_tc_eligible(N, H, W, Cin, Cout, k, stride, g_passes) ? 1 : 0;
+  if (op == 2) return wgrad_tc_eligible(N, H, W, Cin, Cout, k, stride, g_wgrad_passes) ? 1 : 0;
   return 0;
 }
 
 int64_t ledb200_train_wgrad_tc_workspace_bytes(int32_t N, int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t k,
                                                int32_t stride) {
-  return wgrad_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride, g_passes);
+  return wgrad_tc_workspace_bytes(N, H, W, Cin, Cout, k, stride, g_wgrad_passes);
 }
 
 int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
                                 int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace, void* stream) {
   if (!x || !dy || !dw_oihw || !workspace) return fail(LEDB200_EINVAL, "train_conv_wgrad_tc: null buffer");
-  return launch_wgrad_tc(x, dy, dw_oihw, N, H, W, Cin, Cout, k, stride, g_passes, workspace, (cudaStream_t)stream);
+  return launch_wgrad_tc(x, dy, dw_oihw, N, H, W, Cin, Cout, k, stride, g_wgrad_passes, workspace, (cudaStream_t)stream);
 }
 
 int64_t ledb200_train_packed_weight_tc_floats(int32_t Cout, int32_t Cin, int32_t k, int32_t mode) {

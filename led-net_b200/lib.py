@@ -28,7 +28,7 @@ SYMBOLS = [
     'ledb200_train_avgpool_fwd', 'ledb200_train_avgpool_bwd', 'ledb200_train_copy_channels',
     'ledb200_train_layout', 'ledb200_train_sgd_step',
     'ledb200_train_conv_tc_ok', 'ledb200_train_packed_weight_tc_floats', 'ledb200_train_pack_weight_tc',
-    'ledb200_train_conv_fwd_tc', 'ledb200_train_conv_dgrad_tc', 'ledb200_train_set_tf32_rounding', 'ledb200_train_set_tf32_passes',
+    'ledb200_train_conv_fwd_tc', 'ledb200_train_conv_dgrad_tc', 'ledb200_train_set_tf32_rounding', 'ledb200_train_set_tf32_passes', 'ledb200_train_set_wgrad_passes',
     'ledb200_train_wgrad_tc_workspace_bytes', 'ledb200_train_conv_wgrad_tc',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
@@ -102,6 +102,7 @@ def get():
     lib.ledb200_train_conv_wgrad.argtypes = [vp, vp, vp, vp] + [i32] * 7 + [vp, vp]
     lib.ledb200_train_set_tf32_rounding.argtypes = [i32]
     lib.ledb200_train_set_tf32_passes.argtypes = [i32]
+    lib.ledb200_train_set_wgrad_passes.argtypes = [i32]
     lib.ledb200_train_wgrad_tc_workspace_bytes.argtypes = [i32] * 7
     lib.ledb200_train_wgrad_tc_workspace_bytes.restype = i64
     lib.ledb200_train_conv_wgrad_tc.argtypes = [vp, vp, vp] + [i32] * 7 + [vp, vp]

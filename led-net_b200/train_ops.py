@@ -82,6 +82,9 @@ def to_nchw(x):
 _env = os.environ.get('LEDB200_TRAIN_TC', '1')
 TENSOR_CORES = _env != '0'
 TC_FAST = _env == 'fast'
+# Passes of the weight-gradient kernel: 1 by default (a leaf of the backward pass, a sum over 1e5..1e6 pixels: one tf32 pass
+# leaves a uniform ~7e-4 shrink, see ledb200_train_set_wgrad_passes); 3 = fp32-grade.  Environment: LEDB200_WGRAD_PASSES.
+WGRAD_PASSES = int(os.environ.get('LEDB200_WGRAD_PASSES', '1'))
 _rounding_synced = None
 _passes_synced = None
 
@@ -105,9 +108,10 @@ def compute_mode():
 
 def _sync_mode():
     global _passes_synced
-    want = 1 if TC_FAST else 3
+    want = (1 if TC_FAST else 3, 1 if TC_FAST else WGRAD_PASSES)
     if _passes_synced != want:
-        L.check(L.get().ledb200_train_set_tf32_passes(want), 'train_set_tf32_passes')
+        L.check(L.get().ledb200_train_set_tf32_passes(want[0]), 'train_set_tf32_passes')
+        L.check(L.get().ledb200_train_set_wgrad_passes(want[1]), 'train_set_wgrad_passes')
         _passes_synced = want
 
 

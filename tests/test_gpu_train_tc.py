@@ -86,15 +86,24 @@ def _assert_tc(cin, cout, k, stride, hw):
         assert lib.ledb200_train_conv_tc_ok(2, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'weight gradient on tensor cores'
 
 
+@pytest.mark.parametrize('wgrad_passes', [3, 1])
 @pytest.mark.parametrize('cin,cout,k,stride,hw,bias', SHAPES)
-def test_conv_tc_three_pass_is_fp32_grade(cin, cout, k, stride, hw, bias):
-    T.set_tensor_cores(True, fast=False)
-    _assert_tc(cin, cout, k, stride, hw)
-    y, yr, dx, dxr, dw, dwr, db, dbr = _run(cin, cout, k, stride, hw, bias, rounded=False)
-    print(f'three-pass {cin}->{cout} k{k} s{stride}: fwd {rel_err(y, yr):.1e} dgrad {rel_err(dx, dxr):.1e} wgrad {rel_err(dw, dwr):.1e}')
+def test_conv_tc_three_pass_is_fp32_grade(cin, cout, k, stride, hw, bias, wgrad_passes):
+    """forward / data gradient: three passes, fp32-grade.  Weight gradient: fp32-grade with three passes; with the default
+    single pass (a leaf of the backward pass, see train_ops.WGRAD_PASSES) within tf32's operand truncation, 2e-3."""
+    prev = T.WGRAD_PASSES
+    T.WGRAD_PASSES = wgrad_passes
+    try:
+        T.set_tensor_cores(True, fast=False)
+        _assert_tc(cin, cout, k, stride, hw)
+        y, yr, dx, dxr, dw, dwr, db, dbr = _run(cin, cout, k, stride, hw, bias, rounded=False)
+    finally:
+        T.WGRAD_PASSES = prev
+    print(f'three-pass {cin}->{cout} k{k} s{stride}: fwd {rel_err(y, yr):.1e} dgrad {rel_err(dx, dxr):.1e} '
+          f'wgrad ({wgrad_passes} pass) {rel_err(dw, dwr):.1e}')
     assert rel_err(y, yr) < 5e-5
     assert rel_err(dx, dxr) < 5e-5
-    assert rel_err(dw, dwr) < 1e-4
+    assert rel_err(dw, dwr) < (1e-4 if wgrad_passes == 3 or k == 1 or cout % 32 else 2e-3)
     if bias:
         assert rel_err(db, dbr) < 1e-5
 
