@@ -56,13 +56,19 @@ struct WgParams {
   int nstages;
   uint32_t tmem_cols;
   int in_ld2;              // stride 2: pixel stride of X in 2-byte units (column-parity offset of the 5-D view)
+  int k1;                  // 1x1 filter: no halo, the four M atoms are four consecutive 32-channel blocks of X (LBO = one slab)
+  int prow;                // accumulator rows a CTA writes per accumulator: 96 (3x3: three filter columns) or 128 (1x1)
   float* part;             // [units * G][nacc][96][ncols]
 };
 
 // X3: error-compensated three-pass mode (see conv_tc.cu): both operands are activations here, so warps 6..9 write the low
 // parts x - trunc_tf32(x) of EVERY slab of a stage (X and dY) into the stage's second half, and each product becomes
 //   X_raw * dY_raw + X_lo * dY_raw + X_raw * dY_lo      (the tensor core truncates the raw operands itself)
-template <bool S2, bool X3>
+// K1: 1x1 filters (single-pass mode only).  X tile = the output tile's own pixels (stride 2: the even-even parity slab), no
+// taps; the four 32-channel atoms of M are four consecutive input-channel blocks, one slab apart, so one MMA covers 128 input
+// channels x N output channels.  Stages always reserve four X slabs: atoms past the last real block read the next slab's
+// bytes (finite or not, those accumulator rows are never read).
+template <bool S2, bool X3, bool K1 = false>
 __global__ void __launch_bounds__(X3 ? kThreads + 128 : kThreads, 1)
 wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmY,
                 const __grid_constant__ WgParams P) {
@@ -79,7 +85,8 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int unit = blockIdx.x / P.G, g = blockIdx.x % P.G;
   const int uci = unit % P.units_ci, uco = unit / P.units_ci;
-  const int nx = S2 ? 4 : 1;      // X slabs per channel block (stride 2: row parity x column parity)
+  const int nx = K1 ? 1 : (S2 ? 4 : 1);      // X slabs per channel block (stride 2: row parity x column parity)
+  const int xregion = K1 ? 4 : P.ncc * nx;   // X slabs a stage reserves
 
   if (threadIdx.x == 0) {
     prefetch_tensormap(&tmX);
@@ -106,7 +113,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         const uint32_t bar = smem_u32(&full[s]);
         for (int c = 0; c < P.ncc; ++c) {
           const int ch = (uci * P.ncc + c) * 64;                  // 2-byte units: 32 fp32 channels = 64 units
-          if (S2) {
+          if (K1) {
+            if (S2) tma_load_5d(smem_u32(st + (size_t)c * P.xslab_bytes), &tmX, bar, ch, w0, 0, h0, n);
+            else tma_load_4d(smem_u32(st + (size_t)c * P.xslab_bytes), &tmX, bar, ch, w0, h0, n);
+          } else if (S2) {
             // slab (pr, pc): rows of parity pr, columns of parity pc.  Odd rows / columns start one half-pixel earlier
             // (filter tap 0 reads input 2*o - 1).
             for (int q = 0; q < 4; ++q) {
@@ -118,7 +128,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             tma_load_4d(smem_u32(st + (size_t)c * P.xslab_bytes), &tmX, bar, ch, w0 - 1, h0 - 1, n);
           }
         }
-        uint8_t* sy = st + (size_t)P.ncc * nx * P.xslab_bytes;
+        uint8_t* sy = st + (size_t)xregion * P.xslab_bytes;
         for (int o = 0; o < P.nco; ++o)
           tma_load_4d(smem_u32(sy + (size_t)o * P.yslab_bytes), &tmY, bar, (uco * P.nco + o) * 64, w0, h0, n);
         if (++s == P.nstages) { s = 0; ph ^= 1; }
@@ -141,7 +151,7 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
         mbar_wait(&full[s], ph);
         tc_fence_after();
         const uint32_t st = smem_u32(stages + (size_t)s * P.stage_bytes);
-        const uint32_t sy = st + (uint32_t)(P.ncc * nx) * P.xslab_bytes;
+        const uint32_t sy = st + (uint32_t)xregion * P.xslab_bytes;
         // pass 0: raw x raw; X3 passes 1, 2 (after the converter warps have arrived): X_lo x dY_raw, X_raw x dY_lo
 #pragma unroll 1
         for (int pass = 0; pass < (X3 ? 3 : 1); ++pass) {
@@ -152,6 +162,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
             // passes 1, 2 accumulate into their own columns (lo_cols after the main ones): pass 1 opens them on the first tile
             const uint32_t acc = pass == 2 ? 1u : (first | (uint32_t)r);
             const uint32_t dcol = pass ? (uint32_t)(P.nacc * P.ncols) : 0u;
+            if (K1) {
+              const uint32_t a_lo = (((st + (uint32_t)(r * TW) * 128u) >> 4) & 0x3FFFu) | ((P.xslab_bytes >> 4) << 16);
+              tc_mma2_tf32(tmem_base, a_lo, a_hi, b_lo, b_hi, idesc, acc);
+            } else
             for (int c = 0; c < P.ncc; ++c) {
 #pragma unroll
               for (int kh = 0; kh < 3; ++kh) {
@@ -213,10 +227,10 @@ wgrad_tc_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__
     const int q = warp & 3;
     const bool has_work = g < P.tiles;                 // a CTA without tiles never touched its accumulators: write zeros
     if (has_work) { mbar_wait(done, 0); tc_fence_after(); }
-    if (q < 3) {
-      float* mine = P.part + (size_t)blockIdx.x * P.nacc * 96 * P.ncols;
+    if (q * 32 < P.prow) {
+      float* mine = P.part + (size_t)blockIdx.x * P.nacc * P.prow * P.ncols;
       for (int a = 0; a < P.nacc; ++a) {
-        float* row = mine + ((size_t)a * 96 + q * 32 + lane) * P.ncols;
+        float* row = mine + ((size_t)a * P.prow + q * 32 + lane) * P.ncols;
         for (int c0 = 0; c0 < P.ncols; c0 += 16) {
           uint32_t v[16];
           if (has_work) {
@@ -274,6 +288,25 @@ wgrad_tc_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int 
   }
 }
 
+// 1x1: dW[co][ci] = sum over the G slots of the unit; accumulator row = (block inside the unit's group) * 32 + ci % 32
+__global__ void __launch_bounds__(256)
+wgrad_tc_sum1_kernel(const float* __restrict__ part, float* __restrict__ dw, int Cin, int Cout, int ncc, int nco, int units_ci,
+                     int G) {
+  const int ncols = nco * 32;
+  const int64_t per_cta = (int64_t)128 * ncols;
+  const int64_t total = (int64_t)Cout * Cin;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += (int64_t)gridDim.x * 256) {
+    const int co = (int)(i % Cout), ci = (int)(i / Cout);
+    const int uco = co / ncols, col = co % ncols;
+    const int cb = ci / 32, uci = cb / ncc, c = cb % ncc;
+    const int unit = uco * units_ci + uci;
+    const float* p = part + (int64_t)unit * G * per_cta + (int64_t)(c * 32 + ci % 32) * ncols + col;
+    float s = 0.f;
+    for (int k = 0; k < G; ++k) s += p[(int64_t)k * per_cta];
+    dw[(int64_t)co * Cin + ci] = s;
+  }
+}
+
 struct WgPlan {
   WgParams P;
   int grid;
@@ -292,14 +325,49 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int passe
   const bool x3 = passes == 3;
   WgPlan pl{};
   pl.ok = false;
-  if (k != 3 || (stride != 1 && stride != 2)) return pl;
+  if ((k != 3 && k != 1) || (stride != 1 && stride != 2)) return pl;
   if (Cin < 32 || Cin % 32 || Cout < 32 || Cout % 32) return pl;
   if (stride == 2 && ((H & 1) || (W & 1))) return pl;
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int pad = k / 2;
+  const int Ho = (H + 2 * pad - k) / stride + 1, Wo = (W + 2 * pad - k) / stride + 1;
   if (Ho % TH || Wo % TW) return pl;
   WgParams& P = pl.P;
   P.s2 = stride == 2;
   const int bi = Cin / 32, bo = Cout / 32;
+  if (k == 1) {
+    if (x3) return pl;                                   // single-pass mode only
+    if (bi > 4 && bi % 4) return pl;
+    P.k1 = 1; P.prow = 128;
+    P.ncc = std::min(bi, 4);
+    P.nco = std::min(bo, 2);
+    while (bo % P.nco) --P.nco;
+    P.ncols = P.nco * 32;
+    P.nacc = 1;
+    P.units_ci = bi / P.ncc; P.units_co = bo / P.nco;
+    const int units = P.units_ci * P.units_co;
+    P.tiles_w = Wo / TW; P.tiles_h = Ho / TH; P.N = N;
+    P.tiles = (int64_t)N * P.tiles_w * P.tiles_h;
+    P.G = (int)std::max<int64_t>(1, std::min<int64_t>(P.tiles, num_sms() / units));
+    P.Cin = Cin; P.Cout = Cout;
+    P.slab_w = TW;
+    P.xslab_bytes = TH * TW * 128;
+    P.yslab_bytes = TH * TW * 128;
+    P.stage_bytes = 4u * P.xslab_bytes + (uint32_t)P.nco * P.yslab_bytes;
+    P.tx_bytes = (uint32_t)P.ncc * P.xslab_bytes + (uint32_t)P.nco * P.yslab_bytes;
+    P.nstages = (int)std::min<uint32_t>(6, (SMEM_MAX - 1024 - 256) / P.stage_bytes);
+    if (P.nstages < 2) return pl;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)P.ncols) cols <<= 1;
+    P.tmem_cols = cols;
+    P.in_ld2 = Cin * 2;
+    pl.grid = units * P.G;
+    pl.smem = 1024 + (size_t)P.nstages * P.stage_bytes + 256;
+    pl.x3 = false;
+    pl.part_floats = (int64_t)pl.grid * 128 * P.ncols;
+    pl.ok = true;
+    return pl;
+  }
+  P.k1 = 0; P.prow = 96;
   const int acc_per_c = P.s2 ? 6 : 3;
   // output-channel blocks per CTA: up to 4 (N = 128); stride 2 keeps 2 so that two stages of four X slabs fit
   P.nco = std::min(bo, (P.s2 && x3) ? 1 : ((P.s2 || x3) ? 2 : 4));   // three-pass mode: every slab and accumulator exists twice
@@ -334,7 +402,7 @@ WgPlan plan(int N, int H, int W, int Cin, int Cout, int k, int stride, int passe
   pl.grid = units * P.G;
   pl.smem = 1024 + (size_t)P.nstages * P.stage_bytes + 256;
   pl.x3 = x3;
-  pl.part_floats = (int64_t)pl.grid * P.nacc * 96 * P.ncols;
+  pl.part_floats = (int64_t)pl.grid * P.nacc * P.prow * P.ncols;
   pl.ok = true;
   return pl;
 }
@@ -356,10 +424,21 @@ int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, in
   if (!pl.ok) return fail(LEDB200_EINVAL, "wgrad_tc: shape not eligible");
   WgParams& P = pl.P;
   P.part = reinterpret_cast<float*>(workspace);
-  const int Ho = (H + 2 - 3) / stride + 1, Wo = (W + 2 - 3) / stride + 1;
+  const int Ho = (H + 2 * (k / 2) - k) / stride + 1, Wo = (W + 2 * (k / 2) - k) / stride + 1;
   CUtensorMap tmX, tmY;
   int rc;
   const uint64_t ld = (uint64_t)Cin * 2;                 // 2-byte units per pixel
+  if (P.k1 && !P.s2) {
+    const uint64_t dims[4] = {ld, (uint64_t)W, (uint64_t)H, (uint64_t)N};
+    const uint64_t str[3] = {ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+    const uint32_t box[4] = {64, TW, TH, 1};
+    rc = tc_encode_tiled(&tmX, x, 4, dims, str, box, 1064);
+  } else if (P.k1) {
+    const uint64_t dims[5] = {2 * ld, (uint64_t)W / 2, 2, (uint64_t)H / 2, (uint64_t)N};
+    const uint64_t str[4] = {2 * ld * 2, (uint64_t)W * ld * 2, 2 * (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+    const uint32_t box[5] = {64, TW, 1, TH, 1};
+    rc = tc_encode_tiled(&tmX, x, 5, dims, str, box, 1064);
+  } else
   if (!P.s2) {
     const uint64_t dims[4] = {ld, (uint64_t)W, (uint64_t)H, (uint64_t)N};
     const uint64_t str[3] = {ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
@@ -383,8 +462,9 @@ int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, in
   static std::once_flag once;
   static cudaError_t attr_err = cudaSuccess;
   std::call_once(once, [] {
-    const void* fns[4] = {(const void*)wgrad_tc_kernel<false, false>, (const void*)wgrad_tc_kernel<true, false>,
-                          (const void*)wgrad_tc_kernel<false, true>, (const void*)wgrad_tc_kernel<true, true>};
+    const void* fns[6] = {(const void*)wgrad_tc_kernel<false, false>, (const void*)wgrad_tc_kernel<true, false>,
+                          (const void*)wgrad_tc_kernel<false, true>, (const void*)wgrad_tc_kernel<true, true>,
+                          (const void*)wgrad_tc_kernel<false, false, true>, (const void*)wgrad_tc_kernel<true, false, true>};
     for (const void* f : fns) {
       cudaError_t e = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SMEM_MAX);
       if (e != cudaSuccess) attr_err = e;
@@ -392,6 +472,16 @@ int launch_wgrad_tc(const float* x, const float* dy, float* dw, int N, int H, in
   });
   if (attr_err != cudaSuccess) return fail(LEDB200_ECUDA, std::string("wgrad_tc: cudaFuncSetAttribute: ") + cudaGetErrorString(attr_err));
   const int nthr = pl.x3 ? kThreads + 128 : kThreads;
+  if (P.k1) {
+    if (P.s2) wgrad_tc_kernel<true, false, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+    else wgrad_tc_kernel<false, false, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
+    LEDB_LAUNCH_OK("wgrad_tc_kernel");
+    const int64_t total1 = (int64_t)Cout * Cin;
+    wgrad_tc_sum1_kernel<<<(int)std::min<int64_t>(ceil_div64(total1, 256), 148 * 8), 256, 0, st>>>(P.part, dw, Cin, Cout, P.ncc, P.nco,
+                                                                                              P.units_ci, P.G);
+    LEDB_LAUNCH_OK("wgrad_tc_sum1_kernel");
+    return LEDB200_OK;
+  }
   if (pl.x3) {
     if (P.s2) wgrad_tc_kernel<true, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);
     else wgrad_tc_kernel<false, true><<<pl.grid, nthr, pl.smem, st>>>(tmX, tmY, P);

@@ -177,25 +177,35 @@ class _Conv(torch.autograd.Function):
         # next multiple of 32 - one extra pass over dY - and slice the weight gradient afterwards.
         ho, wo = _out_hw(h, w, k, ctx.stride)
         cpad = (cout + 31) // 32 * 32
-        if (cpad != cout and TENSOR_CORES and not ctx.has_bias
-                and (_tc_ok(1, n, h, w, cin, cpad, k, ctx.stride) or _tc_ok(2, n, h, w, cin, cpad, k, ctx.stride))):
-            dyp = torch.zeros((n, ho, wo, cpad), dtype=torch.float32, device=dy.device)
-            L.check(lib.ledb200_train_copy_channels(_p(dy), cout, 0, _p(dyp), cpad, 0, n * ho * wo, cout, _st(dy)),
-                    'train_copy_channels')
-            wpad = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=weight.device)
-            wpad[:cout].copy_(weight)
-            dxp, dwp, _ = _Conv._backward_core(ctx, x, wpad, dyp, False)
-            return dxp, (dwp[:cout].contiguous() if dwp is not None else None), None, None
-        dx, dw, db = _Conv._backward_core(ctx, x, weight, dy, ctx.has_bias)
+        want_dx = ctx.needs_input_grad[0]
+        want_dw = ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2])
+        if cpad != cout and TENSOR_CORES:
+            dx_tc = want_dx and _tc_ok(1, n, h, w, cin, cpad, k, ctx.stride)
+            dw_tc = want_dw and not ctx.has_bias and _tc_ok(2, n, h, w, cin, cpad, k, ctx.stride)
+            if dx_tc or dw_tc:
+                dyp = torch.zeros((n, ho, wo, cpad), dtype=torch.float32, device=dy.device)
+                L.check(lib.ledb200_train_copy_channels(_p(dy), cout, 0, _p(dyp), cpad, 0, n * ho * wo, cout, _st(dy)),
+                        'train_copy_channels')
+                wpad = torch.zeros((cpad, cin, k, k), dtype=torch.float32, device=weight.device)
+                wpad[:cout].copy_(weight)
+                dxp, dwp, _ = _Conv._backward_core(ctx, x, wpad, dyp, False, dx_tc, dw_tc)
+                dx, dw, db = _Conv._backward_core(ctx, x, weight, dy, ctx.has_bias, want_dx and not dx_tc,
+                                                  want_dw and not dw_tc)
+                if dx_tc:
+                    dx = dxp
+                if dw_tc:
+                    dw = dwp[:cout].contiguous()
+                return dx, dw, db, None
+        dx, dw, db = _Conv._backward_core(ctx, x, weight, dy, ctx.has_bias, want_dx, want_dw)
         return dx, dw, db, None
 
     @staticmethod
-    def _backward_core(ctx, x, weight, dy, has_bias):
+    def _backward_core(ctx, x, weight, dy, has_bias, want_dx, want_dw):
         lib = L.get()
         n, h, w, cin = x.shape
         cout, _, k, _ = weight.shape
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if want_dx:
             dx = torch.empty_like(x)
             if _tc_ok(1, n, h, w, cin, cout, k, ctx.stride):
                 wp = torch.empty(lib.ledb200_train_packed_weight_tc_floats(cout, cin, k, 1), dtype=torch.float32,
@@ -212,13 +222,13 @@ class _Conv(torch.autograd.Function):
                         'train_pack_weight')
                 L.check(lib.ledb200_train_conv_dgrad(_p(dy), _p(wp), _p(dx), n, h, w, cin, cout, k, ctx.stride,
                                                      _st(x)), 'train_conv_dgrad')
-        if ctx.needs_input_grad[1] and not has_bias and _tc_ok(2, n, h, w, cin, cout, k, ctx.stride):
+        if want_dw and not has_bias and _tc_ok(2, n, h, w, cin, cout, k, ctx.stride):
             dw = torch.empty_like(weight)
             ws = torch.empty(lib.ledb200_train_wgrad_tc_workspace_bytes(n, h, w, cin, cout, k, ctx.stride) // 4,
                              dtype=torch.float32, device=x.device)   # per-CTA partial sums, added in a fixed order
             L.check(lib.ledb200_train_conv_wgrad_tc(_p(x), _p(dy), _p(dw), n, h, w, cin, cout, k, ctx.stride, _p(ws),
                                                     _st(x)), 'train_conv_wgrad_tc')
-        elif ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+        elif want_dw:
             dw = torch.empty_like(weight)
             if has_bias:
                 db = torch.empty(cout, dtype=torch.float32, device=x.device)

@@ -82,7 +82,8 @@ def _run(cin, cout, k, stride, hw, bias, rounded):
 def _assert_tc(cin, cout, k, stride, hw):
     lib = L.lib.get()
     assert lib.ledb200_train_conv_tc_ok(0, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'shape meant for the tensor-core path'
-    if k == 3 and cout % 32 == 0:
+    T._sync_mode()
+    if cout % 32 == 0 and (k == 3 or (T.TC_FAST or T.WGRAD_PASSES == 1)):
         assert lib.ledb200_train_conv_tc_ok(2, 3, hw[0], hw[1], cin, cout, k, stride) == 1, 'weight gradient on tensor cores'
 
 
@@ -103,7 +104,7 @@ def test_conv_tc_three_pass_is_fp32_grade(cin, cout, k, stride, hw, bias, wgrad_
           f'wgrad ({wgrad_passes} pass) {rel_err(dw, dwr):.1e}')
     assert rel_err(y, yr) < 5e-5
     assert rel_err(dx, dxr) < 5e-5
-    assert rel_err(dw, dwr) < (1e-4 if wgrad_passes == 3 or k == 1 or cout % 32 else 2e-3)
+    assert rel_err(dw, dwr) < (1e-4 if wgrad_passes == 3 or cout % 32 else 2e-3)
     if bias:
         assert rel_err(db, dbr) < 1e-5
 
