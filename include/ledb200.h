@@ -300,6 +300,8 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
  *   reduce(mode 0): workspace[0:2C] (double) = (sum y, sum y^2)
  *   reduce(mode 1): workspace[0:2C]          = (sum dz, sum dz * xhat), dz = dout masked by the ReLU
  *   fwd_apply     : mean / invstd / running stats from workspace[0:2C] over `total_count` samples, then apply
+ *                   (total_count < 0: the count is read on the device, from workspace[2C] here and workspace[4C] in bwd_apply -
+ *                   the all-reduced count of a SyncBN layer never visits the host)
  *   bwd_apply     : dgamma / dbeta from workspace[0:2C] (this rank), dy from workspace[2C:4C] (all ranks). */
 int ledb200_train_bn_reduce(const float* a, const float* y_opt, const float* out_opt, const float* mean_opt,
                             const float* invstd_opt, int32_t mode, int32_t relu, int64_t npix, int32_t C,

@@ -452,11 +452,13 @@ __global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__
   if (lane == 0) acc[i] = s;
 }
 
+// npix < 0: the sample count is read from acc[2C] on the device (SyncBN: the all-reduced count, no host round trip)
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double npix, float eps, float momentum,
                                    float* __restrict__ save_mean, float* __restrict__ save_invstd,
                                    float* __restrict__ running_mean, float* __restrict__ running_var) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
+  if (npix < 0.0) npix = acc[2 * C];
   const double m = acc[c] / npix;
   double var = acc[C + c] / npix - m * m;
   if (var < 0.0) var = 0.0;
@@ -494,6 +496,7 @@ bn_bwd_apply_kernel(const float* __restrict__ dout, const float* __restrict__ y,
                     float* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu, int64_t total_,
                     int C_, float invM, int rnd) {
   const IT total = (IT)total_, C = (IT)C_;
+  if (invM < 0.f) invM = (float)(1.0 / acc_local[4 * C_]);      // SyncBN: global sample count kept on the device at workspace[4C]
   for (IT i = blockIdx.x * (IT)kT + threadIdx.x; i < total; i += (IT)gridDim.x * kT) {
     const int c = (int)(i % C);
     float dz = dout[i];
@@ -534,6 +537,7 @@ bn_bwd_apply4_kernel(const float4* __restrict__ dout, const float4* __restrict__
                      float4* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu,
                      uint32_t total4, uint32_t C4, float invM, int rnd) {
   const uint32_t C = C4 * 4;
+  if (invM < 0.f) invM = (float)(1.0 / acc_local[4 * C]);       // SyncBN: global sample count kept on the device at workspace[4C]
   for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < total4; i += gridDim.x * kT) {
     const uint32_t c = (i % C4) * 4;
     float4 dz = __ldg(dout + i);
@@ -1215,7 +1219,8 @@ int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* 
                                const void* workspace, void* stream) {
   if (!y || !gamma || !beta || !out || !save_mean || !save_invstd || !workspace)
     return fail(LEDB200_EINVAL, "train_bn_fwd_apply: null buffer");
-  if (npix < 1 || C < 1 || total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_fwd_apply: bad sample count");
+  if (npix < 1 || C < 1 || (total_count >= 0.0 && total_count < (double)npix))
+    return fail(LEDB200_EINVAL, "train_bn_fwd_apply: bad sample count");
   cudaStream_t st = (cudaStream_t)stream;
   bn_finalize_kernel<<<ceil_div(C, 128), 128, 0, st>>>((const double*)workspace, C, total_count, eps, momentum, save_mean,
                                                        save_invstd, running_mean_opt, running_var_opt);
@@ -1242,21 +1247,21 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
   if (!dout || !y || !gamma || !save_mean || !save_invstd || !dy || !dgamma || !dbeta || !workspace)
     return fail(LEDB200_EINVAL, "train_bn_bwd_apply: null buffer");
   if (relu && !out) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: the ReLU mask needs the forward output");
-  if (total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: bad sample count");
+  if (total_count >= 0.0 && total_count < (double)npix) return fail(LEDB200_EINVAL, "train_bn_bwd_apply: bad sample count");
   const double* acc = (const double*)workspace;
   if (vec4_ok(C, npix * C, dout, y, out, dy, dres_opt) && ((uintptr_t)gamma | (uintptr_t)save_mean | (uintptr_t)save_invstd) % 16 == 0)
     bn_bwd_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
         save_mean, save_invstd, acc + 2 * C, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta,
-        relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), (float)(1.0 / total_count), g_round);
+        relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), total_count < 0.0 ? -1.f : (float)(1.0 / total_count), g_round);
   else if (npix * C < (1ll << 32))
     bn_bwd_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(
         dout, y, out, gamma, save_mean, save_invstd, acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta, relu, npix * C, C,
-        (float)(1.0 / total_count), g_round);
+        total_count < 0.0 ? -1.f : (float)(1.0 / total_count), g_round);
   else
     bn_bwd_apply_kernel<int64_t><<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(
         dout, y, out, gamma, save_mean, save_invstd, acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta, relu, npix * C, C,
-        (float)(1.0 / total_count), g_round);
+        total_count < 0.0 ? -1.f : (float)(1.0 / total_count), g_round);
   LEDB_LAUNCH_OK("train_bn_bwd_apply");
   return LEDB200_OK;
 }

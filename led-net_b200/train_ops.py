@@ -282,10 +282,12 @@ class _BNAct(torch.autograd.Function):
                     'train_bn_reduce')
             ws[2 * c] = npix
             dist.all_reduce(ws[:2 * c + 1], group=group)  # one packed message per layer: (sum, sumsq, count)
-            total = float(ws[2 * c].item())
+            # the all-reduced sample count stays on the device (total_count < 0: the kernels read it from the workspace) -
+            # a .item() here was one host round trip per layer and direction, 5 ms of a 40 ms step at N = 2
+            total = ws[2 * c:2 * c + 1].clone()
             L.check(lib.ledb200_train_bn_fwd_apply(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
                                                    _p(running_mean), _p(running_var), float(momentum), float(eps),
-                                                   int(relu), npix, total, c, _p(ws), _st(y)), 'train_bn_fwd_apply')
+                                                   int(relu), npix, -1.0, c, _p(ws), _st(y)), 'train_bn_fwd_apply')
         ctx.save_for_backward(y, out, gamma, mean, invstd)
         ctx.relu, ctx.has_res, ctx.group, ctx.total = relu, res is not None, group, total
         return out
@@ -315,9 +317,10 @@ class _BNAct(torch.autograd.Function):
                                                 c, _p(ws), _st(y)), 'train_bn_reduce')
             ws[2 * c:4 * c].copy_(ws[:2 * c])
             dist.all_reduce(ws[2 * c:4 * c], group=ctx.group)
+            ws[4 * c:4 * c + 1].copy_(ctx.total)          # global sample count of the forward pass, device to device
             L.check(lib.ledb200_train_bn_bwd_apply(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
                                                    _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta),
-                                                   int(ctx.relu), npix, ctx.total, c, _p(ws), _st(y)),
+                                                   int(ctx.relu), npix, -1.0, c, _p(ws), _st(y)),
                     'train_bn_bwd_apply')
         return dy, dgamma, dbeta, dres, None, None, None, None, None, None
 

@@ -94,9 +94,9 @@ def main():
     good = bad_sync == 0 and n_sync >= 30 and n_plain > 10
     ok = ok and good and bool(torch.isfinite(total))
     if rank == 0:
-        print(f'syncbn model: loss {float(total):.4f}; {n_sync} SyncBN layers, {bad_sync} with rank-dependent running stats; '
+        print(f'syncbn model: loss {float(total.detach()):.4f}; {n_sync} SyncBN layers, {bad_sync} with rank-dependent running stats; '
               f'{n_plain} plain BN layers ({differing_plain} rank-dependent, as in the reference) -> {"ok" if good else "FAIL"}')
-    flag = torch.tensor([0 if ok else 1])
+    flag = torch.tensor([0 if ok else 1], device=dev if dist.get_backend() == 'nccl' else 'cpu')
     dist.all_reduce(flag)
     dist.destroy_process_group()
     sys.exit(int(flag.item() > 0))
