@@ -290,6 +290,15 @@ int ledb200_train_bn_fwd(const float* y, const float* gamma, const float* beta, 
                          float* out, float* save_mean, float* save_invstd, float* running_mean_opt,
                          float* running_var_opt, float momentum, float eps, int32_t relu, int64_t npix,
                          int32_t C, void* workspace, void* stream);
+/* All-reduce (sum) of n <= nmax doubles over the `world` GPUs of one NVSwitch box through peer memory, for the SyncBN
+ * statistics (2C + 1 doubles per layer and direction; NCCL's small-message latency was 6.7 ms of a 41 ms step at N = 8).
+ * peer_buffers[r] = rank r's symmetric buffer as mapped into THIS process (>= ledb200_peer_allreduce_buffer_bytes(nmax)
+ * bytes, zeroed before the first call, e.g. torch.distributed._symmetric_memory); seq = 1, 2, 3, ... advanced identically on
+ * every rank.  One launch: P2P stores of the local vector into every peer's slot, release / acquire flags, slots added in
+ * rank order (identical bits on all ranks).  local may alias out. */
+int64_t ledb200_peer_allreduce_buffer_bytes(int32_t nmax);
+int ledb200_peer_allreduce_f64(const double* local, int32_t n, int32_t rank, int32_t world, const uint64_t* peer_buffers,
+                               uint32_t seq, int32_t nmax, double* out, void* stream);
 /* backward of the above: dy, dres_opt (= masked dout), dgamma, dbeta. */
 int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, const float* gamma,
                          const float* save_mean, const float* save_invstd, float* dy, float* dres_opt,
@@ -299,6 +308,9 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
  * (configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:20; torch.nn.SyncBatchNorm semantics):
  *   reduce(mode 0): workspace[0:2C] (double) = (sum y, sum y^2)
  *   reduce(mode 1): workspace[0:2C]          = (sum dz, sum dz * xhat), dz = dout masked by the ReLU
+ *   reduce(mode 0) also leaves this rank's sample count at workspace[2C]; reduce(mode 3) = mode 1 on the FORWARD pass's
+ *                   workspace: the global count it still holds at [2C] moves to [4C], the sums land at [0:2C] and [2C:4C]
+ *                   (mode 4: the same without the move, for a repeated backward pass)
  *   fwd_apply     : mean / invstd / running stats from workspace[0:2C] over `total_count` samples, then apply
  *                   (total_count < 0: the count is read on the device, from workspace[2C] here and workspace[4C] in bwd_apply -
  *                   the all-reduced count of a SyncBN layer never visits the host)

@@ -441,16 +441,24 @@ chan_reduce4_kernel(const float4* __restrict__ a, const float4* __restrict__ y, 
 // acc[i] = sum over the blocks' partials, one WARP per output: lane l adds blocks l, l + 32, ... in index order and the 32
 // lane sums are combined by a fixed shuffle tree - the order depends only on (nblocks), never on scheduling.
 // (round 2 measured the one-thread-per-output version at 57 us per launch, 7 ms per training step: 592 dependent loads)
+// dup_off > 0: the sums are also written at acc[dup_off + i] (SyncBN backward: the copy that gets all-reduced);
+// tail_idx >= 0: acc[tail_idx] = tail_val (SyncBN forward: this rank's sample count, all-reduced with the sums)
 __global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__ part, int nblocks, int n2c,
-                                                      double* __restrict__ acc) {
+                                                      double* __restrict__ acc, int dup_off, int tail_idx, double tail_val) {
   const int i = (blockIdx.x * kT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n2c) return;
   double s = 0.0;
   for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * n2c + i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
-  if (lane == 0) acc[i] = s;
+  if (lane == 0) {
+    acc[i] = s;
+    if (dup_off > 0) acc[dup_off + i] = s;
+    if (i == 0 && tail_idx >= 0) acc[tail_idx] = tail_val;
+  }
 }
+
+__global__ void move_double_kernel(double* dst, const double* src) { *dst = *src; }
 
 // npix < 0: the sample count is read from acc[2C] on the device (SyncBN: the all-reduced count, no host round trip)
 __global__ void bn_finalize_kernel(const double* __restrict__ acc, int C, double npix, float eps, float momentum,
@@ -575,6 +583,49 @@ __global__ void acc_to_float_kernel(const double* __restrict__ acc, float* __res
   if (c < C) out[c] = (float)acc[c];
 }
 
+// ---------------------------------------------------------------------------------------------
+// All-reduce (sum) of a short double vector over the GPUs of one NVSwitch box through PEER MEMORY, for the SyncBN statistics
+// (configs/LED_Net/LEDNet_80k_cityscapes-1024x1024.py:20): 2C + 1 doubles per layer and direction, 122 times per training
+// step.  NCCL spends ~50 us per such message (launch + protocol latency, 6.7 ms per step at N = 8); here ONE launch per
+// rank stores the rank's vector into its slot of EVERY peer's buffer (NVLink P2P stores), releases a per-source flag on each
+// peer, waits for the flags of all sources in its OWN buffer and adds the slots in rank order - so every rank gets the same
+// bits, whatever the arrival order.  Slots and flags are double-buffered by the parity of a sequence number that all ranks
+// advance in lock step: a peer signals collective s + 1 only after it has finished reading collective s.
+// Buffer layout on every rank (symmetric allocation): data[2][kPeerMax][nmax] doubles, then flags[2][kPeerMax] uint32.
+constexpr int kPeerMax = 16;
+struct PeerPtrs { unsigned long long p[kPeerMax]; };
+
+__global__ void __launch_bounds__(256)
+peer_allreduce_kernel(const double* __restrict__ local, int n, PeerPtrs peers, int rank, int world, unsigned seq, int nmax,
+                      double* __restrict__ out) {
+  const int par = (int)(seq & 1u);
+  for (int p = 0; p < world; ++p) {
+    double* dst = reinterpret_cast<double*>(peers.p[p]) + ((size_t)par * kPeerMax + rank) * nmax;
+    for (int i = threadIdx.x; i < n; i += 256) dst[i] = local[i];
+  }
+  __threadfence_system();
+  __syncthreads();
+  if ((int)threadIdx.x < world) {
+    unsigned* theirs = reinterpret_cast<unsigned*>(reinterpret_cast<double*>(peers.p[threadIdx.x]) + (size_t)2 * kPeerMax * nmax) +
+                       par * kPeerMax + rank;
+    asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(theirs), "r"(seq) : "memory");
+    const unsigned* mine = reinterpret_cast<const unsigned*>(reinterpret_cast<const double*>(peers.p[rank]) + (size_t)2 * kPeerMax * nmax) +
+                           par * kPeerMax + threadIdx.x;
+    unsigned v = 0, spins = 0;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (++spins > (1u << 30)) __trap();          // a peer that never arrives must not hang the GPU
+    } while (v != seq);
+  }
+  __syncthreads();
+  const double* src = reinterpret_cast<const double*>(peers.p[rank]) + (size_t)par * kPeerMax * nmax;
+  for (int i = threadIdx.x; i < n; i += 256) {
+    double s = 0.0;
+    for (int p = 0; p < world; ++p) s += src[(size_t)p * nmax + i];
+    out[i] = s;
+  }
+}
+
 // workspace layout of the per-channel reductions (doubles): [0, 4C + 8) accumulators (2C of a reduction; SyncBN keeps a second
 // copy and the sample count there), then kMaxRedBlocks block partials of 2C each
 inline bool vec4_ok(int C, int64_t total, const void* p0, const void* p1 = nullptr, const void* p2 = nullptr,
@@ -587,7 +638,7 @@ inline int64_t bn_ws_doubles(int C) { return 4 * (int64_t)C + 8 + (int64_t)kMaxR
 
 template <int KIND>
 int chan_reduce(const float* a, const float* y, const float* out, const float* mean, const float* invstd, int relu,
-                int64_t npix, int C, double* ws, cudaStream_t st) {
+                int64_t npix, int C, double* ws, cudaStream_t st, int dup_off = 0, int tail_idx = -1, double tail_val = 0.0) {
   double* part = ws + 4 * (int64_t)C + 8;
   const int grid = grid1d(npix * C, 4);                     // <= kMaxRedBlocks
   if (vec4_ok(C, npix * C, a, y, out) && ((uintptr_t)mean | (uintptr_t)invstd) % 16 == 0)
@@ -596,7 +647,7 @@ int chan_reduce(const float* a, const float* y, const float* out, const float* m
         relu, (uint32_t)npix, (uint32_t)(C / 4), part);
   else
   chan_reduce_kernel<KIND><<<grid, kT, sizeof(double) * 2 * C, st>>>(a, y, out, mean, invstd, relu, npix, C, part);
-  chan_sum_kernel<<<ceil_div(2 * C * 32, kT), kT, 0, st>>>(part, grid, 2 * C, ws);
+  chan_sum_kernel<<<ceil_div(2 * C * 32, kT), kT, 0, st>>>(part, grid, 2 * C, ws, dup_off, tail_idx, tail_val);
   LEDB_LAUNCH_OK("chan_reduce_kernel");
   return LEDB200_OK;
 }
@@ -962,6 +1013,23 @@ int ledb200_train_set_tf32_passes(int32_t passes) {
   return prev;
 }
 
+int64_t ledb200_peer_allreduce_buffer_bytes(int32_t nmax) {
+  return nmax < 1 ? 0 : (int64_t)sizeof(double) * 2 * kPeerMax * nmax + (int64_t)sizeof(unsigned) * 2 * kPeerMax + 64;
+}
+
+int ledb200_peer_allreduce_f64(const double* local, int32_t n, int32_t rank, int32_t world, const uint64_t* peer_buffers,
+                               uint32_t seq, int32_t nmax, double* out, void* stream) {
+  if (!local || !out || !peer_buffers) return fail(LEDB200_EINVAL, "peer_allreduce: null buffer");
+  if (world < 1 || world > kPeerMax || rank < 0 || rank >= world) return fail(LEDB200_EINVAL, "peer_allreduce: bad rank / world size");
+  if (n < 1 || n > nmax) return fail(LEDB200_EINVAL, "peer_allreduce: vector longer than the peer slots");
+  if (seq == 0) return fail(LEDB200_EINVAL, "peer_allreduce: sequence numbers start at 1 (the flags are zero-initialised)");
+  PeerPtrs pp{};
+  for (int i = 0; i < world; ++i) pp.p[i] = peer_buffers[i];
+  peer_allreduce_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(local, n, pp, rank, world, seq, nmax, out);
+  LEDB_LAUNCH_OK("peer_allreduce_kernel");
+  return LEDB200_OK;
+}
+
 int ledb200_train_set_wgrad_passes(int32_t passes) {
   if (passes != 1 && passes != 3) return fail(LEDB200_EINVAL, "train_set_wgrad_passes: 1 or 3");
   const int prev = g_wgrad_passes;
@@ -1201,12 +1269,18 @@ int ledb200_train_bn_reduce(const float* a, const float* y_opt, const float* out
   if (!a || !workspace) return fail(LEDB200_EINVAL, "train_bn_reduce: null buffer");
   if (npix < 1 || C < 1) return fail(LEDB200_EINVAL, "train_bn_reduce: empty input");
   if ((size_t)C * 2 * sizeof(double) > 48 * 1024) return fail(LEDB200_EINVAL, "train_bn_reduce: C too large");
-  if (mode == 1 && (!y_opt || !mean_opt || !invstd_opt || (relu && !out_opt)))
+  if (mode != 0 && mode != 1 && mode != 3 && mode != 4) return fail(LEDB200_EINVAL, "train_bn_reduce: mode must be 0, 1, 3 or 4");
+  if (mode != 0 && (!y_opt || !mean_opt || !invstd_opt || (relu && !out_opt)))
     return fail(LEDB200_EINVAL, "train_bn_reduce: backward statistics need y, mean, invstd (and out for the ReLU mask)");
   cudaStream_t st = (cudaStream_t)stream;
   double* acc = (double*)workspace;
-  int rc = mode == 0 ? chan_reduce<0>(a, nullptr, nullptr, nullptr, nullptr, 0, npix, C, acc, st)
-                     : chan_reduce<1>(a, y_opt, out_opt, mean_opt, invstd_opt, relu, npix, C, acc, st);
+  // mode 0 also leaves this rank's sample count at workspace[2C] (all-reduced together with the sums by a SyncBN caller);
+  // mode 3 = mode 1 for a SyncBN caller that hands the FORWARD workspace back: the global count it still holds at [2C] moves
+  // to [4C] (where bwd_apply reads it), and the sums are written twice, at [0, 2C) (rank-local) and [2C, 4C) (to be all-reduced);
+  // mode 4 = mode 3 without the move (a second backward pass over the same graph: the count already sits at [4C])
+  if (mode == 3) move_double_kernel<<<1, 1, 0, st>>>(acc + 4 * C, acc + 2 * C);
+  int rc = mode == 0 ? chan_reduce<0>(a, nullptr, nullptr, nullptr, nullptr, 0, npix, C, acc, st, 0, 2 * C, (double)npix)
+                     : chan_reduce<1>(a, y_opt, out_opt, mean_opt, invstd_opt, relu, npix, C, acc, st, mode >= 3 ? 2 * C : 0);
   if (rc) return rc;
   LEDB_LAUNCH_OK("train_bn_reduce");
   return LEDB200_OK;

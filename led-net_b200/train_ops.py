@@ -253,6 +253,58 @@ def _sync_group(sync):
     return dist.group.WORLD
 
 
+class _PeerReduce:
+    """SyncBN's statistics all-reduce over NVLink peer memory (ledb200_peer_allreduce_f64) instead of one NCCL call per
+    layer and direction.  The symmetric buffer and its peer mappings come from torch.distributed._symmetric_memory (plumbing);
+    the exchange itself is the library's kernel.  Used when the process group is NCCL over the GPUs of one box and the
+    symmetric-memory rendezvous works; otherwise - or with LEDB200_SYNCBN=nccl - `reduce` falls back to dist.all_reduce."""
+    NMAX = 2 * 2048 + 8
+    _inst = {}
+
+    @classmethod
+    def get(cls, group, device):
+        key = (id(group), device.index)
+        if key not in cls._inst:
+            cls._inst[key] = cls(group, device)
+        return cls._inst[key]
+
+    def __init__(self, group, device):
+        import torch.distributed as dist
+        self.group, self.ok, self.seq = group, False, 0
+        if os.environ.get('LEDB200_SYNCBN', 'peer') != 'peer' or dist.get_backend(group) != 'nccl':
+            return
+        try:
+            import torch.distributed._symmetric_memory as symm
+            lib = L.get()
+            nbytes = lib.ledb200_peer_allreduce_buffer_bytes(self.NMAX)
+            self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.float64, device=device)
+            self.buf.zero_()
+            hdl = symm.rendezvous(self.buf, group)
+            self.rank, self.world = int(hdl.rank), int(hdl.world_size)
+            if self.world > 16:
+                return
+            self.ptrs = (C.c_uint64 * 16)(*[int(p) for p in hdl.buffer_ptrs], *([0] * (16 - self.world)))
+            self._hdl = hdl
+            torch.cuda.synchronize(device)
+            dist.barrier(group)                      # every rank's flags are zero before anyone signals
+            self.ok = True
+        except Exception as e:                       # no symmetric memory on this system / group: NCCL does it
+            import warnings
+            warnings.warn(f'SyncBN peer-memory all-reduce unavailable ({type(e).__name__}: {e}); using NCCL')
+            self.ok = False
+
+    def reduce(self, vec):
+        """in-place sum of the 1-D float64 CUDA tensor `vec` over the group"""
+        if not self.ok or vec.numel() > self.NMAX:
+            import torch.distributed as dist
+            dist.all_reduce(vec, group=self.group)
+            return
+        self.seq += 1
+        L.check(L.get().ledb200_peer_allreduce_f64(_p(vec), vec.numel(), self.rank, self.world, self.ptrs,
+                                                   self.seq & 0xFFFFFFFF or 1, self.NMAX, _p(vec), _st(vec)),
+                'peer_allreduce_f64')
+
+
 class _BNAct(torch.autograd.Function):
     """out = [relu](BatchNorm2d_train(y) [+ res]); running stats updated in place.
     With `group` (SyncBN) the per-channel (sum, sum of squares, count) - and in backward (sum dz, sum dz*xhat) - are
@@ -279,12 +331,12 @@ class _BNAct(torch.autograd.Function):
             import torch.distributed as dist
             ws = _ws(y.device, c)
             L.check(lib.ledb200_train_bn_reduce(_p(y), None, None, None, None, 0, 0, npix, c, _p(ws), _st(y)),
-                    'train_bn_reduce')
-            ws[2 * c] = npix
-            dist.all_reduce(ws[:2 * c + 1], group=group)  # one packed message per layer: (sum, sumsq, count)
+                    'train_bn_reduce')                # (sum, sumsq) at ws[0:2C], this rank's sample count at ws[2C]
+            _PeerReduce.get(group, y.device).reduce(ws[:2 * c + 1])   # one packed message per layer: (sum, sumsq, count)
             # the all-reduced sample count stays on the device (total_count < 0: the kernels read it from the workspace) -
-            # a .item() here was one host round trip per layer and direction, 5 ms of a 40 ms step at N = 2
-            total = ws[2 * c:2 * c + 1].clone()
+            # a .item() here was one host round trip per layer and direction, 5 ms of a 40 ms step at N = 2.  The workspace
+            # goes to the backward pass with it (ctx.total), so no copy either.
+            total = ws
             L.check(lib.ledb200_train_bn_fwd_apply(_p(y), _p(gamma), _p(beta), _p(r), _p(out), _p(mean), _p(invstd),
                                                    _p(running_mean), _p(running_var), float(momentum), float(eps),
                                                    int(relu), npix, -1.0, c, _p(ws), _st(y)), 'train_bn_fwd_apply')
@@ -312,12 +364,12 @@ class _BNAct(torch.autograd.Function):
                                              npix, c, _p(_ws(y.device, c)), _st(y)), 'train_bn_bwd')
         else:
             import torch.distributed as dist
-            ws = _ws(y.device, c)
-            L.check(lib.ledb200_train_bn_reduce(_p(dout), _p(y), _p(out), _p(mean), _p(invstd), 1, int(ctx.relu), npix,
-                                                c, _p(ws), _st(y)), 'train_bn_reduce')
-            ws[2 * c:4 * c].copy_(ws[:2 * c])
-            dist.all_reduce(ws[2 * c:4 * c], group=ctx.group)
-            ws[4 * c:4 * c + 1].copy_(ctx.total)          # global sample count of the forward pass, device to device
+            ws = ctx.total                                # the forward workspace: global sample count still at [2C]
+            mode = 4 if getattr(ctx, 'count_moved', False) else 3      # a repeated backward must not move the count again
+            ctx.count_moved = True
+            L.check(lib.ledb200_train_bn_reduce(_p(dout), _p(y), _p(out), _p(mean), _p(invstd), mode, int(ctx.relu), npix,
+                                                c, _p(ws), _st(y)), 'train_bn_reduce')   # count -> [4C], sums at [0:2C] and [2C:4C]
+            _PeerReduce.get(ctx.group, y.device).reduce(ws[2 * c:4 * c])
             L.check(lib.ledb200_train_bn_bwd_apply(_p(dout), _p(y), _p(out), _p(gamma), _p(mean), _p(invstd), _p(dy),
                                                    _p(dres) if ctx.relu else None, _p(dgamma), _p(dbeta),
                                                    int(ctx.relu), npix, -1.0, c, _p(ws), _st(y)),

@@ -21,6 +21,7 @@ def main():
     ap.add_argument('--classes', type=int, default=19)
     ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=2)
+    ap.add_argument('--syncbn', action='store_true', help="norm_cfg=dict(type='SyncBN') as in the reference config (N > 1)")
     args = ap.parse_args()
     import torch
     import lednet_b200 as L
@@ -35,8 +36,9 @@ def main():
     K, N, S = args.classes, args.batch, args.size
     with warnings.catch_warnings():
         warnings.simplefilter('ignore')
-        m = L.EncoderDecoder(dict(type='LEDNet'),
-                             dict(type='LEDHead', in_channels=128, channels=64, num_classes=K, dropout_ratio=0.),
+        norm = dict(type='SyncBN', requires_grad=True) if args.syncbn else dict(type='BN', requires_grad=True)
+        m = L.EncoderDecoder(dict(type='LEDNet', norm_cfg=norm),
+                             dict(type='LEDHead', in_channels=128, channels=64, num_classes=K, dropout_ratio=0., norm_cfg=norm),
                              data_preprocessor=None, compute_dtype='fp32')
     m.load_state_dict(synth.make_state_dict(m.state_dict(), seed=2))
     m.to(dev).train()
@@ -85,7 +87,7 @@ def main():
     if rank == 0:
         print(json.dumps(dict(metric='LED-Net train img/s @1024x1024', value=world * N / (ms_step * 1e-3),
                               unit='img/s', n_gpus=world, steps=args.steps, warmup=args.warmup, ms_per_step=ms_step,
-                              dtype=L.train_ops.compute_mode(), data='synthetic', loss=float(log['loss'].detach()),
+                              dtype=L.train_ops.compute_mode(), norm='SyncBN' if args.syncbn else 'BN', data='synthetic', loss=float(log['loss'].detach()),
                               phases_ms=dict(forward_loss=phases[0] / args.steps, backward=phases[1] / args.steps,
                                              allreduce_sgd=phases[2] / args.steps),
                               peak_mem_gb=torch.cuda.max_memory_allocated() / 2 ** 30,
