@@ -27,6 +27,22 @@ def main():
     dev = torch.device('cuda', rank % ngpu)
     dist.init_process_group('gloo' if ngpu < world else 'nccl')
     ok = True
+    if dist.get_backend() == 'nccl':
+        # the peer-memory all-reduce of the statistics (ledb200_peer_allreduce_f64) against NCCL's, several rounds so both
+        # parities of its double-buffered slots and flags are exercised; identical bits on every rank
+        pr = T._PeerReduce.get(dist.group.WORLD, dev)
+        for it in range(5):
+            v = (torch.arange(517, dtype=torch.float64, device=dev) * (rank + 1.25) + it) / 7.0
+            ref = v.clone()
+            dist.all_reduce(ref)
+            pr.reduce(v)
+            same = torch.allclose(v, ref, rtol=1e-15, atol=0)
+            gathered = [torch.empty_like(v) for _ in range(world)]
+            dist.all_gather(gathered, v)
+            ident = all(torch.equal(gathered[0], t) for t in gathered)
+            ok = ok and pr.ok and same and ident
+        if rank == 0:
+            print(f'peer all-reduce: in use {pr.ok}, matches NCCL {same}, identical on all ranks {ident} -> {"ok" if ok else "FAIL"}')
     g = torch.Generator().manual_seed(5)
     for (c, hw, relu, res) in [(32, (12, 20), True, True), (19, (9, 7), True, False), (64, (4, 4), False, False)]:
         n = 2 * world
