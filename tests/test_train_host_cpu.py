@@ -129,3 +129,35 @@ def test_confusion_matrix_allreduce_gloo_world2():
     ref = oracle.compute_metrics(res, ['mIoU', 'mFscore'])
     for k, v in ref.items():
         assert abs(float(got[0][3][k]) - float(v)) < 1e-9, k
+
+
+def _stats_worker(rank, world, port, q):
+    """SyncBN's statistics reducer off the NVLink path (gloo group): it must fall back to dist.all_reduce and sum in place"""
+    os.environ.update(MASTER_ADDR='127.0.0.1', MASTER_PORT=str(port))
+    dist.init_process_group('gloo', rank=rank, world_size=world)
+    red = T._PeerReduce.get(dist.group.WORLD, torch.device('cpu'))
+    v = torch.arange(9, dtype=torch.float64) * (rank + 1) + 0.5
+    red.reduce(v[:7])                                   # a slice, as the (sum, sumsq, count) message of a layer is
+    q.put((rank, red.ok, v.tolist()))               # plain lists: no shared-memory handle to outlive this process
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_syncbn_statistics_reducer_falls_back_to_the_group_allreduce_gloo_world2():
+    ctx = mp.get_context('spawn')
+    q = ctx.Queue()
+    port = 33500 + os.getpid() % 2000
+    ps = [ctx.Process(target=_stats_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in ps:
+        p.start()
+    got = sorted([q.get(timeout=120) for _ in ps], key=lambda t: t[0])
+    for p in ps:
+        p.join(60)
+        assert p.exitcode == 0
+    base = torch.arange(9, dtype=torch.float64)
+    want_head = (base * 1 + 0.5) + (base * 2 + 0.5)
+    for rank, ok, v in got:
+        v = torch.tensor(v, dtype=torch.float64)
+        assert ok is False                              # peer memory needs NCCL over GPUs of one box
+        assert torch.equal(v[:7], want_head[:7])
+        assert torch.equal(v[7:], (base * (rank + 1) + 0.5)[7:])   # untouched tail
