@@ -338,6 +338,35 @@ def test_train_step_vs_oracle(K, hw, N, tc):
     assert abs(float(log['loss'].detach()) - tot2_64) < max(loss_tol * abs(tot2_64), 3 * abs(tot2 - tot2_64))
 
 
+def test_train_step_at_benchmark_resolution_vs_oracle():
+    """BASELINE config 4's shapes (1024 x 1024 crops, K = 19; batch 2 so that the CPU float64 oracle finishes in a minute):
+    EVERY convolution of the network is on the tensor-core kernels here - the 1/16 .. 1/64 resolution layers, the 256-channel
+    N-tile split, DAPPM's 512 / 640-channel 1x1 convolutions and the stride-2 parity classes that the small whole-step cases
+    above leave to the CUDA-core kernels.  Same gates: loss 1e-4, whole-vector gradient 1e-2 against float64."""
+    T.set_tensor_cores(True)
+    K, hw, N = 19, (1024, 1024), 2
+    lib = L.lib.get()
+    for (h, cin, cout, k, s) in [(16, 256, 256, 3, 1), (32, 128, 256, 3, 2), (16, 640, 128, 1, 1), (512, 32, 32, 3, 1)]:
+        assert lib.ledb200_train_conv_tc_ok(0, N, h, h, cin, cout, k, s) == 1
+        assert lib.ledb200_train_conv_tc_ok(1, N, h, h, cin, cout, k, s) == 1
+    o, m = _train_pair(K)
+    x = oracle.preprocess(synth.make_images_u8(N, *hw, seed=0))
+    lab = synth.make_labels(N, *hw, K, seed=1)
+    ref, ref_grads = _oracle_grads(o, x, lab)                       # fp32 reference path
+    o64, _ = _train_pair(K)
+    o64 = o64.double()
+    ref64, ref_grads64 = _oracle_grads(o64, x.double(), lab)        # float64 reference path
+    samples = [dict(gt_sem_seg=dict(data=lab[i:i + 1].to(DEV))) for i in range(N)]
+    losses = m.loss(x.to(DEV), samples)
+    total, _ = m.parse_losses(losses)
+    total.backward()
+    torch.cuda.synchronize()
+    for k in ('loss_context', 'loss_spatial'):
+        assert abs(float(losses['decode.' + k].detach()) - float(ref64[k])) < 1e-4 * abs(float(ref64[k])), k
+    mine_grads = {k: p.grad.cpu() for k, p in m.named_parameters()}
+    _check_grads(mine_grads, ref_grads, ref_grads64, 'step 1 @ 1024x1024', cond_mult=10.0)
+
+
 def test_eval_after_train_uses_updated_weights():
     """the folded inference engine must be rebuilt from the trained parameters."""
     o, m = _train_pair(3)
