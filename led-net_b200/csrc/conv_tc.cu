@@ -1026,9 +1026,9 @@ bool conv_tc_eligible(const ConvArgs& a) {
     if (a.sub && a.stride != 1) return false;
     if (a.out_ld < a.Cout) return false;
     const int cp = a.cout_pad_tc > 0 ? a.cout_pad_tc : conv_tc_pad(a.Cout);
-    if (cp > 256 && cp % 256) return false;
+    if (cp > 256 && cp % 128) return false;                          // wide outputs: 128-column N tiles (e.g. 640 = 5 x 128)
     if (cp != 32 && cp % 64) return false;
-    if ((int64_t)a.N * (a.Ho / TH) * (a.Wo / TW) * (cp > 256 ? cp / 256 : 1) >= (1ll << 31)) return false;
+    if ((int64_t)a.N * (a.Ho / TH) * (a.Wo / TW) * (cp > 256 ? cp / 128 : 1) >= (1ll << 31)) return false;
     return true;
   }
   if (a.in_dtype != LEDB200_BF16 || a.out_dtype != LEDB200_BF16) return false;
@@ -1070,6 +1070,7 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   // tiles (e.g. 192 = GETB qkv of a 64-channel block): the epilogue's column split needs a power-of-two tile
   P.NT = cp > 256 ? 256 : ((cp & (cp - 1)) == 0 ? cp : 64);
   if (x3 && P.NT > 128) P.NT = 128;     // two weight halves per tile: keep the B ring inside shared memory
+  if (tf32 && cp > 256) P.NT = 128;     // wide training outputs (DAPPM's 640-channel data gradient): any multiple of 128
   P.ntiles_n = cp / P.NT;
   P.KC = tf32 ? 64 : pick_kc(a.Cin);
   P.nchunks = cinE / P.KC;

@@ -49,7 +49,7 @@ SHAPES = [
     (64, 128, 1, 2, (32, 32), False),
     (64, 19, 1, 1, (16, 16), True),        # conv_seg: 19 of 32 columns stored, bias
     (512, 128, 1, 1, (16, 8), False),
-    (640, 128, 1, 1, (16, 8), False),      # DAPPM compression
+    (640, 128, 1, 1, (16, 8), False),      # DAPPM compression (data gradient: five 128-column N tiles)
     (64, 32, 3, 1, (48, 40), False),
 ]
 
