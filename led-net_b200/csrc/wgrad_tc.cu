@@ -282,8 +282,16 @@ wgrad_tc_sum_kernel(const float* __restrict__ part, float* __restrict__ dw, int 
     else { acc = c * 3 + kh; row = kw * 32 + cil; }
     const int unit = uco * units_ci + uci;
     const float* p = part + (int64_t)unit * G * per_cta + ((int64_t)acc * 96 + row) * ncols + col;
-    float s = 0.f;
-    for (int k = 0; k < G; ++k) s += p[(int64_t)k * per_cta];
+    // four independent partial sums (slots k, k+1, k+2, k+3 in turn): four loads in flight instead of a dependent chain of
+    // up to 148; the grouping depends on G only, so the result is as reproducible as the plain loop's
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= G; k += 4) {
+      s0 += p[(int64_t)k * per_cta]; s1 += p[(int64_t)(k + 1) * per_cta];
+      s2 += p[(int64_t)(k + 2) * per_cta]; s3 += p[(int64_t)(k + 3) * per_cta];
+    }
+    for (; k < G; ++k) s0 += p[(int64_t)k * per_cta];
+    const float s = (s0 + s1) + (s2 + s3);
     dw[(((int64_t)co * Cin + ci) * 3 + kh) * 3 + kw] = s;
   }
 }
@@ -301,8 +309,16 @@ wgrad_tc_sum1_kernel(const float* __restrict__ part, float* __restrict__ dw, int
     const int cb = ci / 32, uci = cb / ncc, c = cb % ncc;
     const int unit = uco * units_ci + uci;
     const float* p = part + (int64_t)unit * G * per_cta + (int64_t)(c * 32 + ci % 32) * ncols + col;
-    float s = 0.f;
-    for (int k = 0; k < G; ++k) s += p[(int64_t)k * per_cta];
+    // four independent partial sums (slots k, k+1, k+2, k+3 in turn): four loads in flight instead of a dependent chain of
+    // up to 148; the grouping depends on G only, so the result is as reproducible as the plain loop's
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    int k = 0;
+    for (; k + 4 <= G; k += 4) {
+      s0 += p[(int64_t)k * per_cta]; s1 += p[(int64_t)(k + 1) * per_cta];
+      s2 += p[(int64_t)(k + 2) * per_cta]; s3 += p[(int64_t)(k + 3) * per_cta];
+    }
+    for (; k < G; ++k) s0 += p[(int64_t)k * per_cta];
+    const float s = (s0 + s1) + (s2 + s3);
     dw[(int64_t)co * Cin + ci] = s;
   }
 }
