@@ -1,8 +1,10 @@
-// Weight gradient of a 3x3 convolution as an implicit GEMM on the 5th-gen tensor cores (north_star kernel 6).
+// Weight gradient of a 3x3 or 1x1 convolution as an implicit GEMM on the 5th-gen tensor cores (north_star kernel 6).
 //
 // Replaces what the reference gets from cuDNN's convolution_backward through autograd
 //   (mmseg/models/segmentors/encoder_decoder.py:161-185 loss -> decode_heads/led_head.py:101-146), for every
-//   Conv2d(3x3, padding 1, stride 1 | 2) of the trunk and head whose channel counts are multiples of 32.
+//   Conv2d(3x3 padding 1 | 1x1, stride 1 | 2) of the trunk and head whose channel counts are multiples of 32.
+// One kind::tf32 pass by default (a weight gradient is a leaf of the backward pass; see train.cu g_wgrad_passes), three
+// error-compensated passes (X3, 3x3 only) on request.
 //
 //   dW[co][ci][kh][kw] = sum over (n, oh, ow) of dY[n, oh, ow, co] * X[n, oh*s + kh - 1, ow*s + kw - 1, ci]
 //
