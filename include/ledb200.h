@@ -273,6 +273,13 @@ int64_t ledb200_train_wgrad_tc_workspace_bytes(int32_t N, int32_t H, int32_t W, 
                                                int32_t stride);
 int ledb200_train_conv_wgrad_tc(const float* x, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
                                 int32_t Cin, int32_t Cout, int32_t k, int32_t stride, void* workspace, void* stream);
+/* The stem's first layer (mmcv ConvModule 3 -> C, 3x3, stride 2; ddrnet.py:121-139) on the NCHW image as the caller holds
+ * it: forward into an NHWC tensor and the weight gradient, without the NHWC copy of the image the generic entry points need.
+ * Cin <= 4; forward: Cout a multiple of 16, <= 128.  workspace: ledb200_train_wgrad_workspace_bytes(Cin, Cout, 3). */
+int ledb200_train_stem_fwd(const float* x_nchw, const float* w_oihw, const float* bias_opt, float* y, int32_t N,
+                           int32_t H, int32_t W, int32_t Cin, int32_t Cout, int32_t stride, void* stream);
+int ledb200_train_stem_wgrad(const float* x_nchw, const float* dy, float* dw_oihw, int32_t N, int32_t H, int32_t W,
+                             int32_t Cin, int32_t Cout, int32_t stride, void* workspace, void* stream);
 /* d(loss)/dW in OIHW (overwritten) and optionally d(loss)/dbias.  Every reduction of the training kernels is order-fixed
  * (per-CTA / per-block partial sums in `workspace`, added in index order: no floating-point atomics), so a training step
  * is bit-reproducible run to run.  workspace: device, >= ledb200_train_wgrad_workspace_bytes(Cin, Cout, k) bytes. */

@@ -30,6 +30,7 @@ SYMBOLS = [
     'ledb200_train_conv_tc_ok', 'ledb200_train_packed_weight_tc_floats', 'ledb200_train_pack_weight_tc',
     'ledb200_train_conv_fwd_tc', 'ledb200_train_conv_dgrad_tc', 'ledb200_train_set_tf32_rounding', 'ledb200_train_set_tf32_passes', 'ledb200_train_set_wgrad_passes',
     'ledb200_peer_allreduce_buffer_bytes', 'ledb200_peer_allreduce_f64',
+    'ledb200_train_stem_fwd', 'ledb200_train_stem_wgrad',
     'ledb200_train_wgrad_tc_workspace_bytes', 'ledb200_train_conv_wgrad_tc',
     'ledb200_sesp_param_floats', 'ledb200_sesp_forward',
     'ledb200_mfaf_param_floats', 'ledb200_mfaf_workspace_bytes', 'ledb200_mfaf_forward',
@@ -104,6 +105,8 @@ def get():
     lib.ledb200_train_set_tf32_rounding.argtypes = [i32]
     lib.ledb200_train_set_tf32_passes.argtypes = [i32]
     lib.ledb200_train_set_wgrad_passes.argtypes = [i32]
+    lib.ledb200_train_stem_fwd.argtypes = [vp, vp, vp, vp] + [i32] * 6 + [vp]
+    lib.ledb200_train_stem_wgrad.argtypes = [vp, vp, vp] + [i32] * 6 + [vp, vp]
     lib.ledb200_peer_allreduce_buffer_bytes.argtypes = [i32]
     lib.ledb200_peer_allreduce_buffer_bytes.restype = i64
     lib.ledb200_peer_allreduce_f64.argtypes = [vp, i32, i32, i32, vp, C.c_uint32, i32, vp, vp]

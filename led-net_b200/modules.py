@@ -262,9 +262,12 @@ class LEDNet(_EngineOwner):
         memory, so no copy is made on either side of the boundary)."""
         from . import train_ops as T
         self.reset_engine()                      # parameters are about to change
-        x = _as_nhwc(x)
-        size8 = (math.ceil(x.shape[1] / 8), math.ceil(x.shape[2] / 8))       # ddrnet.py:185
-        x1 = T.conv_module(x, self.stem[0], relu=True)
+        size8 = (math.ceil(x.shape[2] / 8), math.ceil(x.shape[3] / 8))       # ddrnet.py:185
+        if T.stem_conv_ok(x, self.stem[0].conv):
+            # first layer straight from the NCHW image (no NHWC copy of it): csrc/train.cu stem_fwd_kernel
+            x1 = T.bn_act(T.stem_conv(x, self.stem[0].conv.weight, self.stem[0].conv.stride[0]), self.stem[0].bn, relu=True)
+        else:
+            x1 = T.conv_module(_as_nhwc(x), self.stem[0], relu=True)
         x2 = T.conv_module(x1, self.stem[1], relu=True)
         x = T.relu(_layer_train(x2, self.stem[2]))
         x = T.relu(_layer_train(x, self.stem[4]))

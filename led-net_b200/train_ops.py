@@ -243,6 +243,54 @@ def conv2d(x, weight, bias=None, stride=1):
     return _Conv.apply(x, weight, bias, stride)
 
 
+class _StemConv(torch.autograd.Function):
+    """The stem's first layer on the NCHW image as the caller holds it: nn.Conv2d(Cin <= 4, Cout, 3, stride, padding=1,
+    bias=False) -> NHWC output, without an NHWC copy of the image (ledb200_train_stem_fwd / _stem_wgrad).  The image gets
+    no gradient (it is the network input)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, stride):
+        x, weight = _chk(x, 'stem input'), _chk(weight, 'stem weight')
+        n, cin, h, w = x.shape
+        cout, _, k, _ = weight.shape
+        ho, wo = _out_hw(h, w, k, stride)
+        y = torch.empty((n, ho, wo, cout), dtype=torch.float32, device=x.device)
+        L.check(L.get().ledb200_train_stem_fwd(_p(x), _p(weight), None, _p(y), n, h, w, cin, cout, stride, _st(x)),
+                'train_stem_fwd')
+        ctx.save_for_backward(x, weight)
+        ctx.stride = stride
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        if ctx.needs_input_grad[0]:
+            raise L.LedB200Error('stem_conv: the image does not get a gradient (use conv2d on an NHWC tensor for that)')
+        dw = None
+        if ctx.needs_input_grad[1]:
+            dy = _chk(dy, 'stem grad')
+            lib = L.get()
+            n, cin, h, w = x.shape
+            cout = weight.shape[0]
+            dw = torch.empty_like(weight)
+            ws = torch.empty(lib.ledb200_train_wgrad_workspace_bytes(cin, cout, 3) // 8, dtype=torch.float64, device=x.device)
+            L.check(lib.ledb200_train_stem_wgrad(_p(x), _p(dy), _p(dw), n, h, w, cin, cout, ctx.stride, _p(ws), _st(x)),
+                    'train_stem_wgrad')
+        return None, dw, None
+
+
+def stem_conv_ok(x, conv):
+    """whether `conv` on the NCHW image `x` can take the stem kernels (else: to_nhwc + conv2d)"""
+    return (x.dim() == 4 and x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] <= 4
+            and not x.requires_grad
+            and conv.bias is None and conv.kernel_size == (3, 3) and conv.stride[0] in (1, 2) and conv.padding == (1, 1)
+            and conv.out_channels % 16 == 0 and conv.out_channels <= 128)
+
+
+def stem_conv(x, weight, stride):
+    return _StemConv.apply(x, weight, stride)
+
+
 def _sync_group(sync):
     """The process group to synchronise BatchNorm statistics over, or None (single process / plain BN)."""
     if not sync:

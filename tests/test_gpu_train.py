@@ -59,6 +59,25 @@ def test_conv_fwd_bwd(cin, cout, k, stride, hw, bias):
         assert rel_err(bd.grad.cpu(), b.grad) < 1e-5
 
 
+@pytest.mark.parametrize('cin,cout,stride,hw', [(3, 32, 2, (80, 50)), (3, 32, 1, (33, 47)), (4, 64, 2, (64, 64)),
+                                                (1, 16, 2, (31, 20)), (3, 32, 2, (128, 256))])
+def test_stem_conv_from_nchw_image(cin, cout, stride, hw):
+    """first layer straight from the NCHW image (stem_fwd_kernel, wgrad_small_cin_kernel<., NCHW>) against ATen"""
+    g = torch.Generator().manual_seed(cin * 17 + cout + stride)
+    x = torch.randn(3, cin, *hw, generator=g)
+    w = (torch.randn(cout, cin, 3, 3, generator=g) * (2.0 / (cin * 9)) ** 0.5).requires_grad_()
+    ref = F.conv2d(x, w, None, stride, 1)
+    dy = torch.randn(ref.shape, generator=g)
+    ref.backward(dy)
+    conv = torch.nn.Conv2d(cin, cout, 3, stride, 1, bias=False)
+    assert T.stem_conv_ok(x.to(DEV), conv)
+    wd = w.detach().to(DEV).requires_grad_()
+    out = T.stem_conv(x.to(DEV), wd, stride)
+    out.backward(nhwc(dy))
+    assert rel_err(nchw(out.detach()), ref.detach()) < 1e-5
+    assert rel_err(wd.grad.cpu(), w.grad) < 1e-4
+
+
 @pytest.mark.parametrize('c,hw,relu,res', [(32, (20, 36), True, True), (19, (17, 9), True, False),
                                             (64, (8, 8), False, True), (640, (2, 3), True, False),
                                             (128, (1, 1), True, False)])
