@@ -399,13 +399,14 @@ __device__ __forceinline__ void stage_patch(const float* __restrict__ r1n, float
   }
 }
 
-template <int KT>
+template <int KT, bool EXACT>
 __global__ void __launch_bounds__(kT)
-ohem_up_pixel_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, int K, int h, int w, int H, int W,
+ohem_up_pixel_tiled_kernel(const float* __restrict__ r1, const int64_t* __restrict__ target, int K_, int h, int w, int H, int W,
                            int tiles_x, int tiles_y, int cap, int ignore, const float* __restrict__ cw, float sh, float sw,
                            float* __restrict__ prob, float* __restrict__ loss, OhemState* s) {
   extern __shared__ float sp[];
   __shared__ float shm[kT / 32];
+  const int K = EXACT ? KT : K_;
   const int KS = K | 1;
   const int tx = blockIdx.x % tiles_x, ty = (blockIdx.x / tiles_x) % tiles_y, n = blockIdx.x / (tiles_x * tiles_y);
   const int oy0 = ty * kTileO, ox0 = tx * kTileO, oy1 = min(oy0 + kTileO, H) - 1, ox1 = min(ox0 + kTileO, W) - 1;
@@ -425,21 +426,37 @@ ohem_up_pixel_tiled_kernel(const float* __restrict__ r1, const int64_t* __restri
     const int y = oy0 + o / tw, x = ox0 + o % tw;
     const int64_t i = ((int64_t)n * H + y) * W + x;
     float v[KT];
-    up_logits_smem<KT>(sp, sc, sy0, sx0, y, x, h, w, K, KS, sh, sw, v);
+    {
+      int y0, y1, x0, x1;
+      float ly0, ly1, lx0, lx1;
+      bilinear_coord(y, sh, h, y0, y1, ly0, ly1);
+      bilinear_coord(x, sw, w, x0, x1, lx0, lx1);
+      const float* a = sp + ((y0 - sy0) * sc + (x0 - sx0)) * KS;
+      const float* b = sp + ((y0 - sy0) * sc + (x1 - sx0)) * KS;
+      const float* c = sp + ((y1 - sy0) * sc + (x0 - sx0)) * KS;
+      const float* d = sp + ((y1 - sy0) * sc + (x1 - sx0)) * KS;
+#pragma unroll
+      for (int k = 0; k < KT; ++k)
+        if (EXACT || k < K) {
+          const float r0 = fmaf(b[k], lx1, a[k] * lx0);
+          const float r1v = fmaf(d[k], lx1, c[k] * lx0);
+          v[k] = fmaf(r1v, ly1, r0 * ly0);
+        }
+    }
     const int64_t yt = target[i];
     float m = -INFINITY;
     int am = 0;
 #pragma unroll
     for (int k = 0; k < KT; ++k)
-      if (k < K && v[k] > m) { m = v[k]; am = k; }
+      if ((EXACT || k < K) && v[k] > m) { m = v[k]; am = k; }
     float p = 2.0f, l = 0.f;
     if (yt != ignore) {
       const int yy = (yt >= 0 && yt < K) ? (int)yt : 0;
       float sum = 0.f, xy = 0.f, ey = 0.f;
 #pragma unroll
       for (int k = 0; k < KT; ++k)
-        if (k < K) {
-          const float e = expf(v[k] - m);          // expf costs ~20 instructions: evaluated once per class
+        if (EXACT || k < K) {
+          const float e = expf(v[k] - m);          // expf costs ~10 instructions: evaluated once per class
           sum += e;
           if (k == yy) { xy = v[k] - m; ey = e; }
         }
@@ -703,7 +720,10 @@ int launch_ohem_up(const float* r1, const int64_t* target, int N, int K, int h, 
         LEDB_LAUNCH_OK("ohem_up_pixel_tiled_kernel");
         return LEDB200_OK;
       };
-      const int rc = K <= 8 ? run(ohem_up_pixel_tiled_kernel<8>) : (K <= 20 ? run(ohem_up_pixel_tiled_kernel<20>) : run(ohem_up_pixel_tiled_kernel<32>));
+      const int rc = K == 19 ? run(ohem_up_pixel_tiled_kernel<19, true>)
+                     : K == 2 ? run(ohem_up_pixel_tiled_kernel<2, true>)
+                     : K <= 8 ? run(ohem_up_pixel_tiled_kernel<8, false>)
+                     : K <= 20 ? run(ohem_up_pixel_tiled_kernel<20, false>) : run(ohem_up_pixel_tiled_kernel<32, false>);
       if (rc) return rc;
     }
   }
