@@ -501,8 +501,16 @@ __global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__
                                                       double* __restrict__ acc, int dup_off, int tail_idx, double tail_val) {
   const int i = (blockIdx.x * kT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n2c) return;
-  double s = 0.0;
-  for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * n2c + i];
+  // four independent partial sums per lane (blocks lane, lane + 32, lane + 64, lane + 96 in turn): four loads in flight instead
+  // of a chain of ~19 dependent ones (7 us per launch, 124 launches per step); the grouping depends on nblocks only
+  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
+  int b = lane;
+  for (; b + 96 < nblocks; b += 128) {
+    s0 += part[(int64_t)b * n2c + i]; s1 += part[(int64_t)(b + 32) * n2c + i];
+    s2 += part[(int64_t)(b + 64) * n2c + i]; s3 += part[(int64_t)(b + 96) * n2c + i];
+  }
+  for (; b < nblocks; b += 32) s0 += part[(int64_t)b * n2c + i];
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (lane == 0) {
@@ -628,6 +636,67 @@ bn_bwd_apply4_kernel(const float4* __restrict__ dout, const float4* __restrict__
     if (i < C4) {
 #pragma unroll
       for (int j = 0; j < 4; ++j) { dbeta[c + j] = (float)acc_local[c + j]; dgamma[c + j] = (float)acc_local[C + c + j]; }
+    }
+  }
+}
+
+// C % 4 != 0 (the K-class head BatchNorms, C = 19): the tensor is still a dense array of floats, so it is walked as float4s
+// of the FLAT index; every component looks its channel up on its own ((4 i + j) % C).  Needs total % 4 == 0.
+__global__ void __launch_bounds__(kT)
+bn_apply_flat4_kernel(const float4* __restrict__ y, const float4* __restrict__ res, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ invstd,
+                      float4* __restrict__ out, int relu, uint32_t total4, uint32_t C, int rnd) {
+  const float lo = relu ? 0.f : -INFINITY;
+  for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < total4; i += gridDim.x * kT) {
+    const float4 v = __ldg(y + i);
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (res) r = __ldg(res + i);
+    const float vv[4] = {v.x, v.y, v.z, v.w}, rr[4] = {r.x, r.y, r.z, r.w};
+    float o[4];
+    uint32_t c = (uint32_t)(((uint64_t)i * 4) % C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float t = fmaf((vv[j] - __ldg(mean + c)) * __ldg(invstd + c), __ldg(gamma + c), __ldg(beta + c));
+      if (res) t += rr[j];
+      o[j] = rt(fmaxf(t, lo), rnd);
+      if (++c == C) c = 0;
+    }
+    out[i] = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+__global__ void __launch_bounds__(kT)
+bn_bwd_apply_flat4_kernel(const float4* __restrict__ dout, const float4* __restrict__ y, const float4* __restrict__ out,
+                          const float* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ invstd,
+                          const double* __restrict__ acc, const double* __restrict__ acc_local, float4* __restrict__ dy,
+                          float4* __restrict__ dres, float* __restrict__ dgamma, float* __restrict__ dbeta, int relu,
+                          uint32_t total4, uint32_t C, float invM, int rnd) {
+  if (invM < 0.f) invM = (float)(1.0 / acc_local[4 * C]);
+  for (uint32_t i = blockIdx.x * kT + threadIdx.x; i < total4; i += gridDim.x * kT) {
+    float4 dz = __ldg(dout + i);
+    if (relu) {
+      const float4 o = __ldg(out + i);
+      if (!(o.x > 0.f)) dz.x = 0.f;
+      if (!(o.y > 0.f)) dz.y = 0.f;
+      if (!(o.z > 0.f)) dz.z = 0.f;
+      if (!(o.w > 0.f)) dz.w = 0.f;
+    }
+    const float4 yy = __ldg(y + i);
+    const float dzv[4] = {dz.x, dz.y, dz.z, dz.w}, yv[4] = {yy.x, yy.y, yy.z, yy.w};
+    float o[4];
+    uint32_t c = (uint32_t)(((uint64_t)i * 4) % C);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float is = __ldg(invstd + c);
+      const double xhat = (double)(yv[j] - __ldg(mean + c)) * (double)is;
+      const double br = (double)dzv[j] - acc[c] * (double)invM - xhat * (acc[C + c] * (double)invM);
+      o[j] = rt((float)((double)__ldg(gamma + c) * (double)is * br), rnd);
+      if (++c == C) c = 0;
+    }
+    dy[i] = make_float4(o[0], o[1], o[2], o[3]);
+    if (dres) dres[i] = dz;
+    if (i * 4 < C) {
+      for (uint32_t j = i * 4; j < i * 4 + 4 && j < C; ++j) { dbeta[j] = (float)acc_local[j]; dgamma[j] = (float)acc_local[C + j]; }
     }
   }
 }
@@ -1401,6 +1470,10 @@ int ledb200_train_bn_fwd_apply(const float* y, const float* gamma, const float* 
     bn_apply4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
         reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(res_opt), gamma, beta, save_mean, save_invstd,
         reinterpret_cast<float4*>(out), relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), g_round);
+  else if ((npix * C) % 4 == 0 && npix * C < (1ll << 31) && C >= 4 && ((uintptr_t)y | (uintptr_t)res_opt | (uintptr_t)out) % 16 == 0)
+    bn_apply_flat4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
+        reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(res_opt), gamma, beta, save_mean, save_invstd,
+        reinterpret_cast<float4*>(out), relu, (uint32_t)(npix * C / 4), (uint32_t)C, g_round);
   else if (npix * C < (1ll << 32))
     bn_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, st>>>(y, res_opt, gamma, beta, save_mean, save_invstd, out, relu,
                                                                npix * C, C, g_round);
@@ -1427,6 +1500,12 @@ int ledb200_train_bn_bwd_apply(const float* dout, const float* y, const float* o
         reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
         save_mean, save_invstd, acc + 2 * C, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta,
         relu, (uint32_t)(npix * C / 4), (uint32_t)(C / 4), total_count < 0.0 ? -1.f : (float)(1.0 / total_count), g_round);
+  else if ((npix * C) % 4 == 0 && npix * C < (1ll << 31) && C >= 4 &&
+           ((uintptr_t)dout | (uintptr_t)y | (uintptr_t)out | (uintptr_t)dy | (uintptr_t)dres_opt) % 16 == 0)
+    bn_bwd_apply_flat4_kernel<<<grid1d(npix * C / 4), kT, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
+        save_mean, save_invstd, acc + 2 * C, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta,
+        relu, (uint32_t)(npix * C / 4), (uint32_t)C, total_count < 0.0 ? -1.f : (float)(1.0 / total_count), g_round);
   else if (npix * C < (1ll << 32))
     bn_bwd_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, (cudaStream_t)stream>>>(
         dout, y, out, gamma, save_mean, save_invstd, acc + 2 * C, acc, dy, dres_opt, dgamma, dbeta, relu, npix * C, C,
@@ -1469,6 +1548,12 @@ int ledb200_train_bn_bwd(const float* dout, const float* y, const float* out, co
         reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
         save_mean, save_invstd, acc, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta, relu,
         (uint32_t)(npix * C / 4), (uint32_t)(C / 4), 1.f / (float)npix, g_round);
+  else if ((npix * C) % 4 == 0 && npix * C < (1ll << 31) && C >= 4 &&
+           ((uintptr_t)dout | (uintptr_t)y | (uintptr_t)out | (uintptr_t)dy | (uintptr_t)dres_opt) % 16 == 0)
+    bn_bwd_apply_flat4_kernel<<<grid1d(npix * C / 4), kT, 0, st>>>(
+        reinterpret_cast<const float4*>(dout), reinterpret_cast<const float4*>(y), reinterpret_cast<const float4*>(out), gamma,
+        save_mean, save_invstd, acc, acc, reinterpret_cast<float4*>(dy), reinterpret_cast<float4*>(dres_opt), dgamma, dbeta, relu,
+        (uint32_t)(npix * C / 4), (uint32_t)C, 1.f / (float)npix, g_round);
   else if (npix * C < (1ll << 32))
     bn_bwd_apply_kernel<uint32_t><<<grid1d(npix * C), kT, 0, st>>>(dout, y, out, gamma, save_mean, save_invstd, acc, acc, dy,
                                                                    dres_opt, dgamma, dbeta, relu, npix * C, C,

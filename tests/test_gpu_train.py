@@ -79,6 +79,7 @@ def test_stem_conv_from_nchw_image(cin, cout, stride, hw):
 
 
 @pytest.mark.parametrize('c,hw,relu,res', [(32, (20, 36), True, True), (19, (17, 9), True, False),
+                                            (19, (16, 12), True, True), (19, (8, 8), False, False),   # flat float4 path
                                             (64, (8, 8), False, True), (640, (2, 3), True, False),
                                             (128, (1, 1), True, False)])
 def test_bn_act(c, hw, relu, res):
