@@ -440,6 +440,7 @@ chan_reduce4_kernel(const float4* __restrict__ a, const float4* __restrict__ y, 
     float4 m = make_float4(0.f, 0.f, 0.f, 0.f), is = m;
     if (KIND == 1) { m = *reinterpret_cast<const float4*>(mean + 4 * c4); is = *reinterpret_cast<const float4*>(invstd + 4 * c4); }
     int cnt = 0;
+#pragma unroll 4                                 // four rows' loads in flight; the accumulation order is unchanged
     for (uint32_t r = g / C4; r < npix; r += R) {
       const uint32_t i = r * C4 + c4;
       const float4 v = __ldg(a + i);
@@ -501,16 +502,8 @@ __global__ void __launch_bounds__(kT) chan_sum_kernel(const double* __restrict__
                                                       double* __restrict__ acc, int dup_off, int tail_idx, double tail_val) {
   const int i = (blockIdx.x * kT + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n2c) return;
-  // four independent partial sums per lane (blocks lane, lane + 32, lane + 64, lane + 96 in turn): four loads in flight instead
-  // of a chain of ~19 dependent ones (7 us per launch, 124 launches per step); the grouping depends on nblocks only
-  double s0 = 0.0, s1 = 0.0, s2 = 0.0, s3 = 0.0;
-  int b = lane;
-  for (; b + 96 < nblocks; b += 128) {
-    s0 += part[(int64_t)b * n2c + i]; s1 += part[(int64_t)(b + 32) * n2c + i];
-    s2 += part[(int64_t)(b + 64) * n2c + i]; s3 += part[(int64_t)(b + 96) * n2c + i];
-  }
-  for (; b < nblocks; b += 32) s0 += part[(int64_t)b * n2c + i];
-  double s = (s0 + s1) + (s2 + s3);
+  double s = 0.0;
+  for (int b = lane; b < nblocks; b += 32) s += part[(int64_t)b * n2c + i];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
   if (lane == 0) {
