@@ -128,8 +128,13 @@ def _round_for(shape):
 TC_OPS = 7   # diagnostic mask (tools/diag_tf32_grads.py): 1 forward, 2 data gradient, 4 weight gradient on tensor cores
 
 
+_FWD_MAXCIN = int(os.environ.get('LEDB200_TC_FWD_MAXCIN', '0'))   # diagnostic: forward convolutions wider than this stay on CUDA cores
+
+
 def _tc_ok(op, n, h, w, cin, cout, k, stride):
     _sync_mode()
+    if op == 0 and _FWD_MAXCIN and cin > _FWD_MAXCIN:
+        return False
     return (TENSOR_CORES and bool(TC_OPS & (1 << op))
             and bool(L.get().ledb200_train_conv_tc_ok(op, n, h, w, cin, cout, k, stride)))
 
