@@ -87,6 +87,11 @@ struct TcParams {
   // after the main accumulator of the same stage, and the epilogue adds the two.  The tensor core's accumulator truncates at
   // the magnitude of the running sum; small addends kept apart lose nothing to it (measured: 2e-5 -> 7e-6 at K = 2304).
   int lo_off;
+  // three-pass 3x3 stride-1 launches: kacc = 3 main accumulators, one per filter ROW, added by the epilogue.  The tensor
+  // core's accumulator truncates at every accumulation step, so the error of a long reduction grows with its length (measured
+  // 8.6e-7 at K = 9 x 32, 6.8e-6 at K = 9 x 256 with one accumulator); three chains of a third of the length cut it.
+  // Accumulator j of stage ts lives at column j * acc_plane + ts * NT (j = kacc is the correction accumulator: lo_off).
+  int kacc, acc_plane;
   int tl_launch;                     // launch ordinal (timeline probe builds only: slot of g_tc_tl)
   int dbg;                           // LEDB200_TC_DBG probe bits: 1 no global stores, 2 no MMAs, 4 no A TMA, 8 no residual loads, 32 atom-aligned A row groups, 64 empty epilogue, 128 single MMA issuer
 };
@@ -517,6 +522,13 @@ __device__ __forceinline__ void epilogue_f32(const TcParams& P, int warp, int la
       tc_wait_ld();
       if (P.lo_off) {
         uint32_t u[32];
+        for (int a = 1; a < P.kacc; ++a) {                      // the other filter rows' accumulators
+          tc_ld16(taddr0 + (uint32_t)(a * P.acc_plane) + c0, u);
+          tc_ld16(taddr0 + (uint32_t)(a * P.acc_plane) + c0 + 16, u + 16);
+          tc_wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(u[j]));
+        }
         tc_ld16(taddr0 + (uint32_t)P.lo_off + c0, u);
         tc_ld16(taddr0 + (uint32_t)P.lo_off + c0 + 16, u + 16);
         tc_wait_ld();
@@ -785,13 +797,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) {
-                        tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                        tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
-                      } else {
-                        tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
-                        tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
-                      }
+                      // main product into the accumulator of this tap's filter row (kacc = 3) or the single one
+                      const uint32_t d_main = d_tmem + ((MODE == 0 && P.kacc == 3) ? (uint32_t)((t / 3) * P.acc_plane) : 0u);
+                      if (s == 0 && k == 0 && (t == 0 || (MODE == 0 && P.kacc == 3 && t % 3 == 0)))
+                        tc_mma2_tf32(d_main, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else
+                        tc_mma2_acc_tf32(d_main, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
                     }
                   }
                 }
@@ -818,13 +831,14 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < KSTEPS; ++k) {
                       const uint32_t al = a_lo + (((uint32_t)TAPPIX(s, t) * ROWB + k * 32) >> 4);
-                      if (s == 0 && t == 0 && k == 0) {
-                        tc_mma2_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
-                        tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
-                      } else {
-                        tc_mma2_acc_tf32(d_tmem, al, a_hi, b_lo + 2 * k, b_hi, idesc);
-                        tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
-                      }
+                      // main product into the accumulator of this tap's filter row (kacc = 3) or the single one
+                      const uint32_t d_main = d_tmem + ((MODE == 0 && P.kacc == 3) ? (uint32_t)((t / 3) * P.acc_plane) : 0u);
+                      if (s == 0 && k == 0 && (t == 0 || (MODE == 0 && P.kacc == 3 && t % 3 == 0)))
+                        tc_mma2_tf32(d_main, al, a_hi, b_lo + 2 * k, b_hi, idesc, acc_first);
+                      else
+                        tc_mma2_acc_tf32(d_main, al, a_hi, b_lo + 2 * k, b_hi, idesc);
+                      if (s == 0 && t == 0 && k == 0) tc_mma2_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc, acc_first);
+                      else tc_mma2_acc_tf32(d_lo, al, a_hi, b_lo + b_half16 + 2 * k, b_hi, idesc);
                     }
                     if (t == 0) { mbar_wait(&a_lo_full[sa], pa); tc_fence_after(); }
 #pragma unroll
@@ -1071,6 +1085,8 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   P.NT = cp > 256 ? 256 : ((cp & (cp - 1)) == 0 ? cp : 64);
   if (x3 && P.NT > 128) P.NT = 128;     // two weight halves per tile: keep the B ring inside shared memory
   if (tf32 && cp > 256) P.NT = 128;     // wide training outputs (DAPPM's 640-channel data gradient): any multiple of 128
+  const bool kacc3 = x3 && a.ksize == 3 && !s2 && !a.sub;     // one main accumulator per filter row (see TcParams::kacc)
+  if (kacc3 && P.NT > 64) P.NT = 64;    // (3 main + 1 correction) x 64 columns x 2 stages = the whole TMEM
   P.ntiles_n = cp / P.NT;
   P.KC = tf32 ? 64 : pick_kc(a.Cin);
   P.nchunks = cinE / P.KC;
@@ -1196,10 +1212,13 @@ int launch_conv_tc(const ConvArgs& a, cudaStream_t st) {
   }
   const size_t smem = 1024 + (size_t)P.SA * P.a_stage_bytes +
                       (size_t)(P.b_resident ? P.nchunks * 9 : P.SB) * P.b_tile_bytes + bar_bytes;
-  P.nst = (4 * P.NT * (x3 ? 2 : 1) <= 512) ? 4 : 2;
-  P.lo_off = x3 ? P.nst * P.NT : 0;
+  P.kacc = kacc3 ? 3 : 1;
+  const int nacc = x3 ? P.kacc + 1 : 1;          // accumulators per stage
+  P.nst = (4 * P.NT * nacc <= 512) ? 4 : 2;
+  P.acc_plane = P.nst * P.NT;
+  P.lo_off = x3 ? P.kacc * P.acc_plane : 0;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(P.nst * P.NT * (x3 ? 2 : 1))) cols <<= 1;
+  while (cols < (uint32_t)(P.acc_plane * nacc)) cols <<= 1;
   P.tmem_cols = cols;
   P.out = (__nv_bfloat16*)a.out; P.out_ld = a.out_ld;
   P.out2 = (__nv_bfloat16*)a.out2; P.out2_ld = a.out2_ld; P.o2_scale = a.o2_scale; P.o2_shift = a.o2_shift;
